@@ -1,0 +1,201 @@
+/*
+ * tic_b200.h — C ABI of libtic_b200.so: the B200 (sm_100a) implementation of the late-fusion head and
+ * image-text auxiliary-loss path of danaesavi/SocialMedia-TextImage-Classification-AuxLosses.
+ *
+ * The reference has no FFI: its boundary for this path is the Python surface of models/mm_late.py,
+ * models/utils.py:225-231 (clip_loss) and models/run_mm_late.py (flags).  Each entry point below names the
+ * reference lines it replaces; the Python mirror (package `tic_b200`) binds them with ctypes, and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; the caller owns every buffer,
+ *     outputs and workspaces are caller-allocated (sizes documented per function);
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     (so calls are CUDA-graph capturable) and the library keeps no global state besides an error string;
+ *   - return value: 0 = OK, negative = error (see TIC_E_*); functions never throw across the ABI;
+ *   - thread-safety: re-entrant per stream; the error string is thread-local.
+ */
+#ifndef TIC_B200_H
+#define TIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIC_OK 0
+#define TIC_E_ARG (-1)        /* bad shape / alignment / null pointer */
+#define TIC_E_TMAP (-2)       /* cuTensorMapEncodeTiled failed */
+#define TIC_E_ATTR (-3)       /* cudaFuncSetAttribute failed */
+#define TIC_E_LAUNCH (-4)     /* kernel launch failed */
+#define TIC_E_RANGE (-5)      /* value outside the supported numeric range */
+#define TIC_E_CUDA (-6)       /* other CUDA runtime error */
+
+#define TIC_ITM_UNIFORM 0 /* reference behaviour, mm_late.py:389-414 */
+#define TIC_ITM_HARD 1    /* similarity-weighted extension (not in the reference) */
+
+const char* tic_last_error_string(void);
+int tic_version(void);
+int tic_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------ GEMM
+ * D[m,n] = alpha * sum_k A(m,k) * B(n,k) (+ bias[n]) (relu)   bf16 operands, fp32 accumulate (tcgen05 / TMEM).
+ *   A(m,k) = a_mn_major ? A[k*lda + m] : A[m*lda + k];   B(n,k) = b_mn_major ? B[k*ldb + n] : B[n*ldb + k].
+ * Replaces the ATen/cuBLAS GEMM call sites of the head: nn.Linear forward/backward for text_projection,
+ * visual_projection (HF VisionTextDualEncoderModel.forward, built at mm_late.py:59-61), linear_fusion
+ * (mm_late.py:81,95,112,143), fc_Q/fc_K/fc_V collapsed products (mm_late.py:105), linear_gmu_* (mm_late.py:88-89).
+ * lda/ldb must be multiples of 8 elements and A/B 16-byte aligned (TMA). d_dtype: 0 = fp32, 1 = bf16. */
+int tic_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
+                  int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu,
+                  void* stream);
+/* Reference-quality SIMT fp32-accumulate GEMM with the same semantics (debug / self-test only). */
+int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
+                       int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------ L2 norm
+ * rinv[i] = 1 / ||X[i,:]||_2 (no epsilon, as HF modeling_vision_text_dual_encoder.py:268-269 and
+ * mm_early.py:98-99).  X bf16 [rows, cols]. */
+int tic_row_rnorm_bf16(const void* X, int64_t ldx, int rows, int cols, float* rinv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ ITC (fused)
+ * Logits S[i,j] = scale * rinv_t[i] * rinv_v[j] * <T[i,:], V[j,:]>  (HF :272-273; mm_early.py:101-102), never
+ * materialised unless `logits_out` is given.  T is this rank's row block [m_local, P]; V is the gathered
+ * [n_global, P]; `row_offset` is the global column index of local row 0 (diagonal = positives).
+ *
+ * tic_itc_fwd writes per-tile partial sums of exp(S - shift):
+ *     row_part [tic_itc_row_parts(n_global)][m_local],  col_part [tic_itc_col_parts(m_local)][n_global]
+ * and diag[i] = S[i, row_offset+i].  `shift` must satisfy shift >= max S; scale (=exp(logit_scale)) works since
+ * |cos| <= 1; scale > 40 is rejected with TIC_E_RANGE (fp32 underflow of exp(-2*scale)). */
+int tic_itc_row_parts(int n_global);
+int tic_itc_col_parts(int m_local);
+int tic_itc_fwd(const void* T, int64_t ldt, const void* V, int64_t ldv, const float* rinv_t, const float* rinv_v,
+                int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
+                float* col_part, float* diag, float* logits_out, int64_t ld_logits, void* stream);
+/* out[j] = sum_p part[p][j]  (deterministic fixed-order reduction of the partials above). */
+int tic_reduce_parts(const float* part, int nparts, int n, float* out, void* stream);
+/* lse = shift + log(sum);  loss_sums[0] += sum_i (lse_row[i] - diag[i]),  loss_sums[1] += sum_i (lse_col[row_offset+i] - diag[i])
+ * utils.py:225-231: clip_loss = (loss_sums[0]/B + loss_sums[1]/B) / 2 with B = n_global. */
+int tic_itc_lse_loss(const float* row_sum, const float* col_sum, const float* diag, int m_local, int n_global,
+                     int row_offset, float shift, float* lse_row, float* lse_col, float* loss_sums, void* stream);
+/* Recompute S tiles and emit the bf16 gradient operands (g = dLoss/d(clip_loss), B = n_global):
+ *   Gp[i,j] = g/(2B) * (exp(S-lse_row[i]) + exp(S-lse_col[j]))      (the -I/B diagonal is applied in fp32 later)
+ *   GA [m_local, ld_ga ] row-major:  Gp[i,j] * rinv_v[j]            (A operand of dT = GA * V)
+ *   GBT[n_global, ld_gbt] row-major: Gp[i,j] * rinv_t[i] at [j,i]   (A operand of dV = GBT * T) */
+int tic_itc_bwd_g(const void* T, int64_t ldt, const void* V, int64_t ldv, const float* rinv_t, const float* rinv_v,
+                  const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale,
+                  float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* stream);
+/* Normalise-backward + diagonal term, one warp per row (HF :268-269 backward):
+ *   dxh = scale*acc[i,:] - diag_coef * scale * rinv_o[i] * Xo[i,:]   (diag_coef = g/B, 0 if row has no local positive)
+ *   r = <xh, dxh>, xh = rinv[i]*X[i,:];   dX[i,:] = rinv[i] * (dxh - xh * r);   dscale_part[block] += r (for dlogit_scale)
+ * acc fp32 [rows, P] is the raw GEMM output; X the embedding being differentiated, Xo the other modality's
+ * row with the same global index (may be NULL when diag_coef == 0). dX written as fp32 and/or bf16 (either may be NULL). */
+int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, int64_t ldx, const float* rinv,
+                          const void* Xo, int64_t ldxo, const float* rinv_o, int rows, int P, float scale,
+                          float diag_coef, float* dX_f32, int64_t ld_df, void* dX_bf16, int64_t ld_db,
+                          float* r_sum /* [1], atomically accumulated */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ clip_loss on a given matrix
+ * utils.py:225-231 on a materialised similarity S [B,B] fp32: loss = (CE(S, I) + CE(S^T, I)) / 2.
+ * fwd reads S once; lse_row/lse_col [B] are saved for backward; bwd writes dS = g*(softmax_row+softmax_col-2I)/(2B).
+ * workspace: tic_ce_bidir_workspace_bytes(B). */
+int64_t tic_ce_bidir_workspace_bytes(int B);
+int tic_ce_bidir_fwd(const float* S, int64_t lds, int B, float* lse_row, float* lse_col, float* loss, void* workspace,
+                     void* stream);
+int tic_ce_bidir_bwd(const float* S, int64_t lds, int B, const float* lse_row, const float* lse_col,
+                     const float* grad_loss /* device scalar */, float* dS, int64_t ldds, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ ITM sampling + gather
+ * mm_late.py:389-414 (prepare_itm_inputs).  Row i is swapped iff u_coin[i] < 0.5 (label 0), else kept (label 1);
+ * B == 1 keeps everything.  Uniform mode: k = min(floor(u_pick[i]*(B-1)), B-2), src = k < i ? k : k+1.
+ * Hard mode: src ~ Multinomial(w), w[j] = exp(S[i,j]-max_j S[i,:]) for j != i, by inverse CDF on fixed-point
+ * (2^30) weights with a bit-reproducible exp (see oracle/restatement.py: det_exp_f32).
+ * Gathers nrowsets row-major byte matrices: dst_k[i,:] = src_k[src[i],:]  (ids, mask; any row_bytes).
+ * labels int64 [B], src_idx int32 [B]. */
+int tic_itm_sample(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds,
+                   int64_t* labels, int32_t* src_idx, void* stream);
+int tic_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int64_t row_bytes,
+                    const int32_t* src_idx, int rows, void* stream);
+/* Fused: sample + gather of ids and mask in one launch (the mm_late.py:396-409 loop). */
+int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds,
+                          const void* ids, const void* mask, int64_t row_bytes, void* tim_ids, void* tim_mask,
+                          int64_t* labels, int32_t* src_idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ fusion heads
+ * Pack the CLS rows for linear_fusion (torch.cat at mm_late.py:94,111,141):
+ *   Xcat[i,      :] = [ xt[i*xt_stride : +E]        | xv[i*xv_stride : +E] ]      i < B   (main pass)
+ *   Xcat[B + i,  :] = [ xt[src[i]*xt_stride : +E]   | xv[i*xv_stride : +E] ]      if src != NULL (ITM pass, :170-181)
+ * xt/xv bf16 with row strides in elements (so x_t[:,0,:] of a [B,L,E] tensor is xt_stride = L*E). */
+int tic_pack_cls_pairs(const void* xt, int64_t xt_stride, const void* xv, int64_t xv_stride, int B, int E,
+                       const int32_t* src_idx, void* Xcat, int64_t ldx, void* stream);
+/* Gradient of the pack w.r.t. xt (vision is frozen, mm_late.py:67-69):
+ *   dxt[i,:] = dXcat[i,:E] + sum_{k: src[k]==i} dXcat[B+k,:E]   (fp32, atomics for the scattered part). */
+int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, int B, int E, const int32_t* src_idx, float* dxt, int64_t ld_dxt,
+                        void* stream);
+
+/* Classifier + ITM heads with their losses, forward and backward in one launch (mm_late.py:163-164,182;
+ * losses run_mm_late.py:85,97 and the mix mm_late.py:473-487):
+ *   rows [0,B):   logits_cls = (H*keep_scale) W_cls^T + b_cls;  L_cls = -(1/B) sum_i sum_c w_c y_ic log softmax_ic
+ *   rows [B,2B):  logits_tim = H W_tim^T + b_tim;                L_tim = mean CE(logits_tim, lbl_tim)    (if has_tim)
+ * H fp32 [B or 2B, E] is the post-ReLU fusion output; dH (bf16 and/or fp32) receives c_cls*dL_cls/dH resp.
+ * c_tim*dL_tim/dH, already multiplied by the ReLU mask (H > 0).  dW/db are accumulated (+=) in fp32 with atomics
+ * into zero-initialised buffers.  losses[0] += L_cls, losses[1] += L_tim (unweighted). keep (uint8 dropout mask
+ * [B,E], may be NULL) and keep_scale = 1/(1-p) reproduce nn.Dropout on the classifier branch only. */
+int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* W_cls,
+                      const float* b_cls, const float* W_tim, const float* b_tim, const float* y_soft,
+                      const float* class_w, const int64_t* lbl_tim, const uint8_t* keep, float keep_scale, float c_cls,
+                      float c_tim, float* logits_cls, float* logits_tim, float* losses, void* dH_bf16, int64_t ld_dhb,
+                      float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask, void* stream);
+
+/* attention fusion, CLS-row collapse of mm_late.py:98-113,195-210 (exact algebra):
+ *   q0 = fc_Q(x_t[:,0]);  kq = W_K^T q0;  c = <q0,b_K>;  s_j = (<kq, x_v[j]> + c) * E^-1/2;  a = softmax_j(s)
+ *   xbar = sum_j a_j x_v[j];  ctx0 = W_V xbar + b_V.
+ * This kernel is the HBM-bound middle: one streaming read of x_v [B, Lv, E] (bf16) producing
+ * xbar [B,E] (bf16 + fp32) and the attention weights a [B,Lv] fp32 (saved for backward). */
+int tic_attn_pool_fwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_stride, const void* kq, int64_t ldkq,
+                      const float* cbias, int B, int Lv, int E, float scale, void* xbar_bf16, int64_t ld_xb,
+                      float* attn, int64_t ld_attn, void* stream);
+/* backward w.r.t. kq and cbias (x_v is frozen): ds_j = a_j * (<dxbar, x_v[j]> - sum_l a_l <dxbar, x_v[l]>) * scale,
+ * dkq = sum_j ds_j x_v[j], dc = sum_j ds_j.  Second (and last) streaming read of x_v. */
+int tic_attn_pool_bwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_stride, const float* attn,
+                      int64_t ld_attn, const float* dxbar, int64_t ld_dxb, int B, int Lv, int E, float scale,
+                      float* dkq, int64_t ld_dkq, float* dcbias, void* stream);
+
+/* aspect-att fusion (mm_late.py:115-131) including the reference's stack->reshape row scrambling:
+ * sample i pairs flat rows 2i, 2i+1 of [t_pool; v_pool].  out = relu(sum_k alpha_k V_k), alpha = softmax_k tanh(w.V_k + b). */
+int tic_aspect_fwd(const void* t_pool, int64_t ldt, const void* v_pool, int64_t ldv, int B, int E, const float* w_a,
+                   const float* b_a, float* out, int64_t ldo, float* alpha /* [B,2] saved */, void* stream);
+int tic_aspect_bwd(const void* t_pool, int64_t ldt, const void* v_pool, int64_t ldv, int B, int E, const float* w_a,
+                   const float* b_a, const float* out, int64_t ldo, const float* alpha, const float* dout, int64_t lddo,
+                   float* dt_pool, int64_t lddt, float* dw_a, float* db_a, void* stream);
+
+/* gmu gate (mm_late.py:133-144): G[i,:] = z*tp + (1-z)*vp, z = sigmoid([xt_cls | xv_cls]) (no learned gate).
+ * tp/vp fp32 [B,2E] are linear_gmu_t/v outputs; Xcat bf16 [B,2E] from tic_pack_cls_pairs. */
+int tic_gmu_gate_fwd(const void* Xcat, int64_t ldx, const float* tp, const float* vp, int64_t ldp, int B, int E2,
+                     void* G_bf16, int64_t ldg, void* stream);
+int tic_gmu_gate_bwd(const void* Xcat, int64_t ldx, const float* tp, const float* vp, int64_t ldp, const float* dG,
+                     int64_t lddg, int B, int E2, void* dtp_bf16, void* dvp_bf16, int64_t lddp, float* dXcat_gate,
+                     int64_t lddx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ utilities */
+int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream);
+int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream);
+/* dst[r, c] (+)= column sums etc. are done by GEMMs; bias gradient: db[n] = sum_m dY[m,n] (bf16 in, fp32 out). */
+int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, void* stream);
+/* out[0] = (1-bi-bm)*losses[0] + bi*0.5*(itc[0]+itc[1])/B + bm*losses[1]  (mm_late.py:473-487). */
+int tic_loss_mix(const float* losses, const float* itc_sums, int n_global, float beta_itc, float beta_itm,
+                 int use_itc, int use_itm, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ host-buffer entry point
+ * End-to-end call for reference-side integrators that hold HOST buffers (numpy / torch CPU): copies the step's
+ * inputs H2D, runs the fused ITC step (row norms, logits tiles, bidirectional CE, gradients) and copies the loss and
+ * gradients back.  T_host/V_host bf16 [B,P] pinned or pageable; dT_host/dV_host fp32 [B,P].  Synchronous. */
+int tic_itc_step_host(const void* T_host, const void* V_host, int B, int P, float logit_scale, float* loss_host,
+                      float* dT_host, float* dV_host, float* dlogit_scale_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIC_B200_H */

@@ -1,0 +1,212 @@
+// tic_gemm_bf16: generic bf16 x bf16 -> fp32-accumulate GEMM on tcgen05/TMEM fed by TMA (see tic_umma.cuh),
+// plus the library-wide host helpers (error string, tensor-map encoder) and a SIMT reference GEMM for self-tests.
+#include <mutex>
+#include "common.cuh"
+#include "tic_umma.cuh"
+
+namespace tic {
+
+static thread_local char g_err[512] = "ok";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+TmapEncoder::EncodeFn TmapEncoder::get() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                      uint32_t box_inner, uint32_t box_outer) {
+  auto fn = TmapEncoder::get();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return TIC_E_TMAP;
+  }
+  if (!aligned16(ptr) || (pitch_elems % 8) != 0) {
+    set_error("TMA operand needs 16-byte aligned base and leading dimension multiple of 8 (ptr=%p ld=%llu)", ptr,
+              (unsigned long long)pitch_elems);
+    return TIC_E_ARG;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu pitch=%llu box=%ux%u", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems, box_inner, box_outer);
+    return TIC_E_TMAP;
+  }
+  return 0;
+}
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------ generic store epilogue
+struct StoreEpi {
+  struct Params {
+    void* D;
+    int64_t ldd;
+    int d_bf16;
+    float alpha;
+    const float* bias;
+    int relu;
+  };
+  template <int BN>
+  __device__ static void tile(const Params& p, const EpiCtx& cx) {
+    const int lane = threadIdx.x & 31;
+    const int row = cx.m0 + cx.quad * 32 + lane;
+    const int cols_per_part = BN / cx.nparts;
+    const bool vec_ok = p.d_bf16 ? ((p.ldd & 7) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0)
+                                 : ((p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < cols_per_part / 32; ++c) {
+      const int cl = cx.part * cols_per_part + c * 32;
+      const int col0 = cx.n0 + cl;
+      if (col0 >= cx.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16) + cl, v);
+      tmem_ld_wait();
+      if (row >= cx.M) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = p.alpha * __uint_as_float(v[j]);
+        if (p.bias != nullptr && col0 + j < cx.N) x += __ldg(p.bias + col0 + j);
+        if (p.relu) x = fmaxf(x, 0.f);
+        f[j] = x;
+      }
+      const bool full = (col0 + 32 <= cx.N) && vec_ok;
+      if (p.d_bf16) {
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<int64_t>(row) * p.ldd + col0;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(f[j], f[j + 1]);
+            u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+            u.z = pack_bf16x2(f[j + 4], f[j + 5]);
+            u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+            *reinterpret_cast<uint4*>(d + j) = u;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < cx.N) d[j] = __float2bfloat16_rn(f[j]);
+        }
+      } else {
+        float* d = reinterpret_cast<float*>(p.D) + static_cast<int64_t>(row) * p.ldd + col0;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < cx.N) d[j] = f[j];
+        }
+      }
+    }
+  }
+};
+
+template <int BN>
+static int dispatch_major(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
+                          const StoreEpi::Params& ep, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_umma_gemm<BN, false, false, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+  if (!a_mn && b_mn) return launch_umma_gemm<BN, false, true, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+  if (a_mn && !b_mn) return launch_umma_gemm<BN, true, false, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+  return launch_umma_gemm<BN, true, true, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+}
+
+// ------------------------------------------------------------------ SIMT reference GEMM (self-test only)
+__global__ void simt_gemm_kernel(const __nv_bfloat16* A, int64_t lda, int a_mn, const __nv_bfloat16* B, int64_t ldb,
+                                 int b_mn, void* D, int64_t ldd, int d_bf16, int M, int N, int K, float alpha,
+                                 const float* bias, int relu) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ka = k0 + tx;
+    const int ma = blockIdx.y * 16 + ty;
+    sa[ty][tx] = (ma < M && ka < K) ? __bfloat162float(a_mn ? A[ka * lda + ma] : A[ma * lda + ka]) : 0.f;
+    const int nb = blockIdx.x * 16 + ty;
+    sb[ty][tx] = (nb < N && ka < K) ? __bfloat162float(b_mn ? B[ka * ldb + nb] : B[nb * ldb + ka]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[tx][k], acc);
+    __syncthreads();
+  }
+  if (m < M && n < N) {
+    float x = alpha * acc + (bias ? bias[n] : 0.f);
+    if (relu) x = fmaxf(x, 0.f);
+    if (d_bf16) reinterpret_cast<__nv_bfloat16*>(D)[m * ldd + n] = __float2bfloat16_rn(x);
+    else reinterpret_cast<float*>(D)[m * ldd + n] = x;
+  }
+}
+
+}  // namespace tic
+
+using namespace tic;
+
+extern "C" {
+
+const char* tic_last_error_string(void) { return g_err; }
+int tic_version(void) { return 100; }
+int tic_sm_count(void) { return device_sm_count(); }
+
+int tic_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
+                  int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu, void* stream) {
+  TIC_CHECK_ARG(A && B && D, "tic_gemm_bf16: null pointer");
+  TIC_CHECK_ARG(M > 0 && N > 0 && K > 0, "tic_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  TIC_CHECK_ARG(d_dtype == 0 || d_dtype == 1, "tic_gemm_bf16: d_dtype must be 0 (fp32) or 1 (bf16)");
+  StoreEpi::Params ep{D, ldd, d_dtype, alpha, bias, relu};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sms = device_sm_count();
+  const int m_tiles = ceil_div(M, kBM);
+  // Largest N tile that still gives every SM a tile; small problems prefer more, narrower tiles.
+  int rc;
+  if (m_tiles * ceil_div(N, 256) >= sms) rc = dispatch_major<256>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
+  else if (m_tiles * ceil_div(N, 128) >= sms / 2) rc = dispatch_major<128>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
+  else rc = dispatch_major<64>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
+  if (rc == -3) { set_error("tic_gemm_bf16: cudaFuncSetAttribute(max dynamic smem) failed"); return TIC_E_ATTR; }
+  if (rc == -4) { set_error("tic_gemm_bf16: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TIC_E_LAUNCH; }
+  return rc;
+}
+
+int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
+                       int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu, void* stream) {
+  TIC_CHECK_ARG(A && B && D && M > 0 && N > 0 && K > 0, "tic_gemm_bf16_simt: bad arguments");
+  dim3 grid(ceil_div(N, 16), ceil_div(M, 16)), block(16, 16);
+  simt_gemm_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(A), lda, a_mn, static_cast<const __nv_bfloat16*>(B), ldb, b_mn, D, ldd, d_dtype, M,
+      N, K, alpha, bias, relu);
+  TIC_CHECK_LAUNCH("tic_gemm_bf16_simt");
+  return TIC_OK;
+}
+
+}  // extern "C"

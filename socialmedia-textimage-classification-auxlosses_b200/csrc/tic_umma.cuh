@@ -1,0 +1,232 @@
+// Warp-specialised persistent tcgen05 GEMM mainloop for sm_100a, shared by every dense contraction on the
+// hot path (ITC similarity tiles, ITC gradient GEMMs, projection / fusion linears and their gradients).
+//
+//   D[128 x BN] (fp32, TMEM) = sum_k A[128 x 64] * B[BN x 64]     (bf16 operands, 128B-swizzled smem tiles)
+//
+//   warp 0      : TMA producer   (one lane)  global -> smem ring, mbarrier complete_tx
+//   warp 1      : MMA issuer     (one lane)  tcgen05.mma into one of two TMEM accumulator stages; owns TMEM alloc
+//   warps 2..   : epilogue       (4 or 8 warps) tcgen05.ld -> registers -> Epi::tile(...)
+//
+// Operands may be K-major (row-major [rows, K], the "TN" form) or MN-major (row-major [K, rows]); the choice
+// only changes the TMA box shape and the UMMA descriptors, never the data in HBM (no transposed copies).
+#pragma once
+#include <cuda.h>
+#include "tic_ptx.cuh"
+
+namespace tic {
+
+constexpr int kBM = 128;       // UMMA M (cta_group::1)
+constexpr int kBK = 64;        // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;     // bf16 UMMA K
+constexpr int kABytes = kBM * kBK * 2;
+constexpr int kEpiScratchBytes = 8192;
+
+template <int BN>
+struct UmmaCfg {
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesFit = (220 * 1024 - 1024 - 256 - kEpiScratchBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiScratchBytes;
+};
+
+struct EpiCtx {
+  int m0, n0;          // tile origin
+  int m_blk, n_blk;    // tile indices
+  int M, N;            // problem extents
+  uint32_t tmem_acc;   // TMEM address (lane 0, first column) of this accumulator stage
+  int quad;            // TMEM lane quadrant of this warp: rows m0 + 32*quad + lane
+  int part, nparts;    // column split across epilogue warp groups: columns [part*BN/nparts, (part+1)*BN/nparts)
+  int epi_tid;         // 0 .. 32*EPI_WARPS-1
+  int epi_threads;
+  uint8_t* scratch;    // kEpiScratchBytes of smem shared by the epilogue warps
+};
+
+// Named barrier among the epilogue warps only (id 1); the producer / MMA warps never touch it.
+__device__ __forceinline__ void epi_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
+                 int K, typename Epi::Params ep) {
+  using Cfg = UmmaCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps must cover the 4 TMEM lane quadrants");
+  static_assert(BN % 64 == 0 && BN <= 256, "BN in {64,128,192,256}");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* scratch = smem_gen + STAGES * Cfg::kStageBytes + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
+          const int k0 = kb * kBK;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, full_bar(s), k0, m0);
+          } else {
+            tma_load_2d(sa, &tmap_a, full_bar(s), m0, k0);
+            tma_load_2d(sa + 8192, &tmap_a, full_bar(s), m0 + 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, full_bar(s), k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tmap_b, full_bar(s), n0 + i * 64, k0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN, B_MN);
+      // K-major: 8-row groups 1024 B apart, K advance = 32 B inside the swizzle row.
+      // MN-major: 64-element MN groups 8192 B apart (one TMA box each), 8-k groups 1024 B apart, K advance = 2048 B.
+      constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
+      constexpr uint32_t a_kadv = (A_MN ? 2048u : 32u) >> 4, b_kadv = (B_MN ? 2048u : 32u) >> 4;
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          const uint64_t da = umma_smem_desc_sw128(sa, a_lbo, 1024u);
+          const uint64_t db = umma_smem_desc_sw128(sa + kABytes, b_lbo, 1024u);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(k * a_kadv), db + static_cast<uint64_t>(k * b_kadv), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(s));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    EpiCtx cx;
+    cx.M = M; cx.N = N;
+    cx.quad = warp & 3;
+    cx.part = (warp - 2) >> 2;
+    cx.nparts = EPI_WARPS / 4;
+    cx.epi_tid = threadIdx.x - 64;
+    cx.epi_threads = 32 * EPI_WARPS;
+    cx.scratch = scratch;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      cx.m_blk = t / n_tiles; cx.n_blk = t % n_tiles;
+      cx.m0 = cx.m_blk * kBM; cx.n0 = cx.n_blk * BN;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      cx.tmem_acc = tmem_base + as * BN;
+      Epi::template tile<BN>(ep, cx);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct TmapEncoder {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn get();
+};
+
+// 2D bf16 tensor map over a row-major [outer, inner] matrix with pitch `pitch_elems`, 128B swizzle, zero OOB fill.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                      uint32_t box_inner, uint32_t box_outer);
+
+int device_sm_count();
+
+template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
+int launch_umma_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                     const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0) {
+  using Cfg = UmmaCfg<BN>;
+  if (M <= 0 || N <= 0 || K <= 0) return -1;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM);
+  else       rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, kBK);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_bf16_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, BN);
+  else       rc = make_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kBK);
+  if (rc) return rc;
+  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI_WARPS, Epi>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return -3;
+    attr_set = true;
+  }
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  int cap = max_ctas > 0 ? max_ctas : device_sm_count();
+  if (grid > cap) grid = cap;
+  kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace tic
