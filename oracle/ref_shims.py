@@ -61,7 +61,7 @@ def load_reference(small_encoders: bool = True):
 
     def _from_vision_text_pretrained(cls_or_self=None, *args, **kwargs):
         nl = 2 if small_encoders else 12
-        vcfg = ViTConfig(num_hidden_layers=nl)
+        vcfg = ViTConfig(num_hidden_layers=nl, image_size=32 if small_encoders else 224)
         tcfg = BertConfig(num_hidden_layers=nl)
         cfg = VisionTextDualEncoderConfig.from_vision_text_configs(vcfg, tcfg)
         return VisionTextDualEncoderModel(config=cfg, vision_model=ViTModel(vcfg), text_model=BertModel(tcfg))
