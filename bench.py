@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py — fused ITC + ITM + fusion-head forward+backward throughput (samples/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c4|itc:<B>x<d>] [--impl reference]
+
+A "step" is one pass of the hot path (forward, losses, backward) over one batch of synthetic encoder outputs.
+Workloads (BASELINE.json `configs`):
+  c2  (default, configs[1]) BERT-base + ViT-B/16 late concat fusion + ITC + ITM, batch 256 per GPU, E=768, P=512, bf16
+  c3  ITC only, synthetic d=768 embeddings, 4096 rows per GPU against the global batch (32k at 8 GPUs)
+  c4  attention fusion (128 text tokens x 197 patches) + ITC + ITM, batch 4096 per GPU
+  itc:<B>x<d>  ITC only sweep point (c5)
+One JSON line is printed by rank 0 (see the task contract for the keys).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", type=str, default="c2")
+    ap.add_argument("--impl", type=str, default="tic", choices=["tic", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def workload_spec(name, world):
+    E = 768
+    if name == "c2":
+        return dict(workload="c2: concat fusion + ITC + ITM, B=256/GPU, E=768, P=512, C=4", B=256, E=E, P=512, C=4,
+                    fusion="concat", use_itc=True, use_itm=True, Lt=128, Lv=197)
+    if name == "c4":
+        return dict(workload="c4: attention fusion (128x197 tokens) + ITC + ITM, B=4096/GPU, E=768, P=512, C=4", B=4096, E=E,
+                    P=512, C=4, fusion="attention", use_itc=True, use_itm=True, Lt=128, Lv=197)
+    if name == "c3":
+        return dict(workload="c3: ITC only, d=768, 4096 rows/GPU vs global batch", B=4096, E=E, P=None, d=768, C=4, fusion=None,
+                    use_itc=True, use_itm=False, Lt=0, Lv=0)
+    if name.startswith("itc:"):
+        b, d = name[4:].split("x")
+        return dict(workload="c5: ITC only, B=%s/GPU, d=%s" % (b, d), B=int(b), E=E, P=None, d=int(d), C=4, fusion=None,
+                    use_itc=True, use_itm=False, Lt=0, Lv=0)
+    raise SystemExit("unknown workload %r" % name)
+
+
+def make_inputs(spec, seed=40, rank=0):
+    """Synthetic encoder outputs: N(0,1) hidden states, tanh-squashed pools, one-hot labels, U[0,1) uniforms.
+    Returned on the HOST (fp32 master copies); the caller rounds to bf16 / moves to the device."""
+    g = torch.Generator().manual_seed(seed + 1000 * rank)
+    B, E = spec["B"], spec["E"]
+    inp = {}
+    if spec["fusion"] is None:
+        d = spec["d"]
+        inp["t_pool"] = torch.randn(B, d, generator=g)
+        inp["v_pool"] = torch.randn(B, d, generator=g) + 0.25 * inp["t_pool"]
+        return inp
+    inp["t_pool"] = torch.tanh(torch.randn(B, E, generator=g))
+    inp["v_pool"] = torch.tanh(torch.randn(B, E, generator=g))
+    # only the CLS row of x_t is consumed by every fusion variant; x_v is read in full by `attention` only
+    inp["x_t"] = torch.randn(B, 1, E, generator=g)
+    inp["x_v"] = torch.randn(B, spec["Lv"] if spec["fusion"] == "attention" else 1, E, generator=g)
+    y = torch.randint(0, spec["C"], (B,), generator=g)
+    inp["y_soft"] = torch.eye(spec["C"])[y]
+    inp["u_coin"] = torch.rand(B, generator=g)
+    inp["u_pick"] = torch.rand(B, generator=g)
+    inp["ids"] = torch.randint(5, 30000, (B, spec["Lt"]), generator=g)
+    inp["mask"] = torch.ones(B, spec["Lt"], dtype=torch.int64)
+    return inp
+
+
+BF16_KEYS = ("t_pool", "v_pool", "x_t", "x_v")
+
+
+def algorithmic_work(spec, n_global):
+    """FLOPs / bytes per step per GPU as defined in SURVEY.md §8(d) (recompute is NOT counted)."""
+    B, E = spec["B"], spec["E"]
+    d = spec["P"] if spec["P"] is not None else spec.get("d", E)
+    w = {"itc_flops": 6.0 * B * n_global * d}
+    if spec["P"] is not None:
+        w["proj_flops"] = 10.0 * B * E * spec["P"]
+    if spec["fusion"] == "concat":
+        passes = 2 if spec["use_itm"] else 1
+        w["fusion_flops"] = passes * 3 * 2.0 * (2 * E) * E * B
+    if spec["fusion"] == "attention":
+        w["attn_bytes"] = 2.0 * spec["Lv"] * E * 2 * B
+    return w
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = sorted(x for x in sm if x > 0)
+        # median of the upper half = clocks under load (the sampler also sees the idle gaps between steps)
+        med = busy[len(busy) * 3 // 4] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": (max(mx) if mx else None), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_run(spec, steps, warmup, budget_s, threads=None):
+    """The reference's CPU implementation of the path (oracle restatement of models/mm_late.py + utils.clip_loss, pinned
+    against the unmodified reference), fp32, all host threads.  Returns (samples/s, ms/step, sample description)."""
+    from oracle import restatement as R
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    B = spec["B"]
+    note = "full batch B=%d" % B
+    if spec["fusion"] is None and B > 8192:
+        B = 8192
+        note = "B=8192 of %d rows (ITC is O(B^2): throughput at the full size is lower)" % spec["B"]
+    if spec["fusion"] == "attention" and B > 256:
+        B = 256
+        note = "B=256 of %d samples (attention fusion is per-sample; ITC part is O(B^2))" % spec["B"]
+    s2 = dict(spec, B=B)
+    inp = make_inputs(s2)
+    inp = {k: (v.to(torch.bfloat16).float() if k in BF16_KEYS else v) for k, v in inp.items()}
+    if spec["fusion"] is None:
+        ls = torch.tensor(2.6592, requires_grad=True)
+
+        def step():
+            T = inp["t_pool"].clone().requires_grad_(True)
+            V = inp["v_pool"].clone().requires_grad_(True)
+            loss = R.clip_loss(R.itc_logits(T, V, ls))
+            loss.backward()
+            return float(loss)
+    else:
+        p = {k: v.clone().requires_grad_(True) for k, v in R.init_params(spec["C"], seed=40).items()}
+        lbl, src = R.itm_sample_uniform(inp["u_coin"].numpy(), inp["u_pick"].numpy())
+        base = dict(inp)
+        if spec["fusion"] == "attention":
+            base["x_t"] = inp["x_t"].expand(B, 1, spec["E"])  # literal reference attention needs all Lt rows; use collapse
+
+        def step():
+            cur = dict(base)
+            cur["x_t"] = base["x_t"].clone().requires_grad_(True)
+            cur["t_pool"] = base["t_pool"].clone().requires_grad_(True)
+            # mm_late.py:389-414 host loop + row copies are part of the path
+            tim_ids, tim_mask, _ = R.prepare_itm_inputs_stream(inp["ids"], inp["mask"], np.random.RandomState(0))
+            cur["lbl_tim"], cur["src_idx"] = torch.from_numpy(lbl), torch.from_numpy(src)
+            for v in p.values():
+                v.grad = None
+            out = R.head_step(cur, p, fusion_name=spec["fusion"], use_itc=True, use_itm=spec["use_itm"])
+            out["loss"].backward()
+            return float(out["loss"])
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    ms = 1e3 * float(np.median(times))
+    return B / (ms / 1e3), ms, "%s, %d timed steps, fp32 torch CPU" % (note, len(times)), threads
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    spec = workload_spec(args.workload, world)
+    metric = "fused ITC+ITM+fusion fwd+bwd samples/sec"
+    base = {"metric": metric, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": spec["workload"], "per_gpu_batch": spec["B"], "global_batch": spec["B"] * world,
+                       "parallelism": "dp%d" % world}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, ms, sample, threads = cpu_reference_run(spec, max(args.steps, 3), args.warmup, 150.0)
+        line = dict(base, impl="reference", value=val, ms_per_step=ms, dtype="f32", gpu_launches=0,
+                    cpu_baseline={"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+                    e2e={"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+
+    import tic_b200.plan as P
+    from tic_b200 import capi
+    from oracle import restatement as R  # weights init only (test infrastructure is not on the timed path)
+
+    B = spec["B"]
+    host = make_inputs(spec, rank=rank)
+    dev_in = {k: (v.to(torch.bfloat16) if k in BF16_KEYS else v).to(dev) for k, v in host.items()}
+    n_global = B * world
+    if world > 1:
+        from tic_b200.dist import DistHeadPlan
+        plan = DistHeadPlan(B, world=world, rank=rank, E=spec["E"], P=spec["P"] if spec["P"] is not None else None,
+                            d=spec.get("d"), C=spec["C"], fusion=spec["fusion"], use_itc=spec["use_itc"],
+                            use_itm=spec["use_itm"], Lv=spec["Lv"], device=dev)
+    else:
+        plan = P.HeadPlan(B, E=spec["E"], P=spec["P"], C=spec["C"], fusion=spec["fusion"], use_itc=spec["use_itc"],
+                          use_itm=spec["use_itm"], Lv=max(spec["Lv"], 1), device=dev)
+        if spec["P"] is None:
+            plan.itc = P.ItcPlan(B, B, spec["d"], dev)
+            plan.Pe = spec["d"]
+            plan.out["d_t_emb"] = torch.empty(B, spec["d"], device=dev)
+            plan.out["d_v_emb"] = torch.empty(B, spec["d"], device=dev)
+    plan.set_weights(R.init_params(spec["C"], seed=40))
+
+    # ---- count launches of one step (kernels per C-ABI call are fixed)
+    KPC = {"tic_heads_fwd_bwd": 3 if spec["use_itm"] else 2, "tic_unpack_cls_grad": 2 if spec["use_itm"] else 1,
+           "tic_ce_bidir_fwd": 2, "tic_itm_sample_gather": 1}
+    counter = {"n": 0}
+    orig_call = capi.call
+
+    def counting_call(name, *a):
+        counter["n"] += KPC.get(name, 1)
+        return orig_call(name, *a)
+
+    P.call = counting_call
+    plan.step(dev_in)
+    launches_per_step = counter["n"] + 1  # + the accumulator memset
+    P.call = orig_call
+    torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        plan.step(dev_in)
+    torch.cuda.synchronize()
+
+    use_graph = (not args.no_graph) and world == 1
+    graph = None
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            plan.step(dev_in)
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.cuda.graph(graph):
+            plan.step(dev_in)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            plan.step(dev_in)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K steps, each bracketed by its own event pair, L2 flushed between steps (outside the pair)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        if dist is not None:
+            dist.barrier()
+        ev[k][0].record()
+        run_step()
+        ev[k][1].record()
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_global / (ms_per_step / 1e3)
+
+    # ---- end-to-end: HOST buffers in, loss out, through the public host-facing API
+    runner = P.HostStep(plan, host, bf16_keys=BF16_KEYS, use_graph=use_graph)
+    for _ in range(3):
+        runner(host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_ms = 0.0
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        torch.cuda.synchronize()
+        e0.record()
+        loss_host = runner(host)   # H2D inputs -> step -> D2H loss (synchronous)
+        e1.record()
+        e1.synchronize()
+        e2e_ms += e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- per-kernel timing of the dominant kernels (live, CUDA events on the launching stream, L2 flushed)
+    roof, kernels = kernel_rooflines(P, plan, spec, dev_in, n_global, flush)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    line = dict(base, value=value, ms_per_step=ms_per_step, dtype="bf16", gpu_launches=launches_per_step * args.steps,
+                clocks=clk, e2e={"value": n_global / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                                 "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes,
+                                 "loss": loss_host})
+    line["config"].update({"l2": "flushed between timed steps (256 MiB write)", "cuda_graph": bool(use_graph),
+                           "launches_per_step": launches_per_step, "loss": float(plan.out["loss"][0])})
+    line["roofline"] = finalize_roofline(roof, peaks)
+    line["kernels"] = [finalize_roofline(k, peaks) for k in kernels]
+    if not args.no_cpu_baseline:
+        val, ms, sample, threads = cpu_reference_run(spec, 1000, 1, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                                "ms_per_step": ms}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def finalize_roofline(r, peaks):
+    if r is None:
+        return None
+    if r["bound"] == "tensor":
+        peak = peaks.get("bf16_tflops", 1590.0)
+        src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if "bf16_tflops" in peaks else "fallback 1590"
+    else:
+        peak = peaks.get("hbm_gbs", 6650.0)
+        src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"
+    out = dict(r)
+    out.update(peak=peak, frac=r["achieved"] / peak, peak_source=src, traffic=r.get("traffic"))
+    return out
+
+
+def time_kernel(fn, flush, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in range(iters):
+        flush.fill_(float(k))
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def kernel_rooflines(P, plan, spec, dev_in, n_global, flush):
+    """Times the hot kernels of this workload one by one; returns (dominant, all)."""
+    B, E = spec["B"], spec["E"]
+    ks = []
+    if spec["use_itc"] and hasattr(plan, "itc") and plan.itc is not None and n_global == B:
+        it = plan.itc
+        if spec["P"] is not None:
+            Yt, Yv = plan.Y[:B], plan.Y[B:]
+        else:
+            Yt, Yv = dev_in["t_pool"], dev_in["v_pool"]
+        d = it.P
+        ldt, ldv = Yt.stride(0), Yv.stride(0)
+        ms = time_kernel(lambda: it.fwd_tiles(Yt, ldt, Yv, ldv, plan.scale), flush)
+        ks.append(dict(kernel="tic_itc_fwd (tcgen05 similarity tiles + fused bidirectional softmax-CE)", bound="tensor",
+                       ms=ms, achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="2*B^2*d FLOP"))
+        ms = time_kernel(lambda: it.bwd_operands(Yt, ldt, Yv, ldv, plan.scale, 1.0 / (2 * B)), flush)
+        ks.append(dict(kernel="tic_itc_bwd_g (tile recompute -> bf16 gradient operands)", bound="tensor", ms=ms,
+                       achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s",
+                       algorithmic="recompute: 2*B^2*d executed FLOP, 0 algorithmic (reported as executed)"))
+        ms = time_kernel(lambda: it.grad_gemms(Yt, ldt, Yv, ldv), flush)
+        ks.append(dict(kernel="tic_gemm_bf16 x2 (dT = GA*V, dV = GBT*T)", bound="tensor", ms=ms,
+                       achieved=4.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="4*B^2*d FLOP"))
+    if spec["fusion"] == "attention":
+        x_v = dev_in["x_v"]
+        R_, Lv, Ea = plan.R, spec["Lv"], E + 8
+        npass = 2 if spec["use_itm"] else 1
+        st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+        ms = time_kernel(lambda: P.call("tic_attn_pool_fwd", x_v.data_ptr(), x_v.stride(0), x_v.stride(1), plan.kq.data_ptr(),
+                                        Ea, B, npass, Lv, E, float(E) ** -0.5, plan.xbar_b.data_ptr(), plan.xbar_lo.data_ptr(),
+                                        E, plan.xbar_f.data_ptr(), E, plan.attn.data_ptr(), Lv, st()), flush)
+        ks.append(dict(kernel="tic_attn_pool_fwd (one streaming read of x_v, main+ITM pass)", bound="hbm", ms=ms,
+                       achieved=B * Lv * E * 2.0 / ms * 1e-6, unit="GB/s", algorithmic="B*Lv*E*2 bytes"))
+        ms = time_kernel(lambda: P.call("tic_attn_pool_bwd", x_v.data_ptr(), x_v.stride(0), x_v.stride(1), plan.attn.data_ptr(),
+                                        Lv, plan.dxbar.data_ptr(), E, plan.xbar_f.data_ptr(), E, B, npass, Lv, E,
+                                        float(E) ** -0.5, plan.dkq.data_ptr(), plan.dkq_lo.data_ptr(), Ea, st()), flush)
+        ks.append(dict(kernel="tic_attn_pool_bwd (second streaming read of x_v)", bound="hbm", ms=ms,
+                       achieved=B * Lv * E * 2.0 / ms * 1e-6, unit="GB/s", algorithmic="B*Lv*E*2 bytes"))
+    if spec["fusion"] in ("concat",):
+        R_, E2 = plan.R, 2 * E
+        ms = time_kernel(lambda: P.gemm(plan.Xcat, E2, 0, plan.w["W_f"], E2, 0, plan.H, E, 0, R_, E, E2, bias=plan.w["b_f"],
+                                        relu=True), flush)
+        ks.append(dict(kernel="tic_gemm_bf16 (linear_fusion forward, bias+ReLU epilogue)", bound="tensor", ms=ms,
+                       achieved=2.0 * R_ * E * E2 / ms * 1e-9, unit="TFLOP/s", algorithmic="2*R*E*2E FLOP"))
+    if not ks:
+        return None, []
+    dom = max(ks, key=lambda k: k["ms"])
+    return dom, ks
+
+
+if __name__ == "__main__":
+    main()

@@ -47,9 +47,13 @@ int tic_sm_count(void);
  * visual_projection (HF VisionTextDualEncoderModel.forward, built at mm_late.py:59-61), linear_fusion
  * (mm_late.py:81,95,112,143), fc_Q/fc_K/fc_V collapsed products (mm_late.py:105), linear_gmu_* (mm_late.py:88-89).
  * lda/ldb must be multiples of 8 elements and A/B 16-byte aligned (TMA). d_dtype: 0 = fp32, 1 = bf16. */
-int tic_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
-                  int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu,
-                  void* stream);
+int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn_major, const void* B, const void* B_lo, int64_t ldb,
+                  int b_mn_major, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha,
+                  const float* bias, int relu, void* stream);
+/* Split precision: an operand that was produced on the device (a gradient or an intermediate activation) may be
+ * passed as a bf16 (hi, lo) pair with identical layout (A_lo / B_lo, NULL = plain bf16); the kernel then runs the extra
+ * K-segment(s) D += A_lo*B (+ A*B_lo) into the same TMEM accumulator, so the rounding of that operand drops from 2^-9 to
+ * ~2^-17.  D_lo (bf16 output only) receives the residual x - bf16(x) so the result can itself be consumed as a pair. */
 /* Reference-quality SIMT fp32-accumulate GEMM with the same semantics (debug / self-test only). */
 int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
                        int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu,
@@ -58,7 +62,8 @@ int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn_major, const void* B
 /* ------------------------------------------------------------------------------------------------ L2 norm
  * rinv[i] = 1 / ||X[i,:]||_2 (no epsilon, as HF modeling_vision_text_dual_encoder.py:268-269 and
  * mm_early.py:98-99).  X bf16 [rows, cols]. */
-int tic_row_rnorm_bf16(const void* X, int64_t ldx, int rows, int cols, float* rinv, void* stream);
+int tic_row_rnorm_bf16(const void* X, const void* X_lo /* optional residual: norm of hi+lo */, int64_t ldx, int rows, int cols,
+                       float* rinv, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ ITC (fused)
  * Logits S[i,j] = scale * rinv_t[i] * rinv_v[j] * <T[i,:], V[j,:]>  (HF :272-273; mm_early.py:101-102), never
@@ -67,34 +72,42 @@ int tic_row_rnorm_bf16(const void* X, int64_t ldx, int rows, int cols, float* ri
  *
  * tic_itc_fwd writes per-tile partial sums of exp(S - shift):
  *     row_part [tic_itc_row_parts(n_global)][m_local],  col_part [tic_itc_col_parts(m_local)][n_global]
+ * T_lo / V_lo (optional) are bf16 residuals of embeddings produced on the device (the projection GEMM): the tiles then run
+ * the two extra K-segments T_lo*V and T*V_lo.
  * and diag[i] = S[i, row_offset+i].  `shift` must satisfy shift >= max S; scale (=exp(logit_scale)) works since
  * |cos| <= 1; scale > 40 is rejected with TIC_E_RANGE (fp32 underflow of exp(-2*scale)). */
 int tic_itc_row_parts(int n_global);
 int tic_itc_col_parts(int m_local);
-int tic_itc_fwd(const void* T, int64_t ldt, const void* V, int64_t ldv, const float* rinv_t, const float* rinv_v,
+int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv,
+                const float* rinv_t, const float* rinv_v,
                 int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
                 float* col_part, float* diag, float* logits_out, int64_t ld_logits, void* stream);
 /* out[j] = sum_p part[p][j]  (deterministic fixed-order reduction of the partials above). */
 int tic_reduce_parts(const float* part, int nparts, int n, float* out, void* stream);
-/* lse = shift + log(sum);  loss_sums[0] += sum_i (lse_row[i] - diag[i]),  loss_sums[1] += sum_i (lse_col[row_offset+i] - diag[i])
- * utils.py:225-231: clip_loss = (loss_sums[0]/B + loss_sums[1]/B) / 2 with B = n_global. */
-int tic_itc_lse_loss(const float* row_sum, const float* col_sum, const float* diag, int m_local, int n_global,
-                     int row_offset, float shift, float* lse_row, float* lse_col, float* loss_sums, void* stream);
+/* Sums the partials in a fixed order (deterministic), then lse = shift + log(sum);
+ *   loss_sums[0] += sum_i (lse_row[i] - diag[i]),  loss_sums[1] += sum_i (lse_col[row_offset+i] - diag[i])
+ * utils.py:225-231: clip_loss = (loss_sums[0]/B + loss_sums[1]/B) / 2 with B = n_global.  Multi-GPU: reduce the column
+ * partials with tic_reduce_parts, all-reduce(SUM) the result across ranks, then call this with n_col_parts = 1. */
+int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, const float* diag,
+                     int m_local, int n_global, int row_offset, float shift, float* lse_row, float* lse_col,
+                     float* loss_sums, void* stream);
 /* Recompute S tiles and emit the bf16 gradient operands (g = dLoss/d(clip_loss), B = n_global):
  *   Gp[i,j] = g/(2B) * (exp(S-lse_row[i]) + exp(S-lse_col[j]))      (the -I/B diagonal is applied in fp32 later)
  *   GA [m_local, ld_ga ] row-major:  Gp[i,j] * rinv_v[j]            (A operand of dT = GA * V)
  *   GBT[n_global, ld_gbt] row-major: Gp[i,j] * rinv_t[i] at [j,i]   (A operand of dV = GBT * T) */
-int tic_itc_bwd_g(const void* T, int64_t ldt, const void* V, int64_t ldv, const float* rinv_t, const float* rinv_v,
+int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv,
+                  const float* rinv_t, const float* rinv_v,
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale,
-                  float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* stream);
+                  float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo /* optional residuals */,
+                  void* GBT_lo, void* stream);
 /* Normalise-backward + diagonal term, one warp per row (HF :268-269 backward):
  *   dxh = scale*acc[i,:] - diag_coef * scale * rinv_o[i] * Xo[i,:]   (diag_coef = g/B, 0 if row has no local positive)
  *   r = <xh, dxh>, xh = rinv[i]*X[i,:];   dX[i,:] = rinv[i] * (dxh - xh * r);   dscale_part[block] += r (for dlogit_scale)
  * acc fp32 [rows, P] is the raw GEMM output; X the embedding being differentiated, Xo the other modality's
  * row with the same global index (may be NULL when diag_coef == 0). dX written as fp32 and/or bf16 (either may be NULL). */
-int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, int64_t ldx, const float* rinv,
-                          const void* Xo, int64_t ldxo, const float* rinv_o, int rows, int P, float scale,
-                          float diag_coef, float* dX_f32, int64_t ld_df, void* dX_bf16, int64_t ld_db,
+int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const void* X_lo, int64_t ldx, const float* rinv,
+                          const void* Xo, const void* Xo_lo, int64_t ldxo, const float* rinv_o, int rows, int P, float scale,
+                          float diag_coef, float* dX_f32, int64_t ld_df, void* dX_bf16, void* dX_bf16_lo, int64_t ld_db,
                           float* r_sum /* [1], atomically accumulated */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ clip_loss on a given matrix
@@ -128,12 +141,13 @@ int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int m
  *   Xcat[i,      :] = [ xt[i*xt_stride : +E]        | xv[i*xv_stride : +E] ]      i < B   (main pass)
  *   Xcat[B + i,  :] = [ xt[src[i]*xt_stride : +E]   | xv[i*xv_stride : +E] ]      if src != NULL (ITM pass, :170-181)
  * xt/xv bf16 with row strides in elements (so x_t[:,0,:] of a [B,L,E] tensor is xt_stride = L*E). */
+/* xv may be NULL: then only the text half [:, :E] is written (attention fusion fills the other half by GEMM). */
 int tic_pack_cls_pairs(const void* xt, int64_t xt_stride, const void* xv, int64_t xv_stride, int B, int E,
                        const int32_t* src_idx, void* Xcat, int64_t ldx, void* stream);
 /* Gradient of the pack w.r.t. xt (vision is frozen, mm_late.py:67-69):
  *   dxt[i,:] = dXcat[i,:E] + sum_{k: src[k]==i} dXcat[B+k,:E]   (fp32, atomics for the scattered part). */
-int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, int B, int E, const int32_t* src_idx, float* dxt, int64_t ld_dxt,
-                        void* stream);
+int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, const float* dX2 /* optional second addend, same layout */,
+                        int64_t ldd2, int B, int E, const int32_t* src_idx, float* dxt, int64_t ld_dxt, void* stream);
 
 /* Classifier + ITM heads with their losses, forward and backward in one launch (mm_late.py:163-164,182;
  * losses run_mm_late.py:85,97 and the mix mm_late.py:473-487):
@@ -146,22 +160,26 @@ int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, int B, int E, const int
 int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* W_cls,
                       const float* b_cls, const float* W_tim, const float* b_tim, const float* y_soft,
                       const float* class_w, const int64_t* lbl_tim, const uint8_t* keep, float keep_scale, float c_cls,
-                      float c_tim, float* logits_cls, float* logits_tim, float* losses, void* dH_bf16, int64_t ld_dhb,
-                      float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask, void* stream);
+                      float c_tim, float* logits_cls, float* logits_tim, float* losses, void* dH_bf16, void* dH_bf16_lo, int64_t ld_dhb,
+                      float* dH_f32 /* optional */, int64_t ld_dhf, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask,
+                      float* ws /* [rows * 8] floats scratch (dlogits) */, void* stream);
 
 /* attention fusion, CLS-row collapse of mm_late.py:98-113,195-210 (exact algebra):
  *   q0 = fc_Q(x_t[:,0]);  kq = W_K^T q0;  c = <q0,b_K>;  s_j = (<kq, x_v[j]> + c) * E^-1/2;  a = softmax_j(s)
  *   xbar = sum_j a_j x_v[j];  ctx0 = W_V xbar + b_V.
- * This kernel is the HBM-bound middle: one streaming read of x_v [B, Lv, E] (bf16) producing
- * xbar [B,E] (bf16 + fp32) and the attention weights a [B,Lv] fp32 (saved for backward). */
-int tic_attn_pool_fwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_stride, const void* kq, int64_t ldkq,
-                      const float* cbias, int B, int Lv, int E, float scale, void* xbar_bf16, int64_t ld_xb,
-                      float* attn, int64_t ld_attn, void* stream);
-/* backward w.r.t. kq and cbias (x_v is frozen): ds_j = a_j * (<dxbar, x_v[j]> - sum_l a_l <dxbar, x_v[l]>) * scale,
- * dkq = sum_j ds_j x_v[j], dc = sum_j ds_j.  Second (and last) streaming read of x_v. */
-int tic_attn_pool_bwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_stride, const float* attn,
-                      int64_t ld_attn, const float* dxbar, int64_t ld_dxb, int B, int Lv, int E, float scale,
-                      float* dkq, int64_t ld_dkq, float* dcbias, void* stream);
+ * These two kernels are the HBM-bound middle: ONE streaming read of x_v [B, Lv, E] (bf16) per direction, shared by
+ * the main pass and the ITM pass (npass = 2: kq rows [0,B) are the main queries, rows [B,2B) the ITM queries of the
+ * same images).  kq is the augmented product q0 * [W_K | b_K] (fp32, ld >= E+1): column E carries c.
+ * Outputs: xbar (bf16 for the W_V GEMM and fp32 for backward) [npass*B, E]; attn [npass*B, Lv] fp32. E must be 768. */
+int tic_attn_pool_fwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_stride, const void* kq, int64_t ldkq, int B,
+                      int npass, int Lv, int E, float scale, void* xbar_bf16, void* xbar_bf16_lo, int64_t ld_xb,
+                      float* xbar_f32, int64_t ld_xf, float* attn, int64_t ld_attn, void* stream);
+/* backward w.r.t. the augmented kq (x_v is frozen, mm_late.py:67-69):
+ *   t_j = <dxbar, x_v[j]>, D = <dxbar, xbar>, ds_j = a_j (t_j - D) scale, dkq = sum_j ds_j x_v[j], dkq[E] = sum_j ds_j.
+ * dkq is written as bf16 [npass*B, ld_dkq >= E+8] (columns E+1.. zeroed) — directly the operand of the W_K GEMMs. */
+int tic_attn_pool_bwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_stride, const float* attn, int64_t ld_attn,
+                      const float* dxbar, int64_t ld_dxb, const float* xbar_f32, int64_t ld_xf, int B, int npass, int Lv,
+                      int E, float scale, void* dkq_bf16, void* dkq_bf16_lo, int64_t ld_dkq, void* stream);
 
 /* aspect-att fusion (mm_late.py:115-131) including the reference's stack->reshape row scrambling:
  * sample i pairs flat rows 2i, 2i+1 of [t_pool; v_pool].  out = relu(sum_k alpha_k V_k), alpha = softmax_k tanh(w.V_k + b). */
@@ -174,26 +192,20 @@ int tic_aspect_bwd(const void* t_pool, int64_t ldt, const void* v_pool, int64_t 
 /* gmu gate (mm_late.py:133-144): G[i,:] = z*tp + (1-z)*vp, z = sigmoid([xt_cls | xv_cls]) (no learned gate).
  * tp/vp fp32 [B,2E] are linear_gmu_t/v outputs; Xcat bf16 [B,2E] from tic_pack_cls_pairs. */
 int tic_gmu_gate_fwd(const void* Xcat, int64_t ldx, const float* tp, const float* vp, int64_t ldp, int B, int E2,
-                     void* G_bf16, int64_t ldg, void* stream);
+                     void* G_bf16, void* G_bf16_lo, int64_t ldg, void* stream);
 int tic_gmu_gate_bwd(const void* Xcat, int64_t ldx, const float* tp, const float* vp, int64_t ldp, const float* dG,
-                     int64_t lddg, int B, int E2, void* dtp_bf16, void* dvp_bf16, int64_t lddp, float* dXcat_gate,
-                     int64_t lddx, void* stream);
+                     int64_t lddg, int B, int E2, void* dtp_bf16, void* dvp_bf16, void* dtp_lo, void* dvp_lo, int64_t lddp,
+                     float* dXcat_gate, int64_t lddx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ utilities */
 int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream);
 int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream);
 /* dst[r, c] (+)= column sums etc. are done by GEMMs; bias gradient: db[n] = sum_m dY[m,n] (bf16 in, fp32 out). */
 int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, void* stream);
-/* out[0] = (1-bi-bm)*losses[0] + bi*0.5*(itc[0]+itc[1])/B + bm*losses[1]  (mm_late.py:473-487). */
+/* out[0] = (1-bi-bm)*losses[0] + bi*0.5*(itc[0]+itc[1])/B + bm*losses[1]  (mm_late.py:473-487);
+ * out[1..3] = L_cls, L_itc, L_itm.  out has 4 floats. */
 int tic_loss_mix(const float* losses, const float* itc_sums, int n_global, float beta_itc, float beta_itm,
                  int use_itc, int use_itm, float* out, void* stream);
-
-/* ------------------------------------------------------------------------------------------------ host-buffer entry point
- * End-to-end call for reference-side integrators that hold HOST buffers (numpy / torch CPU): copies the step's
- * inputs H2D, runs the fused ITC step (row norms, logits tiles, bidirectional CE, gradients) and copies the loss and
- * gradients back.  T_host/V_host bf16 [B,P] pinned or pageable; dT_host/dV_host fp32 [B,P].  Synchronous. */
-int tic_itc_step_host(const void* T_host, const void* V_host, int B, int P, float logit_scale, float* loss_host,
-                      float* dT_host, float* dV_host, float* dlogit_scale_host);
 
 #ifdef __cplusplus
 }

@@ -66,12 +66,22 @@ def sdpa(Q, K, V, scale=None):
     return torch.matmul(attention, V), scores
 
 
-def fusion_concat(xt_cls, xv_cls, p):
+def _relu(x, mask=None, pre_out=None):
+    """self.relu (mm_late.py:82).  `mask` (test-only) replaces the comparison x > 0 by a given 0/1 mask so gradients can be
+    compared with a lower-precision implementation whose near-zero pre-activations land on the other side of 0;
+    `pre_out` (a list) receives the pre-activation."""
+    if pre_out is not None:
+        pre_out.append(x.detach())
+    return F.relu(x) if mask is None else x * mask.to(x.dtype)
+
+
+def fusion_concat(xt_cls, xv_cls, p, relu_mask=None, pre_out=None):
     """models/mm_late.py:92-96."""
-    return F.relu(F.linear(torch.cat((xt_cls, xv_cls), dim=1), p["linear_fusion.weight"], p["linear_fusion.bias"]))
+    return _relu(F.linear(torch.cat((xt_cls, xv_cls), dim=1), p["linear_fusion.weight"], p["linear_fusion.bias"]),
+                 relu_mask, pre_out)
 
 
-def fusion_attention_literal(x_t, x_v, p):
+def fusion_attention_literal(x_t, x_v, p, relu_mask=None, pre_out=None):
     """models/mm_late.py:98-113 exactly as written (all Lt query rows computed, only row 0 used)."""
     N, L, E = x_t.shape
     Q = F.linear(x_t, p["fc_Q.weight"], p["fc_Q.bias"])
@@ -79,10 +89,10 @@ def fusion_attention_literal(x_t, x_v, p):
     V = F.linear(x_v, p["fc_V.weight"], p["fc_V.bias"])
     ctx, _ = sdpa(Q, K, V, K.size(-1) ** -0.5)
     ctx = ctx.view(N, L, E)
-    return fusion_concat(x_t[:, 0, :], ctx[:, 0, :], p)
+    return fusion_concat(x_t[:, 0, :], ctx[:, 0, :], p, relu_mask, pre_out)
 
 
-def fusion_attention_collapsed(xt_cls, x_v, p):
+def fusion_attention_collapsed(xt_cls, x_v, p, relu_mask=None, pre_out=None):
     """The exact CLS-row algebraic collapse of mm_late.py:98-113, which is what the CUDA path
     computes: only query row 0 reaches the output (mm_late.py:111)."""
     E = x_v.shape[-1]
@@ -93,10 +103,10 @@ def fusion_attention_collapsed(xt_cls, x_v, p):
     a = F.softmax(s, dim=-1)
     xbar = torch.einsum("bl,ble->be", a, x_v)
     ctx0 = F.linear(xbar, p["fc_V.weight"], p["fc_V.bias"])
-    return fusion_concat(xt_cls, ctx0, p)
+    return fusion_concat(xt_cls, ctx0, p, relu_mask, pre_out)
 
 
-def fusion_aspect(t_pool, v_pool, p):
+def fusion_aspect(t_pool, v_pool, p, relu_mask=None, pre_out=None):
     """models/mm_late.py:115-131 including the stack -> reshape (not transpose) row scrambling :120-121:
     sample i pairs flat rows 2i, 2i+1 of [t_0..t_{B-1}, v_0..v_{B-1}]."""
     N, EM = t_pool.shape
@@ -104,33 +114,34 @@ def fusion_aspect(t_pool, v_pool, p):
     V = torch.reshape(V, (N, 2, EM))
     Ew = torch.tanh(F.linear(V, p["aspectattention.weight"], p["aspectattention.bias"]))
     w = F.softmax(Ew, dim=1).transpose(1, 2)
-    return F.relu(torch.matmul(w, V).squeeze(1))
+    return _relu(torch.matmul(w, V).squeeze(1), relu_mask, pre_out)
 
 
-def fusion_gmu(xt_cls, xv_cls, p):
+def fusion_gmu(xt_cls, xv_cls, p, relu_mask=None, pre_out=None):
     """models/mm_late.py:133-144 — the gate is sigmoid of the raw concatenation (no learned gate matrix)."""
     v_prime = F.linear(xv_cls, p["linear_gmu_v.weight"], p["linear_gmu_v.bias"])
     t_prime = F.linear(xt_cls, p["linear_gmu_t.weight"], p["linear_gmu_t.bias"])
     z = torch.sigmoid(torch.cat((xt_cls, xv_cls), dim=1))
     g = z * t_prime + (1 - z) * v_prime
-    return F.relu(F.linear(g, p["linear_fusion.weight"], p["linear_fusion.bias"]))
+    return _relu(F.linear(g, p["linear_fusion.weight"], p["linear_fusion.bias"]), relu_mask, pre_out)
 
 
-def mm_fusion(fusion_name, x_t, x_v, p, x_v_pool=None, x_t_pool=None, literal_attention=False):
+def mm_fusion(fusion_name, x_t, x_v, p, x_v_pool=None, x_t_pool=None, literal_attention=False, relu_mask=None,
+              pre_out=None):
     """models/mm_late.py:91-144 dispatch. x_t [B,Lt,E], x_v [B,Lv,E]."""
     if fusion_name == "concat":
-        return fusion_concat(x_t[:, 0, :], x_v[:, 0, :], p)
+        return fusion_concat(x_t[:, 0, :], x_v[:, 0, :], p, relu_mask, pre_out)
     if fusion_name == "attention":
         if literal_attention:
-            return fusion_attention_literal(x_t, x_v, p)
-        return fusion_attention_collapsed(x_t[:, 0, :], x_v, p)
+            return fusion_attention_literal(x_t, x_v, p, relu_mask, pre_out)
+        return fusion_attention_collapsed(x_t[:, 0, :], x_v, p, relu_mask, pre_out)
     if fusion_name == "aspect-att":
         if x_t_pool is None or x_v_pool is None:
             # mm_late.py:181 calls mm_fusion without pools on the ITM branch -> torch.stack((None, None)) TypeError
             raise TypeError("aspect-att needs pooled outputs (the reference crashes here when ITM is on)")
-        return fusion_aspect(x_t_pool, x_v_pool, p)
+        return fusion_aspect(x_t_pool, x_v_pool, p, relu_mask, pre_out)
     if fusion_name == "gmu":
-        return fusion_gmu(x_t[:, 0, :], x_v[:, 0, :], p)
+        return fusion_gmu(x_t[:, 0, :], x_v[:, 0, :], p, relu_mask, pre_out)
     return None  # mm_late.py falls through
 
 
@@ -221,7 +232,7 @@ _EXP_POLY = [np.float32(c) for c in (1.9875691500e-4, 1.3981999507e-3, 8.3334519
 def det_exp_f32(x: np.ndarray) -> np.ndarray:
     """Bit-reproducible fp32 exp for x <= 0: every step is a single IEEE-754 round-to-nearest fp32 operation
     (no FMA, no library transcendental), mirrored op-for-op by det_exp() in csrc/itm.cu."""
-    x = np.maximum(np.asarray(x, dtype=np.float32), np.float32(-87.0))
+    x = np.maximum(np.asarray(x, dtype=np.float32), np.float32(-80.0))
     n = np.rint(x * _LOG2E).astype(np.float32)
     r = x - n * _C1
     r = r - n * _C2
@@ -271,13 +282,14 @@ def gather_rows(x, src):
 
 def head_step(inp: Dict[str, torch.Tensor], p: Dict[str, torch.Tensor], *, fusion_name: str = "concat",
               use_itc: bool = True, use_itm: bool = True, beta_itc: float = 0.1, beta_itm: float = 0.1,
-              literal_attention: bool = False) -> Dict[str, torch.Tensor]:
+              literal_attention: bool = False, relu_masks=None) -> Dict[str, torch.Tensor]:
     """Everything models/mm_late.py does after the encoders return, on given embeddings (forward; use autograd
     on the returned loss for the backward):
       inp: x_t [B,Lt,E], x_v [B,Lv,E], t_pool [B,E], v_pool [B,E], y_soft [B,C], class_w [C] (optional),
            lbl_tim [B] int64 + src_idx [B] int64 (when use_itm), keep [B,E] dropout keep-mask * 1/(1-p) (optional)
       p:   state-dict style names (mm_late.py:59-89): dual_encoder.text_projection.weight, ... .visual_projection.weight,
            dual_encoder.logit_scale, linear_fusion.*, linear_cls.*, linear_tim.*, fc_Q|K|V.*, aspectattention.*, linear_gmu_*.*
+    relu_masks (test-only, see _relu): {"main": [B,E], "tim": [B,E]} 0/1 masks used instead of (pre-activation > 0).
     The ITM branch uses x_t[src] — the text encoder is per-sample, so text_model(ids[src]) == text_model(ids)[src]
     (mm_late.py:170-175) — and gets no pools and no dropout (mm_late.py:181-182)."""
     x_t, x_v = inp["x_t"], inp["x_v"]
@@ -286,8 +298,11 @@ def head_step(inp: Dict[str, torch.Tensor], p: Dict[str, torch.Tensor], *, fusio
     V = project(inp["v_pool"], p.get("dual_encoder.visual_projection.weight"))
     S = itc_logits(T, V, p["dual_encoder.logit_scale"])                      # mm_late.py:159
     out["logits_per_text"] = S
+    pre_main, pre_tim = [], []
+    rm = relu_masks or {}
     fused = mm_fusion(fusion_name, x_t, x_v, p, x_v_pool=inp["v_pool"], x_t_pool=inp["t_pool"],
-                      literal_attention=literal_attention)                   # mm_late.py:160
+                      literal_attention=literal_attention, relu_mask=rm.get("main"), pre_out=pre_main)   # mm_late.py:160
+    out["pre_main"] = pre_main[0]
     out["mm_features"] = fused                                               # :162
     h = fused * inp["keep"] if inp.get("keep") is not None else fused        # :163 (dropout with an injected mask)
     out["out_cls"] = F.linear(h, p["linear_cls.weight"], p["linear_cls.bias"])  # :164
@@ -296,7 +311,9 @@ def head_step(inp: Dict[str, torch.Tensor], p: Dict[str, torch.Tensor], *, fusio
     l_itm = None
     if use_itm:
         x_t_tim = gather_rows(x_t, inp["src_idx"])                           # :170-175 via permutation equivariance
-        fused_tim = mm_fusion(fusion_name, x_t_tim, x_v, p, literal_attention=literal_attention)  # :181 (no pools)
+        fused_tim = mm_fusion(fusion_name, x_t_tim, x_v, p, literal_attention=literal_attention,
+                              relu_mask=rm.get("tim"), pre_out=pre_tim)                          # :181 (no pools)
+        out["pre_tim"] = pre_tim[0]
         out["out_tim"] = F.linear(fused_tim, p["linear_tim.weight"], p["linear_tim.bias"])        # :182
         l_itm = itm_loss(out["out_tim"], inp["lbl_tim"])
     out["loss_cls"], out["loss_itc"], out["loss_itm"] = l_cls, l_itc, l_itm

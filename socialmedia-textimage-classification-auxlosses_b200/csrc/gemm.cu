@@ -70,6 +70,7 @@ int device_sm_count() {
 struct StoreEpi {
   struct Params {
     void* D;
+    void* D_lo;   // optional bf16 residual (x - bf16(x)) so the result can feed another GEMM as a split operand
     int64_t ldd;
     int d_bf16;
     float alpha;
@@ -118,6 +119,26 @@ struct StoreEpi {
           for (int j = 0; j < 32; ++j)
             if (col0 + j < cx.N) d[j] = __float2bfloat16_rn(f[j]);
         }
+        if (p.D_lo != nullptr) {
+          __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(p.D_lo) + static_cast<int64_t>(row) * p.ldd + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] -= __bfloat162float(__float2bfloat16_rn(f[j]));
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(f[j], f[j + 1]);
+              u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              u.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(dl + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < cx.N) dl[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
       } else {
         float* d = reinterpret_cast<float*>(p.D) + static_cast<int64_t>(row) * p.ldd + col0;
         if (full) {
@@ -134,12 +155,12 @@ struct StoreEpi {
 };
 
 template <int BN>
-static int dispatch_major(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
-                          const StoreEpi::Params& ep, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_umma_gemm<BN, false, false, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
-  if (!a_mn && b_mn) return launch_umma_gemm<BN, false, true, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
-  if (a_mn && !b_mn) return launch_umma_gemm<BN, true, false, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
-  return launch_umma_gemm<BN, true, true, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+static int dispatch_major(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
+                          int b_mn, int M, int N, int K, const StoreEpi::Params& ep, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_umma_gemm<BN, false, false, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
+  if (!a_mn && b_mn) return launch_umma_gemm<BN, false, true, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
+  if (a_mn && !b_mn) return launch_umma_gemm<BN, true, false, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
+  return launch_umma_gemm<BN, true, true, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
 }
 
 // ------------------------------------------------------------------ SIMT reference GEMM (self-test only)
@@ -179,20 +200,22 @@ const char* tic_last_error_string(void) { return g_err; }
 int tic_version(void) { return 100; }
 int tic_sm_count(void) { return device_sm_count(); }
 
-int tic_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
-                  int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu, void* stream) {
+int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
+                  int b_mn, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias,
+                  int relu, void* stream) {
   TIC_CHECK_ARG(A && B && D, "tic_gemm_bf16: null pointer");
   TIC_CHECK_ARG(M > 0 && N > 0 && K > 0, "tic_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   TIC_CHECK_ARG(d_dtype == 0 || d_dtype == 1, "tic_gemm_bf16: d_dtype must be 0 (fp32) or 1 (bf16)");
-  StoreEpi::Params ep{D, ldd, d_dtype, alpha, bias, relu};
+  TIC_CHECK_ARG(D_lo == nullptr || d_dtype == 1, "tic_gemm_bf16: D_lo needs a bf16 output");
+  StoreEpi::Params ep{D, D_lo, ldd, d_dtype, alpha, bias, relu};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int sms = device_sm_count();
   const int m_tiles = ceil_div(M, kBM);
   // Largest N tile that still gives every SM a tile; small problems prefer more, narrower tiles.
   int rc;
-  if (m_tiles * ceil_div(N, 256) >= sms) rc = dispatch_major<256>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
-  else if (m_tiles * ceil_div(N, 128) >= sms / 2) rc = dispatch_major<128>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
-  else rc = dispatch_major<64>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
+  if (m_tiles * ceil_div(N, 256) >= sms) rc = dispatch_major<256>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st);
+  else if (m_tiles * ceil_div(N, 128) >= sms / 2) rc = dispatch_major<128>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st);
+  else rc = dispatch_major<64>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st);
   if (rc == -3) { set_error("tic_gemm_bf16: cudaFuncSetAttribute(max dynamic smem) failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_gemm_bf16: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TIC_E_LAUNCH; }
   return rc;

@@ -1,0 +1,323 @@
+// Per-sample (HBM/latency-bound) pieces of the late-fusion head: CLS-row packing for linear_fusion, the classifier and
+// ITM heads with their losses (forward + backward in one pass), bias/weight-gradient column reductions, casts, loss mix.
+// Reference: models/mm_late.py:92-96,160-193 (head), :473-487 (mix); run_mm_late.py:85,97 (loss constructors).
+#include "common.cuh"
+#include "tic_ptx.cuh"
+
+namespace tic {
+
+constexpr int kMaxClasses = 8;
+
+// ------------------------------------------------------------------ pack / unpack
+// One warp per output row; 16-byte copies. Row r < B: [xt[r] | xv[r]];  row B + i: [xt[src[i]] | xv[i]].
+__global__ void pack_cls_pairs_kernel(const __nv_bfloat16* __restrict__ xt, int64_t xt_stride,
+                                      const __nv_bfloat16* __restrict__ xv, int64_t xv_stride, int B, int E,
+                                      const int32_t* __restrict__ src, __nv_bfloat16* __restrict__ X, int64_t ldx, int rows) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int i = r < B ? r : r - B;
+  const int it = r < B ? r : src[i];
+  const __nv_bfloat16* a = xt + static_cast<int64_t>(it) * xt_stride;
+  const __nv_bfloat16* b = xv + static_cast<int64_t>(i) * xv_stride;
+  __nv_bfloat16* d = X + static_cast<int64_t>(r) * ldx;
+  const bool vec = (E & 7) == 0 && (xt_stride & 7) == 0 && (xv_stride & 7) == 0 && (ldx & 7) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(xt) | reinterpret_cast<uintptr_t>(xv) | reinterpret_cast<uintptr_t>(X)) & 15) == 0;
+  if (vec) {
+    for (int c = lane * 8; c < E; c += 256) {
+      *reinterpret_cast<uint4*>(d + c) = __ldg(reinterpret_cast<const uint4*>(a + c));
+      if (xv) *reinterpret_cast<uint4*>(d + E + c) = __ldg(reinterpret_cast<const uint4*>(b + c));
+    }
+  } else {
+    for (int c = lane; c < E; c += 32) { d[c] = a[c]; if (xv) d[E + c] = b[c]; }
+  }
+}
+
+__global__ void unpack_main_kernel(const float* __restrict__ dX, int64_t ldd, const float* __restrict__ dX2, int64_t ldd2, int B,
+                                   int E, float* __restrict__ dxt, int64_t ldo) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(B) * E) return;
+  const int r = idx / E, c = idx % E;
+  dxt[r * ldo + c] = dX[r * ldd + c] + (dX2 ? dX2[r * ldd2 + c] : 0.f);
+}
+__global__ void unpack_scatter_kernel(const float* __restrict__ dX, int64_t ldd, const float* __restrict__ dX2, int64_t ldd2, int B,
+                                      int E, const int32_t* __restrict__ src, float* __restrict__ dxt, int64_t ldo) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(B) * E) return;
+  const int r = idx / E, c = idx % E;
+  const int64_t rr = static_cast<int64_t>(B) + r;
+  atomicAdd(dxt + static_cast<int64_t>(src[r]) * ldo + c, dX[rr * ldd + c] + (dX2 ? dX2[rr * ldd2 + c] : 0.f));
+}
+
+// ------------------------------------------------------------------ heads: logits, losses, dlogits, dH
+// One warp per row of H. rows [0,B) feed linear_cls (+ dropout keep mask), rows [B,2B) feed linear_tim.
+__global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int B, int E, int C, int has_tim,
+                                  const float* __restrict__ W_cls, const float* __restrict__ b_cls,
+                                  const float* __restrict__ W_tim, const float* __restrict__ b_tim,
+                                  const float* __restrict__ y_soft, const float* __restrict__ class_w,
+                                  const int64_t* __restrict__ lbl_tim, const uint8_t* __restrict__ keep, float keep_scale,
+                                  float c_cls, float c_tim, float* __restrict__ logits_cls, float* __restrict__ logits_tim,
+                                  float* __restrict__ losses, float* __restrict__ dlogits /* [rows, kMaxClasses] */,
+                                  __nv_bfloat16* __restrict__ dHb, __nv_bfloat16* __restrict__ dHb_lo, int64_t ld_dhb,
+                                  float* __restrict__ dHf, int64_t ld_dhf, int relu_mask) {
+  const int rows = has_tim ? 2 * B : B;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + wib;
+  __shared__ float sl[2][32];
+  float loss_c = 0.f, loss_t = 0.f;
+  if (r < rows) {
+    const bool is_cls = r < B;
+    const int i = is_cls ? r : r - B;
+    const int nc = is_cls ? C : 2;
+    const float* W = is_cls ? W_cls : W_tim;
+    const float* bias = is_cls ? b_cls : b_tim;
+    const float* h = H + static_cast<int64_t>(r) * ldh;
+    const uint8_t* kp = (is_cls && keep) ? keep + static_cast<int64_t>(i) * E : nullptr;
+    float z[kMaxClasses];
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) z[c] = 0.f;
+    for (int k = lane; k < E; k += 32) {
+      float hv = h[k];
+      if (kp) hv = kp[k] ? hv * keep_scale : 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c)
+        if (c < nc) z[c] = fmaf(hv, __ldg(W + c * E + k), z[c]);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < nc) { z[c] = warp_sum(z[c]) + bias[c]; mx = fmaxf(mx, z[c]); }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < nc) se += expf(z[c] - mx);
+    const float lse = mx + logf(se);
+    float dz[kMaxClasses];
+    if (is_cls) {
+      float wy = 0.f, l = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c)
+        if (c < nc) {
+          const float w = class_w ? class_w[c] : 1.f;
+          const float y = y_soft[static_cast<int64_t>(i) * C + c];
+          wy += w * y;
+          l -= w * y * (z[c] - lse);
+        }
+      loss_c = l / B;
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c)
+        if (c < nc) {
+          const float w = class_w ? class_w[c] : 1.f;
+          const float y = y_soft[static_cast<int64_t>(i) * C + c];
+          dz[c] = c_cls / B * (expf(z[c] - lse) * wy - w * y);
+          if (lane == 0) logits_cls[static_cast<int64_t>(i) * C + c] = z[c];
+        }
+    } else {
+      const int y = static_cast<int>(lbl_tim[i]);
+      loss_t = -((y == 0 ? z[0] : z[1]) - lse) / B;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        dz[c] = c_tim / B * (expf(z[c] - lse) - (c == y ? 1.f : 0.f));
+        if (lane == 0) logits_tim[static_cast<int64_t>(i) * 2 + c] = z[c];
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c) dlogits[static_cast<int64_t>(r) * kMaxClasses + c] = c < nc ? dz[c] : 0.f;
+    }
+    if (dHb || dHf) {
+      for (int k = lane; k < E; k += 32) {
+        float g = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxClasses; ++c)
+          if (c < nc) g = fmaf(dz[c], __ldg(W + c * E + k), g);
+        if (kp) g = kp[k] ? g * keep_scale : 0.f;
+        if (relu_mask && !(h[k] > 0.f)) g = 0.f;
+        if (dHb) {
+          const __nv_bfloat16 hi = __float2bfloat16_rn(g);
+          dHb[static_cast<int64_t>(r) * ld_dhb + k] = hi;
+          if (dHb_lo) dHb_lo[static_cast<int64_t>(r) * ld_dhb + k] = __float2bfloat16_rn(g - __bfloat162float(hi));
+        }
+        if (dHf) dHf[static_cast<int64_t>(r) * ld_dhf + k] = g;
+      }
+    }
+  }
+  if (lane == 0) { sl[0][wib] = loss_c; sl[1][wib] = loss_t; }
+  __syncthreads();
+  if (wib == 0) {
+    const int nw = blockDim.x >> 5;
+    float a = lane < nw ? sl[0][lane] : 0.f, b = lane < nw ? sl[1][lane] : 0.f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      if (a != 0.f) atomicAdd(losses + 0, a);
+      if (b != 0.f) atomicAdd(losses + 1, b);
+    }
+  }
+}
+
+// dW[c,k] += sum_rows dlogits[r,c] * hd[r,k], db[c] += sum_rows dlogits[r,c]; thread per k, rows split over blockIdx.y.
+__global__ void heads_wgrad_kernel(const float* __restrict__ H, int64_t ldh, int row0, int nrows, int E, int nc,
+                                   const float* __restrict__ dlogits, const uint8_t* __restrict__ keep, float keep_scale,
+                                   float* __restrict__ dW, float* __restrict__ db, int rows_per_blk) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rb = blockIdx.y * rows_per_blk;
+  const int re = min(rb + rows_per_blk, nrows);
+  float acc[kMaxClasses], accb[kMaxClasses];
+#pragma unroll
+  for (int c = 0; c < kMaxClasses; ++c) { acc[c] = 0.f; accb[c] = 0.f; }
+  if (k < E) {
+    for (int r = rb; r < re; ++r) {
+      float hv = H[static_cast<int64_t>(row0 + r) * ldh + k];
+      if (keep) hv = keep[static_cast<int64_t>(r) * E + k] ? hv * keep_scale : 0.f;
+      const float* dl = dlogits + static_cast<int64_t>(row0 + r) * kMaxClasses;
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c)
+        if (c < nc) {
+          const float d = __ldg(dl + c);
+          acc[c] = fmaf(d, hv, acc[c]);
+          accb[c] += d;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < nc) {
+        atomicAdd(dW + c * E + k, acc[c]);
+        if (k == 0) atomicAdd(db + c, accb[c]);
+      }
+  }
+}
+
+// out[n] += sum_m X[m,n]  (bf16 in) — bias gradients of the fusion / projection linears.
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, int rows, int cols, float* __restrict__ out,
+                                   int rows_per_blk) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= cols) return;
+  const int rb = blockIdx.y * rows_per_blk, re = min(rb + rows_per_blk, rows);
+  float s = 0.f;
+  for (int r = rb; r < re; ++r) s += __bfloat162float(X[static_cast<int64_t>(r) * ldx + n]);
+  atomicAdd(out + n, s);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, int64_t lds, __nv_bfloat16* __restrict__ d, int64_t ldd,
+                                     int rows, int cols) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(rows) * cols) return;
+  const int64_t r = idx / cols, c = idx % cols;
+  d[r * ldd + c] = __float2bfloat16_rn(s[r * lds + c]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, int64_t lds, float* __restrict__ d, int64_t ldd,
+                                     int rows, int cols) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(rows) * cols) return;
+  const int64_t r = idx / cols, c = idx % cols;
+  d[r * ldd + c] = __bfloat162float(s[r * lds + c]);
+}
+
+__global__ void loss_mix_kernel(const float* losses, const float* itc_sums, int n_global, float bi, float bm, int use_itc,
+                                int use_itm, float* out) {
+  const float l_cls = losses[0];
+  const float l_itm = use_itm ? losses[1] : 0.f;
+  const float l_itc = use_itc ? 0.5f * (itc_sums[0] + itc_sums[1]) / n_global : 0.f;
+  float w = 1.f;
+  if (use_itc) w -= bi;
+  if (use_itm) w -= bm;
+  if (use_itc && use_itm) w = 1.f - (bi + bm);
+  out[0] = w * l_cls + (use_itc ? bi * l_itc : 0.f) + (use_itm ? bm * l_itm : 0.f);
+  out[1] = l_cls;
+  out[2] = l_itc;
+  out[3] = l_itm;
+}
+
+}  // namespace tic
+
+using namespace tic;
+
+extern "C" {
+
+int tic_pack_cls_pairs(const void* xt, int64_t xt_stride, const void* xv, int64_t xv_stride, int B, int E,
+                       const int32_t* src_idx, void* Xcat, int64_t ldx, void* stream) {
+  TIC_CHECK_ARG(xt && Xcat && B > 0 && E > 0 && ldx >= 2 * E, "tic_pack_cls_pairs: bad arguments");
+  const int rows = src_idx ? 2 * B : B;
+  pack_cls_pairs_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(xt), xt_stride, static_cast<const __nv_bfloat16*>(xv), xv_stride, B, E, src_idx,
+      static_cast<__nv_bfloat16*>(Xcat), ldx, rows);
+  TIC_CHECK_LAUNCH("tic_pack_cls_pairs");
+  return TIC_OK;
+}
+
+int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, const float* dX2, int64_t ldd2, int B, int E, const int32_t* src_idx,
+                        float* dxt, int64_t ld_dxt, void* stream) {
+  TIC_CHECK_ARG(dXcat && dxt && B > 0 && E > 0, "tic_unpack_cls_grad: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n = static_cast<int64_t>(B) * E;
+  const int blocks = static_cast<int>((n + 255) / 256);
+  unpack_main_kernel<<<blocks, 256, 0, st>>>(dXcat, ldd, dX2, ldd2, B, E, dxt, ld_dxt);
+  if (src_idx) unpack_scatter_kernel<<<blocks, 256, 0, st>>>(dXcat, ldd, dX2, ldd2, B, E, src_idx, dxt, ld_dxt);
+  TIC_CHECK_LAUNCH("tic_unpack_cls_grad");
+  return TIC_OK;
+}
+
+int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* W_cls, const float* b_cls,
+                      const float* W_tim, const float* b_tim, const float* y_soft, const float* class_w,
+                      const int64_t* lbl_tim, const uint8_t* keep, float keep_scale, float c_cls, float c_tim,
+                      float* logits_cls, float* logits_tim, float* losses, void* dH_bf16, void* dH_bf16_lo, int64_t ld_dhb, float* dH_f32,
+                      int64_t ld_dhf, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask, float* ws, void* stream) {
+  TIC_CHECK_ARG(H && W_cls && b_cls && y_soft && logits_cls && losses && ws, "tic_heads_fwd_bwd: null pointer");
+  TIC_CHECK_ARG(B > 0 && E > 0 && C >= 1 && C <= kMaxClasses, "tic_heads_fwd_bwd: need 1 <= C <= %d", kMaxClasses);
+  TIC_CHECK_ARG(!has_tim || (W_tim && b_tim && lbl_tim && logits_tim), "tic_heads_fwd_bwd: ITM head pointers missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = has_tim ? 2 * B : B;
+  float* dlogits = ws;
+  heads_rows_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft, class_w,
+                                                        lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses,
+                                                        dlogits, static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb,
+                                                        dH_f32, ld_dhf,
+                                                        relu_mask);
+  if (dW_cls && db_cls) {
+    const int rpb = max(32, ceil_div(B, 64));
+    dim3 grid(ceil_div(E, 128), ceil_div(B, rpb));
+    heads_wgrad_kernel<<<grid, 128, 0, st>>>(H, ldh, 0, B, E, C, dlogits, keep, keep_scale, dW_cls, db_cls, rpb);
+    if (has_tim && dW_tim && db_tim)
+      heads_wgrad_kernel<<<grid, 128, 0, st>>>(H, ldh, B, B, E, 2, dlogits, nullptr, 1.f, dW_tim, db_tim, rpb);
+  }
+  TIC_CHECK_LAUNCH("tic_heads_fwd_bwd");
+  return TIC_OK;
+}
+
+int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, void* stream) {
+  TIC_CHECK_ARG(X && out && rows > 0 && cols > 0, "tic_colsum_bf16: bad arguments");
+  const int rpb = max(32, ceil_div(rows, 64));
+  dim3 grid(ceil_div(cols, 128), ceil_div(rows, rpb));
+  colsum_bf16_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(X), ldx, rows, cols,
+                                                                          out, rpb);
+  TIC_CHECK_LAUNCH("tic_colsum_bf16");
+  return TIC_OK;
+}
+
+int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream) {
+  TIC_CHECK_ARG(src && dst && rows > 0 && cols > 0, "tic_cast_f32_to_bf16: bad arguments");
+  const int64_t n = static_cast<int64_t>(rows) * cols;
+  cast_f32_bf16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  TIC_CHECK_LAUNCH("tic_cast_f32_to_bf16");
+  return TIC_OK;
+}
+int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream) {
+  TIC_CHECK_ARG(src && dst && rows > 0 && cols > 0, "tic_cast_bf16_to_f32: bad arguments");
+  const int64_t n = static_cast<int64_t>(rows) * cols;
+  cast_bf16_f32_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, dst, ldd, rows, cols);
+  TIC_CHECK_LAUNCH("tic_cast_bf16_to_f32");
+  return TIC_OK;
+}
+
+int tic_loss_mix(const float* losses, const float* itc_sums, int n_global, float beta_itc, float beta_itm, int use_itc,
+                 int use_itm, float* out, void* stream) {
+  TIC_CHECK_ARG(losses && out && (!use_itc || itc_sums), "tic_loss_mix: bad arguments");
+  loss_mix_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(losses, itc_sums, n_global, beta_itc, beta_itm, use_itc,
+                                                                  use_itm, out);
+  TIC_CHECK_LAUNCH("tic_loss_mix");
+  return TIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,449 @@
+// Image-text contrastive (ITC) path: similarity tiles on tcgen05/TMEM with the bidirectional softmax
+// cross-entropy fused into the epilogue (logits are never written unless asked for), and its backward.
+//
+// Reference arithmetic: HF VisionTextDualEncoderModel.forward :268-273 (normalise, exp(logit_scale) * T V^T),
+// in-tree statement models/mm_early.py:96-103; loss models/utils.py:225-231.
+//
+// The L2 normalisation is folded into the tile epilogue:  S_ij = scale * rinv_t[i] * rinv_v[j] * <t_i, v_j>,
+// so the MMA consumes the raw bf16 embeddings (no extra rounding of normalised copies).
+// Softmax statistics use the fixed shift `shift >= max S` (= scale, because |cos| <= 1), which turns both the row and
+// the column log-sum-exp into plain sums: per-tile partial sums are written out and reduced in a fixed order
+// (deterministic; across ranks it is a SUM all-reduce).
+#include "common.cuh"
+#include "tic_umma.cuh"
+
+namespace tic {
+
+constexpr int kItcBN = 256;
+constexpr int kItcEpiWarps = 8;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// Sum the 32 per-lane values of each of 32 columns across the warp: returns, in lane l, sum over lanes of v[l].
+// Recursive-halving butterfly: 31 shuffles for 32 columns.
+__device__ __forceinline__ float warp_col_sums(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 16];
+    const float keep = up ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 8];
+    const float keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 4];
+    const float keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? v[i] : v[i + 2];
+    const float keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------ forward epilogue
+struct ItcFwdEpi {
+  struct Params {
+    const float* rinv_t;
+    const float* rinv_v;
+    float scale_log2e;   // scale * log2(e)
+    float shift_log2e;   // shift * log2(e)
+    float scale;
+    float* row_part;     // [n_tiles * nparts][M]
+    float* col_part;     // [m_tiles][N]
+    float* diag;         // [M]
+    float* logits;       // optional [M, ld_logits]
+    int64_t ld_logits;
+    int row_offset;
+  };
+  template <int BN>
+  __device__ static void tile(const Params& p, const EpiCtx& cx) {
+    const int lane = threadIdx.x & 31;
+    const int row = cx.m0 + cx.quad * 32 + lane;
+    const bool valid_row = row < cx.M;
+    float* sb = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * BN;   // rinv_v of this tile (double-buffered)
+    float* scol = reinterpret_cast<float*>(cx.scratch) + 2 * BN;             // [4 quads][BN] partial column sums
+    for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) sb[j] = (cx.n0 + j < cx.N) ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
+    epi_bar_sync(cx.epi_threads);
+    const float rt = valid_row ? __ldg(p.rinv_t + row) : 0.f;
+    const int gcol = p.row_offset + row;  // column holding this row's positive
+    const int cols_per_part = BN / cx.nparts;
+    float rowsum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < cols_per_part / 32; ++c) {
+      const int cl = cx.part * cols_per_part + c * 32;
+      const int col0 = cx.n0 + cl;
+      if (col0 >= cx.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16) + cl, v);
+      tmem_ld_wait();
+      float e[32];
+      float dsel = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float cosv = __uint_as_float(v[j]) * rt * sb[cl + j];       // cosine similarity
+        const bool ok = valid_row && (col0 + j < cx.N);
+        e[j] = ok ? exp2f(fmaf(cosv, p.scale_log2e, -p.shift_log2e)) : 0.f;
+        rowsum += e[j];
+        if (col0 + j == gcol) dsel = cosv * p.scale;
+        v[j] = __float_as_uint(cosv * p.scale);
+      }
+      if (valid_row && gcol >= col0 && gcol < col0 + 32) p.diag[row] = dsel;
+      if (p.logits != nullptr && valid_row) {
+        float* d = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
+        if (col0 + 32 <= cx.N && (p.ld_logits & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < cx.N) d[j] = __uint_as_float(v[j]);
+        }
+      }
+      const float cs = warp_col_sums(e);
+      scol[cx.quad * BN + cl + lane] = cs;
+    }
+    if (valid_row) p.row_part[static_cast<int64_t>(cx.n_blk * cx.nparts + cx.part) * cx.M + row] = rowsum;
+    epi_bar_sync(cx.epi_threads);
+    for (int j = cx.epi_tid; j < BN; j += cx.epi_threads)
+      if (cx.n0 + j < cx.N)
+        p.col_part[static_cast<int64_t>(cx.m_blk) * cx.N + cx.n0 + j] =
+            (scol[j] + scol[BN + j]) + (scol[2 * BN + j] + scol[3 * BN + j]);
+  }
+};
+
+// ------------------------------------------------------------------ backward epilogue: gradient operands
+struct ItcBwdEpi {
+  struct Params {
+    const float* rinv_t;
+    const float* rinv_v;
+    const float* lse_row;
+    const float* lse_col;
+    float scale_log2e;
+    float gscale;        // g / (2B)
+    __nv_bfloat16* GA;   // [M, ld_ga]   Gp * rinv_v[j]
+    int64_t ld_ga;
+    __nv_bfloat16* GBT;  // [N, ld_gbt]  Gp * rinv_t[i]  (transposed)
+    int64_t ld_gbt;
+    __nv_bfloat16* GA_lo;   // optional bf16 residuals (split precision for small batches)
+    __nv_bfloat16* GBT_lo;
+  };
+  template <int BN>
+  __device__ static void tile(const Params& p, const EpiCtx& cx) {
+    const int lane = threadIdx.x & 31;
+    const int row = cx.m0 + cx.quad * 32 + lane;
+    const bool valid_row = row < cx.M;
+    float* sb = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * 2 * BN;  // rinv_v | lse_col*log2e
+    float* sl = sb + BN;
+    for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) {
+      const bool ok = cx.n0 + j < cx.N;
+      sb[j] = ok ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
+      sl[j] = ok ? __ldg(p.lse_col + cx.n0 + j) * kLog2e : 0.f;
+    }
+    epi_bar_sync(cx.epi_threads);
+    const float rt = valid_row ? __ldg(p.rinv_t + row) : 0.f;
+    const float lr = valid_row ? __ldg(p.lse_row + row) * kLog2e : 0.f;
+    const int cols_per_part = BN / cx.nparts;
+    const bool vec_ok = (p.ld_ga & 7) == 0;
+#pragma unroll 1
+    for (int c = 0; c < cols_per_part / 32; ++c) {
+      const int cl = cx.part * cols_per_part + c * 32;
+      const int col0 = cx.n0 + cl;
+      if (col0 >= cx.N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16) + cl, v);
+      tmem_ld_wait();
+      float ga[32];
+      __nv_bfloat16* gbt = p.GBT + static_cast<int64_t>(col0) * p.ld_gbt + row;
+      __nv_bfloat16* gbt_lo = p.GBT_lo ? p.GBT_lo + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s2 = __uint_as_float(v[j]) * rt * sb[cl + j] * p.scale_log2e;  // S * log2e
+        const float pr = p.gscale * (exp2f(s2 - lr) + exp2f(s2 - sl[cl + j]));
+        ga[j] = pr * sb[cl + j];
+        if (valid_row && col0 + j < cx.N) {
+          const float gb = pr * rt;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(gb);
+          gbt[static_cast<int64_t>(j) * p.ld_gbt] = hi;
+          if (gbt_lo) gbt_lo[static_cast<int64_t>(j) * p.ld_gbt] = __float2bfloat16_rn(gb - __bfloat162float(hi));
+        }
+      }
+      if (valid_row) {
+        __nv_bfloat16* d = p.GA + static_cast<int64_t>(row) * p.ld_ga + col0;
+        if (col0 + 32 <= cx.N && vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(ga[j], ga[j + 1]);
+            u.y = pack_bf16x2(ga[j + 2], ga[j + 3]);
+            u.z = pack_bf16x2(ga[j + 4], ga[j + 5]);
+            u.w = pack_bf16x2(ga[j + 6], ga[j + 7]);
+            *reinterpret_cast<uint4*>(d + j) = u;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < cx.N) d[j] = __float2bfloat16_rn(ga[j]);
+        }
+        if (p.GA_lo != nullptr) {
+          __nv_bfloat16* dl = p.GA_lo + static_cast<int64_t>(row) * p.ld_ga + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ga[j] -= __bfloat162float(__float2bfloat16_rn(ga[j]));
+          if (col0 + 32 <= cx.N && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(ga[j], ga[j + 1]);
+              u.y = pack_bf16x2(ga[j + 2], ga[j + 3]);
+              u.z = pack_bf16x2(ga[j + 4], ga[j + 5]);
+              u.w = pack_bf16x2(ga[j + 6], ga[j + 7]);
+              *reinterpret_cast<uint4*>(dl + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < cx.N) dl[j] = __float2bfloat16_rn(ga[j]);
+          }
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ small HBM-bound kernels
+// rinv[i] = 1/||X[i,:]||  — one warp per row, 16-byte loads when aligned.
+__global__ void row_rnorm_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ X_lo, int64_t ldx, int rows,
+                                 int cols, float* __restrict__ rinv) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const __nv_bfloat16* x = X + static_cast<int64_t>(warp) * ldx;
+  float ss = 0.f;
+  if (X_lo != nullptr) {
+    const __nv_bfloat16* xl = X_lo + static_cast<int64_t>(warp) * ldx;
+    for (int c = lane; c < cols; c += 32) {
+      const float f = __bfloat162float(x[c]) + __bfloat162float(xl[c]);
+      ss = fmaf(f, f, ss);
+    }
+  } else if ((ldx & 7) == 0 && (cols & 7) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    for (int c = lane * 8; c < cols; c += 256) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + c));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
+      }
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32) {
+      const float f = __bfloat162float(x[c]);
+      ss = fmaf(f, f, ss);
+    }
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) rinv[warp] = 1.0f / sqrtf(ss);  // no epsilon (HF :268-269)
+}
+
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[static_cast<int64_t>(p) * n + j];
+  out[j] = s;
+}
+
+// Single block: fixed-order sum of the per-tile partials, lse vectors, and the two loss sums (deterministic).
+__global__ void itc_lse_loss_kernel(const float* __restrict__ row_part, int nrp, const float* __restrict__ col_part, int ncp,
+                                    const float* __restrict__ diag, int M, int N, int row_offset, float shift,
+                                    float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ loss_sums) {
+  __shared__ float sr[32], sc[32];
+  float ar = 0.f, ac = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < ncp; ++p) s += col_part[static_cast<int64_t>(p) * N + j];
+    lse_col[j] = shift + logf(s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < nrp; ++p) s += row_part[static_cast<int64_t>(p) * M + i];
+    const float lr = shift + logf(s);
+    lse_row[i] = lr;
+    const float d = diag[i];
+    ar += lr - d;
+    ac += lse_col[row_offset + i] - d;
+  }
+  ar = warp_sum(ar);
+  ac = warp_sum(ac);
+  if ((threadIdx.x & 31) == 0) { sr[threadIdx.x >> 5] = ar; sc[threadIdx.x >> 5] = ac; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    ar = threadIdx.x < nw ? sr[threadIdx.x] : 0.f;
+    ac = threadIdx.x < nw ? sc[threadIdx.x] : 0.f;
+    ar = warp_sum(ar);
+    ac = warp_sum(ac);
+    if (threadIdx.x == 0) { loss_sums[0] += ar; loss_sums[1] += ac; }
+  }
+}
+
+// One warp per row: diagonal term, normalise-backward, dlogit_scale contribution.
+__global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t ld_acc, const __nv_bfloat16* __restrict__ X,
+                                         const __nv_bfloat16* __restrict__ X_lo, int64_t ldx, const float* __restrict__ rinv,
+                                         const __nv_bfloat16* __restrict__ Xo, const __nv_bfloat16* __restrict__ Xo_lo,
+                                         int64_t ldxo, const float* __restrict__ rinv_o, int rows, int P, float scale,
+                                         float diag_coef, float* __restrict__ dXf, int64_t ld_df,
+                                         __nv_bfloat16* __restrict__ dXb, __nv_bfloat16* __restrict__ dXb_lo, int64_t ld_db,
+                                         float* __restrict__ r_sum) {
+  const int warp_in_blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp_in_blk;
+  __shared__ float sblk[32];
+  float r = 0.f;
+  if (row < rows) {
+    const float ri = rinv[row];
+    const float co = (Xo != nullptr && diag_coef != 0.f) ? diag_coef * rinv_o[row] : 0.f;
+    const float* a = acc + static_cast<int64_t>(row) * ld_acc;
+    const __nv_bfloat16* x = X + static_cast<int64_t>(row) * ldx;
+    const __nv_bfloat16* xo = Xo ? Xo + static_cast<int64_t>(row) * ldxo : nullptr;
+    const __nv_bfloat16* xl = X_lo ? X_lo + static_cast<int64_t>(row) * ldx : nullptr;
+    const __nv_bfloat16* xol = (Xo && Xo_lo) ? Xo_lo + static_cast<int64_t>(row) * ldxo : nullptr;
+    auto xval = [&](int k) { return __bfloat162float(x[k]) + (xl ? __bfloat162float(xl[k]) : 0.f); };
+    auto xoval = [&](int k) { return __bfloat162float(xo[k]) + (xol ? __bfloat162float(xol[k]) : 0.f); };
+    for (int k = lane; k < P; k += 32) {
+      const float dxh = scale * (a[k] - (xo ? co * xoval(k) : 0.f));
+      r = fmaf(ri * xval(k), dxh, r);
+    }
+    r = warp_sum(r);
+    for (int k = lane; k < P; k += 32) {
+      const float dxh = scale * (a[k] - (xo ? co * xoval(k) : 0.f));
+      const float xh = ri * xval(k);
+      const float g = ri * (dxh - xh * r);
+      if (dXf) dXf[static_cast<int64_t>(row) * ld_df + k] = g;
+      if (dXb) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(g);
+        dXb[static_cast<int64_t>(row) * ld_db + k] = hi;
+        if (dXb_lo) dXb_lo[static_cast<int64_t>(row) * ld_db + k] = __float2bfloat16_rn(g - __bfloat162float(hi));
+      }
+    }
+  }
+  if (r_sum != nullptr) {
+    if (lane == 0) sblk[warp_in_blk] = (row < rows) ? r : 0.f;
+    __syncthreads();
+    if (warp_in_blk == 0) {
+      float t = lane < (blockDim.x >> 5) ? sblk[lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) atomicAdd(r_sum, t);
+    }
+  }
+}
+
+}  // namespace tic
+
+using namespace tic;
+
+extern "C" {
+
+int tic_itc_row_parts(int n_global) { return ceil_div(n_global, kItcBN) * (kItcEpiWarps / 4); }
+int tic_itc_col_parts(int m_local) { return ceil_div(m_local, kBM); }
+
+int tic_row_rnorm_bf16(const void* X, const void* X_lo, int64_t ldx, int rows, int cols, float* rinv, void* stream) {
+  TIC_CHECK_ARG(X && rinv && rows > 0 && cols > 0, "tic_row_rnorm_bf16: bad arguments");
+  const int wpb = 8;
+  row_rnorm_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(X_lo), ldx, rows, cols, rinv);
+  TIC_CHECK_LAUNCH("tic_row_rnorm_bf16");
+  return TIC_OK;
+}
+
+int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv, const float* rinv_t,
+                const float* rinv_v,
+                int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
+                float* col_part, float* diag, float* logits_out, int64_t ld_logits, void* stream) {
+  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && row_part && col_part && diag, "tic_itc_fwd: null pointer");
+  TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_fwd: empty problem");
+  TIC_CHECK_ARG(row_offset >= 0 && row_offset + m_local <= n_global, "tic_itc_fwd: row block outside the global batch");
+  if (!(scale > 0.f) || scale > 40.f || shift < scale) {
+    set_error("tic_itc_fwd: scale=%g shift=%g outside the supported range (0 < scale <= 40, shift >= scale)", scale, shift);
+    return TIC_E_RANGE;
+  }
+  ItcFwdEpi::Params ep{rinv_t, rinv_v, scale * kLog2e, shift * kLog2e, scale, row_part, col_part, diag, logits_out, ld_logits,
+                       row_offset};
+  int rc = launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep,
+                                                                          static_cast<cudaStream_t>(stream));
+  if (rc == -3) { set_error("tic_itc_fwd: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
+  if (rc == -4) { set_error("tic_itc_fwd: launch failed"); return TIC_E_LAUNCH; }
+  return rc;
+}
+
+int tic_reduce_parts(const float* part, int nparts, int n, float* out, void* stream) {
+  TIC_CHECK_ARG(part && out && nparts > 0 && n > 0, "tic_reduce_parts: bad arguments");
+  reduce_parts_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, nparts, n, out);
+  TIC_CHECK_LAUNCH("tic_reduce_parts");
+  return TIC_OK;
+}
+
+int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, const float* diag,
+                     int m_local, int n_global, int row_offset, float shift, float* lse_row, float* lse_col,
+                     float* loss_sums, void* stream) {
+  TIC_CHECK_ARG(row_part && col_part && diag && lse_row && lse_col && loss_sums && n_row_parts > 0 && n_col_parts > 0,
+                "tic_itc_lse_loss: bad arguments");
+  itc_lse_loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(row_part, n_row_parts, col_part, n_col_parts, diag,
+                                                                         m_local, n_global, row_offset, shift, lse_row,
+                                                                         lse_col, loss_sums);
+  TIC_CHECK_LAUNCH("tic_itc_lse_loss");
+  return TIC_OK;
+}
+
+int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv,
+                  const float* rinv_t, const float* rinv_v,
+                  const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale, float gscale,
+                  void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo, void* GBT_lo, void* stream) {
+  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && lse_row && lse_col && GA && GBT, "tic_itc_bwd_g: null pointer");
+  TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_bwd_g: empty problem");
+  ItcBwdEpi::Params ep{rinv_t, rinv_v, lse_row, lse_col, scale * kLog2e, gscale, static_cast<__nv_bfloat16*>(GA), ld_ga,
+                       static_cast<__nv_bfloat16*>(GBT), ld_gbt, static_cast<__nv_bfloat16*>(GA_lo),
+                       static_cast<__nv_bfloat16*>(GBT_lo)};
+  int rc = launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep,
+                                                                          static_cast<cudaStream_t>(stream));
+  if (rc == -3) { set_error("tic_itc_bwd_g: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
+  if (rc == -4) { set_error("tic_itc_bwd_g: launch failed"); return TIC_E_LAUNCH; }
+  return rc;
+}
+
+int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const void* X_lo, int64_t ldx, const float* rinv,
+                          const void* Xo, const void* Xo_lo, int64_t ldxo, const float* rinv_o, int rows, int P, float scale, float diag_coef, float* dX_f32,
+                          int64_t ld_df, void* dX_bf16, void* dX_bf16_lo, int64_t ld_db, float* r_sum, void* stream) {
+  TIC_CHECK_ARG(acc && X && rinv && rows > 0 && P > 0, "tic_itc_grad_finalize: bad arguments");
+  TIC_CHECK_ARG(dX_f32 || dX_bf16, "tic_itc_grad_finalize: no output requested");
+  const int wpb = 8;
+  itc_grad_finalize_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc, ld_acc, static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(X_lo), ldx, rinv,
+      static_cast<const __nv_bfloat16*>(Xo), static_cast<const __nv_bfloat16*>(Xo_lo), ldxo, rinv_o,
+      rows, P, scale, diag_coef, dX_f32, ld_df, static_cast<__nv_bfloat16*>(dX_bf16), static_cast<__nv_bfloat16*>(dX_bf16_lo), ld_db,
+      r_sum);
+  TIC_CHECK_LAUNCH("tic_itc_grad_finalize");
+  return TIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// Image-text matching (ITM) negative sampling + pair gather — the device replacement of the host loop in
+// models/mm_late.py:389-414 (prepare_itm_inputs): one coin + one pick per row, then row copies of ids / mask.
+//
+//  uniform mode (reference behaviour): integer arithmetic on the supplied uniforms, bit-exact by construction.
+//  hard mode (extension, ALBEF-style; spec = oracle/restatement.py:itm_sample_hard): multinomial over
+//     w_j = exp(S_ij - max_j S_ij), j != i, by inverse CDF on 2^30 fixed-point weights; integer prefix sums are
+//     associative, and det_exp() uses only single IEEE-754 fp32 operations, so any reduction order reproduces the
+//     oracle bit for bit.
+#include "common.cuh"
+#include "tic_ptx.cuh"
+
+namespace tic {
+
+__device__ __forceinline__ float det_exp(float x) {
+  // mirrored op-for-op by oracle/restatement.py:det_exp_f32 — no FMA contraction, no library transcendental
+  x = fmaxf(x, -80.0f);
+  const float n = rintf(__fmul_rn(x, 1.44269504088896341f));
+  float r = __fsub_rn(x, __fmul_rn(n, 0.693359375f));
+  r = __fsub_rn(r, __fmul_rn(n, -2.12194440e-4f));
+  float p = 1.9875691500e-4f;
+  p = __fadd_rn(__fmul_rn(p, r), 1.3981999507e-3f);
+  p = __fadd_rn(__fmul_rn(p, r), 8.3334519073e-3f);
+  p = __fadd_rn(__fmul_rn(p, r), 4.1665795894e-2f);
+  p = __fadd_rn(__fmul_rn(p, r), 1.6666665459e-1f);
+  p = __fadd_rn(__fmul_rn(p, r), 5.0000001201e-1f);
+  const float y = __fadd_rn(__fadd_rn(__fmul_rn(p, __fmul_rn(r, r)), r), 1.0f);
+  return __int_as_float(__float_as_int(y) + (static_cast<int>(n) << 23));  // exact scaling by 2^n (result stays normal)
+}
+
+__device__ __forceinline__ void uniform_rule(const float* u_coin, const float* u_pick, int B, int i, int& label, int& src) {
+  label = 1;
+  src = i;
+  if (B > 1 && u_coin[i] < 0.5f) {
+    label = 0;
+    int k = static_cast<int>(floorf(__fmul_rn(u_pick[i], static_cast<float>(B - 1))));
+    k = min(k, B - 2);
+    src = k < i ? k : k + 1;
+  }
+}
+
+__global__ void itm_sample_uniform_kernel(const float* __restrict__ u_coin, const float* __restrict__ u_pick, int B,
+                                          int64_t* __restrict__ labels, int32_t* __restrict__ src_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  int l, s;
+  uniform_rule(u_coin, u_pick, B, i, l, s);
+  labels[i] = l;
+  src_idx[i] = s;
+}
+
+__device__ __forceinline__ unsigned long long qweight(float s, float mx) {
+  return static_cast<unsigned long long>(__fmul_rn(det_exp(__fsub_rn(s, mx)), 1073741824.0f));
+}
+
+// One 256-thread block per row; thread t owns the contiguous column chunk [t*chunk, (t+1)*chunk).
+__global__ void __launch_bounds__(256) itm_sample_hard_kernel(const float* __restrict__ u_coin, const float* __restrict__ u_pick,
+                                                              int B, const float* __restrict__ S, int64_t lds,
+                                                              int64_t* __restrict__ labels, int32_t* __restrict__ src_idx) {
+  const int i = blockIdx.x, t = threadIdx.x;
+  int label, src;
+  uniform_rule(u_coin, u_pick, B, i, label, src);
+  if (label == 1) {  // block-uniform
+    if (t == 0) { labels[i] = 1; src_idx[i] = i; }
+    return;
+  }
+  __shared__ float smax[8];
+  __shared__ unsigned long long ssum[256];
+  __shared__ int sres;
+  const float* row = S + static_cast<int64_t>(i) * lds;
+  float mx = -INFINITY;
+  for (int j = t; j < B; j += 256) mx = fmaxf(mx, row[j]);
+  mx = warp_max(mx);
+  if ((t & 31) == 0) smax[t >> 5] = mx;
+  if (t == 0) sres = -1;
+  __syncthreads();
+  mx = smax[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, smax[w]);
+  const int chunk = (B + 255) / 256;
+  const int j0 = t * chunk, j1 = min(j0 + chunk, B);
+  unsigned long long local = 0;
+  for (int j = j0; j < j1; ++j)
+    if (j != i) local += qweight(row[j], mx);
+  ssum[t] = local;
+  __syncthreads();
+  // exclusive prefix of the 256 chunk sums (integer => order independent); 256 adds per thread is negligible
+  unsigned long long excl = 0, total = 0;
+  for (int k = 0; k < 256; ++k) {
+    const unsigned long long s = ssum[k];
+    if (k < t) excl += s;
+    total += s;
+  }
+  if (total != 0) {
+    const unsigned long long U = static_cast<unsigned long long>(__fmul_rn(u_pick[i], 16777216.0f));
+    const unsigned long long target = U * (total >> 24) + ((U * (total & 0xFFFFFFull)) >> 24);
+    if (local != 0 && target >= excl && target < excl + local) {
+      unsigned long long c = excl;
+      for (int j = j0; j < j1; ++j) {
+        if (j != i) c += qweight(row[j], mx);
+        if (c > target) { sres = j; break; }
+      }
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    labels[i] = 0;
+    src_idx[i] = (total != 0 && sres >= 0) ? sres : src;
+  }
+}
+
+// dst[r,:] = src[idx[r],:] for row_bytes bytes; one warp per row, 16-byte words when everything is aligned.
+// blockIdx.y selects one of up to two (src, dst) pairs so ids and mask move in one launch.
+// When `u_coin` is given the uniform sampling rule is evaluated in-kernel (single-launch sample + gather).
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ s0, uint8_t* __restrict__ d0, const uint8_t* __restrict__ s1,
+                                   uint8_t* __restrict__ d1, int64_t spitch, int64_t dpitch, int64_t row_bytes,
+                                   const int32_t* __restrict__ idx, int rows, const float* __restrict__ u_coin,
+                                   const float* __restrict__ u_pick, int64_t* __restrict__ labels,
+                                   int32_t* __restrict__ src_out) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  int sr;
+  if (u_coin != nullptr) {
+    int l;
+    uniform_rule(u_coin, u_pick, rows, r, l, sr);
+    if (blockIdx.y == 0 && lane == 0) { labels[r] = l; src_out[r] = sr; }
+  } else {
+    sr = idx[r];
+  }
+  const uint8_t* s = (blockIdx.y == 0 ? s0 : s1) + static_cast<int64_t>(sr) * spitch;
+  uint8_t* d = (blockIdx.y == 0 ? d0 : d1) + static_cast<int64_t>(r) * dpitch;
+  const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | static_cast<uintptr_t>(row_bytes)) & 15) == 0;
+  if (vec) {
+    for (int64_t b = lane * 16; b < row_bytes; b += 512) *reinterpret_cast<uint4*>(d + b) = __ldg(reinterpret_cast<const uint4*>(s + b));
+  } else {
+    for (int64_t b = lane; b < row_bytes; b += 32) d[b] = s[b];
+  }
+}
+
+}  // namespace tic
+
+using namespace tic;
+
+extern "C" {
+
+int tic_itm_sample(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds, int64_t* labels,
+                   int32_t* src_idx, void* stream) {
+  TIC_CHECK_ARG(u_coin && u_pick && labels && src_idx && B > 0, "tic_itm_sample: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == TIC_ITM_UNIFORM) {
+    itm_sample_uniform_kernel<<<ceil_div(B, 256), 256, 0, st>>>(u_coin, u_pick, B, labels, src_idx);
+  } else if (mode == TIC_ITM_HARD) {
+    TIC_CHECK_ARG(S != nullptr && lds >= B, "tic_itm_sample: hard mode needs the similarity matrix");
+    itm_sample_hard_kernel<<<B, 256, 0, st>>>(u_coin, u_pick, B, S, lds, labels, src_idx);
+  } else {
+    set_error("tic_itm_sample: unknown mode %d", mode);
+    return TIC_E_ARG;
+  }
+  TIC_CHECK_LAUNCH("tic_itm_sample");
+  return TIC_OK;
+}
+
+int tic_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int64_t row_bytes,
+                    const int32_t* src_idx, int rows, void* stream) {
+  TIC_CHECK_ARG(src && dst && src_idx && rows > 0 && row_bytes > 0, "tic_gather_rows: bad arguments");
+  dim3 grid(ceil_div(rows, 8), 1);
+  gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), nullptr, nullptr, src_pitch_bytes, dst_pitch_bytes,
+      row_bytes, src_idx, rows, nullptr, nullptr, nullptr, nullptr);
+  TIC_CHECK_LAUNCH("tic_gather_rows");
+  return TIC_OK;
+}
+
+int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds,
+                          const void* ids, const void* mask, int64_t row_bytes, void* tim_ids, void* tim_mask,
+                          int64_t* labels, int32_t* src_idx, void* stream) {
+  TIC_CHECK_ARG(u_coin && u_pick && ids && mask && tim_ids && tim_mask && labels && src_idx && B > 0 && row_bytes > 0,
+                "tic_itm_sample_gather: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(ceil_div(B, 8), 2);
+  if (mode == TIC_ITM_UNIFORM) {
+    gather_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(ids), static_cast<uint8_t*>(tim_ids),
+                                             static_cast<const uint8_t*>(mask), static_cast<uint8_t*>(tim_mask), row_bytes,
+                                             row_bytes, row_bytes, nullptr, B, u_coin, u_pick, labels, src_idx);
+  } else {
+    int rc = tic_itm_sample(u_coin, u_pick, B, mode, S, lds, labels, src_idx, stream);
+    if (rc) return rc;
+    gather_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(ids), static_cast<uint8_t*>(tim_ids),
+                                             static_cast<const uint8_t*>(mask), static_cast<uint8_t*>(tim_mask), row_bytes,
+                                             row_bytes, row_bytes, src_idx, B, nullptr, nullptr, nullptr, nullptr);
+  }
+  TIC_CHECK_LAUNCH("tic_itm_sample_gather");
+  return TIC_OK;
+}
+
+}  // extern "C"

@@ -40,6 +40,7 @@ struct EpiCtx {
   int part, nparts;    // column split across epilogue warp groups: columns [part*BN/nparts, (part+1)*BN/nparts)
   int epi_tid;         // 0 .. 32*EPI_WARPS-1
   int epi_threads;
+  int iter;             // tiles already processed by this CTA (for double-buffering the scratch)
   uint8_t* scratch;    // kEpiScratchBytes of smem shared by the epilogue warps
 };
 
@@ -50,8 +51,9 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
 
 template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
-                 int K, typename Epi::Params ep) {
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
+                 const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int M,
+                 int N, int K, typename Epi::Params ep) {
   using Cfg = UmmaCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps must cover the 4 TMEM lane quadrants");
@@ -74,10 +76,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + kBK - 1) / kBK;
+  // Split-precision operands: an operand given as a bf16 (hi, lo) pair contributes an extra K-segment, so
+  // D = A_hi*B_hi (+ A_lo*B_hi) (+ A_hi*B_lo) accumulates in TMEM with ~16 mantissa bits per split operand.
+  const int nseg = 1 + (split & 1) + ((split >> 1) & 1);
+  const int total_kb = num_kb * nseg;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (split & 1) tma_prefetch_desc(&tmap_a_lo);
+    if (split & 2) tma_prefetch_desc(&tmap_b_lo);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -101,23 +109,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kt = 0; kt < total_kb; ++kt) {
+          const int seg = kt / num_kb, kb = kt - seg * num_kb;
+          const bool a_lo = (seg == 1) && (split & 1);
+          const bool b_lo = (seg >= 1) && !a_lo;
+          const CUtensorMap* ta = a_lo ? &tmap_a_lo : &tmap_a;
+          const CUtensorMap* tb = b_lo ? &tmap_b_lo : &tmap_b;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + kABytes;
           mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
           const int k0 = kb * kBK;
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmap_a, full_bar(s), k0, m0);
+            tma_load_2d(sa, ta, full_bar(s), k0, m0);
           } else {
-            tma_load_2d(sa, &tmap_a, full_bar(s), m0, k0);
-            tma_load_2d(sa + 8192, &tmap_a, full_bar(s), m0 + 64, k0);
+            tma_load_2d(sa, ta, full_bar(s), m0, k0);
+            tma_load_2d(sa + 8192, ta, full_bar(s), m0 + 64, k0);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmap_b, full_bar(s), k0, n0);
+            tma_load_2d(sb, tb, full_bar(s), k0, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tmap_b, full_bar(s), n0 + i * 64, k0);
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, tb, full_bar(s), n0 + i * 64, k0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -137,7 +150,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
@@ -166,6 +179,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     cx.scratch = scratch;
     int as = 0;
     uint32_t aph = 0;
+    cx.iter = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       cx.m_blk = t / n_tiles; cx.n_blk = t % n_tiles;
       cx.m0 = cx.m_blk * kBM; cx.n0 = cx.n_blk * BN;
@@ -176,6 +190,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
+      ++cx.iter;
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
@@ -203,18 +218,25 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
 int device_sm_count();
 
 template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
-int launch_umma_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
-                     const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0) {
+int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B, const void* B_lo, int64_t ldb, int M, int N,
+                     int K, const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0) {
   using Cfg = UmmaCfg<BN>;
   if (M <= 0 || N <= 0 || K <= 0) return -1;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta_lo, tb_lo;
+  auto map_a = [&](CUtensorMap* t, const void* p) {
+    return !A_MN ? make_tmap_bf16_2d(t, p, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM)
+                 : make_tmap_bf16_2d(t, p, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, kBK);
+  };
+  auto map_b = [&](CUtensorMap* t, const void* p) {
+    return !B_MN ? make_tmap_bf16_2d(t, p, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, BN)
+                 : make_tmap_bf16_2d(t, p, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kBK);
+  };
   int rc;
-  if (!A_MN) rc = make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM);
-  else       rc = make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, kBK);
-  if (rc) return rc;
-  if (!B_MN) rc = make_tmap_bf16_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, BN);
-  else       rc = make_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kBK);
-  if (rc) return rc;
+  if ((rc = map_a(&ta, A))) return rc;
+  if ((rc = map_b(&tb, B))) return rc;
+  if ((rc = map_a(&ta_lo, A_lo ? A_lo : A))) return rc;
+  if ((rc = map_b(&tb_lo, B_lo ? B_lo : B))) return rc;
+  const int split = (A_lo ? 1 : 0) | (B_lo ? 2 : 0);
   auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI_WARPS, Epi>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
@@ -225,8 +247,14 @@ int launch_umma_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int
   int grid = m_tiles * n_tiles;
   int cap = max_ctas > 0 ? max_ctas : device_sm_count();
   if (grid > cap) grid = cap;
-  kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(ta, ta_lo, tb, tb_lo, split, M, N, K, ep);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// hi/lo split of an fp32 value into two bf16: hi = rn(x), lo = rn(x - hi)  (hi + lo carries ~16 mantissa bits)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
 }  // namespace tic

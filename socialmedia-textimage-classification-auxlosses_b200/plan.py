@@ -1,0 +1,470 @@
+"""Static-shape execution plans for the late-fusion head + auxiliary-loss step (forward AND backward).
+
+A plan owns every workspace, so a step allocates nothing, performs no host synchronisation and is CUDA-graph
+capturable.  All arithmetic happens in libtic_b200.so (hand-written sm_100a kernels, see csrc/); torch is used only
+for device memory and streams.
+
+  ItcPlan   image-text contrastive loss on embeddings: row norms -> tcgen05 similarity tiles with the bidirectional
+            softmax-CE fused in the epilogue -> tile recompute emitting bf16 gradient operands -> two tcgen05 GEMMs
+            -> normalise-backward.  (HF VisionTextDualEncoderModel.forward :268-273 + models/utils.py:225-231.)
+  HeadPlan  everything models/mm_late.py does after the encoders return (MM_Model.forward :155-193, the loss mix
+            :473-487) for fusion in {concat, attention, gmu, aspect-att}, with ITM sampling/gather (:389-414).
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import capi
+from .capi import call, ptr
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _up8(x):
+    return (x + 7) // 8 * 8
+
+
+def _addr(t):
+    return None if t is None else (t if isinstance(t, int) else t.data_ptr())
+
+
+def gemm(A, lda, a_mn, Bm, ldb, b_mn, D, ldd, d_bf16, M, N, K, alpha=1.0, bias=None, relu=False, A_lo=None, B_lo=None,
+         D_lo=None):
+    """D[M,N] = alpha * op(A) op(B)^T (+bias)(relu) on tcgen05 (tic_gemm_bf16).  A/Bm/D are tensors or raw device
+    addresses; A_lo / B_lo make that operand a split-precision bf16 (hi, lo) pair, D_lo receives the bf16 residual."""
+    call("tic_gemm_bf16", _addr(A), _addr(A_lo), lda, int(a_mn), _addr(Bm), _addr(B_lo), ldb, int(b_mn), _addr(D),
+         _addr(D_lo), ldd, int(d_bf16), M, N, K, float(alpha), ptr(bias), int(relu), _stream())
+
+
+class ItcPlan:
+    """ITC forward+backward for a row block of `m` text rows against `n` gathered image columns (single GPU: m == n)."""
+
+    def __init__(self, m: int, n: int, P: int, device, row_offset: int = 0, materialize_logits: bool = False,
+                 need_dv: bool = True, precise: Optional[bool] = None):
+        assert P % 8 == 0, "embedding width must be a multiple of 8 (16-byte TMA rows)"
+        self.m, self.n, self.P, self.row_offset = m, n, P, row_offset
+        # Split-precision gradient operands (bf16 hi+lo): with few negatives the bf16 rounding of the softmax
+        # probabilities does not average out; from ~4k columns on it does and the second K-segment is skipped.
+        self.precise = (n < 4096) if precise is None else bool(precise)
+        self.nrp = capi.load().tic_itc_row_parts(n)
+        self.ncp = capi.load().tic_itc_col_parts(m)
+        dev = device
+        self.rinv_t = torch.empty(m, dtype=F32, device=dev)
+        self.rinv_v = torch.empty(n, dtype=F32, device=dev)
+        self.row_part = torch.empty(self.nrp, m, dtype=F32, device=dev)
+        self.col_part = torch.empty(self.ncp, n, dtype=F32, device=dev)
+        self.col_sum = torch.empty(n, dtype=F32, device=dev)   # used by the multi-GPU path (all-reduced)
+        self.diag = torch.empty(m, dtype=F32, device=dev)
+        self.lse_row = torch.empty(m, dtype=F32, device=dev)
+        self.lse_col = torch.empty(n, dtype=F32, device=dev)
+        self.ld_ga, self.ld_gbt = _up8(n), _up8(m)
+        self.GA = torch.empty(m, self.ld_ga, dtype=BF16, device=dev)
+        self.GBT = torch.empty(n, self.ld_gbt, dtype=BF16, device=dev) if need_dv else None
+        self.GA_lo = torch.empty(m, self.ld_ga, dtype=BF16, device=dev) if self.precise else None
+        self.GBT_lo = torch.empty(n, self.ld_gbt, dtype=BF16, device=dev) if (need_dv and self.precise) else None
+        self.acc_t = torch.empty(m, P, dtype=F32, device=dev)
+        self.acc_v = torch.empty(n, P, dtype=F32, device=dev) if need_dv else None
+        self.logits = torch.empty(m, n, dtype=F32, device=dev) if materialize_logits else None
+        self.need_dv = need_dv
+
+    # -- pieces (the distributed path interleaves collectives between them) --
+    def norms(self, T, ldt, V, ldv, t_only=False, T_lo=None, V_lo=None):
+        call("tic_row_rnorm_bf16", ptr(T), ptr(T_lo), ldt, self.m, self.P, ptr(self.rinv_t), _stream())
+        if not t_only:
+            call("tic_row_rnorm_bf16", ptr(V), ptr(V_lo), ldv, self.n, self.P, ptr(self.rinv_v), _stream())
+
+    def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None):
+        call("tic_itc_fwd", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), self.m, self.n, self.P,
+             self.row_offset, float(scale), float(scale), ptr(self.row_part), ptr(self.col_part), ptr(self.diag),
+             ptr(self.logits), self.n if self.logits is not None else 0, _stream())
+
+    def lse_loss(self, scale, loss_sums, col_parts=None, n_col_parts=None):
+        cp = self.col_part if col_parts is None else col_parts
+        ncp = self.ncp if n_col_parts is None else n_col_parts
+        call("tic_itc_lse_loss", ptr(self.row_part), self.nrp, ptr(cp), ncp, ptr(self.diag), self.m, self.n,
+             self.row_offset, float(scale), ptr(self.lse_row), ptr(self.lse_col), ptr(loss_sums), _stream())
+
+    def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None):
+        assert self.GBT is not None or not self.need_dv
+        call("tic_itc_bwd_g", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), ptr(self.lse_row),
+             ptr(self.lse_col), self.m, self.n, self.P, float(scale), float(gscale), ptr(self.GA), self.ld_ga,
+             ptr(self.GBT) if self.GBT is not None else ptr(self.GA), self.ld_gbt if self.GBT is not None else self.ld_ga,
+             ptr(self.GA_lo), ptr(self.GBT_lo), _stream())
+
+    def grad_gemms(self, T, ldt, V, ldv, T_lo=None, V_lo=None):
+        # dT_acc[m,P] = GA[m,n] * V[n,P]   (A K-major, B = V read MN-major: no transposed copy of V)
+        gemm(self.GA, self.ld_ga, 0, V, ldv, 1, self.acc_t, self.P, 0, self.m, self.P, self.n, A_lo=self.GA_lo, B_lo=V_lo)
+        if self.need_dv:
+            # dV_acc[n,P] = GBT[n,m] * T[m,P]
+            gemm(self.GBT, self.ld_gbt, 0, T, ldt, 1, self.acc_v, self.P, 0, self.n, self.P, self.m, A_lo=self.GBT_lo,
+                 B_lo=T_lo)
+
+    def finalize_t(self, T, ldt, V_diag, ldv, rinv_v_diag, scale, diag_coef, dT_f32, dT_bf16, r_sum, dT_lo=None,
+                   T_lo=None, V_diag_lo=None):
+        call("tic_itc_grad_finalize", ptr(self.acc_t), self.P, ptr(T), ptr(T_lo), ldt, ptr(self.rinv_t), ptr(V_diag),
+             ptr(V_diag_lo), ldv,
+             ptr(rinv_v_diag), self.m, self.P, float(scale), float(diag_coef), ptr(dT_f32), self.P, ptr(dT_bf16), ptr(dT_lo),
+             self.P, ptr(r_sum), _stream())
+
+    def finalize_v(self, acc_v, V, ldv, rinv_v, T_diag, ldt, rinv_t_diag, rows, scale, diag_coef, dV_f32, dV_bf16,
+                   dV_lo=None, V_lo=None, T_diag_lo=None):
+        call("tic_itc_grad_finalize", ptr(acc_v), self.P, ptr(V), ptr(V_lo), ldv, ptr(rinv_v), ptr(T_diag), ptr(T_diag_lo),
+             ldt, ptr(rinv_t_diag),
+             rows, self.P, float(scale), float(diag_coef), ptr(dV_f32), self.P, ptr(dV_bf16), ptr(dV_lo), self.P, None,
+             _stream())
+
+    # -- single-GPU convenience: full forward + backward --
+    def run(self, T, V, scale, g, loss_sums, r_sum, dT_f32=None, dT_bf16=None, dV_f32=None, dV_bf16=None):
+        """T [m,P], V [n,P] bf16 (m == n, row_offset == 0).  g = dLoss/d(clip_loss).  loss_sums[2], r_sum[1] must be
+        zero on entry: loss_sums -> (sum_i lse_row-diag, sum_i lse_col-diag), r_sum -> dLoss/dlogit_scale."""
+        assert self.m == self.n and self.row_offset == 0
+        ldt, ldv = T.stride(0), V.stride(0)
+        self.norms(T, ldt, V, ldv)
+        self.fwd_tiles(T, ldt, V, ldv, scale)
+        self.lse_loss(scale, loss_sums)
+        self.bwd_operands(T, ldt, V, ldv, scale, g / (2.0 * self.n))
+        self.grad_gemms(T, ldt, V, ldv)
+        self.finalize_t(T, ldt, V, ldv, self.rinv_v, scale, g / self.n, dT_f32, dT_bf16, r_sum)
+        if self.need_dv:
+            self.finalize_v(self.acc_v, V, ldv, self.rinv_v, T, ldt, self.rinv_t, self.n, scale, g / self.n, dV_f32, dV_bf16)
+
+
+class HeadPlan:
+    """One training step of the late-fusion head on given encoder outputs: forward, losses, backward."""
+
+    FUSIONS = ("concat", "attention", "gmu", "aspect-att", None)
+
+    def __init__(self, B: int, *, E: int = 768, P: Optional[int] = 512, C: int = 4, fusion: Optional[str] = "concat",
+                 use_itc: bool = True, use_itm: bool = True, beta_itc: float = 0.1, beta_itm: float = 0.1, Lv: int = 197,
+                 itm_mode: str = "uniform", materialize_logits: bool = False, device="cuda"):
+        if fusion not in self.FUSIONS:
+            raise KeyError("fusion_name %r is not implemented for ViT-family encoders (mm_late.py:92-144 implements "
+                           "concat, attention, aspect-att, gmu; xatt/concat_cnn resolve to undefined names :44-45)" % fusion)
+        if fusion == "aspect-att" and use_itm:
+            # mm_late.py:181 calls mm_fusion without pools on the ITM branch -> torch.stack((None, None)) raises TypeError
+            raise TypeError("aspect-att cannot be combined with the ITM loss (the reference raises TypeError at mm_late.py:181)")
+        capi.load()
+        self.B, self.E, self.P, self.C, self.fusion = B, E, P, C, fusion
+        self.use_itc, self.use_itm = use_itc, use_itm and fusion is not None
+        self.beta_itc, self.beta_itm = (beta_itc if use_itc else 0.0), (beta_itm if self.use_itm else 0.0)
+        self.Lv, self.itm_mode = Lv, {"uniform": 0, "hard": 1}[itm_mode]
+        self.dev = torch.device(device)
+        self.R = 2 * B if self.use_itm else B
+        self.Pe = P if P is not None else E  # width of the contrastive embeddings
+        if fusion is None:
+            self.w_cls = 0.0
+            self.g_itc = 1.0
+        else:
+            self.w_cls = 1.0 - (self.beta_itc + self.beta_itm)
+            self.g_itc = self.beta_itc
+        if self.itm_mode == 1 and use_itc:
+            materialize_logits = True
+        self.itc = ItcPlan(B, B, self.Pe, self.dev, materialize_logits=materialize_logits) if use_itc else None
+        self._alloc()
+        self.w: Dict[str, torch.Tensor] = {}
+        self.scale = math.exp(2.6592)
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        B, E, C, R, dev = self.B, self.E, self.C, self.R, self.dev
+        e = lambda *s, dt=F32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
+        # one contiguous block of accumulators that must be zero at the start of every step (one memset)
+        sizes = {"losses": 2, "itc_sums": 2, "r_sum": 1, "_pad": 3, "dW_cls": C * E, "db_cls": C, "dW_tim": 2 * E,
+                 "db_tim": 2, "db_f": E, "db_Q": E, "db_V": E, "db_gt": 2 * E, "db_gv": 2 * E, "dw_a": E, "db_a": 1}
+        self.zb = torch.zeros(sum(sizes.values()), dtype=F32, device=dev)
+        self.z, off = {}, 0
+        for k, n in sizes.items():
+            self.z[k] = self.zb[off:off + n]
+            off += n
+        self.out: Dict[str, torch.Tensor] = {"loss": e(4)}
+        o = self.out
+        if self.P is not None:
+            self.Y = e(2 * B, self.P, dt=BF16)       # [Yt ; Yv] projected embeddings (split hi/lo: produced on the device)
+            self.Y_lo = e(2 * B, self.P, dt=BF16)
+            self.dY = e(2 * B, self.P, dt=BF16)      # gradients w.r.t. Y (GEMM operands, split hi/lo)
+            self.dY_lo = e(2 * B, self.P, dt=BF16)
+            o["dW_t"], o["dW_v"] = e(self.P, E), e(self.P, E)
+            o["d_t_pool"] = e(B, E)
+        else:
+            o["d_t_emb"], o["d_v_emb"] = e(B, self.Pe), e(B, self.Pe)
+        o["d_logit_scale"] = self.z["r_sum"]
+        if self.fusion is None:
+            return
+        o["out_cls"], o["lbl_tim"], o["src_idx"] = e(B, C), torch.empty(B, dtype=torch.int64, device=dev), \
+            torch.empty(B, dtype=torch.int32, device=dev)
+        if self.use_itm:
+            o["out_tim"] = e(B, 2)
+        self.H = e(R, E)                              # post-ReLU fusion output (mm_features = H[:B])
+        o["mm_features"] = self.H[:B]
+        self.dHb, self.dHb_lo = e(R, E, dt=BF16), e(R, E, dt=BF16)
+        self.heads_ws = e(R * 8)
+        o["dW_cls"], o["db_cls"] = self.z["dW_cls"].view(C, E), self.z["db_cls"]
+        o["dW_tim"], o["db_tim"] = self.z["dW_tim"].view(2, E), self.z["db_tim"]
+        if self.fusion == "aspect-att":
+            self.alpha = e(B, 2)
+            self.dHf = e(B, E)
+            o["d_t_pool_fusion"] = e(B, E)
+            o["dw_a"], o["db_a"] = self.z["dw_a"], self.z["db_a"]
+            return
+        self.Xcat = e(R, 2 * E, dt=BF16)
+        self.dXt = e(R, E)                            # gradient of the text half of Xcat (fp32)
+        o["d_xt_cls"] = e(B, E)
+        o["dW_f"], o["db_f"] = e(E, 2 * E), self.z["db_f"]
+        if self.fusion == "attention":
+            Ea = E + 8
+            self.Xcat_lo = torch.zeros(R, 2 * E, dtype=BF16, device=dev)   # text half stays 0 (inputs are exact)
+            self.q0, self.q0_lo, self.kq = e(R, E, dt=BF16), e(R, E, dt=BF16), e(R, Ea)
+            self.xbar_b, self.xbar_lo, self.xbar_f, self.attn = e(R, E, dt=BF16), e(R, E, dt=BF16), e(R, E), e(R, self.Lv)
+            self.dctx, self.dctx_lo, self.dxbar = e(R, E, dt=BF16), e(R, E, dt=BF16), e(R, E)
+            self.dkq, self.dkq_lo = e(R, Ea, dt=BF16), e(R, Ea, dt=BF16)
+            self.dq0, self.dq0_lo, self.dXt2 = e(R, E, dt=BF16), e(R, E, dt=BF16), e(R, E)
+            o["dW_Q"], o["db_Q"], o["dW_V"], o["db_V"] = e(E, E), self.z["db_Q"], e(E, E), self.z["db_V"]
+            self.dWK_aug = e(E, Ea)
+            o["dW_K"], o["db_K"] = self.dWK_aug[:, :E], self.dWK_aug[:, E]
+        if self.fusion == "gmu":
+            self.tp, self.vp = e(R, 2 * E), e(R, 2 * E)
+            self.G, self.G_lo, self.dG = e(R, 2 * E, dt=BF16), e(R, 2 * E, dt=BF16), e(R, 2 * E)
+            self.dtp, self.dvp, self.dXg, self.dXt2 = e(R, 2 * E, dt=BF16), e(R, 2 * E, dt=BF16), e(R, 2 * E), e(R, E)
+            self.dtp_lo, self.dvp_lo = e(R, 2 * E, dt=BF16), e(R, 2 * E, dt=BF16)
+            o["dW_gt"], o["db_gt"], o["dW_gv"], o["db_gv"] = e(2 * E, E), self.z["db_gt"], e(2 * E, E), self.z["db_gv"]
+
+    # ------------------------------------------------------------------ weights
+    def set_weights(self, p: Dict[str, torch.Tensor]):
+        """p: fp32 tensors under the reference's state-dict names (mm_late.py:59-89).  Builds the bf16 working copies
+        consumed by the tensor-core GEMMs (one cast kernel per matrix) and reads logit_scale (one host sync)."""
+        E, dev = self.E, self.dev
+        w = self.w
+
+        def cast(name, src, cols_pad=None):
+            src = src.detach().to(device=dev, dtype=F32).contiguous()
+            rows, cols = src.shape
+            ld = cols if cols_pad is None else cols_pad
+            if name not in w or w[name].shape != (rows, ld):
+                w[name] = torch.zeros(rows, ld, dtype=BF16, device=dev)
+            call("tic_cast_f32_to_bf16", ptr(src), cols, ptr(w[name]), ld, rows, cols, _stream())
+
+        def keep(name, src):
+            w[name] = src.detach().to(device=dev, dtype=F32).contiguous()
+
+        self.scale = float(torch.exp(p["dual_encoder.logit_scale"].detach().float()).item())
+        if self.P is not None:
+            cast("W_t", p["dual_encoder.text_projection.weight"])
+            cast("W_v", p["dual_encoder.visual_projection.weight"])
+        if self.fusion is None:
+            return
+        keep("W_cls", p["linear_cls.weight"]); keep("b_cls", p["linear_cls.bias"])
+        keep("W_tim", p["linear_tim.weight"]); keep("b_tim", p["linear_tim.bias"])
+        if self.fusion == "aspect-att":
+            keep("w_a", p["aspectattention.weight"].reshape(-1)); keep("b_a", p["aspectattention.bias"].reshape(-1))
+            return
+        cast("W_f", p["linear_fusion.weight"]); keep("b_f", p["linear_fusion.bias"])
+        if self.fusion == "attention":
+            cast("W_Q", p["fc_Q.weight"]); keep("b_Q", p["fc_Q.bias"])
+            cast("W_V", p["fc_V.weight"]); keep("b_V", p["fc_V.bias"])
+            cast("W_Kaug", p["fc_K.weight"], cols_pad=E + 8)  # [W_K | b_K | 0..]: column E carries <q0, b_K>
+            bk = p["fc_K.bias"].detach().to(device=dev, dtype=F32).reshape(E, 1).contiguous()
+            call("tic_cast_f32_to_bf16", ptr(bk), 1, w["W_Kaug"].data_ptr() + 2 * E, E + 8, E, 1, _stream())
+        if self.fusion == "gmu":
+            cast("W_gt", p["linear_gmu_t.weight"]); keep("b_gt", p["linear_gmu_t.bias"])
+            cast("W_gv", p["linear_gmu_v.weight"]); keep("b_gv", p["linear_gmu_v.bias"])
+
+    # ------------------------------------------------------------------ the step
+    def step(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """inp (device tensors): t_pool, v_pool bf16 [B,E]; x_t bf16 [B,Lt,E] or [B,E]; x_v bf16 [B,Lv,E] or [B,E];
+        y_soft fp32 [B,C]; class_w fp32 [C] (optional); ITM: u_coin,u_pick fp32 [B] (+ ids, mask int64 [B,Lt] to
+        gather) or precomputed lbl_tim int64 [B] + src_idx int32 [B]; keep uint8 [B,E] + keep_scale (dropout, optional)."""
+        B, E, R, w, z, o, st = self.B, self.E, self.R, self.w, self.z, self.out, _stream()
+        self.zb.zero_()
+        # ---------------- ITC: projection -> norms -> fused similarity/CE tiles
+        if self.use_itc:
+            it = self.itc
+            if self.P is not None:
+                tp_, vp_ = inp["t_pool"], inp["v_pool"]
+                Yt, Yv, Ytl, Yvl = self.Y[:B], self.Y[B:], self.Y_lo[:B], self.Y_lo[B:]
+                gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)   # HF :265 text_projection
+                gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl)   # HF :262 visual_projection
+            else:
+                Yt, Yv, Ytl, Yvl = inp["t_pool"], inp["v_pool"], None, None
+            ldt, ldv = Yt.stride(0), Yv.stride(0)
+            it.norms(Yt, ldt, Yv, ldv, T_lo=Ytl, V_lo=Yvl)
+            it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl)
+            it.lse_loss(self.scale, z["itc_sums"])
+            if it.logits is not None:
+                o["logits_per_text"] = it.logits
+        if self.fusion is not None:
+            self._fusion_fwd_bwd(inp)
+        call("tic_loss_mix", ptr(z["losses"]), ptr(z["itc_sums"]), B, self.beta_itc if self.fusion is not None else 1.0,
+             self.beta_itm, int(self.use_itc), int(self.use_itm), ptr(o["loss"]), st)
+        # ---------------- ITC backward
+        if self.use_itc:
+            g = self.g_itc
+            it.bwd_operands(Yt, ldt, Yv, ldv, self.scale, g / (2.0 * B), T_lo=Ytl, V_lo=Yvl)
+            it.grad_gemms(Yt, ldt, Yv, ldv, T_lo=Ytl, V_lo=Yvl)
+            if self.P is not None:
+                dYt, dYv, dYt_lo, dYv_lo = self.dY[:B], self.dY[B:], self.dY_lo[:B], self.dY_lo[B:]
+                it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, g / B, None, dYt, z["r_sum"], dT_lo=dYt_lo, T_lo=Ytl,
+                              V_diag_lo=Yvl)
+                it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, g / B, None, dYv, dV_lo=dYv_lo,
+                              V_lo=Yvl, T_diag_lo=Ytl)
+                tp_, vp_ = inp["t_pool"], inp["v_pool"]
+                # dW_t[P,E] = dYt^T t_pool (both operands read MN-major), dW_v likewise; d_t_pool = dYt W_t
+                gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo)
+                gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo)
+                gemm(dYt, self.P, 0, w["W_t"], E, 1, o["d_t_pool"], E, 0, B, E, self.P, A_lo=dYt_lo)
+            else:
+                it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, g / B, o["d_t_emb"], None, z["r_sum"])
+                it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, g / B, o["d_v_emb"], None)
+        return o
+
+    def _sample_itm(self, inp):
+        B, o, st = self.B, self.out, _stream()
+        if "src_idx" in inp:   # decisions made by the caller (e.g. the numpy-stream replay of the CLI)
+            o["lbl_tim"].copy_(inp["lbl_tim"])
+            o["src_idx"].copy_(inp["src_idx"].to(torch.int32))
+            return
+        S = self.itc.logits if (self.itm_mode == 1 and self.itc is not None) else None
+        if inp.get("ids") is not None:
+            ids, mask = inp["ids"], inp["mask"]
+            if "tim_ids" not in o:
+                o["tim_ids"], o["tim_mask"] = torch.empty_like(ids), torch.empty_like(mask)
+            call("tic_itm_sample_gather", ptr(inp["u_coin"]), ptr(inp["u_pick"]), B, self.itm_mode, ptr(S), B, ptr(ids),
+                 ptr(mask), ids.stride(0) * ids.element_size(), ptr(o["tim_ids"]), ptr(o["tim_mask"]), ptr(o["lbl_tim"]),
+                 ptr(o["src_idx"]), st)
+        else:
+            call("tic_itm_sample", ptr(inp["u_coin"]), ptr(inp["u_pick"]), B, self.itm_mode, ptr(S), B, ptr(o["lbl_tim"]),
+                 ptr(o["src_idx"]), st)
+
+    def _heads(self, inp, dH_f32=None):
+        B, E, z, o, w = self.B, self.E, self.z, self.out, self.w
+        call("tic_heads_fwd_bwd", ptr(self.H), E, B, E, self.C, int(self.use_itm), ptr(w["W_cls"]), ptr(w["b_cls"]),
+             ptr(w["W_tim"]), ptr(w["b_tim"]), ptr(inp["y_soft"]), ptr(inp.get("class_w")), ptr(o["lbl_tim"]),
+             ptr(inp.get("keep")), float(inp.get("keep_scale", 1.0)), float(self.w_cls), float(self.beta_itm),
+             ptr(o["out_cls"]), ptr(o.get("out_tim")), ptr(z["losses"]), ptr(self.dHb), ptr(self.dHb_lo), E, ptr(dH_f32), E,
+             ptr(z["dW_cls"]),
+             ptr(z["db_cls"]), ptr(z["dW_tim"]), ptr(z["db_tim"]), 1, ptr(self.heads_ws), _stream())
+
+    def _fusion_fwd_bwd(self, inp):
+        B, E, R, w, z, o, st = self.B, self.E, self.R, self.w, self.z, self.out, _stream()
+        E2 = 2 * E
+        if self.use_itm:
+            self._sample_itm(inp)
+        src = o["src_idx"] if self.use_itm else None
+        if self.fusion == "aspect-att":
+            tp_, vp_ = inp["t_pool"], inp["v_pool"]
+            call("tic_aspect_fwd", ptr(tp_), tp_.stride(0), ptr(vp_), vp_.stride(0), B, E, ptr(w["w_a"]), ptr(w["b_a"]),
+                 ptr(self.H), E, ptr(self.alpha), st)
+            self._heads(inp, dH_f32=self.dHf)
+            call("tic_aspect_bwd", ptr(tp_), tp_.stride(0), ptr(vp_), vp_.stride(0), B, E, ptr(w["w_a"]), ptr(w["b_a"]),
+                 ptr(self.H), E, ptr(self.alpha), ptr(self.dHf), E, ptr(o["d_t_pool_fusion"]), E, ptr(z["dw_a"]),
+                 ptr(z["db_a"]), st)
+            return
+        x_t, x_v = inp["x_t"], inp["x_v"]
+        xt_stride, xv_stride = x_t.stride(0), x_v.stride(0)   # CLS rows: x[:,0,:]
+        X = self.Xcat
+        if self.fusion == "concat" or self.fusion == "gmu":
+            call("tic_pack_cls_pairs", ptr(x_t), xt_stride, ptr(x_v), xv_stride, B, E, ptr(src), ptr(X), E2, st)
+        X_lo = None
+        if self.fusion == "attention":
+            Ea, Lv = E + 8, self.Lv
+            X_lo = self.Xcat_lo
+            call("tic_pack_cls_pairs", ptr(x_t), xt_stride, None, 0, B, E, ptr(src), ptr(X), E2, st)
+            gemm(X, E2, 0, w["W_Q"], E, 0, self.q0, E, 1, R, E, E, bias=w["b_Q"], D_lo=self.q0_lo)  # q0 = fc_Q(x_t[:,0])
+            gemm(self.q0, E, 0, w["W_Kaug"], Ea, 1, self.kq, Ea, 0, R, Ea, E, A_lo=self.q0_lo)       # [W_K^T q0 | <q0,b_K>] fp32
+            call("tic_attn_pool_fwd", ptr(x_v), x_v.stride(0), x_v.stride(1), ptr(self.kq), Ea, B, 2 if self.use_itm else 1,
+                 Lv, E, float(E) ** -0.5, ptr(self.xbar_b), ptr(self.xbar_lo), E, ptr(self.xbar_f), E, ptr(self.attn), Lv, st)
+            gemm(self.xbar_b, E, 0, w["W_V"], E, 0, X.data_ptr() + 2 * E, E2, 1, R, E, E, bias=w["b_V"], A_lo=self.xbar_lo,
+                 D_lo=X_lo.data_ptr() + 2 * E)                                                      # ctx0 -> Xcat[:,E:]
+        Hin, Hin_lo = X, X_lo
+        if self.fusion == "gmu":
+            gemm(X, E2, 0, w["W_gt"], E, 0, self.tp, E2, 0, R, E2, E, bias=w["b_gt"])               # linear_gmu_t(x_t[:,0])
+            gemm(X.data_ptr() + 2 * E, E2, 0, w["W_gv"], E, 0, self.vp, E2, 0, R, E2, E, bias=w["b_gv"])
+            call("tic_gmu_gate_fwd", ptr(X), E2, ptr(self.tp), ptr(self.vp), E2, R, E2, ptr(self.G), ptr(self.G_lo), E2, st)
+            Hin, Hin_lo = self.G, self.G_lo
+        gemm(Hin, E2, 0, w["W_f"], E2, 0, self.H, E, 0, R, E, E2, bias=w["b_f"], relu=True, A_lo=Hin_lo)  # relu(linear_fusion)
+        self._heads(inp)
+        # ---------------- backward through linear_fusion (dH is a split bf16 pair: hi + lo)
+        dH, dHl = self.dHb, self.dHb_lo
+        call("tic_colsum_bf16", ptr(dH), E, R, E, ptr(z["db_f"]), st)
+        call("tic_colsum_bf16", ptr(dHl), E, R, E, ptr(z["db_f"]), st)
+        gemm(dH, E, 1, Hin, E2, 1, o["dW_f"], E2, 0, E, E2, R, A_lo=dHl, B_lo=Hin_lo)               # dW_f = dH^T Hin
+        if self.fusion == "concat":
+            gemm(dH, E, 0, w["W_f"], E2, 1, self.dXt, E, 0, R, E, E, A_lo=dHl)                      # dX_text = dH W_f[:, :E]
+            call("tic_unpack_cls_grad", ptr(self.dXt), E, None, 0, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
+        elif self.fusion == "attention":
+            Ea, Lv = E + 8, self.Lv
+            gemm(dH, E, 0, w["W_f"], E2, 1, self.dXt, E, 0, R, E, E, A_lo=dHl)
+            gemm(dH, E, 0, w["W_f"].data_ptr() + 2 * E, E2, 1, self.dctx, E, 1, R, E, E, A_lo=dHl, D_lo=self.dctx_lo)
+            call("tic_colsum_bf16", ptr(self.dctx), E, R, E, ptr(z["db_V"]), st)
+            call("tic_colsum_bf16", ptr(self.dctx_lo), E, R, E, ptr(z["db_V"]), st)
+            gemm(self.dctx, E, 1, self.xbar_b, E, 1, o["dW_V"], E, 0, E, E, R, A_lo=self.dctx_lo, B_lo=self.xbar_lo)
+            gemm(self.dctx, E, 0, w["W_V"], E, 1, self.dxbar, E, 0, R, E, E, A_lo=self.dctx_lo)
+            call("tic_attn_pool_bwd", ptr(x_v), x_v.stride(0), x_v.stride(1), ptr(self.attn), Lv, ptr(self.dxbar), E,
+                 ptr(self.xbar_f), E, B, 2 if self.use_itm else 1, Lv, E, float(E) ** -0.5, ptr(self.dkq), ptr(self.dkq_lo),
+                 Ea, st)
+            gemm(self.dkq, Ea, 0, w["W_Kaug"], Ea, 0, self.dq0, E, 1, R, E, Ea, A_lo=self.dkq_lo, D_lo=self.dq0_lo)
+            gemm(self.q0, E, 1, self.dkq, Ea, 1, self.dWK_aug, Ea, 0, E, Ea, R, A_lo=self.q0_lo, B_lo=self.dkq_lo)  # [dW_K|db_K]
+            call("tic_colsum_bf16", ptr(self.dq0), E, R, E, ptr(z["db_Q"]), st)
+            call("tic_colsum_bf16", ptr(self.dq0_lo), E, R, E, ptr(z["db_Q"]), st)
+            gemm(self.dq0, E, 1, X, E2, 1, o["dW_Q"], E, 0, E, E, R, A_lo=self.dq0_lo)
+            gemm(self.dq0, E, 0, w["W_Q"], E, 1, self.dXt2, E, 0, R, E, E, A_lo=self.dq0_lo)
+            call("tic_unpack_cls_grad", ptr(self.dXt), E, ptr(self.dXt2), E, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
+        elif self.fusion == "gmu":
+            gemm(dH, E, 0, w["W_f"], E2, 1, self.dG, E2, 0, R, E2, E, A_lo=dHl)                     # dG = dH W_f
+            call("tic_gmu_gate_bwd", ptr(X), E2, ptr(self.tp), ptr(self.vp), E2, ptr(self.dG), E2, R, E2, ptr(self.dtp),
+                 ptr(self.dvp), ptr(self.dtp_lo), ptr(self.dvp_lo), E2, ptr(self.dXg), E2, st)
+            for buf, acc in ((self.dtp, "db_gt"), (self.dtp_lo, "db_gt"), (self.dvp, "db_gv"), (self.dvp_lo, "db_gv")):
+                call("tic_colsum_bf16", ptr(buf), E2, R, E2, ptr(z[acc]), st)
+            gemm(self.dtp, E2, 1, X, E2, 1, o["dW_gt"], E, 0, E2, E, R, A_lo=self.dtp_lo)
+            gemm(self.dvp, E2, 1, X.data_ptr() + 2 * E, E2, 1, o["dW_gv"], E, 0, E2, E, R, A_lo=self.dvp_lo)
+            gemm(self.dtp, E2, 0, w["W_gt"], E, 1, self.dXt2, E, 0, R, E, E2, A_lo=self.dtp_lo)
+            call("tic_unpack_cls_grad", ptr(self.dXg), E2, ptr(self.dXt2), E, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
+
+class HostStep:
+    """Host-facing entry point: takes the step's inputs as HOST tensors (what a reference-side caller holds), stages them
+    through pinned memory, copies them to the device, runs the plan (optionally as a CUDA-graph replay) and returns the
+    losses as Python floats.  Every call moves `h2d_bytes` host->device and `d2h_bytes` device->host."""
+
+    def __init__(self, plan, host_example: Dict[str, torch.Tensor], bf16_keys=(), use_graph: bool = True):
+        self.plan, self.bf16_keys = plan, tuple(bf16_keys)
+        dev = plan.dev
+        self.pinned, self.dev_in = {}, {}
+        for k, v in host_example.items():
+            dt = BF16 if k in self.bf16_keys else v.dtype
+            self.pinned[k] = torch.empty(v.shape, dtype=dt, pin_memory=True)
+            self.dev_in[k] = torch.empty(v.shape, dtype=dt, device=dev)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned.values())
+        self.loss_pinned = torch.empty(4, dtype=F32, pin_memory=True)
+        self.d2h_bytes = self.loss_pinned.numel() * 4
+        self.graph = None
+        if use_graph:
+            for k, v in host_example.items():
+                self.dev_in[k].copy_(v.to(self.dev_in[k].dtype))
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                plan.step(self.dev_in)
+            torch.cuda.current_stream().wait_stream(s)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                plan.step(self.dev_in)
+
+    def __call__(self, host: Dict[str, torch.Tensor]):
+        for k, v in host.items():
+            p = self.pinned[k]
+            if v.dtype == p.dtype:
+                p.copy_(v)
+            else:
+                p.copy_(v.to(p.dtype))   # host-side bf16 rounding of fp32 inputs is part of the end-to-end cost
+            self.dev_in[k].copy_(p, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.plan.step(self.dev_in)
+        self.loss_pinned.copy_(self.plan.out["loss"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return [float(x) for x in self.loss_pinned]
