@@ -37,6 +37,7 @@ def parse_args():
     ap.add_argument("--impl", type=str, default="tic", choices=["tic", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e leg, no per-kernel timing, no CPU leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline leg")
     return ap.parse_args()
 
@@ -268,7 +269,7 @@ def main():
     plan.set_weights(R.init_params(spec["C"], seed=40))
 
     # ---- count launches of one step (kernels per C-ABI call are fixed)
-    KPC = {"tic_heads_fwd_bwd": 3 if spec["use_itm"] else 2, "tic_unpack_cls_grad": 2 if spec["use_itm"] else 1,
+    KPC = {"tic_itc_lse_loss": 2, "tic_heads_fwd_bwd": 3 if spec["use_itm"] else 2, "tic_unpack_cls_grad": 2 if spec["use_itm"] else 1,
            "tic_ce_bidir_fwd": 2, "tic_itm_sample_gather": 1}
     counter = {"n": 0}
     orig_call = capi.call
@@ -337,6 +338,11 @@ def main():
     ms_per_step = total_ms / args.steps
     value = n_global / (ms_per_step / 1e3)
 
+    if args.profile:
+        if rank == 0:
+            clocks.stop()
+            print(json.dumps(dict(base, value=value, ms_per_step=ms_per_step, profile_run=True)))
+        return
     # ---- end-to-end: HOST buffers in, loss out, through the public host-facing API
     runner = P.HostStep(plan, host, bf16_keys=BF16_KEYS, use_graph=use_graph)
     for _ in range(3):

@@ -100,6 +100,10 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale,
                   float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo /* optional residuals */,
                   void* GBT_lo, void* stream);
+/* Autograd path (materialised logits, drop-in batch sizes): the same operands from an upstream dL/dS [m_local, n_global]:
+ *   GA[i,j] = dS[i,j]*rinv_v[j],  GBT[j,i] = dS[i,j]*rinv_t[i]  (+ optional bf16 residuals). Use diag_coef = 0 afterwards. */
+int tic_itc_ds_operands(const float* dS, int64_t ldds, int m_local, int n_global, const float* rinv_t, const float* rinv_v,
+                        void* GA, void* GA_lo, int64_t ld_ga, void* GBT, void* GBT_lo, int64_t ld_gbt, void* stream);
 /* Normalise-backward + diagonal term, one warp per row (HF :268-269 backward):
  *   dxh = scale*acc[i,:] - diag_coef * scale * rinv_o[i] * Xo[i,:]   (diag_coef = g/B, 0 if row has no local positive)
  *   r = <xh, dxh>, xh = rinv[i]*X[i,:];   dX[i,:] = rinv[i] * (dxh - xh * r);   dscale_part[block] += r (for dlogit_scale)
@@ -162,7 +166,9 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
                       const float* class_w, const int64_t* lbl_tim, const uint8_t* keep, float keep_scale, float c_cls,
                       float c_tim, float* logits_cls, float* logits_tim, float* losses, void* dH_bf16, void* dH_bf16_lo, int64_t ld_dhb,
                       float* dH_f32 /* optional */, int64_t ld_dhf, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask,
-                      float* ws /* [rows * 8] floats scratch (dlogits) */, void* stream);
+                      float* ws /* [rows * 8] floats scratch (dlogits) */,
+                      const float* dlogits_ext /* NULL = fused losses; else upstream dL/dlogits [rows, 8] (autograd mode) */,
+                      void* stream);
 
 /* attention fusion, CLS-row collapse of mm_late.py:98-113,195-210 (exact algebra):
  *   q0 = fc_Q(x_t[:,0]);  kq = W_K^T q0;  c = <q0,b_K>;  s_j = (<kq, x_v[j]> + c) * E^-1/2;  a = softmax_j(s)

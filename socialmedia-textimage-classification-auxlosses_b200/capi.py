@@ -28,6 +28,7 @@ _SIGS = {
     "tic_reduce_parts": ("piipp", ctypes.c_int),
     "tic_itc_lse_loss": ("pipipiiifpppp", ctypes.c_int),
     "tic_itc_bwd_g": ("pplpplppppiiiffplplppp", ctypes.c_int),
+    "tic_itc_ds_operands": ("pliipppplpplp", ctypes.c_int),
     "tic_itc_grad_finalize": ("plpplppplpiiffplpplpp", ctypes.c_int),
     "tic_ce_bidir_workspace_bytes": ("i", ctypes.c_int64),
     "tic_ce_bidir_fwd": ("plippppp", ctypes.c_int),
@@ -37,7 +38,7 @@ _SIGS = {
     "tic_itm_sample_gather": ("ppiiplpplppppp", ctypes.c_int),
     "tic_pack_cls_pairs": ("plpliipplp", ctypes.c_int),
     "tic_unpack_cls_grad": ("plpliipplp", ctypes.c_int),
-    "tic_heads_fwd_bwd": ("pliiiippppppppfffppppplplppppipp", ctypes.c_int),
+    "tic_heads_fwd_bwd": ("pliiiippppppppfffppppplplppppippp", ctypes.c_int),
     "tic_attn_pool_fwd": ("pllpliiiifpplplplp", ctypes.c_int),
     "tic_attn_pool_bwd": ("pllplplpliiiifpplp", ctypes.c_int),
     "tic_aspect_fwd": ("plpliippplpp", ctypes.c_int),

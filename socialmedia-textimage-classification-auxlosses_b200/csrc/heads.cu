@@ -57,6 +57,7 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
                                   const int64_t* __restrict__ lbl_tim, const uint8_t* __restrict__ keep, float keep_scale,
                                   float c_cls, float c_tim, float* __restrict__ logits_cls, float* __restrict__ logits_tim,
                                   float* __restrict__ losses, float* __restrict__ dlogits /* [rows, kMaxClasses] */,
+                                  const float* __restrict__ dz_ext /* upstream dL/dlogits or nullptr (fused losses) */,
                                   __nv_bfloat16* __restrict__ dHb, __nv_bfloat16* __restrict__ dHb_lo, int64_t ld_dhb,
                                   float* __restrict__ dHf, int64_t ld_dhf, int relu_mask) {
   const int rows = has_tim ? 2 * B : B;
@@ -119,6 +120,12 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
         dz[c] = c_tim / B * (expf(z[c] - lse) - (c == y ? 1.f : 0.f));
         if (lane == 0) logits_tim[static_cast<int64_t>(i) * 2 + c] = z[c];
       }
+    }
+    if (dz_ext != nullptr) {  // autograd mode: the caller owns the loss; use its gradient w.r.t. the logits
+      loss_c = 0.f;
+      loss_t = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c) dz[c] = c < nc ? __ldg(dz_ext + static_cast<int64_t>(r) * kMaxClasses + c) : 0.f;
     }
     if (lane == 0) {
 #pragma unroll
@@ -261,7 +268,7 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
                       const float* W_tim, const float* b_tim, const float* y_soft, const float* class_w,
                       const int64_t* lbl_tim, const uint8_t* keep, float keep_scale, float c_cls, float c_tim,
                       float* logits_cls, float* logits_tim, float* losses, void* dH_bf16, void* dH_bf16_lo, int64_t ld_dhb, float* dH_f32,
-                      int64_t ld_dhf, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask, float* ws, void* stream) {
+                      int64_t ld_dhf, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask, float* ws, const float* dlogits_ext, void* stream) {
   TIC_CHECK_ARG(H && W_cls && b_cls && y_soft && logits_cls && losses && ws, "tic_heads_fwd_bwd: null pointer");
   TIC_CHECK_ARG(B > 0 && E > 0 && C >= 1 && C <= kMaxClasses, "tic_heads_fwd_bwd: need 1 <= C <= %d", kMaxClasses);
   TIC_CHECK_ARG(!has_tim || (W_tim && b_tim && lbl_tim && logits_tim), "tic_heads_fwd_bwd: ITM head pointers missing");
@@ -270,7 +277,7 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
   float* dlogits = ws;
   heads_rows_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft, class_w,
                                                         lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses,
-                                                        dlogits, static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb,
+                                                        dlogits, dlogits_ext, static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb,
                                                         dH_f32, ld_dhf,
                                                         relu_mask);
   if (dW_cls && db_cls) {

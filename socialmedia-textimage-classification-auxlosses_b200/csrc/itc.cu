@@ -273,25 +273,29 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, 
   out[j] = s;
 }
 
-// Single block: fixed-order sum of the per-tile partials, lse vectors, and the two loss sums (deterministic).
-__global__ void itc_lse_loss_kernel(const float* __restrict__ row_part, int nrp, const float* __restrict__ col_part, int ncp,
-                                    const float* __restrict__ diag, int M, int N, int row_offset, float shift,
-                                    float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ loss_sums) {
+// Multi-block: fixed-order sum of the per-tile partials -> lse vectors (thread t owns row t and column t).
+__global__ void itc_lse_kernel(const float* __restrict__ row_part, int nrp, const float* __restrict__ col_part, int ncp, int M,
+                               int N, float shift, float* __restrict__ lse_row, float* __restrict__ lse_col) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < N) {
+    float s = 0.f;
+    for (int p = 0; p < ncp; ++p) s += col_part[static_cast<int64_t>(p) * N + t];
+    lse_col[t] = shift + logf(s);
+  }
+  if (t < M) {
+    float s = 0.f;
+    for (int p = 0; p < nrp; ++p) s += row_part[static_cast<int64_t>(p) * M + t];
+    lse_row[t] = shift + logf(s);
+  }
+}
+// Single block, fixed-order tree: the two loss sums (deterministic).
+__global__ void itc_loss_kernel(const float* __restrict__ lse_row, const float* __restrict__ lse_col,
+                                const float* __restrict__ diag, int M, int row_offset, float* __restrict__ loss_sums) {
   __shared__ float sr[32], sc[32];
   float ar = 0.f, ac = 0.f;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < ncp; ++p) s += col_part[static_cast<int64_t>(p) * N + j];
-    lse_col[j] = shift + logf(s);
-  }
-  __syncthreads();
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < nrp; ++p) s += row_part[static_cast<int64_t>(p) * M + i];
-    const float lr = shift + logf(s);
-    lse_row[i] = lr;
     const float d = diag[i];
-    ar += lr - d;
+    ar += lse_row[i] - d;
     ac += lse_col[row_offset + i] - d;
   }
   ar = warp_sum(ar);
@@ -358,6 +362,40 @@ __global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t 
   }
 }
 
+// Gradient operands from a MATERIALISED dL/dS (autograd path at drop-in batch sizes):
+//   GA[i,j] = dS[i,j] * rinv_v[j],  GBT[j,i] = dS[i,j] * rinv_t[i]   (+ bf16 residuals).  32x32 smem-tile transpose.
+__global__ void itc_ds_operands_kernel(const float* __restrict__ dS, int64_t ldds, int M, int N, const float* __restrict__ rinv_t,
+                                       const float* __restrict__ rinv_v, __nv_bfloat16* __restrict__ GA,
+                                       __nv_bfloat16* __restrict__ GA_lo, int64_t ld_ga, __nv_bfloat16* __restrict__ GBT,
+                                       __nv_bfloat16* __restrict__ GBT_lo, int64_t ld_gbt) {
+  __shared__ float t[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, j = j0 + threadIdx.x;
+    float v = 0.f;
+    if (i < M && j < N) {
+      v = dS[static_cast<int64_t>(i) * ldds + j];
+      const float ga = v * rinv_v[j];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(ga);
+      GA[static_cast<int64_t>(i) * ld_ga + j] = hi;
+      if (GA_lo) GA_lo[static_cast<int64_t>(i) * ld_ga + j] = __float2bfloat16_rn(ga - __bfloat162float(hi));
+      v *= rinv_t[i];
+    }
+    t[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (GBT == nullptr) return;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int j = j0 + r, i = i0 + threadIdx.x;
+    if (i < M && j < N) {
+      const float gb = t[threadIdx.x][r];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(gb);
+      GBT[static_cast<int64_t>(j) * ld_gbt + i] = hi;
+      if (GBT_lo) GBT_lo[static_cast<int64_t>(j) * ld_gbt + i] = __float2bfloat16_rn(gb - __bfloat162float(hi));
+    }
+  }
+}
+
 }  // namespace tic
 
 using namespace tic;
@@ -408,9 +446,11 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
                      float* loss_sums, void* stream) {
   TIC_CHECK_ARG(row_part && col_part && diag && lse_row && lse_col && loss_sums && n_row_parts > 0 && n_col_parts > 0,
                 "tic_itc_lse_loss: bad arguments");
-  itc_lse_loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(row_part, n_row_parts, col_part, n_col_parts, diag,
-                                                                         m_local, n_global, row_offset, shift, lse_row,
-                                                                         lse_col, loss_sums);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int mx = m_local > n_global ? m_local : n_global;
+  itc_lse_kernel<<<ceil_div(mx, 256), 256, 0, st>>>(row_part, n_row_parts, col_part, n_col_parts, m_local, n_global, shift,
+                                                     lse_row, lse_col);
+  itc_loss_kernel<<<1, 1024, 0, st>>>(lse_row, lse_col, diag, m_local, row_offset, loss_sums);
   TIC_CHECK_LAUNCH("tic_itc_lse_loss");
   return TIC_OK;
 }
@@ -443,6 +483,17 @@ int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const
       rows, P, scale, diag_coef, dX_f32, ld_df, static_cast<__nv_bfloat16*>(dX_bf16), static_cast<__nv_bfloat16*>(dX_bf16_lo), ld_db,
       r_sum);
   TIC_CHECK_LAUNCH("tic_itc_grad_finalize");
+  return TIC_OK;
+}
+
+int tic_itc_ds_operands(const float* dS, int64_t ldds, int m_local, int n_global, const float* rinv_t, const float* rinv_v,
+                        void* GA, void* GA_lo, int64_t ld_ga, void* GBT, void* GBT_lo, int64_t ld_gbt, void* stream) {
+  TIC_CHECK_ARG(dS && rinv_t && rinv_v && GA && m_local > 0 && n_global > 0, "tic_itc_ds_operands: bad arguments");
+  dim3 grid(ceil_div(n_global, 32), ceil_div(m_local, 32)), block(32, 8);
+  itc_ds_operands_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      dS, ldds, m_local, n_global, rinv_t, rinv_v, static_cast<__nv_bfloat16*>(GA), static_cast<__nv_bfloat16*>(GA_lo), ld_ga,
+      static_cast<__nv_bfloat16*>(GBT), static_cast<__nv_bfloat16*>(GBT_lo), ld_gbt);
+  TIC_CHECK_LAUNCH("tic_itc_ds_operands");
   return TIC_OK;
 }
 

@@ -203,8 +203,11 @@ class HeadPlan:
         o["mm_features"] = self.H[:B]
         self.dHb, self.dHb_lo = e(R, E, dt=BF16), e(R, E, dt=BF16)
         self.heads_ws = e(R * 8)
+        self.dz_ext = e(R, 8)                          # autograd mode: upstream dL/dlogits, padded to 8 columns
+        self.y_dummy = torch.zeros(B, C, dtype=F32, device=dev)
         o["dW_cls"], o["db_cls"] = self.z["dW_cls"].view(C, E), self.z["db_cls"]
         o["dW_tim"], o["db_tim"] = self.z["dW_tim"].view(2, E), self.z["db_tim"]
+        self.dHf = None
         if self.fusion == "aspect-att":
             self.alpha = e(B, 2)
             self.dHf = e(B, E)
@@ -273,53 +276,116 @@ class HeadPlan:
             cast("W_gt", p["linear_gmu_t.weight"]); keep("b_gt", p["linear_gmu_t.bias"])
             cast("W_gv", p["linear_gmu_v.weight"]); keep("b_gv", p["linear_gmu_v.bias"])
 
-    # ------------------------------------------------------------------ the step
-    def step(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        """inp (device tensors): t_pool, v_pool bf16 [B,E]; x_t bf16 [B,Lt,E] or [B,E]; x_v bf16 [B,Lv,E] or [B,E];
-        y_soft fp32 [B,C]; class_w fp32 [C] (optional); ITM: u_coin,u_pick fp32 [B] (+ ids, mask int64 [B,Lt] to
-        gather) or precomputed lbl_tim int64 [B] + src_idx int32 [B]; keep uint8 [B,E] + keep_scale (dropout, optional)."""
-        B, E, R, w, z, o, st = self.B, self.E, self.R, self.w, self.z, self.out, _stream()
-        self.zb.zero_()
-        # ---------------- ITC: projection -> norms -> fused similarity/CE tiles
-        if self.use_itc:
-            it = self.itc
-            if self.P is not None:
-                tp_, vp_ = inp["t_pool"], inp["v_pool"]
-                Yt, Yv, Ytl, Yvl = self.Y[:B], self.Y[B:], self.Y_lo[:B], self.Y_lo[B:]
-                gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)   # HF :265 text_projection
-                gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl)   # HF :262 visual_projection
-            else:
-                Yt, Yv, Ytl, Yvl = inp["t_pool"], inp["v_pool"], None, None
-            ldt, ldv = Yt.stride(0), Yv.stride(0)
-            it.norms(Yt, ldt, Yv, ldv, T_lo=Ytl, V_lo=Yvl)
-            it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl)
-            it.lse_loss(self.scale, z["itc_sums"])
-            if it.logits is not None:
-                o["logits_per_text"] = it.logits
-        if self.fusion is not None:
-            self._fusion_fwd_bwd(inp)
-        call("tic_loss_mix", ptr(z["losses"]), ptr(z["itc_sums"]), B, self.beta_itc if self.fusion is not None else 1.0,
-             self.beta_itm, int(self.use_itc), int(self.use_itm), ptr(o["loss"]), st)
-        # ---------------- ITC backward
-        if self.use_itc:
+    # ------------------------------------------------------------------ phases
+    # fused mode   : step()                      = itc_fwd, fusion_fwd, heads (losses fused), loss mix, fusion_bwd, itc_bwd
+    # autograd mode: forward() + backward(grads) = the same kernels, the losses live in the caller (reference train loop)
+    def _itc_operands(self, inp):
+        B, E, w = self.B, self.E, self.w
+        if self.P is not None:
+            tp_, vp_ = inp["t_pool"], inp["v_pool"]
+            Yt, Yv, Ytl, Yvl = self.Y[:B], self.Y[B:], self.Y_lo[:B], self.Y_lo[B:]
+            return Yt, Yv, Ytl, Yvl
+        return inp["t_pool"], inp["v_pool"], None, None
+
+    def _itc_fwd(self, inp, with_loss=True):
+        B, E, w, it = self.B, self.E, self.w, self.itc
+        Yt, Yv, Ytl, Yvl = self._itc_operands(inp)
+        if self.P is not None:
+            tp_, vp_ = inp["t_pool"], inp["v_pool"]
+            gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)   # HF :265 text_projection
+            gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl)   # HF :262 visual_projection
+        ldt, ldv = Yt.stride(0), Yv.stride(0)
+        it.norms(Yt, ldt, Yv, ldv, T_lo=Ytl, V_lo=Yvl)
+        it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl)
+        if with_loss:
+            it.lse_loss(self.scale, self.z["itc_sums"])
+        if it.logits is not None:
+            self.out["logits_per_text"] = it.logits
+
+    def _itc_bwd(self, inp, dS=None):
+        """dS None: fused loss (tile recompute, g = beta_itc); else operands from the upstream gradient of the logits."""
+        B, E, w, z, o, it = self.B, self.E, self.w, self.z, self.out, self.itc
+        Yt, Yv, Ytl, Yvl = self._itc_operands(inp)
+        ldt, ldv = Yt.stride(0), Yv.stride(0)
+        if dS is None:
             g = self.g_itc
             it.bwd_operands(Yt, ldt, Yv, ldv, self.scale, g / (2.0 * B), T_lo=Ytl, V_lo=Yvl)
-            it.grad_gemms(Yt, ldt, Yv, ldv, T_lo=Ytl, V_lo=Yvl)
-            if self.P is not None:
-                dYt, dYv, dYt_lo, dYv_lo = self.dY[:B], self.dY[B:], self.dY_lo[:B], self.dY_lo[B:]
-                it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, g / B, None, dYt, z["r_sum"], dT_lo=dYt_lo, T_lo=Ytl,
-                              V_diag_lo=Yvl)
-                it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, g / B, None, dYv, dV_lo=dYv_lo,
-                              V_lo=Yvl, T_diag_lo=Ytl)
-                tp_, vp_ = inp["t_pool"], inp["v_pool"]
-                # dW_t[P,E] = dYt^T t_pool (both operands read MN-major), dW_v likewise; d_t_pool = dYt W_t
-                gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo)
-                gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo)
-                gemm(dYt, self.P, 0, w["W_t"], E, 1, o["d_t_pool"], E, 0, B, E, self.P, A_lo=dYt_lo)
-            else:
-                it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, g / B, o["d_t_emb"], None, z["r_sum"])
-                it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, g / B, o["d_v_emb"], None)
+            dcoef = g / B
+        else:
+            call("tic_itc_ds_operands", ptr(dS), dS.stride(0), B, B, ptr(it.rinv_t), ptr(it.rinv_v), ptr(it.GA), ptr(it.GA_lo),
+                 it.ld_ga, ptr(it.GBT), ptr(it.GBT_lo), it.ld_gbt, _stream())
+            dcoef = 0.0
+        it.grad_gemms(Yt, ldt, Yv, ldv, T_lo=Ytl, V_lo=Yvl)
+        if self.P is not None:
+            dYt, dYv, dYt_lo, dYv_lo = self.dY[:B], self.dY[B:], self.dY_lo[:B], self.dY_lo[B:]
+            it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, dcoef, None, dYt, z["r_sum"], dT_lo=dYt_lo, T_lo=Ytl,
+                          V_diag_lo=Yvl)
+            it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, dcoef, None, dYv, dV_lo=dYv_lo,
+                          V_lo=Yvl, T_diag_lo=Ytl)
+            tp_, vp_ = inp["t_pool"], inp["v_pool"]
+            # dW_t[P,E] = dYt^T t_pool (both operands read MN-major), dW_v likewise; d_t_pool = dYt W_t
+            gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo)
+            gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo)
+            gemm(dYt, self.P, 0, w["W_t"], E, 1, o["d_t_pool"], E, 0, B, E, self.P, A_lo=dYt_lo)
+        else:
+            it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, dcoef, o["d_t_emb"], None, z["r_sum"])
+            it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, dcoef, o["d_v_emb"], None)
+
+    def step(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Fused forward + losses + backward.  inp (device tensors): t_pool, v_pool bf16 [B,E]; x_t bf16 [B,Lt,E] or
+        [B,1,E]; x_v bf16 [B,Lv,E]; y_soft fp32 [B,C]; class_w fp32 [C] (optional); ITM: u_coin,u_pick fp32 [B] (+ ids, mask
+        int64 [B,Lt] to gather) or precomputed lbl_tim int64 [B] + src_idx int32 [B]; keep uint8 [B,E] + keep_scale
+        (dropout, optional)."""
+        B, z, o, st = self.B, self.z, self.out, _stream()
+        self.zb.zero_()
+        if self.use_itc:
+            self._itc_fwd(inp)
+        if self.fusion is not None:
+            if self.use_itm:
+                self._sample_itm(inp)
+            self._fusion_fwd(inp)
+            self._heads(inp, dH_f32=self.dHf if self.fusion == "aspect-att" else None)
+        call("tic_loss_mix", ptr(z["losses"]), ptr(z["itc_sums"]), getattr(self, "n_global", B),
+             self.beta_itc if self.fusion is not None else 1.0,
+             self.beta_itm, int(self.use_itc), int(self.use_itm), ptr(o["loss"]), st)
+        if self.fusion is not None:
+            self._fusion_bwd(inp)
+        if self.use_itc:
+            self._itc_bwd(inp)
         return o
+
+    def forward(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Autograd mode, forward half: logits_per_text (materialised), mm_features, out_cls, out_tim.  ITM decisions come
+        from the caller (`lbl_tim`, `src_idx`) exactly as the reference passes `tim_inputs`."""
+        assert self.itc is None or self.itc.logits is not None, "autograd mode needs materialize_logits=True"
+        self.zb.zero_()
+        if self.use_itc:
+            self._itc_fwd(inp, with_loss=False)
+        if self.fusion is not None:
+            if self.use_itm:
+                self._sample_itm(inp)
+            self._fusion_fwd(inp)
+            self._heads(inp, forward_only=True)
+        return self.out
+
+    def backward(self, inp, d_out_cls=None, d_logits=None, d_out_tim=None) -> Dict[str, torch.Tensor]:
+        """Autograd mode, backward half: upstream gradients of the three outputs -> gradients of inputs and parameters."""
+        B, C = self.B, self.C
+        self.zb.zero_()
+        if self.fusion is not None:
+            dz = self.dz_ext
+            dz.zero_()
+            if d_out_cls is not None:
+                dz[:B, :C].copy_(d_out_cls)
+            if self.use_itm and d_out_tim is not None:
+                dz[B:, :2].copy_(d_out_tim)
+            self._heads(inp, dH_f32=self.dHf if self.fusion == "aspect-att" else None, dz_ext=dz)
+            self._fusion_bwd(inp)
+        if self.use_itc:
+            if d_logits is None:
+                d_logits = torch.zeros(B, B, dtype=F32, device=self.dev)
+            self._itc_bwd(inp, dS=d_logits.to(F32).contiguous())
+        return self.out
 
     def _sample_itm(self, inp):
         B, o, st = self.B, self.out, _stream()
@@ -339,36 +405,35 @@ class HeadPlan:
             call("tic_itm_sample", ptr(inp["u_coin"]), ptr(inp["u_pick"]), B, self.itm_mode, ptr(S), B, ptr(o["lbl_tim"]),
                  ptr(o["src_idx"]), st)
 
-    def _heads(self, inp, dH_f32=None):
+    def _heads(self, inp, dH_f32=None, forward_only=False, dz_ext=None):
         B, E, z, o, w = self.B, self.E, self.z, self.out, self.w
+        y_soft = inp.get("y_soft")
+        if y_soft is None:   # autograd mode: the classification loss is the caller's
+            y_soft = self.y_dummy
+        no = forward_only
         call("tic_heads_fwd_bwd", ptr(self.H), E, B, E, self.C, int(self.use_itm), ptr(w["W_cls"]), ptr(w["b_cls"]),
-             ptr(w["W_tim"]), ptr(w["b_tim"]), ptr(inp["y_soft"]), ptr(inp.get("class_w")), ptr(o["lbl_tim"]),
+             ptr(w["W_tim"]), ptr(w["b_tim"]), ptr(y_soft), ptr(inp.get("class_w")), ptr(o["lbl_tim"]),
              ptr(inp.get("keep")), float(inp.get("keep_scale", 1.0)), float(self.w_cls), float(self.beta_itm),
-             ptr(o["out_cls"]), ptr(o.get("out_tim")), ptr(z["losses"]), ptr(self.dHb), ptr(self.dHb_lo), E, ptr(dH_f32), E,
-             ptr(z["dW_cls"]),
-             ptr(z["db_cls"]), ptr(z["dW_tim"]), ptr(z["db_tim"]), 1, ptr(self.heads_ws), _stream())
+             ptr(o["out_cls"]), ptr(o.get("out_tim")), ptr(z["losses"]), None if no else ptr(self.dHb),
+             None if no else ptr(self.dHb_lo), E, None if no else ptr(dH_f32), E, None if no else ptr(z["dW_cls"]),
+             None if no else ptr(z["db_cls"]), None if no else ptr(z["dW_tim"]), None if no else ptr(z["db_tim"]), 1,
+             ptr(self.heads_ws), ptr(dz_ext), _stream())
 
-    def _fusion_fwd_bwd(self, inp):
-        B, E, R, w, z, o, st = self.B, self.E, self.R, self.w, self.z, self.out, _stream()
+    def _fusion_fwd(self, inp):
+        B, E, R, w, o, st = self.B, self.E, self.R, self.w, self.out, _stream()
         E2 = 2 * E
-        if self.use_itm:
-            self._sample_itm(inp)
         src = o["src_idx"] if self.use_itm else None
         if self.fusion == "aspect-att":
             tp_, vp_ = inp["t_pool"], inp["v_pool"]
             call("tic_aspect_fwd", ptr(tp_), tp_.stride(0), ptr(vp_), vp_.stride(0), B, E, ptr(w["w_a"]), ptr(w["b_a"]),
                  ptr(self.H), E, ptr(self.alpha), st)
-            self._heads(inp, dH_f32=self.dHf)
-            call("tic_aspect_bwd", ptr(tp_), tp_.stride(0), ptr(vp_), vp_.stride(0), B, E, ptr(w["w_a"]), ptr(w["b_a"]),
-                 ptr(self.H), E, ptr(self.alpha), ptr(self.dHf), E, ptr(o["d_t_pool_fusion"]), E, ptr(z["dw_a"]),
-                 ptr(z["db_a"]), st)
             return
         x_t, x_v = inp["x_t"], inp["x_v"]
         xt_stride, xv_stride = x_t.stride(0), x_v.stride(0)   # CLS rows: x[:,0,:]
         X = self.Xcat
+        X_lo = None
         if self.fusion == "concat" or self.fusion == "gmu":
             call("tic_pack_cls_pairs", ptr(x_t), xt_stride, ptr(x_v), xv_stride, B, E, ptr(src), ptr(X), E2, st)
-        X_lo = None
         if self.fusion == "attention":
             Ea, Lv = E + 8, self.Lv
             X_lo = self.Xcat_lo
@@ -379,15 +444,27 @@ class HeadPlan:
                  Lv, E, float(E) ** -0.5, ptr(self.xbar_b), ptr(self.xbar_lo), E, ptr(self.xbar_f), E, ptr(self.attn), Lv, st)
             gemm(self.xbar_b, E, 0, w["W_V"], E, 0, X.data_ptr() + 2 * E, E2, 1, R, E, E, bias=w["b_V"], A_lo=self.xbar_lo,
                  D_lo=X_lo.data_ptr() + 2 * E)                                                      # ctx0 -> Xcat[:,E:]
-        Hin, Hin_lo = X, X_lo
+        self.Hin, self.Hin_lo = X, X_lo
         if self.fusion == "gmu":
             gemm(X, E2, 0, w["W_gt"], E, 0, self.tp, E2, 0, R, E2, E, bias=w["b_gt"])               # linear_gmu_t(x_t[:,0])
             gemm(X.data_ptr() + 2 * E, E2, 0, w["W_gv"], E, 0, self.vp, E2, 0, R, E2, E, bias=w["b_gv"])
             call("tic_gmu_gate_fwd", ptr(X), E2, ptr(self.tp), ptr(self.vp), E2, R, E2, ptr(self.G), ptr(self.G_lo), E2, st)
-            Hin, Hin_lo = self.G, self.G_lo
-        gemm(Hin, E2, 0, w["W_f"], E2, 0, self.H, E, 0, R, E, E2, bias=w["b_f"], relu=True, A_lo=Hin_lo)  # relu(linear_fusion)
-        self._heads(inp)
-        # ---------------- backward through linear_fusion (dH is a split bf16 pair: hi + lo)
+            self.Hin, self.Hin_lo = self.G, self.G_lo
+        gemm(self.Hin, E2, 0, w["W_f"], E2, 0, self.H, E, 0, R, E, E2, bias=w["b_f"], relu=True, A_lo=self.Hin_lo)
+
+    def _fusion_bwd(self, inp):
+        B, E, R, w, z, o, st = self.B, self.E, self.R, self.w, self.z, self.out, _stream()
+        E2 = 2 * E
+        src = o["src_idx"] if self.use_itm else None
+        if self.fusion == "aspect-att":
+            tp_, vp_ = inp["t_pool"], inp["v_pool"]
+            call("tic_aspect_bwd", ptr(tp_), tp_.stride(0), ptr(vp_), vp_.stride(0), B, E, ptr(w["w_a"]), ptr(w["b_a"]),
+                 ptr(self.H), E, ptr(self.alpha), ptr(self.dHf), E, ptr(o["d_t_pool_fusion"]), E, ptr(z["dw_a"]),
+                 ptr(z["db_a"]), st)
+            return
+        x_v = inp["x_v"]
+        X, Hin, Hin_lo = self.Xcat, self.Hin, self.Hin_lo
+        # backward through linear_fusion (dH is a split bf16 pair: hi + lo)
         dH, dHl = self.dHb, self.dHb_lo
         call("tic_colsum_bf16", ptr(dH), E, R, E, ptr(z["db_f"]), st)
         call("tic_colsum_bf16", ptr(dHl), E, R, E, ptr(z["db_f"]), st)
