@@ -49,11 +49,13 @@ int tic_sm_count(void);
  * lda/ldb must be multiples of 8 elements and A/B 16-byte aligned (TMA). d_dtype: 0 = fp32, 1 = bf16. */
 int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn_major, const void* B, const void* B_lo, int64_t ldb,
                   int b_mn_major, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha,
-                  const float* bias, int relu, void* stream);
+                  const float* bias, int relu, int accumulate, void* stream);
 /* Split precision: an operand that was produced on the device (a gradient or an intermediate activation) may be
  * passed as a bf16 (hi, lo) pair with identical layout (A_lo / B_lo, NULL = plain bf16); the kernel then runs the extra
  * K-segment(s) D += A_lo*B (+ A*B_lo) into the same TMEM accumulator, so the rounding of that operand drops from 2^-9 to
- * ~2^-17.  D_lo (bf16 output only) receives the residual x - bf16(x) so the result can itself be consumed as a pair. */
+ * ~2^-17.  D_lo (bf16 output only) receives the residual x - bf16(x) so the result can itself be consumed as a pair.
+ * accumulate = 1 (fp32 output, no ReLU): D += result with fp32 atomics (D must hold its initial value, e.g. zeros); this
+ * also lets the library split K across CTAs so that long-K weight-gradient GEMMs with few output tiles fill all SMs. */
 /* Reference-quality SIMT fp32-accumulate GEMM with the same semantics (debug / self-test only). */
 int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
                        int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu,

@@ -19,7 +19,7 @@ _SIGS = {
     "tic_last_error_string": ("", ctypes.c_char_p),
     "tic_version": ("", ctypes.c_int),
     "tic_sm_count": ("", ctypes.c_int),
-    "tic_gemm_bf16": ("pplipplippliiiifpip", ctypes.c_int),
+    "tic_gemm_bf16": ("pplipplippliiiifpiip", ctypes.c_int),
     "tic_gemm_bf16_simt": ("pliplipliiiifpip", ctypes.c_int),
     "tic_row_rnorm_bf16": ("ppliipp", ctypes.c_int),
     "tic_itc_row_parts": ("i", ctypes.c_int),

@@ -198,6 +198,290 @@ attn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, int6
   }
 }
 
+// ------------------------------------------------------------------ attention pool, bulk-async pipeline (v2)
+// Same arithmetic as the kernels above, but x_v is streamed by a dedicated producer warp with cp.async.bulk (the TMA
+// engine's 1-D form) into a 6-stage shared-memory ring, 16 token rows (24 KB) per stage, completion on mbarriers.
+// One persistent CTA per SM keeps ~144 KB in flight regardless of register pressure, which is what the HBM system
+// needs (the register-staged v1 ran at 12 % warp occupancy and ~25 % of HBM peak).  Requires contiguous token rows.
+constexpr int kApRows = 16, kApStages = 6, kApE = 768;
+constexpr int kApChunkBytes = kApRows * kApE * 2;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void lds8_bf16(const uint8_t* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+
+struct ApSmem {
+  uint8_t* ring;
+  uint32_t ring_u32, full0, empty0;
+  float* fl;
+};
+__device__ __forceinline__ ApSmem ap_carve(uint8_t* raw) {
+  ApSmem s;
+  const uint32_t base = (smem_u32(raw) + 127u) & ~127u;
+  s.ring = raw + (base - smem_u32(raw));
+  s.ring_u32 = base;
+  s.full0 = base + kApStages * kApChunkBytes;
+  s.empty0 = s.full0 + 8 * kApStages;
+  s.fl = reinterpret_cast<float*>(s.ring + kApStages * kApChunkBytes + 16 * kApStages);
+  return s;
+}
+__device__ __forceinline__ void ap_producer(const ApSmem& sm, const __nv_bfloat16* xv, int64_t bstride, int B, int Lv) {
+  const int nchunks = (Lv + kApRows - 1) / kApRows;
+  uint32_t it = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const __nv_bfloat16* xb = xv + static_cast<int64_t>(b) * bstride;
+    for (int c = 0; c < nchunks; ++c, ++it) {
+      const uint32_t st = it % kApStages, ph = (it / kApStages) & 1u;
+      mbar_wait(sm.empty0 + 8 * st, ph ^ 1u);
+      const int rows = min(kApRows, Lv - c * kApRows);
+      const uint32_t bytes = static_cast<uint32_t>(rows) * kApE * 2;
+      mbar_arrive_expect_tx(sm.full0 + 8 * st, bytes);
+      bulk_g2s(sm.ring_u32 + st * kApChunkBytes, xb + static_cast<int64_t>(c) * kApRows * kApE, bytes, sm.full0 + 8 * st);
+    }
+  }
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(288, 1)
+attn_pool_fwd_v2_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, const float* __restrict__ kq, int64_t ldkq, int B,
+                        int Lv, float scale, __nv_bfloat16* __restrict__ xbar_b, __nv_bfloat16* __restrict__ xbar_lo,
+                        int64_t ld_xb, float* __restrict__ xbar_f, int64_t ld_xf, float* __restrict__ attn, int64_t ld_attn) {
+  constexpr int NV = 3, E = kApE;
+  extern __shared__ uint8_t ap_raw[];
+  const ApSmem sm = ap_carve(ap_raw);
+  float* s_scores = sm.fl;                          // [NPASS][Lv]
+  float* s_ml = s_scores + NPASS * Lv;              // [NPASS][8][2]
+  float* s_acc = s_ml + NPASS * 16;                 // [8][E]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kApStages; ++i) { mbar_init(sm.full0 + 8 * i, 1); mbar_init(sm.empty0 + 8 * i, 8); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    if (lane == 0) ap_producer(sm, xv, bstride, B, Lv);
+    return;
+  }
+  const int nchunks = (Lv + kApRows - 1) / kApRows;
+  uint32_t it = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float q[NPASS][NV][8], cb[NPASS], m[NPASS], l[NPASS], acc[NPASS][NV][8];
+#pragma unroll
+    for (int p = 0; p < NPASS; ++p) {
+      const float* kr = kq + static_cast<int64_t>(p * B + b) * ldkq;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(kr + v * 256 + lane * 8));
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(kr + v * 256 + lane * 8 + 4));
+        q[p][v][0] = a.x; q[p][v][1] = a.y; q[p][v][2] = a.z; q[p][v][3] = a.w;
+        q[p][v][4] = c4.x; q[p][v][5] = c4.y; q[p][v][6] = c4.z; q[p][v][7] = c4.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[p][v][k] = 0.f;
+      }
+      cb[p] = __ldg(kr + E);
+      m[p] = -INFINITY;
+      l[p] = 0.f;
+    }
+    for (int c = 0; c < nchunks; ++c, ++it) {
+      const uint32_t st = it % kApStages, ph = (it / kApStages) & 1u;
+      mbar_wait(sm.full0 + 8 * st, ph);
+      const uint8_t* chunk = sm.ring + st * kApChunkBytes;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = c * kApRows + warp + 8 * h;
+        if (j < Lv) {
+          float x[NV][8];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) lds8_bf16(chunk + (warp + 8 * h) * (E * 2) + (v * 256 + lane * 8) * 2, x[v]);
+#pragma unroll
+          for (int p = 0; p < NPASS; ++p) {
+            float d = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) d = fmaf(q[p][v][k], x[v][k], d);
+            d = (warp_sum(d) + cb[p]) * scale;
+            if (lane == 0) s_scores[p * Lv + j] = d;
+            const float mn = fmaxf(m[p], d);
+            const float corr = __expf(m[p] - mn), w = __expf(d - mn);
+            l[p] = l[p] * corr + w;
+            m[p] = mn;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[p][v][k] = fmaf(acc[p][v][k], corr, w * x[v][k]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.empty0 + 8 * st);
+    }
+    // combine the 8 consumer warps (the producer keeps prefetching the next samples meanwhile)
+#pragma unroll
+    for (int p = 0; p < NPASS; ++p)
+      if (lane == 0) { s_ml[(p * 8 + warp) * 2] = m[p]; s_ml[(p * 8 + warp) * 2 + 1] = l[p]; }
+    consumer_bar();
+#pragma unroll
+    for (int p = 0; p < NPASS; ++p) {
+      float M = -INFINITY;
+      for (int w = 0; w < 8; ++w) M = fmaxf(M, s_ml[(p * 8 + w) * 2]);
+      float L = 0.f;
+      for (int w = 0; w < 8; ++w) L += s_ml[(p * 8 + w) * 2 + 1] * __expf(s_ml[(p * 8 + w) * 2] - M);
+      const float mine = (m[p] == -INFINITY) ? 0.f : __expf(m[p] - M) / L;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_acc[warp * E + v * 256 + lane * 8 + k] = acc[p][v][k] * mine;
+      consumer_bar();
+      const int64_t r = static_cast<int64_t>(p * B + b);
+      for (int e = threadIdx.x; e < E; e += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_acc[w * E + e];
+        if (xbar_b) {
+          const __nv_bfloat16 hi = __float2bfloat16_rn(s);
+          xbar_b[r * ld_xb + e] = hi;
+          if (xbar_lo) xbar_lo[r * ld_xb + e] = __float2bfloat16_rn(s - __bfloat162float(hi));
+        }
+        if (xbar_f) xbar_f[r * ld_xf + e] = s;
+      }
+      for (int j = threadIdx.x; j < Lv; j += 256) attn[r * ld_attn + j] = __expf(s_scores[p * Lv + j] - M) / L;
+      consumer_bar();
+    }
+  }
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(288, 1)
+attn_pool_bwd_v2_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, const float* __restrict__ attn, int64_t ld_attn,
+                        const float* __restrict__ dxbar, int64_t ld_dxb, const float* __restrict__ xbar_f, int64_t ld_xf, int B,
+                        int Lv, float scale, __nv_bfloat16* __restrict__ dkq, __nv_bfloat16* __restrict__ dkq_lo, int64_t ld_dkq) {
+  constexpr int NV = 3, E = kApE;
+  extern __shared__ uint8_t ap_raw[];
+  const ApSmem sm = ap_carve(ap_raw);
+  float* s_acc = sm.fl;                 // [8][E]
+  float* s_dc = s_acc + 8 * E;          // [NPASS][8]
+  float* s_attn = s_dc + NPASS * 8;     // [NPASS][Lv]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kApStages; ++i) { mbar_init(sm.full0 + 8 * i, 1); mbar_init(sm.empty0 + 8 * i, 8); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    if (lane == 0) ap_producer(sm, xv, bstride, B, Lv);
+    return;
+  }
+  const int nchunks = (Lv + kApRows - 1) / kApRows;
+  uint32_t it = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float g[NPASS][NV][8], D[NPASS], acc[NPASS][NV][8], dc[NPASS];
+#pragma unroll
+    for (int p = 0; p < NPASS; ++p) {
+      const int64_t r = static_cast<int64_t>(p * B + b);
+      for (int j = threadIdx.x; j < Lv; j += 256) s_attn[p * Lv + j] = __ldg(attn + r * ld_attn + j);
+      float d = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float* gp = dxbar + r * ld_dxb + v * 256 + lane * 8;
+        const float* xp = xbar_f + r * ld_xf + v * 256 + lane * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(gp)), a2 = __ldg(reinterpret_cast<const float4*>(gp + 4));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(xp)), c2 = __ldg(reinterpret_cast<const float4*>(xp + 4));
+        g[p][v][0] = a.x; g[p][v][1] = a.y; g[p][v][2] = a.z; g[p][v][3] = a.w;
+        g[p][v][4] = a2.x; g[p][v][5] = a2.y; g[p][v][6] = a2.z; g[p][v][7] = a2.w;
+        d += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w + a2.x * c2.x + a2.y * c2.y + a2.z * c2.z + a2.w * c2.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[p][v][k] = 0.f;
+      }
+      D[p] = warp_sum(d);
+      dc[p] = 0.f;
+    }
+    consumer_bar();   // s_attn visible
+    for (int c = 0; c < nchunks; ++c, ++it) {
+      const uint32_t st = it % kApStages, ph = (it / kApStages) & 1u;
+      mbar_wait(sm.full0 + 8 * st, ph);
+      const uint8_t* chunk = sm.ring + st * kApChunkBytes;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = c * kApRows + warp + 8 * h;
+        if (j < Lv) {
+          float x[NV][8];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) lds8_bf16(chunk + (warp + 8 * h) * (E * 2) + (v * 256 + lane * 8) * 2, x[v]);
+#pragma unroll
+          for (int p = 0; p < NPASS; ++p) {
+            float t = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) t = fmaf(g[p][v][k], x[v][k], t);
+            t = warp_sum(t);
+            const float ds = s_attn[p * Lv + j] * (t - D[p]) * scale;
+            dc[p] += ds;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[p][v][k] = fmaf(ds, x[v][k], acc[p][v][k]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.empty0 + 8 * st);
+    }
+#pragma unroll
+    for (int p = 0; p < NPASS; ++p) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_acc[warp * E + v * 256 + lane * 8 + k] = acc[p][v][k];
+      if (lane == 0) s_dc[p * 8 + warp] = dc[p];
+      consumer_bar();
+      const int64_t r = static_cast<int64_t>(p * B + b);
+      for (int e = threadIdx.x; e < E; e += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_acc[w * E + e];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(s);
+        dkq[r * ld_dkq + e] = hi;
+        if (dkq_lo) dkq_lo[r * ld_dkq + e] = __float2bfloat16_rn(s - __bfloat162float(hi));
+      }
+      if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_dc[p * 8 + w];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(s);
+        dkq[r * ld_dkq + E] = hi;
+        if (dkq_lo) dkq_lo[r * ld_dkq + E] = __float2bfloat16_rn(s - __bfloat162float(hi));
+        for (int e = E + 1; e < E + 8; ++e) {
+          dkq[r * ld_dkq + e] = __float2bfloat16_rn(0.f);
+          if (dkq_lo) dkq_lo[r * ld_dkq + e] = __float2bfloat16_rn(0.f);
+        }
+      }
+      consumer_bar();
+    }
+  }
+}
+
+static int ap_grid(int B) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return B < sms ? B : sms;
+}
+
 // ------------------------------------------------------------------ aspect-att
 __device__ __forceinline__ const __nv_bfloat16* aspect_row(const __nv_bfloat16* t, int64_t ldt, const __nv_bfloat16* v, int64_t ldv,
                                                            int B, int f) {
@@ -308,6 +592,24 @@ int tic_attn_pool_fwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
   TIC_CHECK_ARG((xv_batch_stride & 7) == 0 && (xv_tok_stride & 7) == 0 && ldkq >= E + 1 && aligned16(xv),
                 "tic_attn_pool_fwd: 16-byte aligned x_v rows / augmented kq (ld >= E+1) required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (xv_tok_stride == E && (xv_batch_stride & 7) == 0 && (ldkq & 3) == 0 && (reinterpret_cast<uintptr_t>(kq) & 15) == 0) {
+    const size_t sm2 = 128 + kApStages * kApChunkBytes + 16 * kApStages + sizeof(float) * (npass * Lv + npass * 16 + 8 * E);
+    auto xb2 = static_cast<__nv_bfloat16*>(xbar_bf16);
+    auto xl2 = static_cast<__nv_bfloat16*>(xbar_bf16_lo);
+    if (npass == 1) {
+      auto k = attn_pool_fwd_v2_kernel<1>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      k<<<ap_grid(B), 288, sm2, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, static_cast<const float*>(kq), ldkq,
+                                      B, Lv, scale, xb2, xl2, ld_xb, xbar_f32, ld_xf, attn, ld_attn);
+    } else {
+      auto k = attn_pool_fwd_v2_kernel<2>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      k<<<ap_grid(B), 288, sm2, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, static_cast<const float*>(kq), ldkq,
+                                      B, Lv, scale, xb2, xl2, ld_xb, xbar_f32, ld_xf, attn, ld_attn);
+    }
+    TIC_CHECK_LAUNCH("tic_attn_pool_fwd");
+    return TIC_OK;
+  }
   const size_t smem = sizeof(float) * (npass * Lv + npass * kAttnWarps * 2 + kAttnWarps * E);
   auto xb = static_cast<__nv_bfloat16*>(xbar_bf16);
   auto xl = static_cast<__nv_bfloat16*>(xbar_bf16_lo);
@@ -333,6 +635,25 @@ int tic_attn_pool_bwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
   TIC_CHECK_ARG(xv && attn && dxbar && xbar_f32 && dkq_bf16 && B > 0 && Lv > 0, "tic_attn_pool_bwd: bad arguments");
   TIC_CHECK_ARG(E == 768 && (npass == 1 || npass == 2) && ld_dkq >= E + 8, "tic_attn_pool_bwd: E must be 768, npass 1|2, ld_dkq >= E+8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (xv_tok_stride == E && (xv_batch_stride & 7) == 0 && (ld_dxb & 3) == 0 && (ld_xf & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(dxbar) | reinterpret_cast<uintptr_t>(xbar_f32)) & 15) == 0) {
+    const size_t sm2 = 128 + kApStages * kApChunkBytes + 16 * kApStages + sizeof(float) * (8 * E + npass * 8 + npass * Lv);
+    if (npass == 1) {
+      auto k = attn_pool_bwd_v2_kernel<1>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      k<<<ap_grid(B), 288, sm2, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, attn, ld_attn, dxbar, ld_dxb, xbar_f32,
+                                      ld_xf, B, Lv, scale, static_cast<__nv_bfloat16*>(dkq_bf16),
+                                      static_cast<__nv_bfloat16*>(dkq_bf16_lo), ld_dkq);
+    } else {
+      auto k = attn_pool_bwd_v2_kernel<2>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      k<<<ap_grid(B), 288, sm2, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, attn, ld_attn, dxbar, ld_dxb, xbar_f32,
+                                      ld_xf, B, Lv, scale, static_cast<__nv_bfloat16*>(dkq_bf16),
+                                      static_cast<__nv_bfloat16*>(dkq_bf16_lo), ld_dkq);
+    }
+    TIC_CHECK_LAUNCH("tic_attn_pool_bwd");
+    return TIC_OK;
+  }
   const size_t smem = sizeof(float) * (kAttnWarps * E + npass * kAttnWarps);
   if (npass == 1) {
     auto k = attn_pool_bwd_kernel<3, 1>;

@@ -76,6 +76,7 @@ struct StoreEpi {
     float alpha;
     const float* bias;
     int relu;
+    int accumulate;   // D += result with fp32 atomics (D holds the initial value); required for split-K
   };
   template <int BN>
   __device__ static void tile(const Params& p, const EpiCtx& cx) {
@@ -97,7 +98,7 @@ struct StoreEpi {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float x = p.alpha * __uint_as_float(v[j]);
-        if (p.bias != nullptr && col0 + j < cx.N) x += __ldg(p.bias + col0 + j);
+        if (p.bias != nullptr && cx.ks == 0 && col0 + j < cx.N) x += __ldg(p.bias + col0 + j);
         if (p.relu) x = fmaxf(x, 0.f);
         f[j] = x;
       }
@@ -139,6 +140,11 @@ struct StoreEpi {
               if (col0 + j < cx.N) dl[j] = __float2bfloat16_rn(f[j]);
           }
         }
+      } else if (p.accumulate) {
+        float* d = reinterpret_cast<float*>(p.D) + static_cast<int64_t>(row) * p.ldd + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < cx.N) atomicAdd(d + j, f[j]);
       } else {
         float* d = reinterpret_cast<float*>(p.D) + static_cast<int64_t>(row) * p.ldd + col0;
         if (full) {
@@ -156,11 +162,11 @@ struct StoreEpi {
 
 template <int BN>
 static int dispatch_major(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
-                          int b_mn, int M, int N, int K, const StoreEpi::Params& ep, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_umma_gemm<BN, false, false, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
-  if (!a_mn && b_mn) return launch_umma_gemm<BN, false, true, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
-  if (a_mn && !b_mn) return launch_umma_gemm<BN, true, false, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
-  return launch_umma_gemm<BN, true, true, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
+                          int b_mn, int M, int N, int K, const StoreEpi::Params& ep, cudaStream_t st, int ksplit) {
+  if (!a_mn && !b_mn) return launch_umma_gemm<BN, false, false, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st, ksplit);
+  if (!a_mn && b_mn) return launch_umma_gemm<BN, false, true, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st, ksplit);
+  if (a_mn && !b_mn) return launch_umma_gemm<BN, true, false, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st, ksplit);
+  return launch_umma_gemm<BN, true, true, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st, ksplit);
 }
 
 // ------------------------------------------------------------------ SIMT reference GEMM (self-test only)
@@ -202,20 +208,38 @@ int tic_sm_count(void) { return device_sm_count(); }
 
 int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
                   int b_mn, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias,
-                  int relu, void* stream) {
+                  int relu, int accumulate, void* stream) {
   TIC_CHECK_ARG(A && B && D, "tic_gemm_bf16: null pointer");
   TIC_CHECK_ARG(M > 0 && N > 0 && K > 0, "tic_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   TIC_CHECK_ARG(d_dtype == 0 || d_dtype == 1, "tic_gemm_bf16: d_dtype must be 0 (fp32) or 1 (bf16)");
   TIC_CHECK_ARG(D_lo == nullptr || d_dtype == 1, "tic_gemm_bf16: D_lo needs a bf16 output");
-  StoreEpi::Params ep{D, D_lo, ldd, d_dtype, alpha, bias, relu};
+  TIC_CHECK_ARG(!accumulate || (d_dtype == 0 && !relu), "tic_gemm_bf16: accumulate needs an fp32 output and no ReLU");
+  StoreEpi::Params ep{D, D_lo, ldd, d_dtype, alpha, bias, relu, accumulate};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int sms = device_sm_count();
   const int m_tiles = ceil_div(M, kBM);
-  // Largest N tile that still gives every SM a tile; small problems prefer more, narrower tiles.
+  const int total_kb = ceil_div(K, kBK) * (1 + (A_lo ? 1 : 0) + (B_lo ? 1 : 0));
+  // Tile width / split-K by a small cost model: waves x (k-blocks x cycles-per-k-block(BN) + fixed + epilogue(BN)).
+  // Narrow tiles are shared-memory-bandwidth bound (A is re-read per N tile), wide ones leave SMs idle on small problems;
+  // split-K (only when the caller lets us accumulate atomically) fills the machine for long-K weight-gradient GEMMs.
+  static const int bns[3] = {256, 128, 64};
+  static const double cyc_kb[3] = {520.0, 300.0, 200.0};
+  int best_bn = 128, best_ks = 1;
+  double best = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int tiles = m_tiles * ceil_div(N, bns[i]);
+    for (int ks = 1; ks <= (accumulate ? 16 : 1); ks *= 2) {
+      if (ks > total_kb) break;
+      const int items = tiles * ks;
+      const int waves = ceil_div(items, sms);
+      const double t = waves * (ceil_div(total_kb, ks) * cyc_kb[i] + 1500.0 + 8.0 * bns[i] * (accumulate ? 2.0 : 1.0));
+      if (t < best) { best = t; best_bn = bns[i]; best_ks = ks; }
+    }
+  }
   int rc;
-  if (m_tiles * ceil_div(N, 256) >= sms) rc = dispatch_major<256>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st);
-  else if (m_tiles * ceil_div(N, 128) >= sms / 2) rc = dispatch_major<128>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st);
-  else rc = dispatch_major<64>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st);
+  if (best_bn == 256) rc = dispatch_major<256>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
+  else if (best_bn == 128) rc = dispatch_major<128>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
+  else rc = dispatch_major<64>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
   if (rc == -3) { set_error("tic_gemm_bf16: cudaFuncSetAttribute(max dynamic smem) failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_gemm_bf16: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TIC_E_LAUNCH; }
   return rc;

@@ -281,7 +281,7 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
                                                         dH_f32, ld_dhf,
                                                         relu_mask);
   if (dW_cls && db_cls) {
-    const int rpb = max(32, ceil_div(B, 64));
+    const int rpb = max(8, ceil_div(B, 128));
     dim3 grid(ceil_div(E, 128), ceil_div(B, rpb));
     heads_wgrad_kernel<<<grid, 128, 0, st>>>(H, ldh, 0, B, E, C, dlogits, keep, keep_scale, dW_cls, db_cls, rpb);
     if (has_tim && dW_tim && db_tim)
@@ -293,7 +293,7 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
 
 int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, void* stream) {
   TIC_CHECK_ARG(X && out && rows > 0 && cols > 0, "tic_colsum_bf16: bad arguments");
-  const int rpb = max(32, ceil_div(rows, 64));
+  const int rpb = max(8, ceil_div(rows, 128));
   dim3 grid(ceil_div(cols, 128), ceil_div(rows, rpb));
   colsum_bf16_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(X), ldx, rows, cols,
                                                                           out, rpb);

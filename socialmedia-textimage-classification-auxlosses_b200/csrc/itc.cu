@@ -14,7 +14,10 @@
 
 namespace tic {
 
-constexpr int kItcBN = 256;
+constexpr int kItcBN = 256;        // wide tiles: best tensor-pipe efficiency at large batch
+constexpr int kItcBNSmall = 64;    // narrow tiles below kItcSmallN columns: 4x more CTAs for the latency-bound small batch
+constexpr int kItcSmallN = 2048;
+inline int itc_bn(int n_global) { return n_global <= kItcSmallN ? kItcBNSmall : kItcBN; }
 constexpr int kItcEpiWarps = 8;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -402,7 +405,7 @@ using namespace tic;
 
 extern "C" {
 
-int tic_itc_row_parts(int n_global) { return ceil_div(n_global, kItcBN) * (kItcEpiWarps / 4); }
+int tic_itc_row_parts(int n_global) { return ceil_div(n_global, itc_bn(n_global)) * (kItcEpiWarps / 4); }
 int tic_itc_col_parts(int m_local) { return ceil_div(m_local, kBM); }
 
 int tic_row_rnorm_bf16(const void* X, const void* X_lo, int64_t ldx, int rows, int cols, float* rinv, void* stream) {
@@ -427,8 +430,12 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
   }
   ItcFwdEpi::Params ep{rinv_t, rinv_v, scale * kLog2e, shift * kLog2e, scale, row_part, col_part, diag, logits_out, ld_logits,
                        row_offset};
-  int rc = launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep,
-                                                                          static_cast<cudaStream_t>(stream));
+  int rc = itc_bn(n_global) == kItcBN
+               ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
+                                                                                P, ep, static_cast<cudaStream_t>(stream), 1)
+               : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
+                                                                                     n_global, P, ep,
+                                                                                     static_cast<cudaStream_t>(stream), 1);
   if (rc == -3) { set_error("tic_itc_fwd: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_fwd: launch failed"); return TIC_E_LAUNCH; }
   return rc;
@@ -464,8 +471,12 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
   ItcBwdEpi::Params ep{rinv_t, rinv_v, lse_row, lse_col, scale * kLog2e, gscale, static_cast<__nv_bfloat16*>(GA), ld_ga,
                        static_cast<__nv_bfloat16*>(GBT), ld_gbt, static_cast<__nv_bfloat16*>(GA_lo),
                        static_cast<__nv_bfloat16*>(GBT_lo)};
-  int rc = launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep,
-                                                                          static_cast<cudaStream_t>(stream));
+  int rc = itc_bn(n_global) == kItcBN
+               ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
+                                                                                P, ep, static_cast<cudaStream_t>(stream), 1)
+               : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
+                                                                                     n_global, P, ep,
+                                                                                     static_cast<cudaStream_t>(stream), 1);
   if (rc == -3) { set_error("tic_itc_bwd_g: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_bwd_g: launch failed"); return TIC_E_LAUNCH; }
   return rc;

@@ -54,7 +54,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dbias, hbias.data(), N * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0xFF, dbytes));
   CK(cudaMemset(dR, 0xFF, dbytes));
-  int rc = tic_gemm_bf16(dA, nullptr, lda, a_mn, dB, nullptr, ldb, b_mn, dD, nullptr, ldd, d_bf16, M, N, K, 0.5f, dbias, 0, nullptr);
+  int rc = tic_gemm_bf16(dA, nullptr, lda, a_mn, dB, nullptr, ldb, b_mn, dD, nullptr, ldd, d_bf16, M, N, K, 0.5f, dbias, 0, 0, nullptr);
   if (rc) {
     printf("tic_gemm_bf16 rc=%d: %s\n", rc, tic_last_error_string());
     return 3;
@@ -96,9 +96,9 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) tic_gemm_bf16(dA, nullptr, lda, a_mn, dB, nullptr, ldb, b_mn, dD, nullptr, ldd, d_bf16, M, N, K, 0.5f, dbias, 0, nullptr);
+    for (int i = 0; i < 3; ++i) tic_gemm_bf16(dA, nullptr, lda, a_mn, dB, nullptr, ldb, b_mn, dD, nullptr, ldd, d_bf16, M, N, K, 0.5f, dbias, 0, 0, nullptr);
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) tic_gemm_bf16(dA, nullptr, lda, a_mn, dB, nullptr, ldb, b_mn, dD, nullptr, ldd, d_bf16, M, N, K, 0.5f, dbias, 0, nullptr);
+    for (int i = 0; i < iters; ++i) tic_gemm_bf16(dA, nullptr, lda, a_mn, dB, nullptr, ldb, b_mn, dD, nullptr, ldd, d_bf16, M, N, K, 0.5f, dbias, 0, 0, nullptr);
     cudaEventRecord(e1);
     CK(cudaEventSynchronize(e1));
     float ms;

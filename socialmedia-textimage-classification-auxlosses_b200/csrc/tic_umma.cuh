@@ -41,6 +41,7 @@ struct EpiCtx {
   int epi_tid;         // 0 .. 32*EPI_WARPS-1
   int epi_threads;
   int iter;             // tiles already processed by this CTA (for double-buffering the scratch)
+  int ks, ksplit;       // split-K: this work item covers K-slice ks of ksplit (epilogue must accumulate atomically)
   uint8_t* scratch;    // kEpiScratchBytes of smem shared by the epilogue warps
 };
 
@@ -52,8 +53,8 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
 template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
-                 const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int M,
-                 int N, int K, typename Epi::Params ep) {
+                 const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int ksplit,
+                 int M, int N, int K, typename Epi::Params ep) {
   using Cfg = UmmaCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps must cover the 4 TMEM lane quadrants");
@@ -80,6 +81,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // D = A_hi*B_hi (+ A_lo*B_hi) (+ A_hi*B_lo) accumulates in TMEM with ~16 mantissa bits per split operand.
   const int nseg = 1 + (split & 1) + ((split >> 1) & 1);
   const int total_kb = num_kb * nseg;
+  const int num_items = num_tiles * ksplit;   // work item = (tile, K-slice)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -107,9 +109,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+        const int t = w / ksplit, ks = w - t * ksplit;
         const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * BN;
-        for (int kt = 0; kt < total_kb; ++kt) {
+        const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / ksplit);
+        const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / ksplit);
+        for (int kt = kt_begin; kt < kt_end; ++kt) {
           const int seg = kt / num_kb, kb = kt - seg * num_kb;
           const bool a_lo = (seg == 1) && (split & 1);
           const bool b_lo = (seg >= 1) && !a_lo;
@@ -146,11 +151,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t a_kadv = (A_MN ? 2048u : 32u) >> 4, b_kadv = (B_MN ? 2048u : 32u) >> 4;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+        const int ks = w % ksplit;
+        const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / ksplit);
+        const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / ksplit);
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < total_kb; ++kb) {
+        for (int kb = 0; kb < kt_end - kt_begin; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
@@ -180,7 +188,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int as = 0;
     uint32_t aph = 0;
     cx.iter = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+      const int t = w / ksplit;
+      cx.ks = w - t * ksplit; cx.ksplit = ksplit;
       cx.m_blk = t / n_tiles; cx.n_blk = t % n_tiles;
       cx.m0 = cx.m_blk * kBM; cx.n0 = cx.n_blk * BN;
       mbar_wait(tfull_bar(as), aph);
@@ -219,7 +229,7 @@ int device_sm_count();
 
 template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
 int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B, const void* B_lo, int64_t ldb, int M, int N,
-                     int K, const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0) {
+                     int K, const typename Epi::Params& ep, cudaStream_t stream, int ksplit = 1, int max_ctas = 0) {
   using Cfg = UmmaCfg<BN>;
   if (M <= 0 || N <= 0 || K <= 0) return -1;
   CUtensorMap ta, tb, ta_lo, tb_lo;
@@ -244,10 +254,13 @@ int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B
     attr_set = true;
   }
   const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles;
+  const int total_kb = ((K + kBK - 1) / kBK) * (1 + (A_lo ? 1 : 0) + (B_lo ? 1 : 0));
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > total_kb) ksplit = total_kb;
+  int grid = m_tiles * n_tiles * ksplit;
   int cap = max_ctas > 0 ? max_ctas : device_sm_count();
   if (grid > cap) grid = cap;
-  kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(ta, ta_lo, tb, tb_lo, split, M, N, K, ep);
+  kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -34,11 +34,46 @@ def _addr(t):
 
 
 def gemm(A, lda, a_mn, Bm, ldb, b_mn, D, ldd, d_bf16, M, N, K, alpha=1.0, bias=None, relu=False, A_lo=None, B_lo=None,
-         D_lo=None):
+         D_lo=None, accumulate=False):
     """D[M,N] = alpha * op(A) op(B)^T (+bias)(relu) on tcgen05 (tic_gemm_bf16).  A/Bm/D are tensors or raw device
     addresses; A_lo / B_lo make that operand a split-precision bf16 (hi, lo) pair, D_lo receives the bf16 residual."""
     call("tic_gemm_bf16", _addr(A), _addr(A_lo), lda, int(a_mn), _addr(Bm), _addr(B_lo), ldb, int(b_mn), _addr(D),
-         _addr(D_lo), ldd, int(d_bf16), M, N, K, float(alpha), ptr(bias), int(relu), _stream())
+         _addr(D_lo), ldd, int(d_bf16), M, N, K, float(alpha), ptr(bias), int(relu), int(accumulate), _stream())
+
+
+class _Branches:
+    """Fork/join helper: `with br(k):` issues the enclosed launches on side stream k (after everything issued so far on
+    the current stream); `br.join(k)` makes the current stream wait for it.  Under CUDA-graph capture the branches become
+    parallel paths of the graph — the small-batch step is a chain of latency-bound kernels, so width matters."""
+
+    def __init__(self, device, enabled=True):
+        self.dev, self.enabled, self.side = device, enabled, {}
+
+    class _Ctx:
+        def __init__(self, outer, k):
+            self.o, self.k = outer, k
+
+        def __enter__(self):
+            o = self.o
+            if not o.enabled:
+                return
+            if self.k not in o.side:
+                o.side[self.k] = torch.cuda.Stream(device=o.dev)
+            s = o.side[self.k]
+            s.wait_stream(torch.cuda.current_stream())
+            self.cm = torch.cuda.stream(s)
+            self.cm.__enter__()
+
+        def __exit__(self, *a):
+            if self.o.enabled:
+                self.cm.__exit__(*a)
+
+    def __call__(self, k):
+        return self._Ctx(self, k)
+
+    def join(self, k):
+        if self.enabled and k in self.side:
+            torch.cuda.current_stream().wait_stream(self.side[k])
 
 
 class ItcPlan:
@@ -96,13 +131,18 @@ class ItcPlan:
              ptr(self.GBT) if self.GBT is not None else ptr(self.GA), self.ld_gbt if self.GBT is not None else self.ld_ga,
              ptr(self.GA_lo), ptr(self.GBT_lo), _stream())
 
-    def grad_gemms(self, T, ldt, V, ldv, T_lo=None, V_lo=None):
+    def grad_gemm_t(self, V, ldv, V_lo=None):
         # dT_acc[m,P] = GA[m,n] * V[n,P]   (A K-major, B = V read MN-major: no transposed copy of V)
         gemm(self.GA, self.ld_ga, 0, V, ldv, 1, self.acc_t, self.P, 0, self.m, self.P, self.n, A_lo=self.GA_lo, B_lo=V_lo)
+
+    def grad_gemm_v(self, T, ldt, T_lo=None):
+        # dV_acc[n,P] = GBT[n,m] * T[m,P]
+        gemm(self.GBT, self.ld_gbt, 0, T, ldt, 1, self.acc_v, self.P, 0, self.n, self.P, self.m, A_lo=self.GBT_lo, B_lo=T_lo)
+
+    def grad_gemms(self, T, ldt, V, ldv, T_lo=None, V_lo=None):
+        self.grad_gemm_t(V, ldv, V_lo=V_lo)
         if self.need_dv:
-            # dV_acc[n,P] = GBT[n,m] * T[m,P]
-            gemm(self.GBT, self.ld_gbt, 0, T, ldt, 1, self.acc_v, self.P, 0, self.n, self.P, self.m, A_lo=self.GBT_lo,
-                 B_lo=T_lo)
+            self.grad_gemm_v(T, ldt, T_lo=T_lo)
 
     def finalize_t(self, T, ldt, V_diag, ldv, rinv_v_diag, scale, diag_coef, dT_f32, dT_bf16, r_sum, dT_lo=None,
                    T_lo=None, V_diag_lo=None):
@@ -168,6 +208,9 @@ class HeadPlan:
         self._alloc()
         self.w: Dict[str, torch.Tensor] = {}
         self.scale = math.exp(2.6592)
+        self.parallel_streams = True
+        self._side = None
+        self.br = _Branches(self.dev, enabled=True)
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self):
@@ -176,6 +219,17 @@ class HeadPlan:
         # one contiguous block of accumulators that must be zero at the start of every step (one memset)
         sizes = {"losses": 2, "itc_sums": 2, "r_sum": 1, "_pad": 3, "dW_cls": C * E, "db_cls": C, "dW_tim": 2 * E,
                  "db_tim": 2, "db_f": E, "db_Q": E, "db_V": E, "db_gt": 2 * E, "db_gv": 2 * E, "dw_a": E, "db_a": 1}
+        # weight gradients are accumulated with fp32 atomics by split-K GEMMs: they start every step at zero too
+        if self.P is not None:
+            sizes.update(dW_t=self.P * E, dW_v=self.P * E)
+        if self.fusion in ("concat", "attention", "gmu"):
+            sizes.update(dW_f=E * 2 * E)
+        if self.fusion == "attention":
+            sizes.update(dW_Q=E * E, dW_V=E * E, dWK_aug=E * (E + 8))
+        if self.fusion == "gmu":
+            sizes.update(dW_gt=2 * E * E, dW_gv=2 * E * E)
+        pad = (-sum(sizes.values())) % 4
+        sizes["_pad2"] = pad
         self.zb = torch.zeros(sum(sizes.values()), dtype=F32, device=dev)
         self.z, off = {}, 0
         for k, n in sizes.items():
@@ -188,7 +242,7 @@ class HeadPlan:
             self.Y_lo = e(2 * B, self.P, dt=BF16)
             self.dY = e(2 * B, self.P, dt=BF16)      # gradients w.r.t. Y (GEMM operands, split hi/lo)
             self.dY_lo = e(2 * B, self.P, dt=BF16)
-            o["dW_t"], o["dW_v"] = e(self.P, E), e(self.P, E)
+            o["dW_t"], o["dW_v"] = self.z["dW_t"].view(self.P, E), self.z["dW_v"].view(self.P, E)
             o["d_t_pool"] = e(B, E)
         else:
             o["d_t_emb"], o["d_v_emb"] = e(B, self.Pe), e(B, self.Pe)
@@ -217,7 +271,7 @@ class HeadPlan:
         self.Xcat = e(R, 2 * E, dt=BF16)
         self.dXt = e(R, E)                            # gradient of the text half of Xcat (fp32)
         o["d_xt_cls"] = e(B, E)
-        o["dW_f"], o["db_f"] = e(E, 2 * E), self.z["db_f"]
+        o["dW_f"], o["db_f"] = self.z["dW_f"].view(E, 2 * E), self.z["db_f"]
         if self.fusion == "attention":
             Ea = E + 8
             self.Xcat_lo = torch.zeros(R, 2 * E, dtype=BF16, device=dev)   # text half stays 0 (inputs are exact)
@@ -226,15 +280,17 @@ class HeadPlan:
             self.dctx, self.dctx_lo, self.dxbar = e(R, E, dt=BF16), e(R, E, dt=BF16), e(R, E)
             self.dkq, self.dkq_lo = e(R, Ea, dt=BF16), e(R, Ea, dt=BF16)
             self.dq0, self.dq0_lo, self.dXt2 = e(R, E, dt=BF16), e(R, E, dt=BF16), e(R, E)
-            o["dW_Q"], o["db_Q"], o["dW_V"], o["db_V"] = e(E, E), self.z["db_Q"], e(E, E), self.z["db_V"]
-            self.dWK_aug = e(E, Ea)
+            o["dW_Q"], o["db_Q"] = self.z["dW_Q"].view(E, E), self.z["db_Q"]
+            o["dW_V"], o["db_V"] = self.z["dW_V"].view(E, E), self.z["db_V"]
+            self.dWK_aug = self.z["dWK_aug"].view(E, Ea)
             o["dW_K"], o["db_K"] = self.dWK_aug[:, :E], self.dWK_aug[:, E]
         if self.fusion == "gmu":
             self.tp, self.vp = e(R, 2 * E), e(R, 2 * E)
             self.G, self.G_lo, self.dG = e(R, 2 * E, dt=BF16), e(R, 2 * E, dt=BF16), e(R, 2 * E)
             self.dtp, self.dvp, self.dXg, self.dXt2 = e(R, 2 * E, dt=BF16), e(R, 2 * E, dt=BF16), e(R, 2 * E), e(R, E)
             self.dtp_lo, self.dvp_lo = e(R, 2 * E, dt=BF16), e(R, 2 * E, dt=BF16)
-            o["dW_gt"], o["db_gt"], o["dW_gv"], o["db_gv"] = e(2 * E, E), self.z["db_gt"], e(2 * E, E), self.z["db_gv"]
+            o["dW_gt"], o["db_gt"] = self.z["dW_gt"].view(2 * E, E), self.z["db_gt"]
+            o["dW_gv"], o["db_gv"] = self.z["dW_gv"].view(2 * E, E), self.z["db_gv"]
 
     # ------------------------------------------------------------------ weights
     def set_weights(self, p: Dict[str, torch.Tensor]):
@@ -290,12 +346,19 @@ class HeadPlan:
     def _itc_fwd(self, inp, with_loss=True):
         B, E, w, it = self.B, self.E, self.w, self.itc
         Yt, Yv, Ytl, Yvl = self._itc_operands(inp)
-        if self.P is not None:
-            tp_, vp_ = inp["t_pool"], inp["v_pool"]
-            gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)   # HF :265 text_projection
-            gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl)   # HF :262 visual_projection
         ldt, ldv = Yt.stride(0), Yv.stride(0)
-        it.norms(Yt, ldt, Yv, ldv, T_lo=Ytl, V_lo=Yvl)
+        br = self.br
+        br.enabled = self.parallel_streams
+        with br("v"):   # image tower branch: projection + row norms
+            if self.P is not None:
+                vp_ = inp["v_pool"]
+                gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl)   # HF :262 visual_projection
+            call("tic_row_rnorm_bf16", ptr(Yv), ptr(Yvl), ldv, B, it.P, ptr(it.rinv_v), _stream())
+        if self.P is not None:
+            tp_ = inp["t_pool"]
+            gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)       # HF :265 text_projection
+        call("tic_row_rnorm_bf16", ptr(Yt), ptr(Ytl), ldt, B, it.P, ptr(it.rinv_t), _stream())
+        br.join("v")
         it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl)
         if with_loss:
             it.lse_loss(self.scale, self.z["itc_sums"])
@@ -315,44 +378,75 @@ class HeadPlan:
             call("tic_itc_ds_operands", ptr(dS), dS.stride(0), B, B, ptr(it.rinv_t), ptr(it.rinv_v), ptr(it.GA), ptr(it.GA_lo),
                  it.ld_ga, ptr(it.GBT), ptr(it.GBT_lo), it.ld_gbt, _stream())
             dcoef = 0.0
-        it.grad_gemms(Yt, ldt, Yv, ldv, T_lo=Ytl, V_lo=Yvl)
+        br = self.br
+        br.enabled = self.parallel_streams
         if self.P is not None:
             dYt, dYv, dYt_lo, dYv_lo = self.dY[:B], self.dY[B:], self.dY_lo[:B], self.dY_lo[B:]
+            tp_, vp_ = inp["t_pool"], inp["v_pool"]
+            with br("v"):   # image-side gradient branch
+                it.grad_gemm_v(Yt, ldt, T_lo=Ytl)
+                it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, dcoef, None, dYv,
+                              dV_lo=dYv_lo, V_lo=Yvl, T_diag_lo=Ytl)
+                gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=True)
+            it.grad_gemm_t(Yv, ldv, V_lo=Yvl)
             it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, dcoef, None, dYt, z["r_sum"], dT_lo=dYt_lo, T_lo=Ytl,
                           V_diag_lo=Yvl)
-            it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, dcoef, None, dYv, dV_lo=dYv_lo,
-                          V_lo=Yvl, T_diag_lo=Ytl)
-            tp_, vp_ = inp["t_pool"], inp["v_pool"]
-            # dW_t[P,E] = dYt^T t_pool (both operands read MN-major), dW_v likewise; d_t_pool = dYt W_t
-            gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo)
-            gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo)
+            with br("w"):   # dW_t = dYt^T t_pool (both operands read MN-major)  ||  d_t_pool = dYt W_t
+                gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo, accumulate=True)
             gemm(dYt, self.P, 0, w["W_t"], E, 1, o["d_t_pool"], E, 0, B, E, self.P, A_lo=dYt_lo)
+            br.join("v")
+            br.join("w")
         else:
+            with br("v"):
+                it.grad_gemm_v(Yt, ldt, T_lo=Ytl)
+                it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, dcoef, o["d_v_emb"], None)
+            it.grad_gemm_t(Yv, ldv, V_lo=Yvl)
             it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, dcoef, o["d_t_emb"], None, z["r_sum"])
-            it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, dcoef, o["d_v_emb"], None)
+            br.join("v")
 
     def step(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Fused forward + losses + backward.  inp (device tensors): t_pool, v_pool bf16 [B,E]; x_t bf16 [B,Lt,E] or
         [B,1,E]; x_v bf16 [B,Lv,E]; y_soft fp32 [B,C]; class_w fp32 [C] (optional); ITM: u_coin,u_pick fp32 [B] (+ ids, mask
         int64 [B,Lt] to gather) or precomputed lbl_tim int64 [B] + src_idx int32 [B]; keep uint8 [B,E] + keep_scale
-        (dropout, optional)."""
-        B, z, o, st = self.B, self.z, self.out, _stream()
+        (dropout, optional).
+
+        The ITC chain and the fusion/heads chain are independent until the loss mix, so they are issued on two streams
+        (fork/join with events; captured as parallel branches of one CUDA graph) — the small-batch step is latency-bound."""
+        B, z, o = self.B, self.z, self.out
+        s0 = torch.cuda.current_stream()
         self.zb.zero_()
-        if self.use_itc:
-            self._itc_fwd(inp)
-        if self.fusion is not None:
-            if self.use_itm:
-                self._sample_itm(inp)
-            self._fusion_fwd(inp)
-            self._heads(inp, dH_f32=self.dHf if self.fusion == "aspect-att" else None)
-        call("tic_loss_mix", ptr(z["losses"]), ptr(z["itc_sums"]), getattr(self, "n_global", B),
-             self.beta_itc if self.fusion is not None else 1.0,
-             self.beta_itm, int(self.use_itc), int(self.use_itm), ptr(o["loss"]), st)
-        if self.fusion is not None:
-            self._fusion_bwd(inp)
-        if self.use_itc:
+        two = self.use_itc and self.fusion is not None and self.parallel_streams
+        if two:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            s1 = self._side
+            if self.itm_mode == 1:       # hard negatives read the materialised logits: sampling waits for the ITC tiles
+                self._itc_fwd(inp)
+            s1.wait_stream(s0)
+            with torch.cuda.stream(s1):
+                self._fusion_chain(inp)
+            if self.itm_mode != 1:
+                self._itc_fwd(inp)
             self._itc_bwd(inp)
+            s0.wait_stream(s1)
+        else:
+            if self.use_itc:
+                self._itc_fwd(inp)
+            if self.fusion is not None:
+                self._fusion_chain(inp)
+            if self.use_itc:
+                self._itc_bwd(inp)
+        call("tic_loss_mix", ptr(z["losses"]), ptr(z["itc_sums"]), getattr(self, "n_global", B),
+             self.beta_itc if self.fusion is not None else 1.0, self.beta_itm, int(self.use_itc), int(self.use_itm),
+             ptr(o["loss"]), _stream())
         return o
+
+    def _fusion_chain(self, inp):
+        if self.use_itm:
+            self._sample_itm(inp)
+        self._fusion_fwd(inp)
+        self._heads(inp, dH_f32=self.dHf if self.fusion == "aspect-att" else None)
+        self._fusion_bwd(inp)
 
     def forward(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Autograd mode, forward half: logits_per_text (materialised), mm_features, out_cls, out_tim.  ITM decisions come
@@ -466,9 +560,12 @@ class HeadPlan:
         X, Hin, Hin_lo = self.Xcat, self.Hin, self.Hin_lo
         # backward through linear_fusion (dH is a split bf16 pair: hi + lo)
         dH, dHl = self.dHb, self.dHb_lo
-        call("tic_colsum_bf16", ptr(dH), E, R, E, ptr(z["db_f"]), st)
-        call("tic_colsum_bf16", ptr(dHl), E, R, E, ptr(z["db_f"]), st)
-        gemm(dH, E, 1, Hin, E2, 1, o["dW_f"], E2, 0, E, E2, R, A_lo=dHl, B_lo=Hin_lo)               # dW_f = dH^T Hin
+        br = self.br
+        br.enabled = self.parallel_streams
+        with br("f"):   # parameter gradients of linear_fusion run beside the input-gradient chain
+            call("tic_colsum_bf16", ptr(dH), E, R, E, ptr(z["db_f"]), _stream())
+            call("tic_colsum_bf16", ptr(dHl), E, R, E, ptr(z["db_f"]), _stream())
+            gemm(dH, E, 1, Hin, E2, 1, o["dW_f"], E2, 0, E, E2, R, A_lo=dHl, B_lo=Hin_lo, accumulate=True)           # dW_f = dH^T Hin
         if self.fusion == "concat":
             gemm(dH, E, 0, w["W_f"], E2, 1, self.dXt, E, 0, R, E, E, A_lo=dHl)                      # dX_text = dH W_f[:, :E]
             call("tic_unpack_cls_grad", ptr(self.dXt), E, None, 0, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
@@ -478,16 +575,16 @@ class HeadPlan:
             gemm(dH, E, 0, w["W_f"].data_ptr() + 2 * E, E2, 1, self.dctx, E, 1, R, E, E, A_lo=dHl, D_lo=self.dctx_lo)
             call("tic_colsum_bf16", ptr(self.dctx), E, R, E, ptr(z["db_V"]), st)
             call("tic_colsum_bf16", ptr(self.dctx_lo), E, R, E, ptr(z["db_V"]), st)
-            gemm(self.dctx, E, 1, self.xbar_b, E, 1, o["dW_V"], E, 0, E, E, R, A_lo=self.dctx_lo, B_lo=self.xbar_lo)
+            gemm(self.dctx, E, 1, self.xbar_b, E, 1, o["dW_V"], E, 0, E, E, R, A_lo=self.dctx_lo, B_lo=self.xbar_lo, accumulate=True)
             gemm(self.dctx, E, 0, w["W_V"], E, 1, self.dxbar, E, 0, R, E, E, A_lo=self.dctx_lo)
             call("tic_attn_pool_bwd", ptr(x_v), x_v.stride(0), x_v.stride(1), ptr(self.attn), Lv, ptr(self.dxbar), E,
                  ptr(self.xbar_f), E, B, 2 if self.use_itm else 1, Lv, E, float(E) ** -0.5, ptr(self.dkq), ptr(self.dkq_lo),
                  Ea, st)
             gemm(self.dkq, Ea, 0, w["W_Kaug"], Ea, 0, self.dq0, E, 1, R, E, Ea, A_lo=self.dkq_lo, D_lo=self.dq0_lo)
-            gemm(self.q0, E, 1, self.dkq, Ea, 1, self.dWK_aug, Ea, 0, E, Ea, R, A_lo=self.q0_lo, B_lo=self.dkq_lo)  # [dW_K|db_K]
+            gemm(self.q0, E, 1, self.dkq, Ea, 1, self.dWK_aug, Ea, 0, E, Ea, R, A_lo=self.q0_lo, B_lo=self.dkq_lo, accumulate=True)  # [dW_K|db_K]
             call("tic_colsum_bf16", ptr(self.dq0), E, R, E, ptr(z["db_Q"]), st)
             call("tic_colsum_bf16", ptr(self.dq0_lo), E, R, E, ptr(z["db_Q"]), st)
-            gemm(self.dq0, E, 1, X, E2, 1, o["dW_Q"], E, 0, E, E, R, A_lo=self.dq0_lo)
+            gemm(self.dq0, E, 1, X, E2, 1, o["dW_Q"], E, 0, E, E, R, A_lo=self.dq0_lo, accumulate=True)
             gemm(self.dq0, E, 0, w["W_Q"], E, 1, self.dXt2, E, 0, R, E, E, A_lo=self.dq0_lo)
             call("tic_unpack_cls_grad", ptr(self.dXt), E, ptr(self.dXt2), E, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
         elif self.fusion == "gmu":
@@ -496,10 +593,11 @@ class HeadPlan:
                  ptr(self.dvp), ptr(self.dtp_lo), ptr(self.dvp_lo), E2, ptr(self.dXg), E2, st)
             for buf, acc in ((self.dtp, "db_gt"), (self.dtp_lo, "db_gt"), (self.dvp, "db_gv"), (self.dvp_lo, "db_gv")):
                 call("tic_colsum_bf16", ptr(buf), E2, R, E2, ptr(z[acc]), st)
-            gemm(self.dtp, E2, 1, X, E2, 1, o["dW_gt"], E, 0, E2, E, R, A_lo=self.dtp_lo)
-            gemm(self.dvp, E2, 1, X.data_ptr() + 2 * E, E2, 1, o["dW_gv"], E, 0, E2, E, R, A_lo=self.dvp_lo)
+            gemm(self.dtp, E2, 1, X, E2, 1, o["dW_gt"], E, 0, E2, E, R, A_lo=self.dtp_lo, accumulate=True)
+            gemm(self.dvp, E2, 1, X.data_ptr() + 2 * E, E2, 1, o["dW_gv"], E, 0, E2, E, R, A_lo=self.dvp_lo, accumulate=True)
             gemm(self.dtp, E2, 0, w["W_gt"], E, 1, self.dXt2, E, 0, R, E, E2, A_lo=self.dtp_lo)
             call("tic_unpack_cls_grad", ptr(self.dXg), E2, ptr(self.dXt2), E, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
+        br.join("f")
 
 class HostStep:
     """Host-facing entry point: takes the step's inputs as HOST tensors (what a reference-side caller holds), stages them

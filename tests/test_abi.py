@@ -40,11 +40,12 @@ def test_version_and_error_string_without_gpu(lib_path):
     lib = capi.load()
     assert lib.tic_version() >= 100
     assert isinstance(capi.last_error(), str)
-    assert lib.tic_itc_row_parts(1000) == 8 and lib.tic_itc_col_parts(1000) == 8
+    assert lib.tic_itc_row_parts(1000) == 32 and lib.tic_itc_col_parts(1000) == 8   # 64-wide tiles below 2048 columns
+    assert lib.tic_itc_row_parts(4096) == 32                                           # 256-wide tiles above
     assert lib.tic_ce_bidir_workspace_bytes(128) > 0
     # argument validation happens before any CUDA call, so error codes are observable on a CPU-only box
     with pytest.raises(capi.TicError):
-        capi.call("tic_gemm_bf16", None, None, 8, 0, None, None, 8, 0, None, None, 8, 0, 16, 16, 16, 1.0, None, 0, None)
+        capi.call("tic_gemm_bf16", None, None, 8, 0, None, None, 8, 0, None, None, 8, 0, 16, 16, 16, 1.0, None, 0, 0, None)
     assert "null pointer" in capi.last_error()
 
 
