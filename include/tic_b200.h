@@ -65,7 +65,7 @@ int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn_major, const void* B
  * rinv[i] = 1 / ||X[i,:]||_2 (no epsilon, as HF modeling_vision_text_dual_encoder.py:268-269 and
  * mm_early.py:98-99).  X bf16 [rows, cols]. */
 int tic_row_rnorm_bf16(const void* X, const void* X_lo /* optional residual: norm of hi+lo */, int64_t ldx, int rows, int cols,
-                       float* rinv, void* stream);
+                       float* rinv, void* Xhat /* optional normalised bf16 copy [rows, ldh] */, int64_t ldh, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ ITC (fused)
  * Logits S[i,j] = scale * rinv_t[i] * rinv_v[j] * <T[i,:], V[j,:]>  (HF :272-273; mm_early.py:101-102), never
@@ -96,7 +96,10 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
 /* Recompute S tiles and emit the bf16 gradient operands (g = dLoss/d(clip_loss), B = n_global):
  *   Gp[i,j] = g/(2B) * (exp(S-lse_row[i]) + exp(S-lse_col[j]))      (the -I/B diagonal is applied in fp32 later)
  *   GA [m_local, ld_ga ] row-major:  Gp[i,j] * rinv_v[j]            (A operand of dT = GA * V)
- *   GBT[n_global, ld_gbt] row-major: Gp[i,j] * rinv_t[i] at [j,i]   (A operand of dV = GBT * T) */
+ *   GBT[n_global, ld_gbt] row-major: Gp[i,j] * rinv_t[i] at [j,i]   (A operand of dV = GBT * T)
+ * GBT may be NULL ("GA-shared" mode, used from 4096 columns on): the image-side gradient is then computed as
+ *   dV_acc'[j,:] = sum_i GA[i,j] * That[i,:]  (GA read MN-major, That = normalised bf16 text embeddings from
+ *   tic_row_rnorm_bf16), which equals rinv_v[j] * dV_acc[j,:]; tic_itc_grad_finalize(acc_div_rinv=1) divides it out. */
 int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv,
                   const float* rinv_t, const float* rinv_v,
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale,
@@ -114,7 +117,9 @@ int tic_itc_ds_operands(const float* dS, int64_t ldds, int m_local, int n_global
 int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const void* X_lo, int64_t ldx, const float* rinv,
                           const void* Xo, const void* Xo_lo, int64_t ldxo, const float* rinv_o, int rows, int P, float scale,
                           float diag_coef, float* dX_f32, int64_t ld_df, void* dX_bf16, void* dX_bf16_lo, int64_t ld_db,
-                          float* r_sum /* [1], atomically accumulated */, void* stream);
+                          float* r_sum /* [1], atomically accumulated */,
+                          int acc_div_rinv /* 1: acc rows carry an extra factor rinv[row] (GA-shared mode, see tic_itc_bwd_g) */,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------ clip_loss on a given matrix
  * utils.py:225-231 on a materialised similarity S [B,B] fp32: loss = (CE(S, I) + CE(S^T, I)) / 2.

@@ -21,7 +21,7 @@ _SIGS = {
     "tic_sm_count": ("", ctypes.c_int),
     "tic_gemm_bf16": ("pplipplippliiiifpiip", ctypes.c_int),
     "tic_gemm_bf16_simt": ("pliplipliiiifpip", ctypes.c_int),
-    "tic_row_rnorm_bf16": ("ppliipp", ctypes.c_int),
+    "tic_row_rnorm_bf16": ("ppliipplp", ctypes.c_int),
     "tic_itc_row_parts": ("i", ctypes.c_int),
     "tic_itc_col_parts": ("i", ctypes.c_int),
     "tic_itc_fwd": ("pplpplppiiiiffpppplp", ctypes.c_int),
@@ -29,7 +29,7 @@ _SIGS = {
     "tic_itc_lse_loss": ("pipipiiifpppp", ctypes.c_int),
     "tic_itc_bwd_g": ("pplpplppppiiiffplplppp", ctypes.c_int),
     "tic_itc_ds_operands": ("pliipppplpplp", ctypes.c_int),
-    "tic_itc_grad_finalize": ("plpplppplpiiffplpplpp", ctypes.c_int),
+    "tic_itc_grad_finalize": ("plpplppplpiiffplpplpip", ctypes.c_int),
     "tic_ce_bidir_workspace_bytes": ("i", ctypes.c_int64),
     "tic_ce_bidir_fwd": ("plippppp", ctypes.c_int),
     "tic_ce_bidir_bwd": ("plipppplp", ctypes.c_int),

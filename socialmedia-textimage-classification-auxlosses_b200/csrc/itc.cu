@@ -9,6 +9,7 @@
 // Softmax statistics use the fixed shift `shift >= max S` (= scale, because |cos| <= 1), which turns both the row and
 // the column log-sum-exp into plain sums: per-tile partial sums are written out and reduced in a fixed order
 // (deterministic; across ranks it is a SUM all-reduce).
+#include <cstdlib>
 #include "common.cuh"
 #include "tic_umma.cuh"
 
@@ -18,6 +19,12 @@ constexpr int kItcBN = 256;        // wide tiles: best tensor-pipe efficiency at
 constexpr int kItcBNSmall = 64;    // narrow tiles below kItcSmallN columns: 4x more CTAs for the latency-bound small batch
 constexpr int kItcSmallN = 2048;
 inline int itc_bn(int n_global) { return n_global <= kItcSmallN ? kItcBNSmall : kItcBN; }
+// TIC_ITC_MULTICAST=0 disables the 2-CTA TMA-multicast variant (A/B measurement switch, not a fallback).
+inline bool itc_multicast() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIC_ITC_MULTICAST"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 constexpr int kItcEpiWarps = 8;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -90,14 +97,20 @@ struct ItcFwdEpi {
     const int gcol = p.row_offset + row;  // column holding this row's positive
     const int cols_per_part = BN / cx.nparts;
     float rowsum = 0.f;
+    const uint32_t trow = cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16);
+    const int nchunk = cols_per_part / 32;
+    uint32_t vn[32];
+    if (cx.n0 + cx.part * cols_per_part < cx.N) tmem_ld_32x32(trow + cx.part * cols_per_part, vn);
 #pragma unroll 1
-    for (int c = 0; c < cols_per_part / 32; ++c) {
+    for (int c = 0; c < nchunk; ++c) {
       const int cl = cx.part * cols_per_part + c * 32;
       const int col0 = cx.n0 + cl;
       if (col0 >= cx.N) break;  // warp-uniform
       uint32_t v[32];
-      tmem_ld_32x32(cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16) + cl, v);
       tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = vn[j];
+      if (c + 1 < nchunk && col0 + 32 < cx.N) tmem_ld_32x32(trow + cl + 32, vn);   // prefetch the next 32 columns
       float e[32];
       float dsel = 0.f;
 #pragma unroll
@@ -168,23 +181,29 @@ struct ItcBwdEpi {
     const float lr = valid_row ? __ldg(p.lse_row + row) * kLog2e : 0.f;
     const int cols_per_part = BN / cx.nparts;
     const bool vec_ok = (p.ld_ga & 7) == 0;
+    const uint32_t trow = cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16);
+    const int nchunk = cols_per_part / 32;
+    uint32_t vn[32];
+    if (cx.n0 + cx.part * cols_per_part < cx.N) tmem_ld_32x32(trow + cx.part * cols_per_part, vn);
 #pragma unroll 1
-    for (int c = 0; c < cols_per_part / 32; ++c) {
+    for (int c = 0; c < nchunk; ++c) {
       const int cl = cx.part * cols_per_part + c * 32;
       const int col0 = cx.n0 + cl;
       if (col0 >= cx.N) break;
       uint32_t v[32];
-      tmem_ld_32x32(cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16) + cl, v);
       tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = vn[j];
+      if (c + 1 < nchunk && col0 + 32 < cx.N) tmem_ld_32x32(trow + cl + 32, vn);   // prefetch the next 32 columns
       float ga[32];
-      __nv_bfloat16* gbt = p.GBT + static_cast<int64_t>(col0) * p.ld_gbt + row;
-      __nv_bfloat16* gbt_lo = p.GBT_lo ? p.GBT_lo + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
+      __nv_bfloat16* gbt = p.GBT ? p.GBT + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
+      __nv_bfloat16* gbt_lo = (p.GBT && p.GBT_lo) ? p.GBT_lo + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float s2 = __uint_as_float(v[j]) * rt * sb[cl + j] * p.scale_log2e;  // S * log2e
         const float pr = p.gscale * (exp2f(s2 - lr) + exp2f(s2 - sl[cl + j]));
         ga[j] = pr * sb[cl + j];
-        if (valid_row && col0 + j < cx.N) {
+        if (gbt != nullptr && valid_row && col0 + j < cx.N) {
           const float gb = pr * rt;
           const __nv_bfloat16 hi = __float2bfloat16_rn(gb);
           gbt[static_cast<int64_t>(j) * p.ld_gbt] = hi;
@@ -236,7 +255,7 @@ struct ItcBwdEpi {
 // ------------------------------------------------------------------ small HBM-bound kernels
 // rinv[i] = 1/||X[i,:]||  — one warp per row, 16-byte loads when aligned.
 __global__ void row_rnorm_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ X_lo, int64_t ldx, int rows,
-                                 int cols, float* __restrict__ rinv) {
+                                 int cols, float* __restrict__ rinv, __nv_bfloat16* __restrict__ Xhat, int64_t ldh) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const __nv_bfloat16* x = X + static_cast<int64_t>(warp) * ldx;
@@ -265,7 +284,12 @@ __global__ void row_rnorm_kernel(const __nv_bfloat16* __restrict__ X, const __nv
     }
   }
   ss = warp_sum(ss);
-  if (lane == 0) rinv[warp] = 1.0f / sqrtf(ss);  // no epsilon (HF :268-269)
+  const float ri = 1.0f / sqrtf(ss);  // no epsilon (HF :268-269)
+  if (lane == 0) rinv[warp] = ri;
+  if (Xhat != nullptr) {               // normalised bf16 copy: B operand of the image-side gradient GEMM at large batch
+    __nv_bfloat16* h = Xhat + static_cast<int64_t>(warp) * ldh;
+    for (int c = lane; c < cols; c += 32) h[c] = __float2bfloat16_rn(ri * __bfloat162float(x[c]));
+  }
 }
 
 __global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
@@ -322,7 +346,7 @@ __global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t 
                                          int64_t ldxo, const float* __restrict__ rinv_o, int rows, int P, float scale,
                                          float diag_coef, float* __restrict__ dXf, int64_t ld_df,
                                          __nv_bfloat16* __restrict__ dXb, __nv_bfloat16* __restrict__ dXb_lo, int64_t ld_db,
-                                         float* __restrict__ r_sum) {
+                                         float* __restrict__ r_sum, int acc_div_rinv) {
   const int warp_in_blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp_in_blk;
   __shared__ float sblk[32];
@@ -330,6 +354,7 @@ __global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t 
   if (row < rows) {
     const float ri = rinv[row];
     const float co = (Xo != nullptr && diag_coef != 0.f) ? diag_coef * rinv_o[row] : 0.f;
+    const float asc = acc_div_rinv ? 1.0f / ri : 1.0f;   // accumulator carries an extra factor rinv[row] (GA-shared mode)
     const float* a = acc + static_cast<int64_t>(row) * ld_acc;
     const __nv_bfloat16* x = X + static_cast<int64_t>(row) * ldx;
     const __nv_bfloat16* xo = Xo ? Xo + static_cast<int64_t>(row) * ldxo : nullptr;
@@ -338,12 +363,12 @@ __global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t 
     auto xval = [&](int k) { return __bfloat162float(x[k]) + (xl ? __bfloat162float(xl[k]) : 0.f); };
     auto xoval = [&](int k) { return __bfloat162float(xo[k]) + (xol ? __bfloat162float(xol[k]) : 0.f); };
     for (int k = lane; k < P; k += 32) {
-      const float dxh = scale * (a[k] - (xo ? co * xoval(k) : 0.f));
+      const float dxh = scale * (a[k] * asc - (xo ? co * xoval(k) : 0.f));
       r = fmaf(ri * xval(k), dxh, r);
     }
     r = warp_sum(r);
     for (int k = lane; k < P; k += 32) {
-      const float dxh = scale * (a[k] - (xo ? co * xoval(k) : 0.f));
+      const float dxh = scale * (a[k] * asc - (xo ? co * xoval(k) : 0.f));
       const float xh = ri * xval(k);
       const float g = ri * (dxh - xh * r);
       if (dXf) dXf[static_cast<int64_t>(row) * ld_df + k] = g;
@@ -408,11 +433,13 @@ extern "C" {
 int tic_itc_row_parts(int n_global) { return ceil_div(n_global, itc_bn(n_global)) * (kItcEpiWarps / 4); }
 int tic_itc_col_parts(int m_local) { return ceil_div(m_local, kBM); }
 
-int tic_row_rnorm_bf16(const void* X, const void* X_lo, int64_t ldx, int rows, int cols, float* rinv, void* stream) {
+int tic_row_rnorm_bf16(const void* X, const void* X_lo, int64_t ldx, int rows, int cols, float* rinv, void* Xhat, int64_t ldh,
+                       void* stream) {
   TIC_CHECK_ARG(X && rinv && rows > 0 && cols > 0, "tic_row_rnorm_bf16: bad arguments");
   const int wpb = 8;
   row_rnorm_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(X_lo), ldx, rows, cols, rinv);
+      static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(X_lo), ldx, rows, cols, rinv,
+      static_cast<__nv_bfloat16*>(Xhat), ldh);
   TIC_CHECK_LAUNCH("tic_row_rnorm_bf16");
   return TIC_OK;
 }
@@ -430,7 +457,10 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
   }
   ItcFwdEpi::Params ep{rinv_t, rinv_v, scale * kLog2e, shift * kLog2e, scale, row_part, col_part, diag, logits_out, ld_logits,
                        row_offset};
-  int rc = itc_bn(n_global) == kItcBN
+  const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
+  int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, ldt, V, ldv, m_local, n_global, P, ep,
+                                                                                        static_cast<cudaStream_t>(stream))
+           : itc_bn(n_global) == kItcBN
                ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
                                                                                 P, ep, static_cast<cudaStream_t>(stream), 1)
                : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
@@ -466,12 +496,15 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
                   const float* rinv_t, const float* rinv_v,
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale, float gscale,
                   void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo, void* GBT_lo, void* stream) {
-  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && lse_row && lse_col && GA && GBT, "tic_itc_bwd_g: null pointer");
+  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && lse_row && lse_col && GA, "tic_itc_bwd_g: null pointer");
   TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_bwd_g: empty problem");
   ItcBwdEpi::Params ep{rinv_t, rinv_v, lse_row, lse_col, scale * kLog2e, gscale, static_cast<__nv_bfloat16*>(GA), ld_ga,
                        static_cast<__nv_bfloat16*>(GBT), ld_gbt, static_cast<__nv_bfloat16*>(GA_lo),
                        static_cast<__nv_bfloat16*>(GBT_lo)};
-  int rc = itc_bn(n_global) == kItcBN
+  const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
+  int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, ldt, V, ldv, m_local, n_global, P, ep,
+                                                                                        static_cast<cudaStream_t>(stream))
+           : itc_bn(n_global) == kItcBN
                ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
                                                                                 P, ep, static_cast<cudaStream_t>(stream), 1)
                : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
@@ -484,7 +517,8 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
 
 int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const void* X_lo, int64_t ldx, const float* rinv,
                           const void* Xo, const void* Xo_lo, int64_t ldxo, const float* rinv_o, int rows, int P, float scale, float diag_coef, float* dX_f32,
-                          int64_t ld_df, void* dX_bf16, void* dX_bf16_lo, int64_t ld_db, float* r_sum, void* stream) {
+                          int64_t ld_df, void* dX_bf16, void* dX_bf16_lo, int64_t ld_db, float* r_sum, int acc_div_rinv,
+                          void* stream) {
   TIC_CHECK_ARG(acc && X && rinv && rows > 0 && P > 0, "tic_itc_grad_finalize: bad arguments");
   TIC_CHECK_ARG(dX_f32 || dX_bf16, "tic_itc_grad_finalize: no output requested");
   const int wpb = 8;
@@ -492,7 +526,7 @@ int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const
       acc, ld_acc, static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(X_lo), ldx, rinv,
       static_cast<const __nv_bfloat16*>(Xo), static_cast<const __nv_bfloat16*>(Xo_lo), ldxo, rinv_o,
       rows, P, scale, diag_coef, dX_f32, ld_df, static_cast<__nv_bfloat16*>(dX_bf16), static_cast<__nv_bfloat16*>(dX_bf16_lo), ld_db,
-      r_sum);
+      r_sum, acc_div_rinv);
   TIC_CHECK_LAUNCH("tic_itc_grad_finalize");
   return TIC_OK;
 }

@@ -50,11 +50,16 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
+// CLUSTER = 2: two CTAs of a cluster work on M-adjacent tiles of the same N block and SHARE the B tile — each loads half
+// of it and TMA-multicasts it into both CTAs' shared memory (operand traffic from L2 per tile drops by 1/3 for 128x256
+// tiles; the K=768 similarity tiles are L2-bandwidth-bound otherwise).  Stage release is a multicast tcgen05.commit to
+// the `empty` barrier of both CTAs.  In that mode tmap_b_lo holds the half-height box map of B (no split operands).
+template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi, int CLUSTER = 1>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int ksplit,
                  int M, int N, int K, typename Epi::Params ep) {
+  static_assert(CLUSTER == 1 || (CLUSTER == 2 && BN >= 128), "cluster multicast needs BN >= 128");
   using Cfg = UmmaCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps must cover the 4 TMEM lane quadrants");
@@ -81,7 +86,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // D = A_hi*B_hi (+ A_lo*B_hi) (+ A_hi*B_lo) accumulates in TMEM with ~16 mantissa bits per split operand.
   const int nseg = 1 + (split & 1) + ((split >> 1) & 1);
   const int total_kb = num_kb * nseg;
-  const int num_items = num_tiles * ksplit;   // work item = (tile, K-slice)
+  // work item = (tile, K-slice); in cluster mode an item is a PAIR of M-adjacent tiles, one per CTA of the cluster
+  const int m_groups = (m_tiles + CLUSTER - 1) / CLUSTER;
+  const int num_items = (CLUSTER == 1 ? num_tiles : m_groups * n_tiles) * ksplit;
+  const uint32_t crank = CLUSTER == 1 ? 0u : cluster_ctarank();
+  const int worker = CLUSTER == 1 ? blockIdx.x : blockIdx.x / CLUSTER;
+  const int nworkers = CLUSTER == 1 ? gridDim.x : gridDim.x / CLUSTER;
+  auto tile_of = [&](int item, int& m_blk, int& n_blk) {
+    m_blk = (item / n_tiles) * CLUSTER + static_cast<int>(crank);
+    n_blk = item % n_tiles;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -90,7 +104,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (split & 2) tma_prefetch_desc(&tmap_b_lo);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CLUSTER);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -101,6 +115,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CLUSTER > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -109,9 +124,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+      for (int w = worker; w < num_items; w += nworkers) {
         const int t = w / ksplit, ks = w - t * ksplit;
-        const int m0 = (t / n_tiles) * kBM, n0 = (t % n_tiles) * BN;
+        int m_blk, n_blk;
+        tile_of(t, m_blk, n_blk);
+        const int m0 = m_blk * kBM, n0 = n_blk * BN;
         const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / ksplit);
         const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / ksplit);
         for (int kt = kt_begin; kt < kt_end; ++kt) {
@@ -131,7 +148,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tma_load_2d(sa, ta, full_bar(s), m0, k0);
             tma_load_2d(sa + 8192, ta, full_bar(s), m0 + 64, k0);
           }
-          if constexpr (!B_MN) {
+          if constexpr (CLUSTER == 2) {
+            // my half of the shared B tile, multicast into both CTAs of the pair
+            if constexpr (!B_MN) {
+              tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tmap_b_lo, full_bar(s), k0, n0 + static_cast<int>(crank) * (BN / 2),
+                             uint16_t(3));
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {
+                const int bi = static_cast<int>(crank) * (BN / 128) + i;
+                tma_load_2d_mc(sb + bi * 8192, tb, full_bar(s), n0 + bi * 64, k0, uint16_t(3));
+              }
+            }
+          } else if constexpr (!B_MN) {
             tma_load_2d(sb, tb, full_bar(s), k0, n0);
           } else {
 #pragma unroll
@@ -151,7 +180,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t a_kadv = (A_MN ? 2048u : 32u) >> 4, b_kadv = (B_MN ? 2048u : 32u) >> 4;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+      for (int w = worker; w < num_items; w += nworkers) {
         const int ks = w % ksplit;
         const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / ksplit);
         const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / ksplit);
@@ -168,7 +197,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < kBK / kUmmaK; ++k)
             umma_bf16(d_tmem, da + static_cast<uint64_t>(k * a_kadv), db + static_cast<uint64_t>(k * b_kadv), idesc,
                       (kb | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(s));
+          if constexpr (CLUSTER == 2) umma_commit_mc(empty_bar(s), uint16_t(3));   // frees the stage in both CTAs
+          else umma_commit(empty_bar(s));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         umma_commit(tfull_bar(as));
@@ -188,15 +218,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int as = 0;
     uint32_t aph = 0;
     cx.iter = 0;
-    for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+    for (int w = worker; w < num_items; w += nworkers) {
       const int t = w / ksplit;
       cx.ks = w - t * ksplit; cx.ksplit = ksplit;
-      cx.m_blk = t / n_tiles; cx.n_blk = t % n_tiles;
+      tile_of(t, cx.m_blk, cx.n_blk);
       cx.m0 = cx.m_blk * kBM; cx.n0 = cx.n_blk * BN;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       cx.tmem_acc = tmem_base + as * BN;
-      Epi::template tile<BN>(ep, cx);
+      if (cx.m0 < M) Epi::template tile<BN>(ep, cx);   // the odd tail tile of a cluster pair has no rows
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -207,6 +237,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CLUSTER > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -262,6 +293,50 @@ int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B
   if (grid > cap) grid = cap;
   kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// Cluster (TMA multicast) launch: pairs of M-adjacent tiles share B. No split operands, no split-K.
+template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
+int launch_umma_gemm_cluster2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                              const typename Epi::Params& ep, cudaStream_t stream) {
+  using Cfg = UmmaCfg<BN>;
+  if (M <= 0 || N <= 0 || K <= 0) return -1;
+  CUtensorMap ta, tb, tb_half;
+  int rc;
+  rc = !A_MN ? make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM)
+             : make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, kBK);
+  if (rc) return rc;
+  rc = !B_MN ? make_tmap_bf16_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, BN)
+             : make_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kBK);
+  if (rc) return rc;
+  rc = !B_MN ? make_tmap_bf16_2d(&tb_half, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, BN / 2)
+             : make_tmap_bf16_2d(&tb_half, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kBK);
+  if (rc) return rc;
+  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI_WARPS, Epi, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return -3;
+    attr_set = true;
+  }
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
+  const int items = ((m_tiles + 1) / 2) * n_tiles;
+  int clusters = device_sm_count() / 2;
+  if (clusters > items) clusters = items;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(64 + 32 * EPI_WARPS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int split = 0, ksplit = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta, tb, tb_half, split, ksplit, M, N, K, ep);
+  return e == cudaSuccess ? 0 : -4;
 }
 
 // hi/lo split of an fp32 value into two bf16: hi = rn(x), lo = rn(x - hi)  (hi + lo carries ~16 mantissa bits)

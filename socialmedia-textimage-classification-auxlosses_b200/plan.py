@@ -99,19 +99,29 @@ class ItcPlan:
         self.lse_col = torch.empty(n, dtype=F32, device=dev)
         self.ld_ga, self.ld_gbt = _up8(n), _up8(m)
         self.GA = torch.empty(m, self.ld_ga, dtype=BF16, device=dev)
-        self.GBT = torch.empty(n, self.ld_gbt, dtype=BF16, device=dev) if need_dv else None
+        # precise (small batch): separate transposed operand GBT with residuals.  Otherwise "GA-shared": the image-side
+        # gradient GEMM reads GA MN-major against a normalised bf16 copy of the text embeddings (no GBT at all).
+        self.shared_ga = need_dv and not self.precise
+        self.GBT = torch.empty(n, self.ld_gbt, dtype=BF16, device=dev) if (need_dv and self.precise) else None
         self.GA_lo = torch.empty(m, self.ld_ga, dtype=BF16, device=dev) if self.precise else None
         self.GBT_lo = torch.empty(n, self.ld_gbt, dtype=BF16, device=dev) if (need_dv and self.precise) else None
+        self.That = torch.empty(m, P, dtype=BF16, device=dev) if self.shared_ga else None
         self.acc_t = torch.empty(m, P, dtype=F32, device=dev)
         self.acc_v = torch.empty(n, P, dtype=F32, device=dev) if need_dv else None
         self.logits = torch.empty(m, n, dtype=F32, device=dev) if materialize_logits else None
         self.need_dv = need_dv
 
     # -- pieces (the distributed path interleaves collectives between them) --
+    def norm_t(self, T, ldt, T_lo=None):
+        call("tic_row_rnorm_bf16", ptr(T), ptr(T_lo), ldt, self.m, self.P, ptr(self.rinv_t), ptr(self.That), self.P, _stream())
+
+    def norm_v(self, V, ldv, V_lo=None):
+        call("tic_row_rnorm_bf16", ptr(V), ptr(V_lo), ldv, self.n, self.P, ptr(self.rinv_v), None, 0, _stream())
+
     def norms(self, T, ldt, V, ldv, t_only=False, T_lo=None, V_lo=None):
-        call("tic_row_rnorm_bf16", ptr(T), ptr(T_lo), ldt, self.m, self.P, ptr(self.rinv_t), _stream())
+        self.norm_t(T, ldt, T_lo=T_lo)
         if not t_only:
-            call("tic_row_rnorm_bf16", ptr(V), ptr(V_lo), ldv, self.n, self.P, ptr(self.rinv_v), _stream())
+            self.norm_v(V, ldv, V_lo=V_lo)
 
     def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None):
         call("tic_itc_fwd", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), self.m, self.n, self.P,
@@ -125,19 +135,22 @@ class ItcPlan:
              self.row_offset, float(scale), ptr(self.lse_row), ptr(self.lse_col), ptr(loss_sums), _stream())
 
     def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None):
-        assert self.GBT is not None or not self.need_dv
         call("tic_itc_bwd_g", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), ptr(self.lse_row),
              ptr(self.lse_col), self.m, self.n, self.P, float(scale), float(gscale), ptr(self.GA), self.ld_ga,
-             ptr(self.GBT) if self.GBT is not None else ptr(self.GA), self.ld_gbt if self.GBT is not None else self.ld_ga,
-             ptr(self.GA_lo), ptr(self.GBT_lo), _stream())
+             ptr(self.GBT), self.ld_gbt, ptr(self.GA_lo), ptr(self.GBT_lo), _stream())
 
     def grad_gemm_t(self, V, ldv, V_lo=None):
         # dT_acc[m,P] = GA[m,n] * V[n,P]   (A K-major, B = V read MN-major: no transposed copy of V)
         gemm(self.GA, self.ld_ga, 0, V, ldv, 1, self.acc_t, self.P, 0, self.m, self.P, self.n, A_lo=self.GA_lo, B_lo=V_lo)
 
     def grad_gemm_v(self, T, ldt, T_lo=None):
-        # dV_acc[n,P] = GBT[n,m] * T[m,P]
-        gemm(self.GBT, self.ld_gbt, 0, T, ldt, 1, self.acc_v, self.P, 0, self.n, self.P, self.m, A_lo=self.GBT_lo, B_lo=T_lo)
+        if self.shared_ga:
+            # dV_acc'[n,P] = GA^T[n,m] * That[m,P]: GA is read MN-major (no transposed operand in HBM); rows carry rinv_v[j]
+            gemm(self.GA, self.ld_ga, 1, self.That, self.P, 1, self.acc_v, self.P, 0, self.n, self.P, self.m)
+        else:
+            # dV_acc[n,P] = GBT[n,m] * T[m,P]
+            gemm(self.GBT, self.ld_gbt, 0, T, ldt, 1, self.acc_v, self.P, 0, self.n, self.P, self.m, A_lo=self.GBT_lo,
+                 B_lo=T_lo)
 
     def grad_gemms(self, T, ldt, V, ldv, T_lo=None, V_lo=None):
         self.grad_gemm_t(V, ldv, V_lo=V_lo)
@@ -149,14 +162,14 @@ class ItcPlan:
         call("tic_itc_grad_finalize", ptr(self.acc_t), self.P, ptr(T), ptr(T_lo), ldt, ptr(self.rinv_t), ptr(V_diag),
              ptr(V_diag_lo), ldv,
              ptr(rinv_v_diag), self.m, self.P, float(scale), float(diag_coef), ptr(dT_f32), self.P, ptr(dT_bf16), ptr(dT_lo),
-             self.P, ptr(r_sum), _stream())
+             self.P, ptr(r_sum), 0, _stream())
 
     def finalize_v(self, acc_v, V, ldv, rinv_v, T_diag, ldt, rinv_t_diag, rows, scale, diag_coef, dV_f32, dV_bf16,
                    dV_lo=None, V_lo=None, T_diag_lo=None):
         call("tic_itc_grad_finalize", ptr(acc_v), self.P, ptr(V), ptr(V_lo), ldv, ptr(rinv_v), ptr(T_diag), ptr(T_diag_lo),
              ldt, ptr(rinv_t_diag),
              rows, self.P, float(scale), float(diag_coef), ptr(dV_f32), self.P, ptr(dV_bf16), ptr(dV_lo), self.P, None,
-             _stream())
+             1 if self.shared_ga else 0, _stream())
 
     # -- single-GPU convenience: full forward + backward --
     def run(self, T, V, scale, g, loss_sums, r_sum, dT_f32=None, dT_bf16=None, dV_f32=None, dV_bf16=None):
@@ -353,11 +366,11 @@ class HeadPlan:
             if self.P is not None:
                 vp_ = inp["v_pool"]
                 gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl)   # HF :262 visual_projection
-            call("tic_row_rnorm_bf16", ptr(Yv), ptr(Yvl), ldv, B, it.P, ptr(it.rinv_v), _stream())
+            it.norm_v(Yv, ldv, V_lo=Yvl)
         if self.P is not None:
             tp_ = inp["t_pool"]
             gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)       # HF :265 text_projection
-        call("tic_row_rnorm_bf16", ptr(Yt), ptr(Ytl), ldt, B, it.P, ptr(it.rinv_t), _stream())
+        it.norm_t(Yt, ldt, T_lo=Ytl)
         br.join("v")
         it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl)
         if with_loss:
@@ -375,6 +388,7 @@ class HeadPlan:
             it.bwd_operands(Yt, ldt, Yv, ldv, self.scale, g / (2.0 * B), T_lo=Ytl, V_lo=Yvl)
             dcoef = g / B
         else:
+            assert it.precise, "autograd mode (materialised dS) is meant for drop-in batch sizes (< 4096)"
             call("tic_itc_ds_operands", ptr(dS), dS.stride(0), B, B, ptr(it.rinv_t), ptr(it.rinv_v), ptr(it.GA), ptr(it.GA_lo),
                  it.ld_ga, ptr(it.GBT), ptr(it.GBT_lo), it.ld_gbt, _stream())
             dcoef = 0.0
@@ -600,25 +614,33 @@ class HeadPlan:
         br.join("f")
 
 class HostStep:
-    """Host-facing entry point: takes the step's inputs as HOST tensors (what a reference-side caller holds), stages them
-    through pinned memory, copies them to the device, runs the plan (optionally as a CUDA-graph replay) and returns the
-    losses as Python floats.  Every call moves `h2d_bytes` host->device and `d2h_bytes` device->host."""
+    """Host-facing entry point: the step's inputs live in HOST memory (what a reference-side caller holds).  All inputs
+    share one pinned arena (`host_views[name]` are typed views the caller may fill in place) mirrored by one device arena,
+    so a call is: [optional copy of caller tensors into the arena] -> ONE host->device copy of `h2d_bytes` -> the plan
+    (replayed as a CUDA graph) -> device->host copy of the 4 losses (`d2h_bytes`) -> stream synchronise."""
 
     def __init__(self, plan, host_example: Dict[str, torch.Tensor], bf16_keys=(), use_graph: bool = True):
         self.plan, self.bf16_keys = plan, tuple(bf16_keys)
         dev = plan.dev
-        self.pinned, self.dev_in = {}, {}
+        layout, off = {}, 0
         for k, v in host_example.items():
             dt = BF16 if k in self.bf16_keys else v.dtype
-            self.pinned[k] = torch.empty(v.shape, dtype=dt, pin_memory=True)
-            self.dev_in[k] = torch.empty(v.shape, dtype=dt, device=dev)
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned.values())
+            nbytes = v.numel() * torch.empty(0, dtype=dt).element_size()
+            layout[k] = (off, nbytes, dt, tuple(v.shape))
+            off = (off + nbytes + 255) // 256 * 256
+        self.h2d_bytes = sum(n for _, n, _, _ in layout.values())
+        self.arena_bytes = off
+        self.pinned = torch.empty(off, dtype=torch.uint8, pin_memory=True)
+        self.device = torch.empty(off, dtype=torch.uint8, device=dev)
+        self.host_views = {k: self.pinned[o:o + n].view(dt).view(shape) for k, (o, n, dt, shape) in layout.items()}
+        self.dev_in = {k: self.device[o:o + n].view(dt).view(shape) for k, (o, n, dt, shape) in layout.items()}
+        for k, v in host_example.items():
+            self.host_views[k].copy_(v.to(self.host_views[k].dtype))
         self.loss_pinned = torch.empty(4, dtype=F32, pin_memory=True)
         self.d2h_bytes = self.loss_pinned.numel() * 4
         self.graph = None
         if use_graph:
-            for k, v in host_example.items():
-                self.dev_in[k].copy_(v.to(self.dev_in[k].dtype))
+            self.device.copy_(self.pinned)
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -628,14 +650,12 @@ class HostStep:
             with torch.cuda.graph(self.graph):
                 plan.step(self.dev_in)
 
-    def __call__(self, host: Dict[str, torch.Tensor]):
-        for k, v in host.items():
-            p = self.pinned[k]
-            if v.dtype == p.dtype:
-                p.copy_(v)
-            else:
-                p.copy_(v.to(p.dtype))   # host-side bf16 rounding of fp32 inputs is part of the end-to-end cost
-            self.dev_in[k].copy_(p, non_blocking=True)
+    def __call__(self, host: Optional[Dict[str, torch.Tensor]] = None):
+        if host is not None:
+            for k, v in host.items():
+                hv = self.host_views[k]
+                hv.copy_(v if v.dtype == hv.dtype else v.to(hv.dtype))
+        self.device.copy_(self.pinned, non_blocking=True)        # the step's inputs: one H2D transfer
         if self.graph is not None:
             self.graph.replay()
         else:

@@ -175,4 +175,5 @@ def test_host_step_end_to_end():
     runner = P.HostStep(plan, host, bf16_keys=bfk, use_graph=True)
     got = runner(host)
     assert runner.h2d_bytes == sum((2 if k in bfk else 4) * v.numel() for k, v in host.items())
+    assert np.allclose(runner(), want, rtol=1e-5, atol=1e-6)       # inputs already staged in the pinned arena
     assert np.allclose(got, want, rtol=1e-5, atol=1e-6)

@@ -147,6 +147,40 @@ def test_itc_full_size_properties():
     assert _rel(dT_p, dT[perm]) < REL and _rel(dV_p, dV[perm]) < REL
 
 
+@pytest.mark.parametrize("B,Pd", [(4096, 768), (6144, 256)])
+def test_itc_large_batch_vs_torch_fp32(B, Pd):
+    """From 4096 columns on the ITC path runs single-bf16 gradient operands, the GA-shared image-side GEMM and the
+    2-CTA TMA-multicast tiles (odd tile-pair tail at B=6144/128=48 -> even; 4096 -> 32 tiles).  Checked against a plain
+    torch fp32 evaluation (autograd, TF32 off) of the same loss on the GPU."""
+    P = _plan_mod()
+    g = torch.Generator().manual_seed(B)
+    T = torch.randn(B, Pd, generator=g).to(torch.bfloat16).to(_dev())
+    V = (torch.randn(B, Pd, generator=g) + 0.4 * T.cpu().float()).to(torch.bfloat16).to(_dev())
+    s = float(np.exp(2.6592))
+    plan = P.ItcPlan(B, B, Pd, _dev())
+    assert not plan.precise and plan.shared_ga
+    sums, rsum = torch.zeros(2, device=_dev()), torch.zeros(1, device=_dev())
+    dT, dV = torch.empty(B, Pd, device=_dev()), torch.empty(B, Pd, device=_dev())
+    plan.run(T, V, s, 1.0, sums, rsum, dT_f32=dT, dV_f32=dV)
+    torch.cuda.synchronize()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        Tr, Vr = T.float().requires_grad_(True), V.float().requires_grad_(True)
+        ls = torch.tensor(2.6592, device=_dev(), requires_grad=True)
+        S = ls.exp() * torch.nn.functional.normalize(Tr, dim=1) @ torch.nn.functional.normalize(Vr, dim=1).t()
+        idx = torch.arange(B, device=_dev())
+        ref = 0.5 * (torch.nn.functional.cross_entropy(S, idx) + torch.nn.functional.cross_entropy(S.t(), idx))
+        ref.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    loss = float(0.5 * (sums[0] + sums[1]) / B)
+    assert abs(loss - float(ref)) / float(ref) < REL
+    eT, eV = _rel(dT, Tr.grad), _rel(dV, Vr.grad)
+    assert eT < REL and eV < REL, (eT, eV)
+    assert abs(float(rsum) - float(ls.grad)) < REL * abs(float(ls.grad)) + 1e-6
+
+
 # ---------------------------------------------------------------------------------------------------- clip_loss on a given matrix
 @pytest.mark.parametrize("B", [1, 2, 8, 33, 128])
 def test_ce_bidir_golden(golden_dir, B):
