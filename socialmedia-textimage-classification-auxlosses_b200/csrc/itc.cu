@@ -28,6 +28,12 @@ inline bool itc_multicast() {
 constexpr int kItcEpiWarps = 8;
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Sum the 32 per-lane values of each of 32 columns across the warp: returns, in lane l, sum over lanes of v[l].
 // Recursive-halving butterfly: 31 shuffles for 32 columns.
 __device__ __forceinline__ float warp_col_sums(float (&v)[32]) {
@@ -94,6 +100,8 @@ struct ItcFwdEpi {
     for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) sb[j] = (cx.n0 + j < cx.N) ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
     epi_bar_sync(cx.epi_threads);
     const float rt = valid_row ? __ldg(p.rinv_t + row) : 0.f;
+    const float rt2 = rt * p.scale_log2e;
+    const float negshift = valid_row ? -p.shift_log2e : -INFINITY;
     const int gcol = p.row_offset + row;  // column holding this row's positive
     const int cols_per_part = BN / cx.nparts;
     float rowsum = 0.f;
@@ -112,28 +120,53 @@ struct ItcFwdEpi {
       for (int j = 0; j < 32; ++j) v[j] = vn[j];
       if (c + 1 < nchunk && col0 + 32 < cx.N) tmem_ld_32x32(trow + cl + 32, vn);   // prefetch the next 32 columns
       float e[32];
-      float dsel = 0.f;
+      if (col0 + 32 <= cx.N && p.logits == nullptr) {
+        // fast path (interior tile, logits not materialised): 1 FMUL + 1 FFMA + 1 MUFU + 1 FADD per element.
+        // invalid rows carry negshift = -inf, so their exp is exactly 0 and they drop out of the column sums.
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float cosv = __uint_as_float(v[j]) * rt * sb[cl + j];       // cosine similarity
-        const bool ok = valid_row && (col0 + j < cx.N);
-        e[j] = ok ? exp2f(fmaf(cosv, p.scale_log2e, -p.shift_log2e)) : 0.f;
-        rowsum += e[j];
-        if (col0 + j == gcol) dsel = cosv * p.scale;
-        v[j] = __float_as_uint(cosv * p.scale);
-      }
-      if (valid_row && gcol >= col0 && gcol < col0 + 32) p.diag[row] = dsel;
-      if (p.logits != nullptr && valid_row) {
-        float* d = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
-        if (col0 + 32 <= cx.N && (p.ld_logits & 3) == 0) {
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j4);
+          e[j4 + 0] = ex2_approx(fmaf(__uint_as_float(v[j4 + 0]) * b4.x, rt2, negshift));
+          e[j4 + 1] = ex2_approx(fmaf(__uint_as_float(v[j4 + 1]) * b4.y, rt2, negshift));
+          e[j4 + 2] = ex2_approx(fmaf(__uint_as_float(v[j4 + 2]) * b4.z, rt2, negshift));
+          e[j4 + 3] = ex2_approx(fmaf(__uint_as_float(v[j4 + 3]) * b4.w, rt2, negshift));
+        }
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        } else {
+        for (int j = 0; j < 32; j += 4) { r0 += e[j]; r1 += e[j + 1]; r2 += e[j + 2]; r3 += e[j + 3]; }
+        rowsum += (r0 + r1) + (r2 + r3);
+        if (gcol >= col0 && gcol < col0 + 32 && valid_row) {   // the positive of this row lives in this chunk (rare)
+          float dv = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < cx.N) d[j] = __uint_as_float(v[j]);
+            if (col0 + j == gcol) dv = __uint_as_float(v[j]) * rt * sb[cl + j] * p.scale;
+          p.diag[row] = dv;
+        }
+      } else {
+        // generic path: edge tiles (column tail) and materialised logits (drop-in API / hard-negative sampling)
+        float dsel = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float cosv = __uint_as_float(v[j]) * rt * sb[cl + j];       // cosine similarity
+          const bool ok = valid_row && (col0 + j < cx.N);
+          e[j] = ok ? exp2f(fmaf(cosv, p.scale_log2e, -p.shift_log2e)) : 0.f;
+          rowsum += e[j];
+          if (col0 + j == gcol) dsel = cosv * p.scale;
+          v[j] = __float_as_uint(cosv * p.scale);
+        }
+        if (valid_row && gcol >= col0 && gcol < col0 + 32) p.diag[row] = dsel;
+        if (p.logits != nullptr && valid_row) {
+          float* d = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
+          if (col0 + 32 <= cx.N && (p.ld_logits & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < cx.N) d[j] = __uint_as_float(v[j]);
+          }
         }
       }
       const float cs = warp_col_sums(e);
@@ -169,16 +202,20 @@ struct ItcBwdEpi {
     const int lane = threadIdx.x & 31;
     const int row = cx.m0 + cx.quad * 32 + lane;
     const bool valid_row = row < cx.M;
-    float* sb = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * 2 * BN;  // rinv_v | lse_col*log2e
+    float* sb = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * 3 * BN;  // rinv_v | -lse_col*log2e | gscale*rinv_v
     float* sl = sb + BN;
+    float* sg = sb + 2 * BN;
     for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) {
       const bool ok = cx.n0 + j < cx.N;
-      sb[j] = ok ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
+      const float b = ok ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
+      sb[j] = b;
       sl[j] = ok ? __ldg(p.lse_col + cx.n0 + j) * kLog2e : 0.f;
+      sg[j] = b * p.gscale;
     }
     epi_bar_sync(cx.epi_threads);
     const float rt = valid_row ? __ldg(p.rinv_t + row) : 0.f;
     const float lr = valid_row ? __ldg(p.lse_row + row) * kLog2e : 0.f;
+    const float rt2 = rt * p.scale_log2e;
     const int cols_per_part = BN / cx.nparts;
     const bool vec_ok = (p.ld_ga & 7) == 0;
     const uint32_t trow = cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16);
@@ -196,6 +233,21 @@ struct ItcBwdEpi {
       for (int j = 0; j < 32; ++j) v[j] = vn[j];
       if (c + 1 < nchunk && col0 + 32 < cx.N) tmem_ld_32x32(trow + cl + 32, vn);   // prefetch the next 32 columns
       float ga[32];
+      if (col0 + 32 <= cx.N && p.GBT == nullptr) {
+        // fast path (interior tile, GA-shared mode): FMUL, FMUL, 2x(FADD + MUFU), FADD, FMUL per element
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j4);
+          const float4 l4 = *reinterpret_cast<const float4*>(sl + cl + j4);
+          const float4 g4 = *reinterpret_cast<const float4*>(sg + cl + j4);
+          const float s0 = __uint_as_float(v[j4 + 0]) * b4.x * rt2, s1 = __uint_as_float(v[j4 + 1]) * b4.y * rt2;
+          const float s2_ = __uint_as_float(v[j4 + 2]) * b4.z * rt2, s3 = __uint_as_float(v[j4 + 3]) * b4.w * rt2;
+          ga[j4 + 0] = (ex2_approx(s0 - lr) + ex2_approx(s0 - l4.x)) * g4.x;
+          ga[j4 + 1] = (ex2_approx(s1 - lr) + ex2_approx(s1 - l4.y)) * g4.y;
+          ga[j4 + 2] = (ex2_approx(s2_ - lr) + ex2_approx(s2_ - l4.z)) * g4.z;
+          ga[j4 + 3] = (ex2_approx(s3 - lr) + ex2_approx(s3 - l4.w)) * g4.w;
+        }
+      } else {
       __nv_bfloat16* gbt = p.GBT ? p.GBT + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
       __nv_bfloat16* gbt_lo = (p.GBT && p.GBT_lo) ? p.GBT_lo + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
 #pragma unroll
@@ -209,6 +261,7 @@ struct ItcBwdEpi {
           gbt[static_cast<int64_t>(j) * p.ld_gbt] = hi;
           if (gbt_lo) gbt_lo[static_cast<int64_t>(j) * p.ld_gbt] = __float2bfloat16_rn(gb - __bfloat162float(hi));
         }
+      }
       }
       if (valid_row) {
         __nv_bfloat16* d = p.GA + static_cast<int64_t>(row) * p.ld_ga + col0;
