@@ -38,6 +38,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no e2e leg, no per-kernel timing, no CPU leg")
+    ap.add_argument("--dist", type=str, default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU exchange: peer = own kernels over CUDA-IPC peer memory (default), nccl = collectives (baseline)")
+    ap.add_argument("--no-scale-point", action="store_true", help="skip the extra ITC-only B=16384 roofline point")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline leg")
     return ap.parse_args()
 
@@ -179,7 +182,7 @@ def cpu_reference_run(spec, steps, warmup, budget_s, threads=None):
             V = inp["v_pool"].clone().requires_grad_(True)
             loss = R.clip_loss(R.itc_logits(T, V, ls))
             loss.backward()
-            return float(loss)
+            return float(loss.detach())
     else:
         p = {k: v.clone().requires_grad_(True) for k, v in R.init_params(spec["C"], seed=40).items()}
         lbl, src = R.itm_sample_uniform(inp["u_coin"].numpy(), inp["u_pick"].numpy())
@@ -198,7 +201,7 @@ def cpu_reference_run(spec, steps, warmup, budget_s, threads=None):
                 v.grad = None
             out = R.head_step(cur, p, fusion_name=spec["fusion"], use_itc=True, use_itm=spec["use_itm"])
             out["loss"].backward()
-            return float(out["loss"])
+            return float(out["loss"].detach())
     for _ in range(max(1, min(warmup, 2))):
         step()
     times = []
@@ -224,7 +227,7 @@ def main():
     base = {"metric": metric, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
             "config": {"workload": spec["workload"], "per_gpu_batch": spec["B"], "global_batch": spec["B"] * world,
-                       "parallelism": "dp%d" % world}}
+                       "parallelism": "dp%d" % world if world == 1 else "dp%d (%s exchange)" % (world, args.dist)}}
 
     if args.impl == "reference":
         if rank != 0:
@@ -254,7 +257,10 @@ def main():
     dev_in = {k: (v.to(torch.bfloat16) if k in BF16_KEYS else v).to(dev) for k, v in host.items()}
     n_global = B * world
     if world > 1:
-        from tic_b200.dist import DistHeadPlan
+        if args.dist == "peer":
+            from tic_b200.peer import PeerHeadPlan as DistHeadPlan
+        else:
+            from tic_b200.dist import DistHeadPlan
         plan = DistHeadPlan(B, world=world, rank=rank, E=spec["E"], P=spec["P"] if spec["P"] is not None else None,
                             d=spec.get("d"), C=spec["C"], fusion=spec["fusion"], use_itc=spec["use_itc"],
                             use_itm=spec["use_itm"], Lv=spec["Lv"], device=dev)
@@ -271,24 +277,23 @@ def main():
     # ---- count launches of one step (kernels per C-ABI call are fixed)
     KPC = {"tic_itc_lse_loss": 2, "tic_heads_fwd_bwd": 3 if spec["use_itm"] else 2, "tic_unpack_cls_grad": 2 if spec["use_itm"] else 1,
            "tic_ce_bidir_fwd": 2, "tic_itm_sample_gather": 1}
+    KPC.update({"tic_peer_alloc": 0, "tic_peer_export": 0, "tic_peer_open": 0, "tic_peer_close": 0})
     counter = {"n": 0}
-    orig_call = capi.call
 
-    def counting_call(name, *a):
+    def hook(name):
         counter["n"] += KPC.get(name, 1)
-        return orig_call(name, *a)
 
-    P.call = counting_call
+    capi.call_hook = hook
     plan.step(dev_in)
     launches_per_step = counter["n"] + 1  # + the accumulator memset
-    P.call = orig_call
+    capi.call_hook = None
     torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
         plan.step(dev_in)
     torch.cuda.synchronize()
 
-    use_graph = (not args.no_graph) and world == 1
+    use_graph = (not args.no_graph) and (world == 1 or args.dist == "peer")
     graph = None
     if use_graph:
         graph = torch.cuda.CUDAGraph()
@@ -316,6 +321,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def align():
+        """Multi-GPU: line the ranks up ON THE DEVICE right before a start event (peer barrier kernel; NCCL barrier in the
+        nccl mode), so host launch skew between the ranks is not billed to the step."""
+        if dist is None:
+            return
+        if hasattr(plan, "pg"):
+            plan.pg.exchange("align")
+        else:
+            dist.barrier()
+
     # ---- timed region: K steps, each bracketed by its own event pair, L2 flushed between steps (outside the pair)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -324,8 +339,7 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
         flush.fill_(float(k))
-        if dist is not None:
-            dist.barrier()
+        align()
         ev[k][0].record()
         run_step()
         ev[k][1].record()
@@ -343,7 +357,8 @@ def main():
             clocks.stop()
             print(json.dumps(dict(base, value=value, ms_per_step=ms_per_step, profile_run=True)))
         return
-    # ---- end-to-end: HOST buffers in, loss out, through the public host-facing API
+    # ---- end-to-end: HOST buffers in, loss out, through the public host-facing API.
+    # (1) synchronous: every call = pinned arena -> H2D -> step -> D2H losses -> host sync; L2 flushed outside the brackets.
     runner = P.HostStep(plan, host, bf16_keys=BF16_KEYS, use_graph=use_graph)
     for _ in range(3):
         runner()
@@ -353,6 +368,7 @@ def main():
     for k in range(args.steps):
         flush.fill_(float(k))
         torch.cuda.synchronize()
+        align()
         e0.record()
         loss_host = runner()       # pinned host arena -> H2D -> step -> D2H losses (synchronous)
         e1.record()
@@ -361,11 +377,40 @@ def main():
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / args.steps
+    e2e_sync_ms = float(t.item()) / args.steps
+    # (2) pipelined (the headline): two slots, the H2D of step k+1 overlaps the kernels of step k; every step still does
+    # its own H2D + D2H, and the L2 flush runs INSIDE the timed region between consecutive steps.
+    e2e_ms, e2e_mode = e2e_sync_ms, "synchronous call per step"
+    if use_graph:
+        flush2 = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+        pipe = P.HostPipeline(plan, host, bf16_keys=BF16_KEYS, between=lambda: flush2.fill_(1.0))
+        for _ in range(3):
+            pipe.submit()
+            pipe.result()
+        barrier()
+        align()
+        e0.record()
+        for k in range(args.steps):
+            pipe.submit()
+            if k >= 1:
+                loss_host = pipe.result()
+        loss_host = pipe.result()
+        e1.record()
+        e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pipe_ms = float(t.item()) / args.steps
+        if pipe_ms < e2e_ms:
+            e2e_ms, e2e_mode = pipe_ms, "pipelined, 2 slots: H2D of step k+1 overlaps step k; 160 MiB L2 flush inside the timed region"
     clk = clocks.stop() if rank == 0 else None
 
     # ---- per-kernel timing of the dominant kernels (live, CUDA events on the launching stream, L2 flushed)
     roof, kernels = kernel_rooflines(P, plan, spec, dev_in, n_global, flush)
+    # the default workload (B=256) is launch-latency-bound: also time the same ITC kernels where a roofline applies
+    at_scale = None
+    if world == 1 and spec["B"] < 4096 and spec["use_itc"] and not args.no_scale_point:
+        at_scale = scale_point(P, dev, flush)
 
     if rank != 0:
         if dist is not None:
@@ -379,11 +424,15 @@ def main():
     line = dict(base, value=value, ms_per_step=ms_per_step, dtype="bf16", gpu_launches=launches_per_step * args.steps,
                 clocks=clk, e2e={"value": n_global / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
                                  "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes,
-                                 "loss": loss_host})
+                                 "loss": loss_host, "mode": e2e_mode, "sync_ms_per_step": e2e_sync_ms})
     line["config"].update({"l2": "flushed between timed steps (256 MiB write)", "cuda_graph": bool(use_graph),
                            "launches_per_step": launches_per_step, "loss": float(plan.out["loss"][0])})
     line["roofline"] = finalize_roofline(roof, peaks)
     line["kernels"] = [finalize_roofline(k, peaks) for k in kernels]
+    if at_scale is not None:
+        line["roofline_at_scale"] = {"workload": at_scale["workload"], "why": at_scale["why"],
+                                     "step": finalize_roofline(at_scale["step"], peaks),
+                                     "kernels": [finalize_roofline(k, peaks) for k in at_scale["kernels"]]}
     if not args.no_cpu_baseline:
         val, ms, sample, threads = cpu_reference_run(spec, 1000, 1, args.cpu_seconds)
         line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
@@ -470,6 +519,37 @@ def kernel_rooflines(P, plan, spec, dev_in, n_global, flush):
         return None, []
     dom = max(ks, key=lambda k: k["ms"])
     return dom, ks
+
+
+def scale_point(P, dev, flush, B=16384, d=768):
+    """ITC-only step at B=16384, d=768 on one GPU (a c5 sweep point): the same kernels as the default workload, at a size
+    where the tensor-core roofline applies.  Reported beside the default workload's (latency-bound) kernel numbers."""
+    g = torch.Generator().manual_seed(41)
+    T = torch.randn(B, d, generator=g).to(torch.bfloat16).to(dev)
+    V = (torch.randn(B, d, generator=g) + 0.25 * T.float().cpu()).to(torch.bfloat16).to(dev)
+    it = P.ItcPlan(B, B, d, dev)
+    sums, rsum = torch.zeros(2, device=dev), torch.zeros(1, device=dev)
+    dT, dV = torch.empty(B, d, device=dev), torch.empty(B, d, device=dev)
+    scale = math.exp(2.6592)
+    ld = T.stride(0)
+    it.run(T, V, scale, 1.0, sums, rsum, dT_f32=dT, dV_f32=dV)
+    ks = []
+    ms = time_kernel(lambda: it.fwd_tiles(T, ld, V, ld, scale), flush)
+    ks.append(dict(kernel="tic_itc_fwd", bound="tensor", ms=ms, achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s",
+                   algorithmic="2*B^2*d FLOP"))
+    ms = time_kernel(lambda: it.bwd_operands(T, ld, V, ld, scale, 1.0 / (2 * B)), flush)
+    ks.append(dict(kernel="tic_itc_bwd_g", bound="tensor", ms=ms, achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s",
+                   algorithmic="recompute: 2*B^2*d executed FLOP, 0 algorithmic (reported as executed)"))
+    ms = time_kernel(lambda: it.grad_gemms(T, ld, V, ld), flush)
+    ks.append(dict(kernel="tic_gemm_bf16 x2 (dT, dV)", bound="tensor", ms=ms, achieved=4.0 * B * B * d / ms * 1e-9,
+                   unit="TFLOP/s", algorithmic="4*B^2*d FLOP"))
+    ms = time_kernel(lambda: it.run(T, V, scale, 1.0, sums, rsum, dT_f32=dT, dV_f32=dV), flush, iters=5)
+    step = dict(kernel="whole ITC fwd+bwd step (norms, tiles, lse, recompute, 2 GEMMs, finalize)", bound="tensor", ms=ms,
+                achieved=6.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="6*B^2*d FLOP (recompute not counted)",
+                samples_per_s=B / (ms * 1e-3))
+    del it
+    return dict(workload="c5 point: ITC only, B=%d, d=%d, 1 GPU" % (B, d), kernels=ks, step=step,
+                why="the default workload (B=256) is launch-latency-bound; this is the same path at a roofline-relevant size")
 
 
 if __name__ == "__main__":

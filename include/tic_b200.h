@@ -93,6 +93,15 @@ int tic_reduce_parts(const float* part, int nparts, int n, float* out, void* str
 int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, const float* diag,
                      int m_local, int n_global, int row_offset, float shift, float* lse_row, float* lse_col,
                      float* loss_sums, void* stream);
+/* Symmetric (peer-memory) multi-GPU mode: rank r runs tic_itc_fwd twice — on its row block S[rows_r, :] and, with the
+ * operands swapped, on S^T[cols_r, :] (col_part = NULL in both) — so BOTH softmax directions are complete row statistics on
+ * the rank that owns them and no cross-rank reduction exists.  This call turns the two sets of row partials into
+ *   lse_a[i] (= lse_row of my text rows), lse_b[i] (= lse_col of my image columns),
+ *   loss_sums[0] += sum_i (lse_a[i]-diag[i]),  loss_sums[1] += sum_i (lse_b[i]-diag[i])   (fixed-order, deterministic).
+ * workspace: tic_itc_lse_rows_workspace_bytes(m) bytes, zero-initialised once (self-resetting). utils.py:225-231. */
+int64_t tic_itc_lse_rows_workspace_bytes(int m);
+int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift, float* lse_a,
+                     float* lse_b, float* loss_sums, void* workspace, void* stream);
 /* Recompute S tiles and emit the bf16 gradient operands (g = dLoss/d(clip_loss), B = n_global):
  *   Gp[i,j] = g/(2B) * (exp(S-lse_row[i]) + exp(S-lse_col[j]))      (the -I/B diagonal is applied in fp32 later)
  *   GA [m_local, ld_ga ] row-major:  Gp[i,j] * rinv_v[j]            (A operand of dT = GA * V)
@@ -219,6 +228,30 @@ int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, 
  * out[1..3] = L_cls, L_itc, L_itm.  out has 4 floats. */
 int tic_loss_mix(const float* losses, const float* itc_sums, int n_global, float beta_itc, float beta_itm,
                  int use_itc, int use_itm, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ peer memory
+ * Multi-GPU exchange of the row-sharded ITC step (the reference is single-device, mm_late.py:30) WITHOUT a
+ * collective library on the data path: every rank owns one block of device memory that all peers map through CUDA IPC,
+ * and loads the other ranks' embeddings / softmax statistics over NVLink with its own kernel.
+ *   tic_peer_alloc   cudaMalloc + zero a block (returns the device pointer in *out_ptr)
+ *   tic_peer_export  64-byte IPC handle of a block (host buffer of tic_peer_handle_bytes() bytes)
+ *   tic_peer_open    map a peer's block from its handle (enables peer access lazily); tic_peer_close unmaps it
+ *   tic_peer_exchange  ONE kernel: system-scope release/acquire barrier across the `world` ranks (flags at byte offset
+ *       flag_off of every block: uint32[8], zero-initialised), then, for each of the nseg byte ranges
+ *       [src_off[s], src_off[s]+bytes[s]) of EVERY rank's block p (its own included), a pull into the local buffer
+ *       dst[s] + p * dst_stride[s].  Offsets, sizes and destinations are multiples of 16 bytes.  `ctr` = 2 zero-initialised
+ *       uint32 in local device memory (epoch + ticket).  All ranks must issue the same sequence of exchanges; nothing
+ *       synchronises with the host, so the call is CUDA-graph capturable.  A peer that never arrives traps after 20 s.
+ * The *_host arguments are HOST arrays (world pointers / nseg values). */
+int tic_peer_handle_bytes(void);
+int tic_peer_alloc(int64_t bytes, void** out_ptr);
+int tic_peer_free(void* ptr);
+int tic_peer_export(const void* ptr, void* handle_out_host);
+int tic_peer_open(const void* handle_host, void** out_ptr);
+int tic_peer_close(void* ptr);
+int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* ctr, int nseg,
+                      const int64_t* src_off_host, const int64_t* bytes_host, void* const* dst_host,
+                      const int64_t* dst_stride_host, void* stream);
 
 #ifdef __cplusplus
 }

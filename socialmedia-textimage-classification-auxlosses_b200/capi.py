@@ -27,6 +27,15 @@ _SIGS = {
     "tic_itc_fwd": ("pplpplppiiiiffpppplp", ctypes.c_int),
     "tic_reduce_parts": ("piipp", ctypes.c_int),
     "tic_itc_lse_loss": ("pipipiiifpppp", ctypes.c_int),
+    "tic_itc_lse_rows_workspace_bytes": ("i", ctypes.c_int64),
+    "tic_itc_lse_rows": ("ppiipfppppp", ctypes.c_int),
+    "tic_peer_handle_bytes": ("", ctypes.c_int),
+    "tic_peer_alloc": ("lp", ctypes.c_int),
+    "tic_peer_free": ("p", ctypes.c_int),
+    "tic_peer_export": ("pp", ctypes.c_int),
+    "tic_peer_open": ("pp", ctypes.c_int),
+    "tic_peer_close": ("p", ctypes.c_int),
+    "tic_peer_exchange": ("piilpippppp", ctypes.c_int),
     "tic_itc_bwd_g": ("pplpplppppiiiffplplppp", ctypes.c_int),
     "tic_itc_ds_operands": ("pliipppplpplp", ctypes.c_int),
     "tic_itc_grad_finalize": ("plpplppplpiiffplpplpip", ctypes.c_int),
@@ -87,9 +96,14 @@ def last_error() -> str:
     return load().tic_last_error_string().decode()
 
 
+call_hook = None   # optional observer `hook(name)` of every C-ABI call (bench.py counts kernel launches with it)
+
+
 def call(name: str, *args):
     """Calls an int-returning entry point and raises TicError (with the library's message) on a non-zero code."""
     lib = load()
+    if call_hook is not None:
+        call_hook(name)
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise TicError("%s failed (rc=%d): %s" % (name, rc, lib.tic_last_error_string().decode()))

@@ -169,10 +169,13 @@ struct ItcFwdEpi {
           }
         }
       }
-      const float cs = warp_col_sums(e);
-      scol[cx.quad * BN + cl + lane] = cs;
+      if (p.col_part != nullptr) {   // symmetric multi-GPU mode computes the column statistics as rows of the swapped block
+        const float cs = warp_col_sums(e);
+        scol[cx.quad * BN + cl + lane] = cs;
+      }
     }
     if (valid_row) p.row_part[static_cast<int64_t>(cx.n_blk * cx.nparts + cx.part) * cx.M + row] = rowsum;
+    if (p.col_part == nullptr) return;
     epi_bar_sync(cx.epi_threads);
     for (int j = cx.epi_tid; j < BN; j += cx.epi_threads)
       if (cx.n0 + j < cx.N)
@@ -392,6 +395,47 @@ __global__ void itc_loss_kernel(const float* __restrict__ lse_row, const float* 
   }
 }
 
+// Symmetric (peer-memory) mode: both softmax directions are ROW statistics — of the row block S[rows_r, :] and of the
+// swapped block S^T[cols_r, :].  blockIdx.y selects the direction; lse = shift + log(sum of the per-tile partials);
+// the loss terms sum_i (lse_i - diag_i) are reduced in a fixed order (block partials, last block adds them up).
+__global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int nparts, int m,
+                                    const float* __restrict__ diag, float shift, float* __restrict__ lse_a,
+                                    float* __restrict__ lse_b, float* __restrict__ loss_sums, float* __restrict__ ws) {
+  const int dir = blockIdx.y;
+  const float* part = dir == 0 ? part_a : part_b;
+  float* lse = dir == 0 ? lse_a : lse_b;
+  float* blk_part = ws + 2 + dir * gridDim.x;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws) + dir;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (i < m) {
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[static_cast<int64_t>(p) * m + i];
+    const float l = shift + logf(s);
+    lse[i] = l;
+    term = l - diag[i];
+  }
+  __shared__ float sw[32];
+  __shared__ bool last;
+  term = warp_sum(term);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += sw[w];
+    blk_part[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (last) {
+      __threadfence();
+      float tot = 0.f;
+      for (int b = 0; b < static_cast<int>(gridDim.x); ++b) tot += reinterpret_cast<volatile float*>(blk_part)[b];
+      loss_sums[dir] += tot;
+      *ticket = 0u;
+    }
+  }
+}
+
 // One warp per row: diagonal term, normalise-backward, dlogit_scale contribution.
 __global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t ld_acc, const __nv_bfloat16* __restrict__ X,
                                          const __nv_bfloat16* __restrict__ X_lo, int64_t ldx, const float* __restrict__ rinv,
@@ -501,7 +545,7 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
                 const float* rinv_v,
                 int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
                 float* col_part, float* diag, float* logits_out, int64_t ld_logits, void* stream) {
-  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && row_part && col_part && diag, "tic_itc_fwd: null pointer");
+  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && row_part && diag, "tic_itc_fwd: null pointer");
   TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_fwd: empty problem");
   TIC_CHECK_ARG(row_offset >= 0 && row_offset + m_local <= n_global, "tic_itc_fwd: row block outside the global batch");
   if (!(scale > 0.f) || scale > 40.f || shift < scale) {
@@ -542,6 +586,19 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
                                                      lse_row, lse_col);
   itc_loss_kernel<<<1, 1024, 0, st>>>(lse_row, lse_col, diag, m_local, row_offset, loss_sums);
   TIC_CHECK_LAUNCH("tic_itc_lse_loss");
+  return TIC_OK;
+}
+
+int64_t tic_itc_lse_rows_workspace_bytes(int m) { return static_cast<int64_t>(2 + 2 * ceil_div(m, 256)) * 4; }
+
+int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift, float* lse_a,
+                     float* lse_b, float* loss_sums, void* workspace, void* stream) {
+  TIC_CHECK_ARG(part_a && part_b && diag && lse_a && lse_b && loss_sums && workspace && n_parts > 0 && m > 0,
+                "tic_itc_lse_rows: bad arguments");
+  dim3 grid(ceil_div(m, 256), 2);
+  itc_lse_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(part_a, part_b, n_parts, m, diag, shift, lse_a, lse_b,
+                                                                          loss_sums, static_cast<float*>(workspace));
+  TIC_CHECK_LAUNCH("tic_itc_lse_rows");
   return TIC_OK;
 }
 

@@ -1,0 +1,200 @@
+// Peer (symmetric) memory over NVLink 5 / NVSwitch for the row-sharded ITC exchange: every rank owns one cudaMalloc'd
+// block, exported as a CUDA IPC handle and mapped by its peers, so a rank's kernels load the other ranks' embeddings and
+// softmax statistics directly through NVLink — the data path has no NCCL call, no host synchronisation, and is CUDA-graph
+// capturable.  The reference is single-device (models/mm_late.py:30); this is the B200 exchange step of SURVEY.md §8(e).
+//
+//   tic_peer_alloc / export / open / close / free : plumbing (host)
+//   tic_peer_exchange                             : ONE kernel = cross-rank barrier (release/acquire flags at system scope)
+//                                                   + pull of up to kMaxSeg byte ranges from every peer into local buffers
+#include "common.cuh"
+
+namespace tic {
+
+constexpr int kMaxPeers = 8;
+constexpr int kMaxSeg = 8;
+
+struct PeerPtrs {
+  uint8_t* base[kMaxPeers];
+};
+struct ExchangeSeg {
+  int64_t src_off;      // byte offset inside every rank's symmetric block
+  int64_t bytes;        // multiple of 16
+  uint8_t* dst;         // local destination of peer 0's range
+  int64_t dst_stride;   // peer p's range lands at dst + p * dst_stride
+};
+struct ExchangeArgs {
+  ExchangeSeg seg[kMaxSeg];
+  int nseg;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ uint4 ld_nc_na(const uint4* p) {   // streaming 16-byte load (peer memory: never re-read)
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// ctr[0] = epoch of the last completed exchange on this rank, ctr[1] = ticket of blocks done (both local, zero-initialised).
+// flags live at base[r] + flag_off: uint32 flags[kMaxPeers]; slot q of rank r's flags is written by rank q only.
+__global__ void __launch_bounds__(256)
+peer_exchange_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32_t* __restrict__ ctr, ExchangeArgs xa,
+                     unsigned long long timeout_ns) {
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
+  // -- signal: everything this rank published (earlier kernels on this stream) is visible before the flag is
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(sym.base[threadIdx.x] + flag_off) + rank, epoch);
+  }
+  // -- wait: every block observes every peer's flag itself (no grid-wide dependency inside the kernel)
+  if (threadIdx.x < world) {
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(sym.base[rank] + flag_off) + threadIdx.x;
+    const uint64_t t0 = globaltimer_ns();
+    while (static_cast<int32_t>(ld_acquire_sys(f) - epoch) < 0) {
+      if (globaltimer_ns() - t0 > timeout_ns) {
+        printf("tic: peer barrier timeout (rank %d waiting for rank %d, epoch %u)\n", rank, threadIdx.x, epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  // -- pull: 16-byte words, all (segment, peer) ranges flattened over the grid
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int s = 0; s < xa.nseg; ++s) {
+    const ExchangeSeg sg = xa.seg[s];
+    const int64_t words = sg.bytes >> 4;
+    const int64_t total = words * world;
+    int64_t i = tid;
+    for (; i + 3 * nthr < total; i += 4 * nthr) {   // 4 independent loads in flight per thread
+      uint4 v[4];
+      int64_t pw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t j = i + u * nthr;
+        const int p = static_cast<int>(j / words);
+        pw[u] = j;
+        v[u] = ld_nc_na(reinterpret_cast<const uint4*>(sym.base[p] + sg.src_off) + (j - p * words));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = static_cast<int>(pw[u] / words);
+        reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride)[pw[u] - p * words] = v[u];
+      }
+    }
+    for (; i < total; i += nthr) {
+      const int p = static_cast<int>(i / words);
+      reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride)[i - p * words] =
+          ld_nc_na(reinterpret_cast<const uint4*>(sym.base[p] + sg.src_off) + (i - p * words));
+    }
+  }
+  // -- the last block to finish publishes the epoch for the next exchange on this rank
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+      ctr[1] = 0u;
+      ctr[0] = epoch;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace tic
+
+using namespace tic;
+
+#define TIC_CUDA_OK(expr, name)                                                   \
+  do {                                                                            \
+    cudaError_t e__ = (expr);                                                     \
+    if (e__ != cudaSuccess) {                                                     \
+      ::tic::set_error("%s: %s", name, cudaGetErrorString(e__));                  \
+      return TIC_E_CUDA;                                                          \
+    }                                                                             \
+  } while (0)
+
+extern "C" {
+
+int tic_peer_handle_bytes(void) { return static_cast<int>(sizeof(cudaIpcMemHandle_t)); }
+
+int tic_peer_alloc(int64_t bytes, void** out_ptr) {
+  TIC_CHECK_ARG(bytes > 0 && out_ptr, "tic_peer_alloc: bad arguments");
+  void* p = nullptr;
+  TIC_CUDA_OK(cudaMalloc(&p, static_cast<size_t>(bytes)), "tic_peer_alloc(cudaMalloc)");
+  TIC_CUDA_OK(cudaMemset(p, 0, static_cast<size_t>(bytes)), "tic_peer_alloc(cudaMemset)");
+  TIC_CUDA_OK(cudaDeviceSynchronize(), "tic_peer_alloc(sync)");
+  *out_ptr = p;
+  return TIC_OK;
+}
+
+int tic_peer_free(void* ptr) {
+  if (ptr) TIC_CUDA_OK(cudaFree(ptr), "tic_peer_free");
+  return TIC_OK;
+}
+
+int tic_peer_export(const void* ptr, void* handle_out_host) {
+  TIC_CHECK_ARG(ptr && handle_out_host, "tic_peer_export: null pointer");
+  cudaIpcMemHandle_t h;
+  TIC_CUDA_OK(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)), "tic_peer_export(cudaIpcGetMemHandle)");
+  memcpy(handle_out_host, &h, sizeof(h));
+  return TIC_OK;
+}
+
+int tic_peer_open(const void* handle_host, void** out_ptr) {
+  TIC_CHECK_ARG(handle_host && out_ptr, "tic_peer_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  void* p = nullptr;
+  TIC_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "tic_peer_open(cudaIpcOpenMemHandle)");
+  *out_ptr = p;
+  return TIC_OK;
+}
+
+int tic_peer_close(void* ptr) {
+  if (ptr) TIC_CUDA_OK(cudaIpcCloseMemHandle(ptr), "tic_peer_close");
+  return TIC_OK;
+}
+
+int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* ctr, int nseg,
+                      const int64_t* src_off_host, const int64_t* bytes_host, void* const* dst_host,
+                      const int64_t* dst_stride_host, void* stream) {
+  TIC_CHECK_ARG(bases_host && ctr && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+                "tic_peer_exchange: bad group (world=%d rank=%d, at most %d peers)", world, rank, kMaxPeers);
+  TIC_CHECK_ARG(nseg >= 0 && nseg <= kMaxSeg && (flag_off & 15) == 0, "tic_peer_exchange: bad segment list");
+  PeerPtrs sym{};
+  for (int p = 0; p < world; ++p) {
+    TIC_CHECK_ARG(bases_host[p] != nullptr, "tic_peer_exchange: rank %d has no mapped block", p);
+    sym.base[p] = static_cast<uint8_t*>(bases_host[p]);
+  }
+  ExchangeArgs xa{};
+  xa.nseg = nseg;
+  int64_t total = 0;
+  for (int s = 0; s < nseg; ++s) {
+    TIC_CHECK_ARG((src_off_host[s] & 15) == 0 && (bytes_host[s] & 15) == 0 && (dst_stride_host[s] & 15) == 0 &&
+                      aligned16(dst_host[s]) && bytes_host[s] >= 0,
+                  "tic_peer_exchange: segment %d is not 16-byte aligned", s);
+    xa.seg[s] = ExchangeSeg{src_off_host[s], bytes_host[s], static_cast<uint8_t*>(dst_host[s]), dst_stride_host[s]};
+    total += bytes_host[s] * world;
+  }
+  // latency-bound below ~1 MB (few blocks: every block spins on the flags); NVLink-bound above (many loads in flight)
+  int grid = static_cast<int>((total / 16 + 256 * 4 - 1) / (256 * 4));
+  if (grid < 1) grid = 1;
+  if (grid > 4 * 148) grid = 4 * 148;
+  peer_exchange_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(sym, world, rank, flag_off, ctr, xa,
+                                                                           20ull * 1000ull * 1000ull * 1000ull);
+  TIC_CHECK_LAUNCH("tic_peer_exchange");
+  return TIC_OK;
+}
+
+}  // extern "C"

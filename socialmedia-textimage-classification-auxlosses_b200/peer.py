@@ -1,0 +1,333 @@
+"""Peer-memory (NVLink 5 / NVSwitch) execution of the row-sharded ITC step: no collective library on the data path.
+
+The reference is single-device (models/mm_late.py:30); SURVEY.md §8(e) shards ITC by batch.  The NCCL sequencing lives in
+`dist.ShardedItc` (all_gather -> tiles -> all_reduce of column sums -> reduce_scatter of dV).  Here the same step is
+restated so that NOTHING has to be reduced across ranks:
+
+    rank r owns text rows and image rows [r*b, (r+1)*b) of the global batch N = b * world, and publishes them (bf16
+    embeddings + inverse norms) in a block of device memory that every peer maps through CUDA IPC.
+
+    exchange #1  (one kernel: system-scope barrier + pull over NVLink)   T_all, V_all, rinv_t_all, rinv_v_all
+    row block    S  [rows_r, :]  = scale * T_r V_all^T   -> row sums    = softmax statistics of my TEXT rows
+    swapped      S^T[cols_r, :]  = scale * V_r T_all^T   -> row sums    = softmax statistics of my IMAGE columns
+    lse + loss terms of my rows/columns (fixed-order, deterministic)
+    exchange #2  lse_row_all, lse_col_all   (N floats each)
+    row block    GA  = G'[rows_r, :] * rinv_v  ->  dT_r = GA  V_all          G' = g/(2N) (e^{S-lse_row} + e^{S-lse_col})
+    swapped      GA' = G'^T[cols_r, :] * rinv_t -> dV_r = GA' T_all
+    finalise dT_r, dV_r locally (diagonal term, normalise-backward, d logit_scale)
+
+Both softmax directions are complete on the rank that owns them, and so are both gradients: compared with the NCCL form
+this trades the all-reduce and the [N, P] fp32 reduce-scatter for recomputing the swapped tile block (tensor-core time,
+which the step has to spare) and leaves two tiny exchanges per step.  Everything is enqueued on CUDA streams — the whole
+multi-GPU step replays as one CUDA graph per rank.
+
+`SymmetricItc` is the backend-agnostic sequencing (the gloo/CPU test plugs in torch stand-ins); `PeerGroup` is the
+IPC plumbing + exchange kernel binding; `PeerHeadPlan` is the multi-GPU HeadPlan built on both.
+"""
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class SymmetricItc:
+    """Sequencing of the symmetric row/column-block ITC step.
+
+    rb / cb: the row block and the swapped block.  Each implements the `plan.ItcPlan` piece interface and carries
+        rinv_t [b] (its A rows: mine), rinv_v [N] (its B rows: gathered), lse_row [b] (mine), lse_col [N] (gathered).
+    exchange(phase): phase "emb" fills T_all/V_all (+ residuals) and the gathered inverse norms from every rank's
+        published block; phase "lse" fills the gathered lse vectors.
+    lse_rows(rb, cb, scale, loss_sums): row partials of both blocks -> rb.lse_row, cb.lse_row (published), loss terms.
+    """
+
+    def __init__(self, rb, cb, exchange, lse_rows, b_local: int, world: int, rank: int, branches=None):
+        self.rb, self.cb, self.exchange, self.lse_rows = rb, cb, exchange, lse_rows
+        self.b, self.world, self.rank, self.N = b_local, world, rank, b_local * world
+        # the row block and the swapped block are independent between the exchanges: issue them on parallel branches
+        self.br = branches if branches is not None else _NoBranches()
+
+    def forward(self, T, V, T_all, V_all, scale, loss_sums, T_lo=None, V_lo=None, T_all_lo=None, V_all_lo=None,
+                produce_t=None, produce_v=None):
+        """produce_t / produce_v: optional callables that compute this rank's T / V into the published block (e.g. the
+        projection GEMMs); they run on the two branches so that neither tower waits for the other."""
+        rb, cb, br = self.rb, self.cb, self.br
+        ldt, ldv = T.stride(0), V.stride(0)
+        with br("cb"):
+            if produce_v is not None:
+                produce_v()
+            cb.norm_t(V, ldv, T_lo=V_lo)                  # -> published inverse norms of my image rows
+        if produce_t is not None:
+            produce_t()
+        rb.norm_t(T, ldt, T_lo=T_lo)                      # -> ... of my text rows
+        br.join("cb")
+        self.exchange("emb")
+        with br("cb"):
+            cb.fwd_tiles(V, ldv, T_all, T_all.stride(0), scale, T_lo=V_lo, V_lo=T_all_lo)
+        rb.fwd_tiles(T, ldt, V_all, V_all.stride(0), scale, T_lo=T_lo, V_lo=V_all_lo)
+        br.join("cb")
+        self.lse_rows(rb, cb, scale, loss_sums)
+        self.exchange("lse")
+
+    def backward(self, T, V, T_all, V_all, scale, g, dT_f32=None, dT_bf16=None, dV_f32=None, dV_bf16=None, r_sum=None,
+                 T_lo=None, V_lo=None, T_all_lo=None, V_all_lo=None, dT_lo=None, dV_lo=None, consume_t=None, consume_v=None):
+        """g = dLoss/d(clip_loss) of the GLOBAL loss; produces this rank's dT, dV [b, P] and its share of d logit_scale.
+        consume_t / consume_v: optional callables issued right after dT / dV exist (projection weight gradients)."""
+        rb, cb, N, br = self.rb, self.cb, self.N, self.br
+        ldt, ldv = T.stride(0), V.stride(0)
+        with br("cb"):
+            cb.bwd_operands(V, ldv, T_all, T_all.stride(0), scale, g / (2.0 * N), T_lo=V_lo, V_lo=T_all_lo)
+            cb.grad_gemm_t(T_all, T_all.stride(0), V_lo=T_all_lo)
+            cb.finalize_t(V, ldv, T, ldt, rb.rinv_t, scale, g / N, dV_f32, dV_bf16, None, dT_lo=dV_lo, T_lo=V_lo, V_diag_lo=T_lo)
+            if consume_v is not None:
+                consume_v()
+        rb.bwd_operands(T, ldt, V_all, V_all.stride(0), scale, g / (2.0 * N), T_lo=T_lo, V_lo=V_all_lo)
+        rb.grad_gemm_t(V_all, V_all.stride(0), V_lo=V_all_lo)
+        rb.finalize_t(T, ldt, V, ldv, cb.rinv_t, scale, g / N, dT_f32, dT_bf16, r_sum, dT_lo=dT_lo, T_lo=T_lo, V_diag_lo=V_lo)
+        if consume_t is not None:
+            consume_t()
+        br.join("cb")
+
+
+class _NoBranches:
+    class _Ctx:
+        def __enter__(self):
+            return None
+
+        def __exit__(self, *a):
+            return False
+
+    def __call__(self, k):
+        return self._Ctx()
+
+    def join(self, k):
+        pass
+
+
+class _RawCuda:
+    """Exposes a raw device allocation through __cuda_array_interface__ so torch can view it without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def _up(x, a=256):
+    return (x + a - 1) // a * a
+
+
+class PeerGroup:
+    """One symmetric block of `nbytes` per rank, mapped by every peer.  Handles are exchanged once through the process
+    group (setup only); `exchange()` is the per-step kernel and touches no collective library."""
+
+    def __init__(self, nbytes: int, world: int, rank: int, device, group=None):
+        from . import capi
+        lib = capi.load()
+        assert 1 <= world <= 8, "tic_peer_exchange supports up to 8 ranks (one NVSwitch domain)"
+        self.capi, self.world, self.rank, self.dev = capi, world, rank, torch.device(device)
+        self.nbytes = _up(nbytes)
+        self.flag_off = self.nbytes
+        total = self.nbytes + 256
+        p = ctypes.c_void_p()
+        capi.call("tic_peer_alloc", total, ctypes.byref(p))
+        self.local = int(p.value)
+        hb = lib.tic_peer_handle_bytes()
+        buf = (ctypes.c_ubyte * hb)()
+        capi.call("tic_peer_export", self.local, buf)
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=self.dev)
+        allh = torch.empty(world * hb, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy().reshape(world, hb)
+        self.bases: List[int] = []
+        for r in range(world):
+            if r == rank:
+                self.bases.append(self.local)
+                continue
+            hbuf = (ctypes.c_ubyte * hb)(*[int(x) for x in allh[r]])
+            q = ctypes.c_void_p()
+            capi.call("tic_peer_open", hbuf, ctypes.byref(q))
+            self.bases.append(int(q.value))
+        self._bases_c = (ctypes.c_void_p * world)(*self.bases)
+        self.ctr = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self._holder = _RawCuda(self.local, total)
+        self.block = torch.as_tensor(self._holder, device=self.dev)
+        assert self.block.data_ptr() == self.local, "torch copied the peer block instead of viewing it"
+        self._phases = {}
+        self.define_phase("align", [])     # barrier only
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=group)     # every block is allocated, zeroed and mapped before the first exchange
+
+    def view(self, off: int, shape: Tuple[int, ...], dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        nb = n * torch.empty(0, dtype=dtype).element_size()
+        assert off % 256 == 0 and off + nb <= self.nbytes
+        return self.block[off:off + nb].view(dtype).view(*shape)
+
+    def define_phase(self, name: str, segs):
+        """segs: [(src_off_bytes, nbytes, dst_tensor, dst_stride_bytes)] — dst receives rank p's range at p*dst_stride."""
+        n = len(segs)
+        self._phases[name] = (n, (ctypes.c_int64 * n)(*[s[0] for s in segs]), (ctypes.c_int64 * n)(*[s[1] for s in segs]),
+                              (ctypes.c_void_p * n)(*[s[2].data_ptr() for s in segs]),
+                              (ctypes.c_int64 * n)(*[s[3] for s in segs]), [s[2] for s in segs])
+
+    def exchange(self, name: str):
+        n, so, nb, dst, ds, _keep = self._phases[name]
+        self.capi.call("tic_peer_exchange", self._bases_c, self.world, self.rank, self.flag_off, self.ctr.data_ptr(), n, so, nb,
+                       dst, ds, torch.cuda.current_stream().cuda_stream)
+
+    def close(self):
+        for r, b in enumerate(self.bases):
+            if r != self.rank and b:
+                self.capi.call("tic_peer_close", b)
+        self.bases = []
+
+
+def _make_peer_head_plan():
+    from . import plan as P
+    from .capi import call, ptr
+
+    BF16, F32 = torch.bfloat16, torch.float32
+
+    class PeerHeadPlan(P.HeadPlan):
+        """Multi-GPU HeadPlan over peer memory: ITC is row-sharded with the symmetric formulation above; fusion heads, ITM
+        sampling/gather and the small heads are per-sample (pure data parallel).  Every rank produces the gradients of the
+        GLOBAL loss restricted to its samples (weight gradients / d logit_scale are summed across ranks by the caller)."""
+
+        def __init__(self, B_local, *, world, rank, group=None, d: Optional[int] = None, **kw):
+            kw.setdefault("use_itc", True)
+            use_itc = kw["use_itc"]
+            kw["use_itc"] = False                       # the parent must not allocate a square single-GPU ItcPlan
+            super().__init__(B_local, **kw)
+            self.use_itc = use_itc
+            self.world, self.rank = world, rank
+            b, dev = B_local, self.dev
+            if self.P is None and d is not None:
+                self.Pe = d
+                self.out["d_t_emb"] = torch.empty(b, d, device=dev)
+                self.out["d_v_emb"] = torch.empty(b, d, device=dev)
+            N = b * world
+            self.n_global = N
+            if use_itc:
+                self.beta_itc = kw.get("beta_itc", 0.1) if self.fusion is not None else 1.0
+                self.g_itc = self.beta_itc if self.fusion is not None else 1.0
+                self.w_cls = (1.0 - (self.beta_itc + self.beta_itm)) if self.fusion is not None else 0.0
+            self.w_cls /= world                          # local means -> contributions to global means
+            self.beta_itm_local = self.beta_itm / world
+            if not use_itc:
+                return
+            assert b % 8 == 0, "per-rank batch must be a multiple of 8 (16-byte exchange segments)"
+            Pe = self.Pe
+            precise = N < 4096
+            self.has_lo = precise and self.P is not None  # residuals exist only for embeddings projected on the device
+            ybytes = 2 * b * Pe * 2
+            off_hi, off_lo = 0, _up(ybytes)
+            off_rinv = off_lo + (_up(ybytes) if self.has_lo else 0)
+            off_lse = off_rinv + _up(2 * b * 4)
+            self.pg = PeerGroup(off_lse + _up(2 * b * 4), world, rank, dev, group)
+            pg = self.pg
+            e = lambda *s, dt=F32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
+            # published (symmetric) views: [text rows ; image rows]
+            self.Y = pg.view(off_hi, (2 * b, Pe), BF16)
+            self.Y_lo = pg.view(off_lo, (2 * b, Pe), BF16) if self.has_lo else (e(2 * b, Pe, dt=BF16) if self.P is not None else None)
+            self.rinv_mine = pg.view(off_rinv, (2 * b,), F32)
+            self.lse_mine = pg.view(off_lse, (2 * b,), F32)
+            # gathered copies in local HBM
+            self.T_all, self.V_all = e(N, Pe, dt=BF16), e(N, Pe, dt=BF16)
+            self.T_all_lo = e(N, Pe, dt=BF16) if self.has_lo else None
+            self.V_all_lo = e(N, Pe, dt=BF16) if self.has_lo else None
+            self.rinv_t_all, self.rinv_v_all, self.lse_row_all, self.lse_col_all = e(N), e(N), e(N), e(N)
+            half = b * Pe * 2
+            segs = [(off_hi, half, self.T_all, half), (off_hi + half, half, self.V_all, half)]
+            if self.has_lo:
+                segs += [(off_lo, half, self.T_all_lo, half), (off_lo + half, half, self.V_all_lo, half)]
+            segs += [(off_rinv, b * 4, self.rinv_t_all, b * 4), (off_rinv + b * 4, b * 4, self.rinv_v_all, b * 4)]
+            pg.define_phase("emb", segs)
+            pg.define_phase("lse", [(off_lse, b * 4, self.lse_row_all, b * 4), (off_lse + b * 4, b * 4, self.lse_col_all, b * 4)])
+            mk = lambda: P.ItcPlan(b, N, Pe, dev, row_offset=rank * b, need_dv=False, precise=precise, col_sums=False)  # noqa: E731
+            self.rb, self.cb = mk(), mk()
+            self.rb.rinv_t, self.rb.rinv_v = self.rinv_mine[:b], self.rinv_v_all
+            self.cb.rinv_t, self.cb.rinv_v = self.rinv_mine[b:], self.rinv_t_all
+            self.rb.lse_row, self.rb.lse_col = self.lse_mine[:b], self.lse_col_all
+            self.cb.lse_row, self.cb.lse_col = self.lse_mine[b:], self.lse_row_all
+            self.itc = self.rb
+            self.lse_ws = torch.zeros(int(capi_load().tic_itc_lse_rows_workspace_bytes(b)) // 4, dtype=F32, device=dev)
+            self.sym = SymmetricItc(self.rb, self.cb, pg.exchange, self._lse_rows, b, world, rank, branches=self.br)
+
+        def _lse_rows(self, rb, cb, scale, loss_sums):
+            call("tic_itc_lse_rows", ptr(rb.row_part), ptr(cb.row_part), rb.nrp, self.B, ptr(rb.diag), float(scale),
+                 ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), P._stream())
+
+        def _heads(self, inp, dH_f32=None, forward_only=False, dz_ext=None):
+            saved = self.beta_itm
+            self.beta_itm = self.beta_itm_local
+            try:
+                super()._heads(inp, dH_f32=dH_f32, forward_only=forward_only, dz_ext=dz_ext)
+            finally:
+                self.beta_itm = saved
+
+        def _ops(self):
+            b = self.B
+            lo = self.has_lo
+            return dict(T=self.Y[:b], V=self.Y[b:], T_all=self.T_all, V_all=self.V_all,
+                        T_lo=self.Y_lo[:b] if lo else None, V_lo=self.Y_lo[b:] if lo else None,
+                        T_all_lo=self.T_all_lo, V_all_lo=self.V_all_lo)
+
+        def _itc_fwd(self, inp, with_loss=True):
+            B, E, w = self.B, self.E, self.w
+            Yt, Yv = self.Y[:B], self.Y[B:]
+            self.br.enabled = self.parallel_streams
+            if self.P is not None:
+                tp_, vp_ = inp["t_pool"], inp["v_pool"]
+                pt = lambda: P.gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=self.Y_lo[:B])  # noqa: E731  HF :265
+                pv = lambda: P.gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=self.Y_lo[B:])  # noqa: E731  HF :262
+            else:   # embeddings handed in by the caller: publish them
+                pt = lambda: Yt.copy_(inp["t_pool"])  # noqa: E731
+                pv = lambda: Yv.copy_(inp["v_pool"])  # noqa: E731
+            self.sym.forward(scale=self.scale, loss_sums=self.z["itc_sums"], produce_t=pt, produce_v=pv, **self._ops())
+
+        def _itc_bwd(self, inp, dS=None):
+            assert dS is None, "the sharded path implements the fused loss only"
+            B, E, w, z, o, br = self.B, self.E, self.w, self.z, self.out, self.br
+            br.enabled = self.parallel_streams
+            if self.P is not None:
+                dYt, dYv, dYt_lo, dYv_lo = self.dY[:B], self.dY[B:], self.dY_lo[:B], self.dY_lo[B:]
+                tp_, vp_ = inp["t_pool"], inp["v_pool"]
+
+                def consume_t():
+                    with br("w"):
+                        P.gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo, accumulate=True)
+                    P.gemm(dYt, self.P, 0, w["W_t"], E, 1, o["d_t_pool"], E, 0, B, E, self.P, A_lo=dYt_lo)
+                    br.join("w")
+
+                def consume_v():
+                    P.gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=True)
+
+                self.sym.backward(scale=self.scale, g=self.g_itc, dT_bf16=dYt, dV_bf16=dYv, r_sum=z["r_sum"], dT_lo=dYt_lo,
+                                  dV_lo=dYv_lo, consume_t=consume_t, consume_v=consume_v, **self._ops())
+            else:
+                self.sym.backward(scale=self.scale, g=self.g_itc, dT_f32=o["d_t_emb"], dV_f32=o["d_v_emb"], r_sum=z["r_sum"],
+                                  **self._ops())
+
+        def global_loss(self):
+            """[mix, cls, itc, itm] of the GLOBAL batch (reporting only; this is the one place a collective is used)."""
+            t = self.out["loss"].clone()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            cls, itc, itm = t[1] / self.world, t[2], t[3] / self.world
+            if self.fusion is None:
+                return torch.stack([itc, cls, itc, itm])
+            mix = (1.0 - (self.beta_itc + self.beta_itm)) * cls + self.beta_itc * itc + self.beta_itm * itm
+            return torch.stack([mix, cls, itc, itm])
+
+    def capi_load():
+        from . import capi
+        return capi.load()
+
+    return PeerHeadPlan
+
+
+def __getattr__(name):
+    if name == "PeerHeadPlan":
+        return _make_peer_head_plan()
+    raise AttributeError(name)

@@ -80,7 +80,7 @@ class ItcPlan:
     """ITC forward+backward for a row block of `m` text rows against `n` gathered image columns (single GPU: m == n)."""
 
     def __init__(self, m: int, n: int, P: int, device, row_offset: int = 0, materialize_logits: bool = False,
-                 need_dv: bool = True, precise: Optional[bool] = None):
+                 need_dv: bool = True, precise: Optional[bool] = None, col_sums: bool = True):
         assert P % 8 == 0, "embedding width must be a multiple of 8 (16-byte TMA rows)"
         self.m, self.n, self.P, self.row_offset = m, n, P, row_offset
         # Split-precision gradient operands (bf16 hi+lo): with few negatives the bf16 rounding of the softmax
@@ -92,8 +92,9 @@ class ItcPlan:
         self.rinv_t = torch.empty(m, dtype=F32, device=dev)
         self.rinv_v = torch.empty(n, dtype=F32, device=dev)
         self.row_part = torch.empty(self.nrp, m, dtype=F32, device=dev)
-        self.col_part = torch.empty(self.ncp, n, dtype=F32, device=dev)
-        self.col_sum = torch.empty(n, dtype=F32, device=dev)   # used by the multi-GPU path (all-reduced)
+        # col_sums=False (symmetric peer-memory mode): column statistics are the row statistics of the swapped block
+        self.col_part = torch.empty(self.ncp, n, dtype=F32, device=dev) if col_sums else None
+        self.col_sum = torch.empty(n, dtype=F32, device=dev) if col_sums else None   # NCCL path (all-reduced)
         self.diag = torch.empty(m, dtype=F32, device=dev)
         self.lse_row = torch.empty(m, dtype=F32, device=dev)
         self.lse_col = torch.empty(n, dtype=F32, device=dev)
@@ -353,6 +354,8 @@ class HeadPlan:
         if self.P is not None:
             tp_, vp_ = inp["t_pool"], inp["v_pool"]
             Yt, Yv, Ytl, Yvl = self.Y[:B], self.Y[B:], self.Y_lo[:B], self.Y_lo[B:]
+            if not self.itc.precise:   # >= 4096 negatives: the residual K-segments are skipped (tensor time matters there)
+                Ytl = Yvl = None
             return Yt, Yv, Ytl, Yvl
         return inp["t_pool"], inp["v_pool"], None, None
 
@@ -663,3 +666,50 @@ class HostStep:
         self.loss_pinned.copy_(self.plan.out["loss"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return [float(x) for x in self.loss_pinned]
+
+
+class HostPipeline:
+    """Pipelined host-facing entry point: `submit()` enqueues one step whose inputs live in a pinned HOST arena (H2D copy
+    on a copy stream -> the plan replayed as a CUDA graph on the compute stream -> D2H of the 4 losses) and returns at once;
+    `result()` blocks until the oldest outstanding step has finished and returns its losses.  Two slots (host arena, device
+    arena, graph) alternate, so the H2D transfer of step k+1 overlaps the kernels of step k — what a training loop whose
+    encoders run elsewhere would do.  Every step still pays its own H2D and D2H inside the pipeline.
+    `between` (optional callable) is enqueued on the compute stream before each step (bench.py: the L2 flush)."""
+
+    DEPTH = 2
+
+    def __init__(self, plan, host_example: Dict[str, torch.Tensor], bf16_keys=(), between=None):
+        self.plan, self.between = plan, between
+        self.slots = [HostStep(plan, host_example, bf16_keys=bf16_keys, use_graph=True) for _ in range(self.DEPTH)]
+        self.h2d_bytes, self.d2h_bytes = self.slots[0].h2d_bytes, self.slots[0].d2h_bytes
+        self.copy_stream = torch.cuda.Stream(device=plan.dev)
+        self.h2d_done = [torch.cuda.Event() for _ in self.slots]
+        self.step_done = [torch.cuda.Event() for _ in self.slots]
+        self.n_submitted = self.n_collected = 0
+
+    def host_views(self, k=None):
+        """Pinned typed views the caller fills in place for the NEXT submitted step."""
+        return self.slots[(self.n_submitted if k is None else k) % self.DEPTH].host_views
+
+    def submit(self):
+        assert self.n_submitted - self.n_collected < self.DEPTH, "collect a result before submitting another step"
+        i = self.n_submitted % self.DEPTH
+        sl, cs = self.slots[i], torch.cuda.current_stream()
+        self.copy_stream.wait_event(self.step_done[i])          # the slot's previous step has consumed its device arena
+        with torch.cuda.stream(self.copy_stream):
+            sl.device.copy_(sl.pinned, non_blocking=True)       # this step's inputs: one H2D transfer
+            self.h2d_done[i].record()
+        if self.between is not None:
+            self.between()
+        cs.wait_event(self.h2d_done[i])
+        sl.graph.replay()
+        sl.loss_pinned.copy_(self.plan.out["loss"], non_blocking=True)
+        self.step_done[i].record()
+        self.n_submitted += 1
+
+    def result(self):
+        assert self.n_collected < self.n_submitted
+        i = self.n_collected % self.DEPTH
+        self.step_done[i].synchronize()
+        self.n_collected += 1
+        return [float(x) for x in self.slots[i].loss_pinned]

@@ -2,7 +2,12 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py
 
-Every rank runs DistHeadPlan on its shard; rank 0 additionally runs the single-GPU HeadPlan on the concatenated batch.
+    ... tests/dist_gpu_check.py [--mode peer|nccl] [--graph]
+
+--mode peer (default): tic_b200.peer.PeerHeadPlan — symmetric row/column blocks over CUDA-IPC peer memory, no collective on
+the data path; --mode nccl: tic_b200.dist.DistHeadPlan — all_gather / all_reduce / reduce_scatter.  --graph replays the step
+as a CUDA graph (peer mode only).
+Every rank runs the plan on its shard; rank 0 additionally runs the single-GPU HeadPlan on the concatenated batch.
 Checked: global loss, this rank's input gradients, and the SUM-all-reduced weight gradients against the single-GPU
 gradients (1e-3 scale-relative).  Exit code 0 = pass."""
 import os
@@ -27,7 +32,14 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     import tic_b200.plan as P
-    from tic_b200.dist import DistHeadPlan
+    mode = "peer"
+    if "--mode" in sys.argv:
+        mode = sys.argv[sys.argv.index("--mode") + 1]
+    use_graph = "--graph" in sys.argv
+    if mode == "peer":
+        from tic_b200.peer import PeerHeadPlan as DistHeadPlan
+    else:
+        from tic_b200.dist import DistHeadPlan
     from oracle import restatement as R   # weight init + sampling rule only
 
     ok = True
@@ -59,6 +71,19 @@ def main():
         dplan.set_weights(w32)
         out = dplan.step(shard)
         torch.cuda.synchronize()
+        if use_graph:      # the whole multi-GPU step (exchanges included) as one CUDA graph, replayed twice
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                dplan.step(shard)
+            torch.cuda.current_stream().wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                dplan.step(shard)
+            for _ in range(2):
+                gr.replay()
+            torch.cuda.synchronize()
+            out = dplan.out
         gl = dplan.global_loss()
         wkeys = [k for k in out if k.startswith("dW_") or k.startswith("db_")] + ["d_logit_scale"]
         wsum = {}
@@ -87,7 +112,7 @@ def main():
                 if k in ref and k in out:
                     errs[k] = rel(out[k], ref[k][:b])
             bad = {k: v for k, v in errs.items() if not v < 1e-3}
-            print("dist check fusion=%s b=%d world=%d: %s" % (fusion, b, world, {k: "%.1e" % v for k, v in errs.items()}))
+            print("dist check mode=%s graph=%s fusion=%s b=%d world=%d: %s" % (mode, use_graph, fusion, b, world, {k: "%.1e" % v for k, v in errs.items()}))
             if bad:
                 print("FAIL", bad)
                 ok = False

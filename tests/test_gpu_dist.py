@@ -12,8 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_dist_head_plan_two_gpus():
+@pytest.mark.parametrize("extra", [["--mode", "peer"], ["--mode", "peer", "--graph"], ["--mode", "nccl"]])
+def test_dist_head_plan_two_gpus(extra):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+           "--master-port", "29517", os.path.join(ROOT, "tests", "dist_gpu_check.py")] + extra
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]

@@ -1,0 +1,123 @@
+"""CPU, world_size 2 over gloo: the SYMMETRIC row/column-block formulation of the sharded ITC step
+(tic_b200.peer.SymmetricItc — two exchanges, no reduction across ranks) reproduces the single-process oracle on the
+concatenated batch: loss, this rank's dT and dV, and the summed d logit_scale.  The exchange kernel and the tile kernels
+need GPUs, so the exchange here is a gloo all_gather and the per-rank block backend a torch (fp64) stand-in with the
+piece interface of plan.ItcPlan; tests/dist_gpu_check.py --mode peer covers the real thing on 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import restatement as R
+
+
+class CpuBlock:
+    """fp64 stand-in for one ItcPlan block: A rows are mine (m), B rows are gathered (n)."""
+
+    def __init__(self, m, n, row_offset):
+        self.m, self.n, self.row_offset = m, n, row_offset
+        self.rinv_t = torch.zeros(m, dtype=torch.float64)     # published by norm_t
+        self.rinv_v = torch.zeros(n, dtype=torch.float64)     # filled by exchange("emb")
+        self.lse_row = torch.zeros(m, dtype=torch.float64)    # published by lse_rows
+        self.lse_col = torch.zeros(n, dtype=torch.float64)    # filled by exchange("lse")
+
+    def norm_t(self, T, ldt, T_lo=None):
+        self.rinv_t.copy_(1.0 / T.norm(dim=1))
+
+    def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None):
+        self.S = scale * (T * self.rinv_t[:, None]) @ (V * self.rinv_v[:, None]).t()
+        self.row_sum = torch.exp(self.S - scale).sum(1)
+        self.diag = self.S[torch.arange(self.m), self.row_offset + torch.arange(self.m)]
+
+    def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None):
+        Gp = gscale * (torch.exp(self.S - self.lse_row[:, None]) + torch.exp(self.S - self.lse_col[None, :]))
+        self.GA = Gp * self.rinv_v[None, :]
+
+    def grad_gemm_t(self, V, ldv, V_lo=None):
+        self.acc_t = self.GA @ V
+
+    def finalize_t(self, T, ldt, V_diag, ldv, rinv_v_diag, scale, diag_coef, dT_f32, dT_bf16, r_sum, **kw):
+        dxh = scale * (self.acc_t - diag_coef * rinv_v_diag[:, None] * V_diag)
+        xh = T * self.rinv_t[:, None]
+        r = (xh * dxh).sum(1)
+        dT_f32.copy_(self.rinv_t[:, None] * (dxh - xh * r[:, None]))
+        if r_sum is not None:
+            r_sum += r.sum()
+
+
+def _worker(rank, world, port, b, P, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tic_b200.peer import SymmetricItc
+        N = b * world
+        g = torch.Generator().manual_seed(7)
+        T_full = torch.randn(N, P, generator=g, dtype=torch.float64)
+        V_full = torch.randn(N, P, generator=g, dtype=torch.float64) + 0.5 * T_full
+        T, V = T_full[rank * b:(rank + 1) * b].clone(), V_full[rank * b:(rank + 1) * b].clone()
+        T_all, V_all = torch.zeros(N, P, dtype=torch.float64), torch.zeros(N, P, dtype=torch.float64)
+        scale = float(np.exp(2.6592))
+        rb, cb = CpuBlock(b, N, rank * b), CpuBlock(b, N, rank * b)
+
+        def exchange(phase):   # stand-in for tic_peer_exchange: gathers what every rank published
+            if phase == "emb":
+                pairs = [(T, T_all), (V, V_all), (rb.rinv_t, cb.rinv_v), (cb.rinv_t, rb.rinv_v)]
+            else:
+                pairs = [(rb.lse_row, cb.lse_col), (cb.lse_row, rb.lse_col)]
+            for mine, full in pairs:
+                dist.all_gather_into_tensor(full, mine.contiguous())
+
+        def lse_rows(rb_, cb_, s, loss_sums):
+            rb_.lse_row.copy_(s + torch.log(rb_.row_sum))
+            cb_.lse_row.copy_(s + torch.log(cb_.row_sum))
+            loss_sums[0] += (rb_.lse_row - rb_.diag).sum()
+            loss_sums[1] += (cb_.lse_row - rb_.diag).sum()
+
+        sym = SymmetricItc(rb, cb, exchange, lse_rows, b, world, rank)
+        sums = torch.zeros(2, dtype=torch.float64)
+        sym.forward(T, V, T_all, V_all, scale, sums)
+        dT, dV = torch.empty(b, P, dtype=torch.float64), torch.empty(b, P, dtype=torch.float64)
+        rsum = torch.zeros(1, dtype=torch.float64)
+        sym.backward(T, V, T_all, V_all, scale, 1.0, dT_f32=dT, dV_f32=dV, r_sum=rsum)
+        dist.all_reduce(sums)
+        dist.all_reduce(rsum)
+        loss = 0.5 * (sums[0] + sums[1]) / N
+        Tq, Vq = T_full.clone().requires_grad_(True), V_full.clone().requires_grad_(True)
+        ls = torch.tensor(2.6592, dtype=torch.float64, requires_grad=True)
+        ref = R.clip_loss(R.itc_logits(Tq, Vq, ls))
+        ref.backward()
+        ok = (abs(float(loss) - float(ref)) < 1e-10
+              and torch.allclose(dT, Tq.grad[rank * b:(rank + 1) * b], rtol=1e-8, atol=1e-12)
+              and torch.allclose(dV, Vq.grad[rank * b:(rank + 1) * b], rtol=1e-8, atol=1e-12)
+              and abs(float(rsum) - float(ls.grad)) < 1e-9
+              and torch.allclose(rb.diag, cb.diag, rtol=1e-12))
+        out_q.put((rank, bool(ok), float(loss), float(ref)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("b,P", [(8, 16), (40, 64)])
+def test_symmetric_itc_matches_oracle_world2(b, P):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, b, P, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    assert all(ok for _, ok, _, _ in res), res
