@@ -56,6 +56,13 @@ int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn_major, 
  * ~2^-17.  D_lo (bf16 output only) receives the residual x - bf16(x) so the result can itself be consumed as a pair.
  * accumulate = 1 (fp32 output, no ReLU): D += result with fp32 atomics (D must hold its initial value, e.g. zeros); this
  * also lets the library split K across CTAs so that long-K weight-gradient GEMMs with few output tiles fill all SMs. */
+/* Same GEMM (no accumulate) that additionally writes row_ss_part[t][m] = sum over the columns of 64-wide column tile t of
+ * D[m, :]^2 (fp32, before any rounding to bf16), t < tic_gemm_rowss_parts(N): the L2-norm statistics of the projected
+ * embeddings (HF :268-269) for tic_itc_fwd, so the normalisation needs no kernel of its own on the small-batch path. */
+int tic_gemm_rowss_parts(int N);
+int tic_gemm_bf16_rowss(const void* A, const void* A_lo, int64_t lda, int a_mn_major, const void* B, const void* B_lo,
+                        int64_t ldb, int b_mn_major, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K,
+                        float alpha, const float* bias, int relu, float* row_ss_part, void* stream);
 /* Reference-quality SIMT fp32-accumulate GEMM with the same semantics (debug / self-test only). */
 int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
                        int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu,
@@ -81,9 +88,14 @@ int tic_row_rnorm_bf16(const void* X, const void* X_lo /* optional residual: nor
 int tic_itc_row_parts(int n_global);
 int tic_itc_col_parts(int m_local);
 int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv,
-                const float* rinv_t, const float* rinv_v,
+                float* rinv_t, float* rinv_v,
                 int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
-                float* col_part, float* diag, float* logits_out, int64_t ld_logits, void* stream);
+                float* col_part /* NULL: skip the column statistics (symmetric multi-GPU mode) */, float* diag,
+                float* logits_out, int64_t ld_logits, const float* ss_t_part, int n_ss_t, const float* ss_v_part, int n_ss_v,
+                void* stream);
+/* Fused normalisation (small batches): when ss_t_part [n_ss_t][m_local] / ss_v_part [n_ss_v][n_global] — the per-tile row
+ * sums of squares written by tic_gemm_bf16_rowss while it projected the embeddings — are given, the tiles derive
+ * rinv = 1/sqrt(sum of partials) themselves and WRITE rinv_t / rinv_v for the kernels that follow; no norm kernel runs. */
 /* out[j] = sum_p part[p][j]  (deterministic fixed-order reduction of the partials above). */
 int tic_reduce_parts(const float* part, int nparts, int n, float* out, void* stream);
 /* Sums the partials in a fixed order (deterministic), then lse = shift + log(sum);
@@ -113,7 +125,11 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
                   const float* rinv_t, const float* rinv_v,
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale,
                   float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo /* optional residuals */,
-                  void* GBT_lo, void* stream);
+                  void* GBT_lo, const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, float shift,
+                  void* stream);
+/* Inline statistics (small batches): when row_part / col_part (the partials written by tic_itc_fwd) are given, the kernel
+ * derives lse_row / lse_col = shift + log(sum of partials) itself (same expression as tic_itc_lse_loss) and the matching
+ * lse pointer may be NULL — tic_itc_lse_loss then only produces the loss and runs beside the backward, not before it. */
 /* Autograd path (materialised logits, drop-in batch sizes): the same operands from an upstream dL/dS [m_local, n_global]:
  *   GA[i,j] = dS[i,j]*rinv_v[j],  GBT[j,i] = dS[i,j]*rinv_t[i]  (+ optional bf16 residuals). Use diag_coef = 0 afterwards. */
 int tic_itc_ds_operands(const float* dS, int64_t ldds, int m_local, int n_global, const float* rinv_t, const float* rinv_v,
@@ -161,11 +177,15 @@ int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int m
  *   Xcat[i,      :] = [ xt[i*xt_stride : +E]        | xv[i*xv_stride : +E] ]      i < B   (main pass)
  *   Xcat[B + i,  :] = [ xt[src[i]*xt_stride : +E]   | xv[i*xv_stride : +E] ]      if src != NULL (ITM pass, :170-181)
  * xt/xv bf16 with row strides in elements (so x_t[:,0,:] of a [B,L,E] tensor is xt_stride = L*E). */
-/* xv may be NULL: then only the text half [:, :E] is written (attention fusion fills the other half by GEMM). */
+/* xv may be NULL: then only the text half [:, :E] is written (attention fusion fills the other half by GEMM).
+ * u_coin / u_pick (both or neither): evaluate the uniform ITM rule (mm_late.py:396-409, as tic_itm_sample) in place
+ * instead of reading src_idx, so the pack does not have to wait for the sampler kernel (src_idx is then ignored). */
 int tic_pack_cls_pairs(const void* xt, int64_t xt_stride, const void* xv, int64_t xv_stride, int B, int E,
-                       const int32_t* src_idx, void* Xcat, int64_t ldx, void* stream);
+                       const int32_t* src_idx, void* Xcat, int64_t ldx, const float* u_coin, const float* u_pick,
+                       void* stream);
 /* Gradient of the pack w.r.t. xt (vision is frozen, mm_late.py:67-69):
- *   dxt[i,:] = dXcat[i,:E] + sum_{k: src[k]==i} dXcat[B+k,:E]   (fp32, atomics for the scattered part). */
+ *   dxt[i,:] += dXcat[i,:E] + sum_{k: src[k]==i} dXcat[B+k,:E]   (fp32 atomics, ONE launch: dxt must be zero on entry;
+ *   E, ldd, ldd2 multiples of 4). */
 int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, const float* dX2 /* optional second addend, same layout */,
                         int64_t ldd2, int B, int E, const int32_t* src_idx, float* dxt, int64_t ld_dxt, void* stream);
 

@@ -20,11 +20,13 @@ _SIGS = {
     "tic_version": ("", ctypes.c_int),
     "tic_sm_count": ("", ctypes.c_int),
     "tic_gemm_bf16": ("pplipplippliiiifpiip", ctypes.c_int),
+    "tic_gemm_rowss_parts": ("i", ctypes.c_int),
+    "tic_gemm_bf16_rowss": ("pplipplippliiiifpipp", ctypes.c_int),
     "tic_gemm_bf16_simt": ("pliplipliiiifpip", ctypes.c_int),
     "tic_row_rnorm_bf16": ("ppliipplp", ctypes.c_int),
     "tic_itc_row_parts": ("i", ctypes.c_int),
     "tic_itc_col_parts": ("i", ctypes.c_int),
-    "tic_itc_fwd": ("pplpplppiiiiffpppplp", ctypes.c_int),
+    "tic_itc_fwd": ("pplpplppiiiiffpppplpipip", ctypes.c_int),
     "tic_reduce_parts": ("piipp", ctypes.c_int),
     "tic_itc_lse_loss": ("pipipiiifpppp", ctypes.c_int),
     "tic_itc_lse_rows_workspace_bytes": ("i", ctypes.c_int64),
@@ -36,7 +38,7 @@ _SIGS = {
     "tic_peer_open": ("pp", ctypes.c_int),
     "tic_peer_close": ("p", ctypes.c_int),
     "tic_peer_exchange": ("piilpippppp", ctypes.c_int),
-    "tic_itc_bwd_g": ("pplpplppppiiiffplplppp", ctypes.c_int),
+    "tic_itc_bwd_g": ("pplpplppppiiiffplplpppipifp", ctypes.c_int),
     "tic_itc_ds_operands": ("pliipppplpplp", ctypes.c_int),
     "tic_itc_grad_finalize": ("plpplppplpiiffplpplpip", ctypes.c_int),
     "tic_ce_bidir_workspace_bytes": ("i", ctypes.c_int64),
@@ -45,7 +47,7 @@ _SIGS = {
     "tic_itm_sample": ("ppiiplppp", ctypes.c_int),
     "tic_gather_rows": ("plpllpip", ctypes.c_int),
     "tic_itm_sample_gather": ("ppiiplpplppppp", ctypes.c_int),
-    "tic_pack_cls_pairs": ("plpliipplp", ctypes.c_int),
+    "tic_pack_cls_pairs": ("plpliipplppp", ctypes.c_int),
     "tic_unpack_cls_grad": ("plpliipplp", ctypes.c_int),
     "tic_heads_fwd_bwd": ("pliiiippppppppfffppppplplppppippp", ctypes.c_int),
     "tic_attn_pool_fwd": ("pllpliiiifpplplplp", ctypes.c_int),

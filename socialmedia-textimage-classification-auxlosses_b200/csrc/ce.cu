@@ -31,6 +31,8 @@ __device__ __forceinline__ void ms_combine(float& m, float& s, float m2, float s
 __global__ void __launch_bounds__(256)
 ce_bidir_fwd_kernel(const float* __restrict__ S, int64_t lds, int B, float2* __restrict__ rp, float2* __restrict__ cp,
                     float* __restrict__ diag) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   __shared__ float tile[kCeRows][kCeCols + 4];
   __shared__ float2 ccomb[kCeCols];
   const int strip = blockIdx.x, seg = blockIdx.y, nseg = gridDim.y;
@@ -98,6 +100,8 @@ ce_bidir_fwd_kernel(const float* __restrict__ S, int64_t lds, int B, float2* __r
 __global__ void ce_bidir_finalize_kernel(const float2* __restrict__ rp, int nstrips, const float2* __restrict__ cp, int nseg,
                                          const float* __restrict__ diag, int B, float* __restrict__ lse_row,
                                          float* __restrict__ lse_col, float* __restrict__ loss) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   __shared__ float sred[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
@@ -124,6 +128,8 @@ __global__ void ce_bidir_finalize_kernel(const float2* __restrict__ rp, int nstr
 __global__ void ce_bidir_bwd_kernel(const float* __restrict__ S, int64_t lds, int B, const float* __restrict__ lse_row,
                                     const float* __restrict__ lse_col, const float* __restrict__ grad_loss,
                                     float* __restrict__ dS, int64_t ldds) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int r = blockIdx.y;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= B) return;
@@ -175,8 +181,8 @@ int tic_ce_bidir_fwd(const float* S, int64_t lds, int B, float* lse_row, float* 
   float2* rp = static_cast<float2*>(workspace);
   float2* cp = rp + static_cast<int64_t>(ns) * B;
   float* diag = reinterpret_cast<float*>(cp + static_cast<int64_t>(ng) * B);
-  ce_bidir_fwd_kernel<<<dim3(ns, ng), 256, 0, st>>>(S, lds, B, rp, cp, diag);
-  ce_bidir_finalize_kernel<<<1, 1024, 0, st>>>(rp, ns, cp, ng, diag, B, lse_row, lse_col, loss);
+  launch_k(ce_bidir_fwd_kernel, dim3(dim3(ns, ng)), dim3(256), 0, st, S, lds, B, rp, cp, diag);
+  launch_k(ce_bidir_finalize_kernel, dim3(1), dim3(1024), 0, st, rp, ns, cp, ng, diag, B, lse_row, lse_col, loss);
   TIC_CHECK_LAUNCH("tic_ce_bidir_fwd");
   return TIC_OK;
 }
@@ -185,7 +191,7 @@ int tic_ce_bidir_bwd(const float* S, int64_t lds, int B, const float* lse_row, c
                      float* dS, int64_t ldds, void* stream) {
   TIC_CHECK_ARG(S && lse_row && lse_col && grad_loss && dS && B > 0, "tic_ce_bidir_bwd: bad arguments");
   dim3 grid(ceil_div(ceil_div(B, 4), 256), B);
-  ce_bidir_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, B, lse_row, lse_col, grad_loss, dS, ldds);
+  launch_k(ce_bidir_bwd_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), S, lds, B, lse_row, lse_col, grad_loss, dS, ldds);
   TIC_CHECK_LAUNCH("tic_ce_bidir_bwd");
   return TIC_OK;
 }

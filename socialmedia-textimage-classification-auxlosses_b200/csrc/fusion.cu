@@ -30,6 +30,8 @@ attn_pool_fwd_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, int6
                      int64_t ldkq, int B, int Lv, float scale, __nv_bfloat16* __restrict__ xbar_b,
                      __nv_bfloat16* __restrict__ xbar_lo, int64_t ld_xb,
                      float* __restrict__ xbar_f, int64_t ld_xf, float* __restrict__ attn, int64_t ld_attn) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   constexpr int E = NV * 256;
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   extern __shared__ float sm[];
@@ -123,6 +125,8 @@ attn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, int6
                      int64_t ld_attn, const float* __restrict__ dxbar, int64_t ld_dxb, const float* __restrict__ xbar_f,
                      int64_t ld_xf, int B, int Lv, float scale, __nv_bfloat16* __restrict__ dkq,
                      __nv_bfloat16* __restrict__ dkq_lo, int64_t ld_dkq) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   constexpr int E = NV * 256;
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   extern __shared__ float sm[];
@@ -260,6 +264,8 @@ __global__ void __launch_bounds__(288, 1)
 attn_pool_fwd_v2_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, const float* __restrict__ kq, int64_t ldkq, int B,
                         int Lv, float scale, __nv_bfloat16* __restrict__ xbar_b, __nv_bfloat16* __restrict__ xbar_lo,
                         int64_t ld_xb, float* __restrict__ xbar_f, int64_t ld_xf, float* __restrict__ attn, int64_t ld_attn) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   constexpr int NV = 3, E = kApE;
   extern __shared__ uint8_t ap_raw[];
   const ApSmem sm = ap_carve(ap_raw);
@@ -370,6 +376,8 @@ __global__ void __launch_bounds__(288, 1)
 attn_pool_bwd_v2_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, const float* __restrict__ attn, int64_t ld_attn,
                         const float* __restrict__ dxbar, int64_t ld_dxb, const float* __restrict__ xbar_f, int64_t ld_xf, int B,
                         int Lv, float scale, __nv_bfloat16* __restrict__ dkq, __nv_bfloat16* __restrict__ dkq_lo, int64_t ld_dkq) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   constexpr int NV = 3, E = kApE;
   extern __shared__ uint8_t ap_raw[];
   const ApSmem sm = ap_carve(ap_raw);
@@ -491,6 +499,8 @@ __device__ __forceinline__ const __nv_bfloat16* aspect_row(const __nv_bfloat16* 
 __global__ void aspect_fwd_kernel(const __nv_bfloat16* __restrict__ t, int64_t ldt, const __nv_bfloat16* __restrict__ v, int64_t ldv,
                                   int B, int E, const float* __restrict__ w_a, const float* __restrict__ b_a,
                                   float* __restrict__ out, int64_t ldo, float* __restrict__ alpha) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= B) return;
   const __nv_bfloat16* r0 = aspect_row(t, ldt, v, ldv, B, 2 * i);
@@ -515,6 +525,8 @@ __global__ void aspect_bwd_kernel(const __nv_bfloat16* __restrict__ t, int64_t l
                                   const float* __restrict__ out, int64_t ldo, const float* __restrict__ alpha,
                                   const float* __restrict__ dout, int64_t lddo, float* __restrict__ dt, int64_t lddt,
                                   float* __restrict__ dw_a, float* __restrict__ db_a) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= B) return;
   const int f0 = 2 * i, f1 = 2 * i + 1;
@@ -550,6 +562,8 @@ __global__ void aspect_bwd_kernel(const __nv_bfloat16* __restrict__ t, int64_t l
 __global__ void gmu_gate_fwd_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const float* __restrict__ tp,
                                     const float* __restrict__ vp, int64_t ldp, int B, int E2, __nv_bfloat16* __restrict__ G,
                                     __nv_bfloat16* __restrict__ G_lo, int64_t ldg) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(B) * E2) return;
   const int64_t r = idx / E2, c = idx % E2;
@@ -564,6 +578,8 @@ __global__ void gmu_gate_bwd_kernel(const __nv_bfloat16* __restrict__ X, int64_t
                                     int E2, __nv_bfloat16* __restrict__ dtp, __nv_bfloat16* __restrict__ dvp,
                                     __nv_bfloat16* __restrict__ dtp_lo, __nv_bfloat16* __restrict__ dvp_lo, int64_t lddp,
                                     float* __restrict__ dX, int64_t lddx) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(B) * E2) return;
   const int64_t r = idx / E2, c = idx % E2;
@@ -599,12 +615,12 @@ int tic_attn_pool_fwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
     if (npass == 1) {
       auto k = attn_pool_fwd_v2_kernel<1>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-      k<<<ap_grid(B), 288, sm2, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, static_cast<const float*>(kq), ldkq,
+      launch_k(k, dim3(ap_grid(B)), dim3(288), sm2, st, static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, static_cast<const float*>(kq), ldkq,
                                       B, Lv, scale, xb2, xl2, ld_xb, xbar_f32, ld_xf, attn, ld_attn);
     } else {
       auto k = attn_pool_fwd_v2_kernel<2>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-      k<<<ap_grid(B), 288, sm2, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, static_cast<const float*>(kq), ldkq,
+      launch_k(k, dim3(ap_grid(B)), dim3(288), sm2, st, static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, static_cast<const float*>(kq), ldkq,
                                       B, Lv, scale, xb2, xl2, ld_xb, xbar_f32, ld_xf, attn, ld_attn);
     }
     TIC_CHECK_LAUNCH("tic_attn_pool_fwd");
@@ -617,12 +633,12 @@ int tic_attn_pool_fwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
   if (npass == 1) {
     auto k = attn_pool_fwd_kernel<3, 1>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    k<<<B, kAttnWarps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, xv_tok_stride,
+    launch_k(k, dim3(B), dim3(kAttnWarps * 32), smem, st, static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, xv_tok_stride,
                                         kqf, ldkq, B, Lv, scale, xb, xl, ld_xb, xbar_f32, ld_xf, attn, ld_attn);
   } else {
     auto k = attn_pool_fwd_kernel<3, 2>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    k<<<B, kAttnWarps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, xv_tok_stride,
+    launch_k(k, dim3(B), dim3(kAttnWarps * 32), smem, st, static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, xv_tok_stride,
                                         kqf, ldkq, B, Lv, scale, xb, xl, ld_xb, xbar_f32, ld_xf, attn, ld_attn);
   }
   TIC_CHECK_LAUNCH("tic_attn_pool_fwd");
@@ -641,13 +657,13 @@ int tic_attn_pool_bwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
     if (npass == 1) {
       auto k = attn_pool_bwd_v2_kernel<1>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-      k<<<ap_grid(B), 288, sm2, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, attn, ld_attn, dxbar, ld_dxb, xbar_f32,
+      launch_k(k, dim3(ap_grid(B)), dim3(288), sm2, st, static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, attn, ld_attn, dxbar, ld_dxb, xbar_f32,
                                       ld_xf, B, Lv, scale, static_cast<__nv_bfloat16*>(dkq_bf16),
                                       static_cast<__nv_bfloat16*>(dkq_bf16_lo), ld_dkq);
     } else {
       auto k = attn_pool_bwd_v2_kernel<2>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-      k<<<ap_grid(B), 288, sm2, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, attn, ld_attn, dxbar, ld_dxb, xbar_f32,
+      launch_k(k, dim3(ap_grid(B)), dim3(288), sm2, st, static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, attn, ld_attn, dxbar, ld_dxb, xbar_f32,
                                       ld_xf, B, Lv, scale, static_cast<__nv_bfloat16*>(dkq_bf16),
                                       static_cast<__nv_bfloat16*>(dkq_bf16_lo), ld_dkq);
     }
@@ -658,13 +674,13 @@ int tic_attn_pool_bwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
   if (npass == 1) {
     auto k = attn_pool_bwd_kernel<3, 1>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    k<<<B, kAttnWarps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, xv_tok_stride, attn, ld_attn,
+    launch_k(k, dim3(B), dim3(kAttnWarps * 32), smem, st, static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, xv_tok_stride, attn, ld_attn,
                                         dxbar, ld_dxb, xbar_f32, ld_xf, B, Lv, scale, static_cast<__nv_bfloat16*>(dkq_bf16),
                                         static_cast<__nv_bfloat16*>(dkq_bf16_lo), ld_dkq);
   } else {
     auto k = attn_pool_bwd_kernel<3, 2>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    k<<<B, kAttnWarps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, xv_tok_stride, attn, ld_attn,
+    launch_k(k, dim3(B), dim3(kAttnWarps * 32), smem, st, static_cast<const __nv_bfloat16*>(xv), xv_batch_stride, xv_tok_stride, attn, ld_attn,
                                         dxbar, ld_dxb, xbar_f32, ld_xf, B, Lv, scale, static_cast<__nv_bfloat16*>(dkq_bf16),
                                         static_cast<__nv_bfloat16*>(dkq_bf16_lo), ld_dkq);
   }
@@ -675,7 +691,7 @@ int tic_attn_pool_bwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
 int tic_aspect_fwd(const void* t_pool, int64_t ldt, const void* v_pool, int64_t ldv, int B, int E, const float* w_a,
                    const float* b_a, float* out, int64_t ldo, float* alpha, void* stream) {
   TIC_CHECK_ARG(t_pool && v_pool && w_a && b_a && out && alpha && B > 0 && E > 0, "tic_aspect_fwd: bad arguments");
-  aspect_fwd_kernel<<<ceil_div(B, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(aspect_fwd_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(t_pool), ldt, static_cast<const __nv_bfloat16*>(v_pool), ldv, B, E, w_a, b_a, out, ldo, alpha);
   TIC_CHECK_LAUNCH("tic_aspect_fwd");
   return TIC_OK;
@@ -686,7 +702,7 @@ int tic_aspect_bwd(const void* t_pool, int64_t ldt, const void* v_pool, int64_t 
                    float* dt_pool, int64_t lddt, float* dw_a, float* db_a, void* stream) {
   TIC_CHECK_ARG(t_pool && v_pool && w_a && b_a && out && alpha && dout && dt_pool && dw_a && db_a && B > 0,
                 "tic_aspect_bwd: bad arguments");
-  aspect_bwd_kernel<<<ceil_div(B, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(aspect_bwd_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(t_pool), ldt, static_cast<const __nv_bfloat16*>(v_pool), ldv, B, E, w_a, b_a, out, ldo,
       alpha, dout, lddo, dt_pool, lddt, dw_a, db_a);
   TIC_CHECK_LAUNCH("tic_aspect_bwd");
@@ -697,7 +713,7 @@ int tic_gmu_gate_fwd(const void* Xcat, int64_t ldx, const float* tp, const float
                      void* G_bf16_lo, int64_t ldg, void* stream) {
   TIC_CHECK_ARG(Xcat && tp && vp && G_bf16 && B > 0 && E2 > 0, "tic_gmu_gate_fwd: bad arguments");
   const int64_t n = static_cast<int64_t>(B) * E2;
-  gmu_gate_fwd_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(gmu_gate_fwd_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(Xcat), ldx, tp, vp, ldp, B, E2, static_cast<__nv_bfloat16*>(G_bf16),
       static_cast<__nv_bfloat16*>(G_bf16_lo), ldg);
   TIC_CHECK_LAUNCH("tic_gmu_gate_fwd");
@@ -709,7 +725,7 @@ int tic_gmu_gate_bwd(const void* Xcat, int64_t ldx, const float* tp, const float
                      int64_t lddx, void* stream) {
   TIC_CHECK_ARG(Xcat && tp && vp && dG && dtp_bf16 && dvp_bf16 && B > 0 && E2 > 0, "tic_gmu_gate_bwd: bad arguments");
   const int64_t n = static_cast<int64_t>(B) * E2;
-  gmu_gate_bwd_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(gmu_gate_bwd_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(Xcat), ldx, tp, vp, ldp, dG, lddg, B, E2, static_cast<__nv_bfloat16*>(dtp_bf16),
       static_cast<__nv_bfloat16*>(dvp_bf16), static_cast<__nv_bfloat16*>(dtp_lo), static_cast<__nv_bfloat16*>(dvp_lo), lddp,
       dXcat_gate, lddx);

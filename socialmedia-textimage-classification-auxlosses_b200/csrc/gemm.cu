@@ -7,12 +7,19 @@
 namespace tic {
 
 static thread_local char g_err[512] = "ok";
+constexpr int kRowSsBN = 64;   // tile width of tic_gemm_bf16_rowss (fixes the layout of the row statistics)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIC_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
 }
 
 TmapEncoder::EncodeFn TmapEncoder::get() {
@@ -77,6 +84,7 @@ struct StoreEpi {
     const float* bias;
     int relu;
     int accumulate;   // D += result with fp32 atomics (D holds the initial value); required for split-K
+    float* row_ss_part;   // optional [n_tiles][M]: per-tile sum of squares of each output row (fused L2-norm statistics)
   };
   template <int BN>
   __device__ static void tile(const Params& p, const EpiCtx& cx) {
@@ -85,6 +93,7 @@ struct StoreEpi {
     const int cols_per_part = BN / cx.nparts;
     const bool vec_ok = p.d_bf16 ? ((p.ldd & 7) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0)
                                  : ((p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    float ss = 0.f;
 #pragma unroll 1
     for (int c = 0; c < cols_per_part / 32; ++c) {
       const int cl = cx.part * cols_per_part + c * 32;
@@ -101,6 +110,7 @@ struct StoreEpi {
         if (p.bias != nullptr && cx.ks == 0 && col0 + j < cx.N) x += __ldg(p.bias + col0 + j);
         if (p.relu) x = fmaxf(x, 0.f);
         f[j] = x;
+        if (col0 + j < cx.N) ss = fmaf(x, x, ss);
       }
       const bool full = (col0 + 32 <= cx.N) && vec_ok;
       if (p.d_bf16) {
@@ -157,6 +167,10 @@ struct StoreEpi {
         }
       }
     }
+    if (p.row_ss_part != nullptr && row < cx.M) {
+      if (cx.nparts == 1) p.row_ss_part[static_cast<int64_t>(cx.n_blk) * cx.M + row] = ss;
+      else atomicAdd(p.row_ss_part + static_cast<int64_t>(cx.n_blk) * cx.M + row, ss);
+    }
   }
 };
 
@@ -206,15 +220,16 @@ const char* tic_last_error_string(void) { return g_err; }
 int tic_version(void) { return 100; }
 int tic_sm_count(void) { return device_sm_count(); }
 
-int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
-                  int b_mn, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias,
-                  int relu, int accumulate, void* stream) {
+static int gemm_impl(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
+                     int b_mn, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias,
+                     int relu, int accumulate, float* row_ss_part, void* stream) {
   TIC_CHECK_ARG(A && B && D, "tic_gemm_bf16: null pointer");
   TIC_CHECK_ARG(M > 0 && N > 0 && K > 0, "tic_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   TIC_CHECK_ARG(d_dtype == 0 || d_dtype == 1, "tic_gemm_bf16: d_dtype must be 0 (fp32) or 1 (bf16)");
   TIC_CHECK_ARG(D_lo == nullptr || d_dtype == 1, "tic_gemm_bf16: D_lo needs a bf16 output");
   TIC_CHECK_ARG(!accumulate || (d_dtype == 0 && !relu), "tic_gemm_bf16: accumulate needs an fp32 output and no ReLU");
-  StoreEpi::Params ep{D, D_lo, ldd, d_dtype, alpha, bias, relu, accumulate};
+  TIC_CHECK_ARG(!(accumulate && row_ss_part), "tic_gemm_bf16_rowss: row statistics need the complete K sum (no accumulate)");
+  StoreEpi::Params ep{D, D_lo, ldd, d_dtype, alpha, bias, relu, accumulate, row_ss_part};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int sms = device_sm_count();
   const int m_tiles = ceil_div(M, kBM);
@@ -236,6 +251,7 @@ int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn, const 
       if (t < best) { best = t; best_bn = bns[i]; best_ks = ks; }
     }
   }
+  if (row_ss_part) { best_bn = kRowSsBN; best_ks = 1; }   // the partial layout [ceil(N/64)][M] is part of the ABI
   int rc;
   if (best_bn == 256) rc = dispatch_major<256>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
   else if (best_bn == 128) rc = dispatch_major<128>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
@@ -243,6 +259,23 @@ int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn, const 
   if (rc == -3) { set_error("tic_gemm_bf16: cudaFuncSetAttribute(max dynamic smem) failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_gemm_bf16: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TIC_E_LAUNCH; }
   return rc;
+}
+
+int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
+                  int b_mn, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias,
+                  int relu, int accumulate, void* stream) {
+  return gemm_impl(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, D, D_lo, ldd, d_dtype, M, N, K, alpha, bias, relu, accumulate, nullptr,
+                   stream);
+}
+
+int tic_gemm_rowss_parts(int N) { return ceil_div(N, kRowSsBN); }
+
+int tic_gemm_bf16_rowss(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
+                        int b_mn, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha,
+                        const float* bias, int relu, float* row_ss_part, void* stream) {
+  TIC_CHECK_ARG(row_ss_part != nullptr, "tic_gemm_bf16_rowss: row_ss_part is NULL");
+  return gemm_impl(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, D, D_lo, ldd, d_dtype, M, N, K, alpha, bias, relu, 0, row_ss_part,
+                   stream);
 }
 
 int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,

@@ -3,6 +3,7 @@
 // Reference: models/mm_late.py:92-96,160-193 (head), :473-487 (mix); run_mm_late.py:85,97 (loss constructors).
 #include "common.cuh"
 #include "tic_ptx.cuh"
+#include "itm_rule.cuh"
 
 namespace tic {
 
@@ -12,11 +13,22 @@ constexpr int kMaxClasses = 8;
 // One warp per output row; 16-byte copies. Row r < B: [xt[r] | xv[r]];  row B + i: [xt[src[i]] | xv[i]].
 __global__ void pack_cls_pairs_kernel(const __nv_bfloat16* __restrict__ xt, int64_t xt_stride,
                                       const __nv_bfloat16* __restrict__ xv, int64_t xv_stride, int B, int E,
-                                      const int32_t* __restrict__ src, __nv_bfloat16* __restrict__ X, int64_t ldx, int rows) {
+                                      const int32_t* __restrict__ src, __nv_bfloat16* __restrict__ X, int64_t ldx, int rows,
+                                      const float* __restrict__ u_coin, const float* __restrict__ u_pick) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const int i = r < B ? r : r - B;
-  const int it = r < B ? r : src[i];
+  int it = r;
+  if (r >= B) {
+    if (u_coin != nullptr) {   // uniform ITM rule evaluated in place: the pack does not wait for the sampler kernel
+      int lbl;
+      uniform_rule(u_coin, u_pick, B, i, lbl, it);
+    } else {
+      it = src[i];
+    }
+  }
   const __nv_bfloat16* a = xt + static_cast<int64_t>(it) * xt_stride;
   const __nv_bfloat16* b = xv + static_cast<int64_t>(i) * xv_stride;
   __nv_bfloat16* d = X + static_cast<int64_t>(r) * ldx;
@@ -32,20 +44,24 @@ __global__ void pack_cls_pairs_kernel(const __nv_bfloat16* __restrict__ xt, int6
   }
 }
 
-__global__ void unpack_main_kernel(const float* __restrict__ dX, int64_t ldd, const float* __restrict__ dX2, int64_t ldd2, int B,
-                                   int E, float* __restrict__ dxt, int64_t ldo) {
+// dxt[target(r), :] += dX[r, :E] (+ dX2[r, :])  for every packed row r: target = r (main rows) or src[r - B] (ITM rows).
+// dxt is zero on entry (it lives in the plan's zero block), so the main and the scattered part are ONE launch of fp32 atomics.
+__global__ void unpack_accum_kernel(const float* __restrict__ dX, int64_t ldd, const float* __restrict__ dX2, int64_t ldd2, int B,
+                                    int E, int rows, const int32_t* __restrict__ src, float* __restrict__ dxt, int64_t ldo) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<int64_t>(B) * E) return;
-  const int r = idx / E, c = idx % E;
-  dxt[r * ldo + c] = dX[r * ldd + c] + (dX2 ? dX2[r * ldd2 + c] : 0.f);
-}
-__global__ void unpack_scatter_kernel(const float* __restrict__ dX, int64_t ldd, const float* __restrict__ dX2, int64_t ldd2, int B,
-                                      int E, const int32_t* __restrict__ src, float* __restrict__ dxt, int64_t ldo) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<int64_t>(B) * E) return;
-  const int r = idx / E, c = idx % E;
-  const int64_t rr = static_cast<int64_t>(B) + r;
-  atomicAdd(dxt + static_cast<int64_t>(src[r]) * ldo + c, dX[rr * ldd + c] + (dX2 ? dX2[rr * ldd2 + c] : 0.f));
+  const int E4 = E >> 2;
+  if (idx >= static_cast<int64_t>(rows) * E4) return;
+  const int r = static_cast<int>(idx / E4), c = static_cast<int>(idx % E4) * 4;
+  const int t = r < B ? r : src[r - B];
+  float4 v = *reinterpret_cast<const float4*>(dX + static_cast<int64_t>(r) * ldd + c);
+  if (dX2) {
+    const float4 w = *reinterpret_cast<const float4*>(dX2 + static_cast<int64_t>(r) * ldd2 + c);
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  float* d = dxt + static_cast<int64_t>(t) * ldo + c;
+  atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w);
 }
 
 // ------------------------------------------------------------------ heads: logits, losses, dlogits, dH
@@ -60,6 +76,8 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
                                   const float* __restrict__ dz_ext /* upstream dL/dlogits or nullptr (fused losses) */,
                                   __nv_bfloat16* __restrict__ dHb, __nv_bfloat16* __restrict__ dHb_lo, int64_t ld_dhb,
                                   float* __restrict__ dHf, int64_t ld_dhf, int relu_mask) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int rows = has_tim ? 2 * B : B;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -76,12 +94,35 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
     float z[kMaxClasses];
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c) z[c] = 0.f;
+    // 16-byte path: every lane owns 4 consecutive features per 128-wide chunk (6 independent iterations at E = 768)
+    const bool vec = (E & 3) == 0 && (ldh & 3) == 0 && (ld_dhb & 3) == 0 && (ld_dhf & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W_cls) | reinterpret_cast<uintptr_t>(W_tim) |
+                       reinterpret_cast<uintptr_t>(dHf) | reinterpret_cast<uintptr_t>(keep)) & 15) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(dHb) | reinterpret_cast<uintptr_t>(dHb_lo)) & 7) == 0;
+    if (vec) {
+#pragma unroll 2
+      for (int k = lane * 4; k < E; k += 128) {
+        float4 hv = *reinterpret_cast<const float4*>(h + k);
+        if (kp) {
+          const uchar4 m = *reinterpret_cast<const uchar4*>(kp + k);
+          hv.x = m.x ? hv.x * keep_scale : 0.f; hv.y = m.y ? hv.y * keep_scale : 0.f;
+          hv.z = m.z ? hv.z * keep_scale : 0.f; hv.w = m.w ? hv.w * keep_scale : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxClasses; ++c)
+          if (c < nc) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(W + c * E + k));
+            z[c] = fmaf(hv.x, w.x, fmaf(hv.y, w.y, fmaf(hv.z, w.z, fmaf(hv.w, w.w, z[c]))));
+          }
+      }
+    } else {
     for (int k = lane; k < E; k += 32) {
       float hv = h[k];
       if (kp) hv = kp[k] ? hv * keep_scale : 0.f;
 #pragma unroll
       for (int c = 0; c < kMaxClasses; ++c)
         if (c < nc) z[c] = fmaf(hv, __ldg(W + c * E + k), z[c]);
+    }
     }
     float mx = -INFINITY;
 #pragma unroll
@@ -131,7 +172,43 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
 #pragma unroll
       for (int c = 0; c < kMaxClasses; ++c) dlogits[static_cast<int64_t>(r) * kMaxClasses + c] = c < nc ? dz[c] : 0.f;
     }
-    if (dHb || dHf) {
+    if ((dHb || dHf) && vec) {
+#pragma unroll 2
+      for (int k = lane * 4; k < E; k += 128) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < kMaxClasses; ++c)
+          if (c < nc) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(W + c * E + k));
+            g[0] = fmaf(dz[c], w.x, g[0]); g[1] = fmaf(dz[c], w.y, g[1]);
+            g[2] = fmaf(dz[c], w.z, g[2]); g[3] = fmaf(dz[c], w.w, g[3]);
+          }
+        if (kp) {
+          const uchar4 m = *reinterpret_cast<const uchar4*>(kp + k);
+          g[0] = m.x ? g[0] * keep_scale : 0.f; g[1] = m.y ? g[1] * keep_scale : 0.f;
+          g[2] = m.z ? g[2] * keep_scale : 0.f; g[3] = m.w ? g[3] * keep_scale : 0.f;
+        }
+        if (relu_mask) {
+          const float4 hv = *reinterpret_cast<const float4*>(h + k);
+          if (!(hv.x > 0.f)) g[0] = 0.f;
+          if (!(hv.y > 0.f)) g[1] = 0.f;
+          if (!(hv.z > 0.f)) g[2] = 0.f;
+          if (!(hv.w > 0.f)) g[3] = 0.f;
+        }
+        if (dHf) *reinterpret_cast<float4*>(dHf + static_cast<int64_t>(r) * ld_dhf + k) = make_float4(g[0], g[1], g[2], g[3]);
+        if (dHb) {
+          uint2 u;
+          u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]);
+          *reinterpret_cast<uint2*>(dHb + static_cast<int64_t>(r) * ld_dhb + k) = u;
+          if (dHb_lo) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] -= __bfloat162float(__float2bfloat16_rn(g[j]));
+            u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]);
+            *reinterpret_cast<uint2*>(dHb_lo + static_cast<int64_t>(r) * ld_dhb + k) = u;
+          }
+        }
+      }
+    } else if (dHb || dHf) {
       for (int k = lane; k < E; k += 32) {
         float g = 0.f;
 #pragma unroll
@@ -162,28 +239,47 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
   }
 }
 
-// dW[c,k] += sum_rows dlogits[r,c] * hd[r,k], db[c] += sum_rows dlogits[r,c]; thread per k, rows split over blockIdx.y.
-__global__ void heads_wgrad_kernel(const float* __restrict__ H, int64_t ldh, int row0, int nrows, int E, int nc,
+// dW[c,k] += sum_rows dlogits[r,c] * hd[r,k], db[c] += sum_rows dlogits[r,c]; thread per k, rows split over blockIdx.y,
+// blockIdx.z = head (0: linear_cls on rows [0,B), 1: linear_tim on rows [B,2B)); 4 rows of loads in flight per thread.
+__global__ void heads_wgrad_kernel(const float* __restrict__ H, int64_t ldh, int B, int E, int C,
                                    const float* __restrict__ dlogits, const uint8_t* __restrict__ keep, float keep_scale,
-                                   float* __restrict__ dW, float* __restrict__ db, int rows_per_blk) {
+                                   float* __restrict__ dW_cls, float* __restrict__ db_cls, float* __restrict__ dW_tim,
+                                   float* __restrict__ db_tim, int rows_per_blk) {
+  pdl_trigger();
+  pdl_wait();
+  const int head = blockIdx.z;
+  const int row0 = head ? B : 0, nc = head ? 2 : C;
+  float* dW = head ? dW_tim : dW_cls;
+  float* db = head ? db_tim : db_cls;
+  const uint8_t* kp = head ? nullptr : keep;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int rb = blockIdx.y * rows_per_blk;
-  const int re = min(rb + rows_per_blk, nrows);
+  const int re = min(rb + rows_per_blk, B);
   float acc[kMaxClasses], accb[kMaxClasses];
 #pragma unroll
   for (int c = 0; c < kMaxClasses; ++c) { acc[c] = 0.f; accb[c] = 0.f; }
   if (k < E) {
-    for (int r = rb; r < re; ++r) {
-      float hv = H[static_cast<int64_t>(row0 + r) * ldh + k];
-      if (keep) hv = keep[static_cast<int64_t>(r) * E + k] ? hv * keep_scale : 0.f;
-      const float* dl = dlogits + static_cast<int64_t>(row0 + r) * kMaxClasses;
+    for (int r = rb; r < re; r += 4) {
+      float hv[4];
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c)
-        if (c < nc) {
-          const float d = __ldg(dl + c);
-          acc[c] = fmaf(d, hv, acc[c]);
-          accb[c] += d;
+      for (int u = 0; u < 4; ++u) {
+        const int rr = min(r + u, re - 1);
+        hv[u] = (r + u < re) ? H[static_cast<int64_t>(row0 + rr) * ldh + k] : 0.f;
+        if (kp) hv[u] = kp[static_cast<int64_t>(rr) * E + k] ? hv[u] * keep_scale : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u < re) {
+          const float* dl = dlogits + static_cast<int64_t>(row0 + r + u) * kMaxClasses;
+#pragma unroll
+          for (int c = 0; c < kMaxClasses; ++c)
+            if (c < nc) {
+              const float d = __ldg(dl + c);
+              acc[c] = fmaf(d, hv[u], acc[c]);
+              accb[c] += d;
+            }
         }
+      }
     }
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c)
@@ -197,6 +293,8 @@ __global__ void heads_wgrad_kernel(const float* __restrict__ H, int64_t ldh, int
 // out[n] += sum_m X[m,n]  (bf16 in) — bias gradients of the fusion / projection linears.
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, int rows, int cols, float* __restrict__ out,
                                    int rows_per_blk) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= cols) return;
   const int rb = blockIdx.y * rows_per_blk, re = min(rb + rows_per_blk, rows);
@@ -207,6 +305,8 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t 
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, int64_t lds, __nv_bfloat16* __restrict__ d, int64_t ldd,
                                      int rows, int cols) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(rows) * cols) return;
   const int64_t r = idx / cols, c = idx % cols;
@@ -214,6 +314,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, int64_t lds, _
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, int64_t lds, float* __restrict__ d, int64_t ldd,
                                      int rows, int cols) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(rows) * cols) return;
   const int64_t r = idx / cols, c = idx % cols;
@@ -222,6 +324,8 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, int64_
 
 __global__ void loss_mix_kernel(const float* losses, const float* itc_sums, int n_global, float bi, float bm, int use_itc,
                                 int use_itm, float* out) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const float l_cls = losses[0];
   const float l_itm = use_itm ? losses[1] : 0.f;
   const float l_itc = use_itc ? 0.5f * (itc_sums[0] + itc_sums[1]) / n_global : 0.f;
@@ -242,12 +346,13 @@ using namespace tic;
 extern "C" {
 
 int tic_pack_cls_pairs(const void* xt, int64_t xt_stride, const void* xv, int64_t xv_stride, int B, int E,
-                       const int32_t* src_idx, void* Xcat, int64_t ldx, void* stream) {
+                       const int32_t* src_idx, void* Xcat, int64_t ldx, const float* u_coin, const float* u_pick, void* stream) {
   TIC_CHECK_ARG(xt && Xcat && B > 0 && E > 0 && ldx >= 2 * E, "tic_pack_cls_pairs: bad arguments");
-  const int rows = src_idx ? 2 * B : B;
-  pack_cls_pairs_kernel<<<ceil_div(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  TIC_CHECK_ARG((u_coin == nullptr) == (u_pick == nullptr), "tic_pack_cls_pairs: u_coin and u_pick go together");
+  const int rows = (src_idx || u_coin) ? 2 * B : B;
+  launch_k(pack_cls_pairs_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
       static_cast<const __nv_bfloat16*>(xt), xt_stride, static_cast<const __nv_bfloat16*>(xv), xv_stride, B, E, src_idx,
-      static_cast<__nv_bfloat16*>(Xcat), ldx, rows);
+      static_cast<__nv_bfloat16*>(Xcat), ldx, rows, u_coin, u_pick);
   TIC_CHECK_LAUNCH("tic_pack_cls_pairs");
   return TIC_OK;
 }
@@ -255,11 +360,13 @@ int tic_pack_cls_pairs(const void* xt, int64_t xt_stride, const void* xv, int64_
 int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, const float* dX2, int64_t ldd2, int B, int E, const int32_t* src_idx,
                         float* dxt, int64_t ld_dxt, void* stream) {
   TIC_CHECK_ARG(dXcat && dxt && B > 0 && E > 0, "tic_unpack_cls_grad: bad arguments");
+  TIC_CHECK_ARG((E & 3) == 0 && (ldd & 3) == 0 && (ldd2 & 3) == 0 && aligned16(dXcat) && aligned16(dX2),
+                "tic_unpack_cls_grad: E and the leading dimensions must be multiples of 4 (16-byte rows)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t n = static_cast<int64_t>(B) * E;
-  const int blocks = static_cast<int>((n + 255) / 256);
-  unpack_main_kernel<<<blocks, 256, 0, st>>>(dXcat, ldd, dX2, ldd2, B, E, dxt, ld_dxt);
-  if (src_idx) unpack_scatter_kernel<<<blocks, 256, 0, st>>>(dXcat, ldd, dX2, ldd2, B, E, src_idx, dxt, ld_dxt);
+  const int rows = src_idx ? 2 * B : B;
+  const int64_t n = static_cast<int64_t>(rows) * (E / 4);
+  launch_k(unpack_accum_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, st, dXcat, ldd, dX2, ldd2, B, E, rows, src_idx,
+           dxt, ld_dxt);
   TIC_CHECK_LAUNCH("tic_unpack_cls_grad");
   return TIC_OK;
 }
@@ -275,17 +382,17 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rows = has_tim ? 2 * B : B;
   float* dlogits = ws;
-  heads_rows_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft, class_w,
+  launch_k(heads_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft, class_w,
                                                         lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses,
                                                         dlogits, dlogits_ext, static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb,
                                                         dH_f32, ld_dhf,
                                                         relu_mask);
   if (dW_cls && db_cls) {
     const int rpb = max(8, ceil_div(B, 128));
-    dim3 grid(ceil_div(E, 128), ceil_div(B, rpb));
-    heads_wgrad_kernel<<<grid, 128, 0, st>>>(H, ldh, 0, B, E, C, dlogits, keep, keep_scale, dW_cls, db_cls, rpb);
-    if (has_tim && dW_tim && db_tim)
-      heads_wgrad_kernel<<<grid, 128, 0, st>>>(H, ldh, B, B, E, 2, dlogits, nullptr, 1.f, dW_tim, db_tim, rpb);
+    const int heads = (has_tim && dW_tim && db_tim) ? 2 : 1;
+    dim3 grid(ceil_div(E, 128), ceil_div(B, rpb), heads);
+    launch_k(heads_wgrad_kernel, grid, dim3(128), 0, st, H, ldh, B, E, C, dlogits, keep, keep_scale, dW_cls, db_cls, dW_tim, db_tim,
+             rpb);
   }
   TIC_CHECK_LAUNCH("tic_heads_fwd_bwd");
   return TIC_OK;
@@ -295,7 +402,7 @@ int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, 
   TIC_CHECK_ARG(X && out && rows > 0 && cols > 0, "tic_colsum_bf16: bad arguments");
   const int rpb = max(8, ceil_div(rows, 128));
   dim3 grid(ceil_div(cols, 128), ceil_div(rows, rpb));
-  colsum_bf16_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(X), ldx, rows, cols,
+  launch_k(colsum_bf16_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(X), ldx, rows, cols,
                                                                           out, rpb);
   TIC_CHECK_LAUNCH("tic_colsum_bf16");
   return TIC_OK;
@@ -304,7 +411,7 @@ int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, 
 int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream) {
   TIC_CHECK_ARG(src && dst && rows > 0 && cols > 0, "tic_cast_f32_to_bf16: bad arguments");
   const int64_t n = static_cast<int64_t>(rows) * cols;
-  cast_f32_bf16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cast_f32_bf16_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       src, lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
   TIC_CHECK_LAUNCH("tic_cast_f32_to_bf16");
   return TIC_OK;
@@ -312,7 +419,7 @@ int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, 
 int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream) {
   TIC_CHECK_ARG(src && dst && rows > 0 && cols > 0, "tic_cast_bf16_to_f32: bad arguments");
   const int64_t n = static_cast<int64_t>(rows) * cols;
-  cast_bf16_f32_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cast_bf16_f32_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(src), lds, dst, ldd, rows, cols);
   TIC_CHECK_LAUNCH("tic_cast_bf16_to_f32");
   return TIC_OK;
@@ -321,7 +428,7 @@ int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, 
 int tic_loss_mix(const float* losses, const float* itc_sums, int n_global, float beta_itc, float beta_itm, int use_itc,
                  int use_itm, float* out, void* stream) {
   TIC_CHECK_ARG(losses && out && (!use_itc || itc_sums), "tic_loss_mix: bad arguments");
-  loss_mix_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(losses, itc_sums, n_global, beta_itc, beta_itm, use_itc,
+  launch_k(loss_mix_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), losses, itc_sums, n_global, beta_itc, beta_itm, use_itc,
                                                                   use_itm, out);
   TIC_CHECK_LAUNCH("tic_loss_mix");
   return TIC_OK;

@@ -78,8 +78,11 @@ __device__ __forceinline__ float warp_col_sums(float (&v)[32]) {
 // ------------------------------------------------------------------ forward epilogue
 struct ItcFwdEpi {
   struct Params {
-    const float* rinv_t;
-    const float* rinv_v;
+    float* rinv_t;       // inputs, or OUTPUTS when the sum-of-squares partials below are given
+    float* rinv_v;
+    const float* ss_t_part;   // optional [n_ss_t][M] / [n_ss_v][N] row sum-of-squares partials from tic_gemm_bf16_rowss:
+    const float* ss_v_part;   // the L2 normalisation (HF :268-269) then costs no kernel of its own
+    int n_ss_t, n_ss_v;
     float scale_log2e;   // scale * log2(e)
     float shift_log2e;   // shift * log2(e)
     float scale;
@@ -97,9 +100,32 @@ struct ItcFwdEpi {
     const bool valid_row = row < cx.M;
     float* sb = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * BN;   // rinv_v of this tile (double-buffered)
     float* scol = reinterpret_cast<float*>(cx.scratch) + 2 * BN;             // [4 quads][BN] partial column sums
-    for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) sb[j] = (cx.n0 + j < cx.N) ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
+    for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) {
+      float b = 0.f;
+      if (cx.n0 + j < cx.N) {
+        if (p.ss_v_part != nullptr) {
+          float ssum = 0.f;
+          for (int q = 0; q < p.n_ss_v; ++q) ssum += __ldg(p.ss_v_part + static_cast<int64_t>(q) * cx.N + cx.n0 + j);
+          b = 1.0f / sqrtf(ssum);   // no epsilon (HF :268-269)
+          if (cx.m_blk == 0) p.rinv_v[cx.n0 + j] = b;
+        } else {
+          b = p.rinv_v[cx.n0 + j];
+        }
+      }
+      sb[j] = b;
+    }
     epi_bar_sync(cx.epi_threads);
-    const float rt = valid_row ? __ldg(p.rinv_t + row) : 0.f;
+    float rt = 0.f;
+    if (valid_row) {
+      if (p.ss_t_part != nullptr) {
+        float ssum = 0.f;
+        for (int q = 0; q < p.n_ss_t; ++q) ssum += __ldg(p.ss_t_part + static_cast<int64_t>(q) * cx.M + row);
+        rt = 1.0f / sqrtf(ssum);
+        if (cx.n_blk == 0 && cx.part == 0) p.rinv_t[row] = rt;
+      } else {
+        rt = p.rinv_t[row];
+      }
+    }
     const float rt2 = rt * p.scale_log2e;
     const float negshift = valid_row ? -p.shift_log2e : -INFINITY;
     const int gcol = p.row_offset + row;  // column holding this row's positive
@@ -199,6 +225,11 @@ struct ItcBwdEpi {
     int64_t ld_gbt;
     __nv_bfloat16* GA_lo;   // optional bf16 residuals (split precision for small batches)
     __nv_bfloat16* GBT_lo;
+    // inline statistics (small batch): lse straight from the forward partials, so the lse kernel leaves the critical path
+    const float* row_part;  // [n_row_parts][M] or nullptr -> lse_row
+    const float* col_part;  // [n_col_parts][N] or nullptr -> lse_col
+    int n_row_parts, n_col_parts;
+    float shift;
   };
   template <int BN>
   __device__ static void tile(const Params& p, const EpiCtx& cx) {
@@ -212,12 +243,31 @@ struct ItcBwdEpi {
       const bool ok = cx.n0 + j < cx.N;
       const float b = ok ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
       sb[j] = b;
-      sl[j] = ok ? __ldg(p.lse_col + cx.n0 + j) * kLog2e : 0.f;
+      float lc = 0.f;
+      if (ok) {
+        if (p.col_part != nullptr) {
+          float cs = 0.f;
+          for (int q = 0; q < p.n_col_parts; ++q) cs += __ldg(p.col_part + static_cast<int64_t>(q) * cx.N + cx.n0 + j);
+          lc = p.shift + logf(cs);
+        } else {
+          lc = __ldg(p.lse_col + cx.n0 + j);
+        }
+      }
+      sl[j] = lc * kLog2e;
       sg[j] = b * p.gscale;
     }
     epi_bar_sync(cx.epi_threads);
     const float rt = valid_row ? __ldg(p.rinv_t + row) : 0.f;
-    const float lr = valid_row ? __ldg(p.lse_row + row) * kLog2e : 0.f;
+    float lr = 0.f;
+    if (valid_row) {
+      if (p.row_part != nullptr) {
+        float rs = 0.f;
+        for (int q = 0; q < p.n_row_parts; ++q) rs += __ldg(p.row_part + static_cast<int64_t>(q) * cx.M + row);
+        lr = (p.shift + logf(rs)) * kLog2e;
+      } else {
+        lr = __ldg(p.lse_row + row) * kLog2e;
+      }
+    }
     const float rt2 = rt * p.scale_log2e;
     const int cols_per_part = BN / cx.nparts;
     const bool vec_ok = (p.ld_ga & 7) == 0;
@@ -312,6 +362,8 @@ struct ItcBwdEpi {
 // rinv[i] = 1/||X[i,:]||  — one warp per row, 16-byte loads when aligned.
 __global__ void row_rnorm_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ X_lo, int64_t ldx, int rows,
                                  int cols, float* __restrict__ rinv, __nv_bfloat16* __restrict__ Xhat, int64_t ldh) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const __nv_bfloat16* x = X + static_cast<int64_t>(warp) * ldx;
@@ -349,6 +401,8 @@ __global__ void row_rnorm_kernel(const __nv_bfloat16* __restrict__ X, const __nv
 }
 
 __global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   float s = 0.f;
@@ -359,6 +413,8 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, 
 // Multi-block: fixed-order sum of the per-tile partials -> lse vectors (thread t owns row t and column t).
 __global__ void itc_lse_kernel(const float* __restrict__ row_part, int nrp, const float* __restrict__ col_part, int ncp, int M,
                                int N, float shift, float* __restrict__ lse_row, float* __restrict__ lse_col) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < N) {
     float s = 0.f;
@@ -374,6 +430,8 @@ __global__ void itc_lse_kernel(const float* __restrict__ row_part, int nrp, cons
 // Single block, fixed-order tree: the two loss sums (deterministic).
 __global__ void itc_loss_kernel(const float* __restrict__ lse_row, const float* __restrict__ lse_col,
                                 const float* __restrict__ diag, int M, int row_offset, float* __restrict__ loss_sums) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   __shared__ float sr[32], sc[32];
   float ar = 0.f, ac = 0.f;
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
@@ -401,6 +459,8 @@ __global__ void itc_loss_kernel(const float* __restrict__ lse_row, const float* 
 __global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int nparts, int m,
                                     const float* __restrict__ diag, float shift, float* __restrict__ lse_a,
                                     float* __restrict__ lse_b, float* __restrict__ loss_sums, float* __restrict__ ws) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int dir = blockIdx.y;
   const float* part = dir == 0 ? part_a : part_b;
   float* lse = dir == 0 ? lse_a : lse_b;
@@ -444,6 +504,8 @@ __global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t 
                                          float diag_coef, float* __restrict__ dXf, int64_t ld_df,
                                          __nv_bfloat16* __restrict__ dXb, __nv_bfloat16* __restrict__ dXb_lo, int64_t ld_db,
                                          float* __restrict__ r_sum, int acc_div_rinv) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int warp_in_blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp_in_blk;
   __shared__ float sblk[32];
@@ -487,12 +549,112 @@ __global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t 
   }
 }
 
+// Vector form of the kernel above (P % 8 == 0, P <= 1024, 16-byte aligned rows): every lane owns 8 consecutive elements
+// of each 256-wide chunk, everything is read once with 16-byte loads and stays in registers between the two passes.
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void add8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
+  float t[8];
+  ld8_bf16(p, t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] += t[k];
+}
+__global__ void __launch_bounds__(256)
+itc_grad_finalize_vec_kernel(const float* __restrict__ acc, int64_t ld_acc, const __nv_bfloat16* __restrict__ X,
+                             const __nv_bfloat16* __restrict__ X_lo, int64_t ldx, const float* __restrict__ rinv,
+                             const __nv_bfloat16* __restrict__ Xo, const __nv_bfloat16* __restrict__ Xo_lo, int64_t ldxo,
+                             const float* __restrict__ rinv_o, int rows, int P, float scale, float diag_coef,
+                             float* __restrict__ dXf, int64_t ld_df, __nv_bfloat16* __restrict__ dXb,
+                             __nv_bfloat16* __restrict__ dXb_lo, int64_t ld_db, float* __restrict__ r_sum, int acc_div_rinv) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int MAXC = 4;
+  const int warp_in_blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp_in_blk;
+  __shared__ float sblk[32];
+  float r = 0.f;
+  if (row < rows) {
+    const float ri = rinv[row];
+    const bool has_o = Xo != nullptr && diag_coef != 0.f;
+    const float co = has_o ? diag_coef * rinv_o[row] : 0.f;
+    const float asc = acc_div_rinv ? 1.0f / ri : 1.0f;
+    float xh[MAXC][8], dxh[MAXC][8];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int k = c * 256 + lane * 8;
+      if (k < P) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(acc + static_cast<int64_t>(row) * ld_acc + k));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(acc + static_cast<int64_t>(row) * ld_acc + k + 4));
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        ld8_bf16(X + static_cast<int64_t>(row) * ldx + k, xh[c]);
+        if (X_lo) add8_bf16(X_lo + static_cast<int64_t>(row) * ldx + k, xh[c]);
+        float xo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (has_o) {
+          ld8_bf16(Xo + static_cast<int64_t>(row) * ldxo + k, xo);
+          if (Xo_lo) add8_bf16(Xo_lo + static_cast<int64_t>(row) * ldxo + k, xo);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dxh[c][j] = scale * (a[j] * asc - co * xo[j]);
+          xh[c][j] *= ri;
+          r = fmaf(xh[c][j], dxh[c][j], r);
+        }
+      }
+    }
+    r = warp_sum(r);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int k = c * 256 + lane * 8;
+      if (k < P) {
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = ri * (dxh[c][j] - xh[c][j] * r);
+        if (dXf) {
+          float* d = dXf + static_cast<int64_t>(row) * ld_df + k;
+          *reinterpret_cast<float4*>(d) = make_float4(g[0], g[1], g[2], g[3]);
+          *reinterpret_cast<float4*>(d + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        }
+        if (dXb) {
+          uint4 u;
+          u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]); u.z = pack_bf16x2(g[4], g[5]); u.w = pack_bf16x2(g[6], g[7]);
+          *reinterpret_cast<uint4*>(dXb + static_cast<int64_t>(row) * ld_db + k) = u;
+          if (dXb_lo) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] -= __bfloat162float(__float2bfloat16_rn(g[j]));
+            u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]); u.z = pack_bf16x2(g[4], g[5]); u.w = pack_bf16x2(g[6], g[7]);
+            *reinterpret_cast<uint4*>(dXb_lo + static_cast<int64_t>(row) * ld_db + k) = u;
+          }
+        }
+      }
+    }
+  }
+  if (r_sum != nullptr) {
+    if (lane == 0) sblk[warp_in_blk] = (row < rows) ? r : 0.f;
+    __syncthreads();
+    if (warp_in_blk == 0) {
+      float t = lane < (blockDim.x >> 5) ? sblk[lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) atomicAdd(r_sum, t);
+    }
+  }
+}
+
 // Gradient operands from a MATERIALISED dL/dS (autograd path at drop-in batch sizes):
 //   GA[i,j] = dS[i,j] * rinv_v[j],  GBT[j,i] = dS[i,j] * rinv_t[i]   (+ bf16 residuals).  32x32 smem-tile transpose.
 __global__ void itc_ds_operands_kernel(const float* __restrict__ dS, int64_t ldds, int M, int N, const float* __restrict__ rinv_t,
                                        const float* __restrict__ rinv_v, __nv_bfloat16* __restrict__ GA,
                                        __nv_bfloat16* __restrict__ GA_lo, int64_t ld_ga, __nv_bfloat16* __restrict__ GBT,
                                        __nv_bfloat16* __restrict__ GBT_lo, int64_t ld_gbt) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   __shared__ float t[32][33];
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -534,17 +696,18 @@ int tic_row_rnorm_bf16(const void* X, const void* X_lo, int64_t ldx, int rows, i
                        void* stream) {
   TIC_CHECK_ARG(X && rinv && rows > 0 && cols > 0, "tic_row_rnorm_bf16: bad arguments");
   const int wpb = 8;
-  row_rnorm_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(row_rnorm_kernel, dim3(ceil_div(rows, wpb)), dim3(wpb * 32), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(X_lo), ldx, rows, cols, rinv,
       static_cast<__nv_bfloat16*>(Xhat), ldh);
   TIC_CHECK_LAUNCH("tic_row_rnorm_bf16");
   return TIC_OK;
 }
 
-int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv, const float* rinv_t,
-                const float* rinv_v,
+int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv, float* rinv_t,
+                float* rinv_v,
                 int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
-                float* col_part, float* diag, float* logits_out, int64_t ld_logits, void* stream) {
+                float* col_part, float* diag, float* logits_out, int64_t ld_logits, const float* ss_t_part, int n_ss_t,
+                const float* ss_v_part, int n_ss_v, void* stream) {
   TIC_CHECK_ARG(T && V && rinv_t && rinv_v && row_part && diag, "tic_itc_fwd: null pointer");
   TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_fwd: empty problem");
   TIC_CHECK_ARG(row_offset >= 0 && row_offset + m_local <= n_global, "tic_itc_fwd: row block outside the global batch");
@@ -552,7 +715,8 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
     set_error("tic_itc_fwd: scale=%g shift=%g outside the supported range (0 < scale <= 40, shift >= scale)", scale, shift);
     return TIC_E_RANGE;
   }
-  ItcFwdEpi::Params ep{rinv_t, rinv_v, scale * kLog2e, shift * kLog2e, scale, row_part, col_part, diag, logits_out, ld_logits,
+  TIC_CHECK_ARG((!ss_t_part || n_ss_t > 0) && (!ss_v_part || n_ss_v > 0), "tic_itc_fwd: empty sum-of-squares partial list");
+  ItcFwdEpi::Params ep{rinv_t, rinv_v, ss_t_part, ss_v_part, n_ss_t, n_ss_v, scale * kLog2e, shift * kLog2e, scale, row_part, col_part, diag, logits_out, ld_logits,
                        row_offset};
   const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
   int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, ldt, V, ldv, m_local, n_global, P, ep,
@@ -570,7 +734,7 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
 
 int tic_reduce_parts(const float* part, int nparts, int n, float* out, void* stream) {
   TIC_CHECK_ARG(part && out && nparts > 0 && n > 0, "tic_reduce_parts: bad arguments");
-  reduce_parts_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, nparts, n, out);
+  launch_k(reduce_parts_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), part, nparts, n, out);
   TIC_CHECK_LAUNCH("tic_reduce_parts");
   return TIC_OK;
 }
@@ -582,9 +746,9 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
                 "tic_itc_lse_loss: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int mx = m_local > n_global ? m_local : n_global;
-  itc_lse_kernel<<<ceil_div(mx, 256), 256, 0, st>>>(row_part, n_row_parts, col_part, n_col_parts, m_local, n_global, shift,
+  launch_k(itc_lse_kernel, dim3(ceil_div(mx, 256)), dim3(256), 0, st, row_part, n_row_parts, col_part, n_col_parts, m_local, n_global, shift,
                                                      lse_row, lse_col);
-  itc_loss_kernel<<<1, 1024, 0, st>>>(lse_row, lse_col, diag, m_local, row_offset, loss_sums);
+  launch_k(itc_loss_kernel, dim3(1), dim3(1024), 0, st, lse_row, lse_col, diag, m_local, row_offset, loss_sums);
   TIC_CHECK_LAUNCH("tic_itc_lse_loss");
   return TIC_OK;
 }
@@ -596,7 +760,7 @@ int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int 
   TIC_CHECK_ARG(part_a && part_b && diag && lse_a && lse_b && loss_sums && workspace && n_parts > 0 && m > 0,
                 "tic_itc_lse_rows: bad arguments");
   dim3 grid(ceil_div(m, 256), 2);
-  itc_lse_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(part_a, part_b, n_parts, m, diag, shift, lse_a, lse_b,
+  launch_k(itc_lse_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), part_a, part_b, n_parts, m, diag, shift, lse_a, lse_b,
                                                                           loss_sums, static_cast<float*>(workspace));
   TIC_CHECK_LAUNCH("tic_itc_lse_rows");
   return TIC_OK;
@@ -605,12 +769,15 @@ int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int 
 int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv,
                   const float* rinv_t, const float* rinv_v,
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale, float gscale,
-                  void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo, void* GBT_lo, void* stream) {
-  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && lse_row && lse_col && GA, "tic_itc_bwd_g: null pointer");
+                  void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo, void* GBT_lo, const float* row_part,
+                  int n_row_parts, const float* col_part, int n_col_parts, float shift, void* stream) {
+  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && GA, "tic_itc_bwd_g: null pointer");
+  TIC_CHECK_ARG((lse_row || (row_part && n_row_parts > 0)) && (lse_col || (col_part && n_col_parts > 0)),
+                "tic_itc_bwd_g: need lse_row/lse_col or the forward partials");
   TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_bwd_g: empty problem");
   ItcBwdEpi::Params ep{rinv_t, rinv_v, lse_row, lse_col, scale * kLog2e, gscale, static_cast<__nv_bfloat16*>(GA), ld_ga,
                        static_cast<__nv_bfloat16*>(GBT), ld_gbt, static_cast<__nv_bfloat16*>(GA_lo),
-                       static_cast<__nv_bfloat16*>(GBT_lo)};
+                       static_cast<__nv_bfloat16*>(GBT_lo), row_part, col_part, n_row_parts, n_col_parts, shift};
   const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
   int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, ldt, V, ldv, m_local, n_global, P, ep,
                                                                                         static_cast<cudaStream_t>(stream))
@@ -631,8 +798,12 @@ int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const
                           void* stream) {
   TIC_CHECK_ARG(acc && X && rinv && rows > 0 && P > 0, "tic_itc_grad_finalize: bad arguments");
   TIC_CHECK_ARG(dX_f32 || dX_bf16, "tic_itc_grad_finalize: no output requested");
-  const int wpb = 8;
-  itc_grad_finalize_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  const bool vec = (P & 7) == 0 && P <= 1024 && (ld_acc & 3) == 0 && (ldx & 7) == 0 && (ldxo & 7) == 0 && (ld_df & 3) == 0 &&
+                   (ld_db & 7) == 0 && aligned16(acc) && aligned16(X) && aligned16(X_lo) && aligned16(Xo) && aligned16(Xo_lo) &&
+                   aligned16(dX_f32) && aligned16(dX_bf16) && aligned16(dX_bf16_lo);
+  const int wpb = vec ? 4 : 8;   // small blocks: the small-batch step has few rows, spread them over the SMs
+  auto kern = vec ? itc_grad_finalize_vec_kernel : itc_grad_finalize_kernel;
+  launch_k(kern, dim3(ceil_div(rows, wpb)), dim3(wpb * 32), 0, static_cast<cudaStream_t>(stream),
       acc, ld_acc, static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(X_lo), ldx, rinv,
       static_cast<const __nv_bfloat16*>(Xo), static_cast<const __nv_bfloat16*>(Xo_lo), ldxo, rinv_o,
       rows, P, scale, diag_coef, dX_f32, ld_df, static_cast<__nv_bfloat16*>(dX_bf16), static_cast<__nv_bfloat16*>(dX_bf16_lo), ld_db,
@@ -645,7 +816,7 @@ int tic_itc_ds_operands(const float* dS, int64_t ldds, int m_local, int n_global
                         void* GA, void* GA_lo, int64_t ld_ga, void* GBT, void* GBT_lo, int64_t ld_gbt, void* stream) {
   TIC_CHECK_ARG(dS && rinv_t && rinv_v && GA && m_local > 0 && n_global > 0, "tic_itc_ds_operands: bad arguments");
   dim3 grid(ceil_div(n_global, 32), ceil_div(m_local, 32)), block(32, 8);
-  itc_ds_operands_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(itc_ds_operands_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
       dS, ldds, m_local, n_global, rinv_t, rinv_v, static_cast<__nv_bfloat16*>(GA), static_cast<__nv_bfloat16*>(GA_lo), ld_ga,
       static_cast<__nv_bfloat16*>(GBT), static_cast<__nv_bfloat16*>(GBT_lo), ld_gbt);
   TIC_CHECK_LAUNCH("tic_itc_ds_operands");

@@ -8,6 +8,7 @@
 //     oracle bit for bit.
 #include "common.cuh"
 #include "tic_ptx.cuh"
+#include "itm_rule.cuh"
 
 namespace tic {
 
@@ -27,19 +28,10 @@ __device__ __forceinline__ float det_exp(float x) {
   return __int_as_float(__float_as_int(y) + (static_cast<int>(n) << 23));  // exact scaling by 2^n (result stays normal)
 }
 
-__device__ __forceinline__ void uniform_rule(const float* u_coin, const float* u_pick, int B, int i, int& label, int& src) {
-  label = 1;
-  src = i;
-  if (B > 1 && u_coin[i] < 0.5f) {
-    label = 0;
-    int k = static_cast<int>(floorf(__fmul_rn(u_pick[i], static_cast<float>(B - 1))));
-    k = min(k, B - 2);
-    src = k < i ? k : k + 1;
-  }
-}
-
 __global__ void itm_sample_uniform_kernel(const float* __restrict__ u_coin, const float* __restrict__ u_pick, int B,
                                           int64_t* __restrict__ labels, int32_t* __restrict__ src_idx) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   int l, s;
@@ -56,6 +48,8 @@ __device__ __forceinline__ unsigned long long qweight(float s, float mx) {
 __global__ void __launch_bounds__(256) itm_sample_hard_kernel(const float* __restrict__ u_coin, const float* __restrict__ u_pick,
                                                               int B, const float* __restrict__ S, int64_t lds,
                                                               int64_t* __restrict__ labels, int32_t* __restrict__ src_idx) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int i = blockIdx.x, t = threadIdx.x;
   int label, src;
   uniform_rule(u_coin, u_pick, B, i, label, src);
@@ -116,6 +110,8 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ s0, uint8_t* __re
                                    const int32_t* __restrict__ idx, int rows, const float* __restrict__ u_coin,
                                    const float* __restrict__ u_pick, int64_t* __restrict__ labels,
                                    int32_t* __restrict__ src_out) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   int sr;
@@ -147,10 +143,10 @@ int tic_itm_sample(const float* u_coin, const float* u_pick, int B, int mode, co
   TIC_CHECK_ARG(u_coin && u_pick && labels && src_idx && B > 0, "tic_itm_sample: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == TIC_ITM_UNIFORM) {
-    itm_sample_uniform_kernel<<<ceil_div(B, 256), 256, 0, st>>>(u_coin, u_pick, B, labels, src_idx);
+    launch_k(itm_sample_uniform_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, st, u_coin, u_pick, B, labels, src_idx);
   } else if (mode == TIC_ITM_HARD) {
     TIC_CHECK_ARG(S != nullptr && lds >= B, "tic_itm_sample: hard mode needs the similarity matrix");
-    itm_sample_hard_kernel<<<B, 256, 0, st>>>(u_coin, u_pick, B, S, lds, labels, src_idx);
+    launch_k(itm_sample_hard_kernel, dim3(B), dim3(256), 0, st, u_coin, u_pick, B, S, lds, labels, src_idx);
   } else {
     set_error("tic_itm_sample: unknown mode %d", mode);
     return TIC_E_ARG;
@@ -163,7 +159,7 @@ int tic_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t
                     const int32_t* src_idx, int rows, void* stream) {
   TIC_CHECK_ARG(src && dst && src_idx && rows > 0 && row_bytes > 0, "tic_gather_rows: bad arguments");
   dim3 grid(ceil_div(rows, 8), 1);
-  gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(gather_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), nullptr, nullptr, src_pitch_bytes, dst_pitch_bytes,
       row_bytes, src_idx, rows, nullptr, nullptr, nullptr, nullptr);
   TIC_CHECK_LAUNCH("tic_gather_rows");
@@ -178,13 +174,13 @@ int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int m
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(B, 8), 2);
   if (mode == TIC_ITM_UNIFORM) {
-    gather_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(ids), static_cast<uint8_t*>(tim_ids),
+    launch_k(gather_rows_kernel, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(ids), static_cast<uint8_t*>(tim_ids),
                                              static_cast<const uint8_t*>(mask), static_cast<uint8_t*>(tim_mask), row_bytes,
                                              row_bytes, row_bytes, nullptr, B, u_coin, u_pick, labels, src_idx);
   } else {
     int rc = tic_itm_sample(u_coin, u_pick, B, mode, S, lds, labels, src_idx, stream);
     if (rc) return rc;
-    gather_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(ids), static_cast<uint8_t*>(tim_ids),
+    launch_k(gather_rows_kernel, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(ids), static_cast<uint8_t*>(tim_ids),
                                              static_cast<const uint8_t*>(mask), static_cast<uint8_t*>(tim_mask), row_bytes,
                                              row_bytes, row_bytes, src_idx, B, nullptr, nullptr, nullptr, nullptr);
   }

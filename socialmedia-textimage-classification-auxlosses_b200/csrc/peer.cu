@@ -51,6 +51,8 @@ __device__ __forceinline__ uint4 ld_nc_na(const uint4* p) {   // streaming 16-by
 __global__ void __launch_bounds__(256)
 peer_exchange_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32_t* __restrict__ ctr, ExchangeArgs xa,
                      unsigned long long timeout_ns) {
+  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
+  pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
   // -- signal: everything this rank published (earlier kernels on this stream) is visible before the flag is
   if (blockIdx.x == 0 && threadIdx.x < world) {
@@ -191,7 +193,7 @@ int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag
   int grid = static_cast<int>((total / 16 + 256 * 4 - 1) / (256 * 4));
   if (grid < 1) grid = 1;
   if (grid > 4 * 148) grid = 4 * 148;
-  peer_exchange_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(sym, world, rank, flag_off, ctr, xa,
+  launch_k(peer_exchange_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), sym, world, rank, flag_off, ctr, xa,
                                                                            20ull * 1000ull * 1000ull * 1000ull);
   TIC_CHECK_LAUNCH("tic_peer_exchange");
   return TIC_OK;

@@ -105,6 +105,23 @@ int main(int argc, char** argv) {
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= iters;
     printf("  time %.3f ms  %.1f TFLOP/s\n", ms, 2.0 * M * N * K / ms * 1e-9);
+    // the same launches as ONE CUDA graph (serialised kernel nodes): device-side time per kernel, no host submission cost
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    cudaGraph_t g;
+    cudaGraphExec_t ge;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < iters; ++i) tic_gemm_bf16(dA, nullptr, lda, a_mn, dB, nullptr, ldb, b_mn, dD, nullptr, ldd, d_bf16, M, N, K, 0.5f, dbias, 0, 0, st);
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    CK(cudaGraphLaunch(ge, st));
+    CK(cudaStreamSynchronize(st));
+    cudaEventRecord(e0, st);
+    CK(cudaGraphLaunch(ge, st));
+    cudaEventRecord(e1, st);
+    CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("  as a graph of %d serialised nodes: %.2f us per kernel\n", iters, 1e3 * ms / iters);
   }
   return bad ? 4 : 0;
 }

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda.h>
 #include "tic_ptx.cuh"
+#include "common.cuh"
 
 namespace tic {
 
@@ -118,6 +119,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (CLUSTER > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  pdl_wait();      // prologue done (barriers, TMEM, descriptors); from here on global memory of the predecessors is read
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -169,6 +171,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
+      // all operand loads of this CTA are in flight: the next kernel of the stream may be launched now and run its prologue
+      // while the last MMAs and the last epilogue drain (triggering earlier lets waiting CTAs of later kernels pile up on
+      // the SMs and starve the parallel branches of the step — measured slower).
+      pdl_trigger();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -291,7 +297,7 @@ int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B
   int grid = m_tiles * n_tiles * ksplit;
   int cap = max_ctas > 0 ? max_ctas : device_sm_count();
   if (grid > cap) grid = cap;
-  kern<<<grid, 64 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep);
+  launch_k(kern, dim3(grid), dim3(64 + 32 * EPI_WARPS), Cfg::kSmemBytes, stream, ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -34,9 +34,14 @@ def _addr(t):
 
 
 def gemm(A, lda, a_mn, Bm, ldb, b_mn, D, ldd, d_bf16, M, N, K, alpha=1.0, bias=None, relu=False, A_lo=None, B_lo=None,
-         D_lo=None, accumulate=False):
+         D_lo=None, accumulate=False, row_ss=None):
     """D[M,N] = alpha * op(A) op(B)^T (+bias)(relu) on tcgen05 (tic_gemm_bf16).  A/Bm/D are tensors or raw device
-    addresses; A_lo / B_lo make that operand a split-precision bf16 (hi, lo) pair, D_lo receives the bf16 residual."""
+    addresses; A_lo / B_lo make that operand a split-precision bf16 (hi, lo) pair, D_lo receives the bf16 residual.
+    row_ss: fp32 [tic_gemm_rowss_parts(N), M] receiving per-tile row sums of squares (fused L2-norm statistics)."""
+    if row_ss is not None:
+        call("tic_gemm_bf16_rowss", _addr(A), _addr(A_lo), lda, int(a_mn), _addr(Bm), _addr(B_lo), ldb, int(b_mn), _addr(D),
+             _addr(D_lo), ldd, int(d_bf16), M, N, K, float(alpha), ptr(bias), int(relu), ptr(row_ss), _stream())
+        return
     call("tic_gemm_bf16", _addr(A), _addr(A_lo), lda, int(a_mn), _addr(Bm), _addr(B_lo), ldb, int(b_mn), _addr(D),
          _addr(D_lo), ldd, int(d_bf16), M, N, K, float(alpha), ptr(bias), int(relu), int(accumulate), _stream())
 
@@ -124,10 +129,13 @@ class ItcPlan:
         if not t_only:
             self.norm_v(V, ldv, V_lo=V_lo)
 
-    def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None):
+    def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None, ss_t=None, ss_v=None):
+        """ss_t / ss_v: row sum-of-squares partials from the projection GEMMs (gemm(row_ss=...)); the tiles then compute and
+        write rinv_t / rinv_v themselves and norm_t()/norm_v() are not needed."""
         call("tic_itc_fwd", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), self.m, self.n, self.P,
              self.row_offset, float(scale), float(scale), ptr(self.row_part), ptr(self.col_part), ptr(self.diag),
-             ptr(self.logits), self.n if self.logits is not None else 0, _stream())
+             ptr(self.logits), self.n if self.logits is not None else 0, ptr(ss_t), 0 if ss_t is None else ss_t.shape[0],
+             ptr(ss_v), 0 if ss_v is None else ss_v.shape[0], _stream())
 
     def lse_loss(self, scale, loss_sums, col_parts=None, n_col_parts=None):
         cp = self.col_part if col_parts is None else col_parts
@@ -135,10 +143,18 @@ class ItcPlan:
         call("tic_itc_lse_loss", ptr(self.row_part), self.nrp, ptr(cp), ncp, ptr(self.diag), self.m, self.n,
              self.row_offset, float(scale), ptr(self.lse_row), ptr(self.lse_col), ptr(loss_sums), _stream())
 
-    def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None):
+    def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None, inline_lse=False):
+        """inline_lse: derive lse_row/lse_col inside the kernel from the forward partials (few partials = small batch), so
+        that lse_loss() is only needed for the loss value and can run beside the backward instead of before it."""
+        rp = (ptr(self.row_part), self.nrp) if inline_lse else (None, 0)
+        cp = (ptr(self.col_part), self.ncp) if inline_lse else (None, 0)
         call("tic_itc_bwd_g", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), ptr(self.lse_row),
              ptr(self.lse_col), self.m, self.n, self.P, float(scale), float(gscale), ptr(self.GA), self.ld_ga,
-             ptr(self.GBT), self.ld_gbt, ptr(self.GA_lo), ptr(self.GBT_lo), _stream())
+             ptr(self.GBT), self.ld_gbt, ptr(self.GA_lo), ptr(self.GBT_lo), rp[0], rp[1], cp[0], cp[1], float(scale), _stream())
+
+    @property
+    def can_inline_lse(self):
+        return self.col_part is not None and self.nrp <= 64 and self.ncp <= 64
 
     def grad_gemm_t(self, V, ldv, V_lo=None):
         # dT_acc[m,P] = GA[m,n] * V[n,P]   (A K-major, B = V read MN-major: no transposed copy of V)
@@ -237,7 +253,7 @@ class HeadPlan:
         if self.P is not None:
             sizes.update(dW_t=self.P * E, dW_v=self.P * E)
         if self.fusion in ("concat", "attention", "gmu"):
-            sizes.update(dW_f=E * 2 * E)
+            sizes.update(dW_f=E * 2 * E, d_xt_cls=B * E)   # d_xt_cls: accumulated by tic_unpack_cls_grad (atomics)
         if self.fusion == "attention":
             sizes.update(dW_Q=E * E, dW_V=E * E, dWK_aug=E * (E + 8))
         if self.fusion == "gmu":
@@ -284,7 +300,7 @@ class HeadPlan:
             return
         self.Xcat = e(R, 2 * E, dt=BF16)
         self.dXt = e(R, E)                            # gradient of the text half of Xcat (fp32)
-        o["d_xt_cls"] = e(B, E)
+        o["d_xt_cls"] = self.z["d_xt_cls"].view(B, E)
         o["dW_f"], o["db_f"] = self.z["dW_f"].view(E, 2 * E), self.z["db_f"]
         if self.fusion == "attention":
             Ea = E + 8
@@ -365,19 +381,33 @@ class HeadPlan:
         ldt, ldv = Yt.stride(0), Yv.stride(0)
         br = self.br
         br.enabled = self.parallel_streams
+        fused_norm = self.P is not None and B <= 1024     # small batch: norm statistics ride on the projection GEMMs
+        if fused_norm and getattr(self, "ss_t", None) is None:
+            nss = capi.load().tic_gemm_rowss_parts(self.P)
+            self.ss_t = torch.empty(nss, B, dtype=F32, device=self.dev)
+            self.ss_v = torch.empty(nss, B, dtype=F32, device=self.dev)
         with br("v"):   # image tower branch: projection + row norms
             if self.P is not None:
                 vp_ = inp["v_pool"]
-                gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl)   # HF :262 visual_projection
-            it.norm_v(Yv, ldv, V_lo=Yvl)
+                gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl,      # HF :262 visual_projection
+                     row_ss=self.ss_v if fused_norm else None)
+            if not fused_norm:
+                it.norm_v(Yv, ldv, V_lo=Yvl)
         if self.P is not None:
             tp_ = inp["t_pool"]
-            gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)       # HF :265 text_projection
-        it.norm_t(Yt, ldt, T_lo=Ytl)
+            gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl,          # HF :265 text_projection
+                 row_ss=self.ss_t if fused_norm else None)
+        if not fused_norm:
+            it.norm_t(Yt, ldt, T_lo=Ytl)
         br.join("v")
-        it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl)
+        it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl, ss_t=self.ss_t if fused_norm else None,
+                     ss_v=self.ss_v if fused_norm else None)
         if with_loss:
-            it.lse_loss(self.scale, self.z["itc_sums"])
+            if it.can_inline_lse:      # small batch: the backward derives lse itself; the loss runs on a side branch
+                with br("l"):
+                    it.lse_loss(self.scale, self.z["itc_sums"])
+            else:
+                it.lse_loss(self.scale, self.z["itc_sums"])
         if it.logits is not None:
             self.out["logits_per_text"] = it.logits
 
@@ -388,7 +418,7 @@ class HeadPlan:
         ldt, ldv = Yt.stride(0), Yv.stride(0)
         if dS is None:
             g = self.g_itc
-            it.bwd_operands(Yt, ldt, Yv, ldv, self.scale, g / (2.0 * B), T_lo=Ytl, V_lo=Yvl)
+            it.bwd_operands(Yt, ldt, Yv, ldv, self.scale, g / (2.0 * B), T_lo=Ytl, V_lo=Yvl, inline_lse=it.can_inline_lse)
             dcoef = g / B
         else:
             assert it.precise, "autograd mode (materialised dS) is meant for drop-in batch sizes (< 4096)"
@@ -453,15 +483,27 @@ class HeadPlan:
                 self._fusion_chain(inp)
             if self.use_itc:
                 self._itc_bwd(inp)
+        self.br.join("l")      # ITC loss terms (side branch when the backward derives lse inline)
         call("tic_loss_mix", ptr(z["losses"]), ptr(z["itc_sums"]), getattr(self, "n_global", B),
              self.beta_itc if self.fusion is not None else 1.0, self.beta_itm, int(self.use_itc), int(self.use_itm),
              ptr(o["loss"]), _stream())
         return o
 
+    def _inline_rule(self, inp):
+        """Uniform ITM decisions can be re-derived inside the pack kernel from the uniforms (same rule, bit-exact), so the
+        sampler/gather kernel runs beside the fusion forward instead of before it."""
+        return self.use_itm and self.itm_mode == 0 and "src_idx" not in inp and inp.get("u_coin") is not None
+
     def _fusion_chain(self, inp):
         if self.use_itm:
-            self._sample_itm(inp)
+            if self._inline_rule(inp):
+                self.br.enabled = self.parallel_streams
+                with self.br("s"):
+                    self._sample_itm(inp)
+            else:
+                self._sample_itm(inp)
         self._fusion_fwd(inp)
+        self.br.join("s")      # lbl_tim (heads) / src_idx (unpack) come from the sampler
         self._heads(inp, dH_f32=self.dHf if self.fusion == "aspect-att" else None)
         self._fusion_bwd(inp)
 
@@ -543,12 +585,13 @@ class HeadPlan:
         xt_stride, xv_stride = x_t.stride(0), x_v.stride(0)   # CLS rows: x[:,0,:]
         X = self.Xcat
         X_lo = None
+        uc, up = (ptr(inp["u_coin"]), ptr(inp["u_pick"])) if self._inline_rule(inp) else (None, None)
         if self.fusion == "concat" or self.fusion == "gmu":
-            call("tic_pack_cls_pairs", ptr(x_t), xt_stride, ptr(x_v), xv_stride, B, E, ptr(src), ptr(X), E2, st)
+            call("tic_pack_cls_pairs", ptr(x_t), xt_stride, ptr(x_v), xv_stride, B, E, ptr(src), ptr(X), E2, uc, up, st)
         if self.fusion == "attention":
             Ea, Lv = E + 8, self.Lv
             X_lo = self.Xcat_lo
-            call("tic_pack_cls_pairs", ptr(x_t), xt_stride, None, 0, B, E, ptr(src), ptr(X), E2, st)
+            call("tic_pack_cls_pairs", ptr(x_t), xt_stride, None, 0, B, E, ptr(src), ptr(X), E2, uc, up, st)
             gemm(X, E2, 0, w["W_Q"], E, 0, self.q0, E, 1, R, E, E, bias=w["b_Q"], D_lo=self.q0_lo)  # q0 = fc_Q(x_t[:,0])
             gemm(self.q0, E, 0, w["W_Kaug"], Ea, 1, self.kq, Ea, 0, R, Ea, E, A_lo=self.q0_lo)       # [W_K^T q0 | <q0,b_K>] fp32
             call("tic_attn_pool_fwd", ptr(x_v), x_v.stride(0), x_v.stride(1), ptr(self.kq), Ea, B, 2 if self.use_itm else 1,
