@@ -62,6 +62,30 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
   return 0;
 }
 
+int make_tmap_bf16_store32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems) {
+  auto fn = TmapEncoder::get();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return TIC_E_TMAP;
+  }
+  if (!aligned16(ptr) || (pitch_elems % 8) != 0) {
+    set_error("TMA store target needs a 16-byte aligned base and a leading dimension multiple of 8");
+    return TIC_E_ARG;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (store map) failed (%d)", (int)r);
+    return TIC_E_TMAP;
+  }
+  return 0;
+}
+
 int device_sm_count() {
   static int n = 0;
   if (n == 0) {

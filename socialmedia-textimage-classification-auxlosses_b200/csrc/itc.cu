@@ -25,6 +25,12 @@ inline bool itc_multicast() {
   if (v < 0) { const char* e = getenv("TIC_ITC_MULTICAST"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
+// TIC_ITC_TMA_STORE=0 keeps the direct 16-byte stores of the gradient operand (A/B measurement switch).
+inline bool itc_tma_store() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIC_ITC_TMA_STORE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 constexpr int kItcEpiWarps = 8;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -230,6 +236,10 @@ struct ItcBwdEpi {
     const float* col_part;  // [n_col_parts][N] or nullptr -> lse_col
     int n_row_parts, n_col_parts;
     float shift;
+    float shift_log2e;   // common offset of the factored form below (keeps 2^(lr-off), 2^(off-lc) in fp32 range)
+    int factored;        // fast path: ONE ex2 per element (host enables it for scale <= 20)
+    int tma_store;       // GA leaves through shared memory + TMA 32x32 tile stores (full lines) instead of 16-byte pieces
+    alignas(64) CUtensorMap tmap_ga;
   };
   template <int BN>
   __device__ static void tile(const Params& p, const EpiCtx& cx) {
@@ -253,7 +263,9 @@ struct ItcBwdEpi {
           lc = __ldg(p.lse_col + cx.n0 + j);
         }
       }
-      sl[j] = lc * kLog2e;
+      // factored fast path:  e^{S-lse_row} + e^{S-lse_col} = e1 * (1 + Er_i * Ec_j),  e1 = 2^(s2 - lr),
+      //   Er_i = 2^(lr - off), Ec_j = 2^(off - lc)  ->  GA = e1 * (g_j + Er_i * (Ec_j g_j)),  g_j = gscale * rinv_v[j]
+      sl[j] = p.factored ? (ok ? exp2f(p.shift_log2e - lc * kLog2e) * b * p.gscale : 0.f) : lc * kLog2e;
       sg[j] = b * p.gscale;
     }
     epi_bar_sync(cx.epi_threads);
@@ -286,8 +298,23 @@ struct ItcBwdEpi {
       for (int j = 0; j < 32; ++j) v[j] = vn[j];
       if (c + 1 < nchunk && col0 + 32 < cx.N) tmem_ld_32x32(trow + cl + 32, vn);   // prefetch the next 32 columns
       float ga[32];
-      if (col0 + 32 <= cx.N && p.GBT == nullptr) {
-        // fast path (interior tile, GA-shared mode): FMUL, FMUL, 2x(FADD + MUFU), FADD, FMUL per element
+      if (col0 + 32 <= cx.N && p.GBT == nullptr && p.factored) {
+        // fast path (interior tile, no transposed operand): FMUL, FFMA, MUFU, FFMA, FMUL per element — the XU pipe (16 ex2
+        // per clock per SM) is what bounds this epilogue, so the second exponential is replaced by the factored form.
+        const float er = valid_row ? exp2f(lr - p.shift_log2e) : 0.f;
+        const float nlr = valid_row ? -lr : -INFINITY;
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j4);
+          const float4 c4 = *reinterpret_cast<const float4*>(sl + cl + j4);
+          const float4 g4 = *reinterpret_cast<const float4*>(sg + cl + j4);
+          ga[j4 + 0] = ex2_approx(fmaf(__uint_as_float(v[j4 + 0]) * b4.x, rt2, nlr)) * fmaf(er, c4.x, g4.x);
+          ga[j4 + 1] = ex2_approx(fmaf(__uint_as_float(v[j4 + 1]) * b4.y, rt2, nlr)) * fmaf(er, c4.y, g4.y);
+          ga[j4 + 2] = ex2_approx(fmaf(__uint_as_float(v[j4 + 2]) * b4.z, rt2, nlr)) * fmaf(er, c4.z, g4.z);
+          ga[j4 + 3] = ex2_approx(fmaf(__uint_as_float(v[j4 + 3]) * b4.w, rt2, nlr)) * fmaf(er, c4.w, g4.w);
+        }
+      } else if (col0 + 32 <= cx.N && p.GBT == nullptr) {
+        // two-exponential form of the same fast path (scale > 20: the factored product could leave the fp32 range)
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j4);
@@ -306,6 +333,10 @@ struct ItcBwdEpi {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float s2 = __uint_as_float(v[j]) * rt * sb[cl + j] * p.scale_log2e;  // S * log2e
+        if (p.factored) {   // (edge tile of the factored mode; GBT is NULL there) sl = Ec_j * g_j, sg = g_j
+          ga[j] = exp2f(s2 - lr) * fmaf(exp2f(lr - p.shift_log2e), sl[cl + j], sg[cl + j]);
+          continue;
+        }
         const float pr = p.gscale * (exp2f(s2 - lr) + exp2f(s2 - sl[cl + j]));
         ga[j] = pr * sb[cl + j];
         if (gbt != nullptr && valid_row && col0 + j < cx.N) {
@@ -316,7 +347,30 @@ struct ItcBwdEpi {
         }
       }
       }
-      if (valid_row) {
+      if (p.tma_store && col0 + 32 <= cx.N) {
+        // Each lane's 32 bf16 (64 B) go to its row of this warp's 32x32 staging tile (64-byte swizzle: 16-byte chunk q of row r
+        // sits at chunk q ^ ((r >> 1) & 3), bank-conflict free), then ONE bulk tensor store writes full 64-byte row segments;
+        // rows past M are clipped by the TMA unit.  The direct form (16-byte pieces at a 2N-byte stride per lane) made every
+        // warp store touch 32 half-filled sectors and its back-pressure was the top stall of this kernel.
+        const int wslot = (threadIdx.x >> 5) - 2;
+        const uint32_t stg = smem_u32(cx.scratch) + kEpiStageOff + wslot * 2048;
+        if (lane == 0) tma_store_wait_read<0>();   // the previous tile store of this warp has read its staging tile
+        __syncwarp();
+        const uint32_t rowb = stg + lane * 64, sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t a = rowb + ((q ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(ga[8 * q], ga[8 * q + 1])),
+                       "r"(pack_bf16x2(ga[8 * q + 2], ga[8 * q + 3])), "r"(pack_bf16x2(ga[8 * q + 4], ga[8 * q + 5])),
+                       "r"(pack_bf16x2(ga[8 * q + 6], ga[8 * q + 7])) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.tmap_ga, stg, col0, cx.m0 + cx.quad * 32);
+          tma_store_commit();
+        }
+      } else if (valid_row) {
         __nv_bfloat16* d = p.GA + static_cast<int64_t>(row) * p.ld_ga + col0;
         if (col0 + 32 <= cx.N && vec_ok) {
 #pragma unroll
@@ -777,7 +831,14 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
   TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_bwd_g: empty problem");
   ItcBwdEpi::Params ep{rinv_t, rinv_v, lse_row, lse_col, scale * kLog2e, gscale, static_cast<__nv_bfloat16*>(GA), ld_ga,
                        static_cast<__nv_bfloat16*>(GBT), ld_gbt, static_cast<__nv_bfloat16*>(GA_lo),
-                       static_cast<__nv_bfloat16*>(GBT_lo), row_part, col_part, n_row_parts, n_col_parts, shift};
+                       static_cast<__nv_bfloat16*>(GBT_lo), row_part, col_part, n_row_parts, n_col_parts, shift,
+                       scale * kLog2e, (scale <= 20.f && GBT == nullptr) ? 1 : 0, 0, {}};
+  if (GA_lo == nullptr && GBT == nullptr && (ld_ga & 7) == 0 && aligned16(GA) && itc_tma_store()) {
+    int trc = make_tmap_bf16_store32(&ep.tmap_ga, GA, static_cast<uint64_t>(n_global), static_cast<uint64_t>(m_local),
+                                     static_cast<uint64_t>(ld_ga));
+    if (trc) return trc;
+    ep.tma_store = 1;
+  }
   const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
   int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, ldt, V, ldv, m_local, n_global, P, ep,
                                                                                         static_cast<cudaStream_t>(stream))

@@ -20,13 +20,16 @@ constexpr int kBM = 128;       // UMMA M (cta_group::1)
 constexpr int kBK = 64;        // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;     // bf16 UMMA K
 constexpr int kABytes = kBM * kBK * 2;
-constexpr int kEpiScratchBytes = 8192;
+// Epilogue scratch: [0, 6912) per-tile vectors of the ITC epilogues (6 * BN floats), [6912, 6912 + 8 * 2048) one
+// 1024-byte-aligned 32x32 bf16 staging tile per epilogue warp for TMA stores (scratch starts at 256 mod 1024).
+constexpr int kEpiStageOff = 6912;
+constexpr int kEpiScratchBytes = kEpiStageOff + 8 * 2048 + 256;
 
 template <int BN>
 struct UmmaCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesFit = (220 * 1024 - 1024 - 256 - kEpiScratchBytes) / kStageBytes;
+  static constexpr int kStagesFit = (227 * 1024 - 1024 - 256 - kEpiScratchBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiScratchBytes;
@@ -59,7 +62,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi, int CLUSTER = 
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int ksplit,
-                 int M, int N, int K, typename Epi::Params ep) {
+                 int M, int N, int K, const __grid_constant__ typename Epi::Params ep) {
   static_assert(CLUSTER == 1 || (CLUSTER == 2 && BN >= 128), "cluster multicast needs BN >= 128");
   using Cfg = UmmaCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
@@ -239,6 +242,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ++cx.iter;
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
+    tma_store_wait<0>();   // bulk stores issued by the epilogue (if any) have completed before the CTA retires
   }
 
   tc_fence_before();
@@ -261,6 +265,9 @@ struct TmapEncoder {
 // 2D bf16 tensor map over a row-major [outer, inner] matrix with pitch `pitch_elems`, 128B swizzle, zero OOB fill.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
                       uint32_t box_inner, uint32_t box_outer);
+
+// 2D bf16 tensor map for TMA STORES of 32x32 tiles (64-byte rows, 64-byte swizzle) into a row-major [outer, inner] matrix.
+int make_tmap_bf16_store32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems);
 
 int device_sm_count();
 
