@@ -207,6 +207,24 @@ static int dispatch_major(const void* A, const void* A_lo, int64_t lda, int a_mn
   return launch_umma_gemm<BN, true, true, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st, ksplit);
 }
 
+// 2-CTA clusters: M-adjacent tile pairs share the B tile through TMA multicast (one L2 read feeds two SMs).  Large GEMMs
+// with 128x256 tiles need ~17 TB/s of L2->SM operand traffic at tensor peak, which the L2 cannot deliver; sharing B
+// cuts the traffic per tile by a third.
+template <int BN>
+static int dispatch_major_cluster(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, int M, int N, int K,
+                                  const StoreEpi::Params& ep, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_umma_gemm_cluster2<BN, false, false, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+  if (!a_mn && b_mn) return launch_umma_gemm_cluster2<BN, false, true, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+  if (a_mn && !b_mn) return launch_umma_gemm_cluster2<BN, true, false, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+  return launch_umma_gemm_cluster2<BN, true, true, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
+}
+// TIC_GEMM_MULTICAST=0 disables the cluster variant (A/B measurement switch).
+static bool gemm_multicast() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIC_GEMM_MULTICAST"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 // ------------------------------------------------------------------ SIMT reference GEMM (self-test only)
 __global__ void simt_gemm_kernel(const __nv_bfloat16* A, int64_t lda, int a_mn, const __nv_bfloat16* B, int64_t ldb,
                                  int b_mn, void* D, int64_t ldd, int d_bf16, int M, int N, int K, float alpha,
@@ -277,7 +295,10 @@ static int gemm_impl(const void* A, const void* A_lo, int64_t lda, int a_mn, con
   }
   if (row_ss_part) { best_bn = kRowSsBN; best_ks = 1; }   // the partial layout [ceil(N/64)][M] is part of the ABI
   int rc;
-  if (best_bn == 256) rc = dispatch_major<256>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
+  const bool cluster = gemm_multicast() && !A_lo && !B_lo && best_ks == 1 && best_bn == 256 && m_tiles >= 16 &&
+                       static_cast<int64_t>(m_tiles) * ceil_div(N, best_bn) >= 2 * sms;
+  if (cluster) rc = dispatch_major_cluster<256>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
+  else if (best_bn == 256) rc = dispatch_major<256>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
   else if (best_bn == 128) rc = dispatch_major<128>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
   else rc = dispatch_major<64>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
   if (rc == -3) { set_error("tic_gemm_bf16: cudaFuncSetAttribute(max dynamic smem) failed"); return TIC_E_ATTR; }
