@@ -89,6 +89,62 @@ class SymmetricItc:
         br.join("cb")
 
 
+class RowBlockItc:
+    """Sequencing of the row-block ITC step with a peer-memory reduction of the image-side gradient — the form used from
+    4096 global negatives on, where recomputing the swapped tile block (SymmetricItc) would cost more tensor time than
+    moving the gradient contributions:
+
+        exchange "emb"   V_all, rinv_v_all                          (text rows never leave their rank)
+        row block        S[rows_r, :] -> row sums (complete), column partial sums [N] (published)
+        exchange "col"   every rank's column sums [R, N] -> summed in rank order -> lse_col (identical on all ranks)
+        row block        GA = G'[rows_r, :] * rinv_v ;  dT_r = GA V_all (local)
+                         dV contributions  GA^T That_r  [N, P] fp32 (published)
+        exchange "dv"    rows [r*b, (r+1)*b) of every rank's contributions [R, b, P] -> summed in rank order -> dV_r
+
+    blk implements the plan.ItcPlan piece interface (GA-shared mode); publish_v_norm / publish_col_sums / lse_loss_gathered
+    / reduce_dv are the pieces that touch the published block."""
+
+    def __init__(self, blk, exchange, b_local: int, world: int, rank: int, branches=None):
+        self.blk, self.exchange = blk, exchange
+        self.b, self.world, self.rank, self.N = b_local, world, rank, b_local * world
+        self.br = branches if branches is not None else _NoBranches()
+
+    def forward(self, T, V, V_all, scale, loss_sums, produce_t=None, produce_v=None):
+        blk, br = self.blk, self.br
+        ldt = T.stride(0)
+        with br("cb"):
+            if produce_v is not None:
+                produce_v()
+            blk.publish_v_norm(V)                               # inverse norms of my image rows -> published
+        if produce_t is not None:
+            produce_t()
+        blk.norm_t(T, ldt)                                      # local (+ normalised bf16 copy for the dV product)
+        br.join("cb")
+        self.exchange("emb")
+        blk.fwd_tiles(T, ldt, V_all, V_all.stride(0), scale)
+        blk.publish_col_sums()
+        self.exchange("col")
+        blk.lse_loss_gathered(scale, loss_sums)
+
+    def backward(self, T, V, V_all, scale, g, dT_f32=None, dT_bf16=None, dV_f32=None, dV_bf16=None, r_sum=None, dT_lo=None,
+                 dV_lo=None, consume_t=None, consume_v=None):
+        blk, N, b, br = self.blk, self.N, self.b, self.br
+        ldt, ldv = T.stride(0), V.stride(0)
+        blk.bwd_operands(T, ldt, V_all, V_all.stride(0), scale, g / (2.0 * N))
+        with br("cb"):   # image side first: its exchange overlaps the text-side GEMM on the main stream
+            blk.grad_gemm_v(T, ldt)                             # -> published contributions [N, P]
+            self.exchange("dv")
+            acc_v = blk.reduce_dv()                             # [b, P], fixed rank order
+            blk.finalize_v(acc_v, V, ldv, blk.rinv_v_mine(), T, ldt, blk.rinv_t, b, scale, g / N, dV_f32, dV_bf16, dV_lo=dV_lo)
+            if consume_v is not None:
+                consume_v()
+        blk.grad_gemm_t(V_all, V_all.stride(0))
+        blk.finalize_t(T, ldt, V, ldv, blk.rinv_v_mine(), scale, g / N, dT_f32, dT_bf16, r_sum, dT_lo=dT_lo)
+        if consume_t is not None:
+            consume_t()
+        br.join("cb")
+
+
 class _NoBranches:
     class _Ctx:
         def __enter__(self):
@@ -195,7 +251,7 @@ def _make_peer_head_plan():
         sampling/gather and the small heads are per-sample (pure data parallel).  Every rank produces the gradients of the
         GLOBAL loss restricted to its samples (weight gradients / d logit_scale are summed across ranks by the caller)."""
 
-        def __init__(self, B_local, *, world, rank, group=None, d: Optional[int] = None, **kw):
+        def __init__(self, B_local, *, world, rank, group=None, d: Optional[int] = None, itc_mode: Optional[str] = None, **kw):
             kw.setdefault("use_itc", True)
             use_itc = kw["use_itc"]
             kw["use_itc"] = False                       # the parent must not allocate a square single-GPU ItcPlan
@@ -218,7 +274,18 @@ def _make_peer_head_plan():
             if not use_itc:
                 return
             assert b % 8 == 0, "per-rank batch must be a multiple of 8 (16-byte exchange segments)"
-            Pe = self.Pe
+            # symmetric blocks while the step is latency-bound; row block + peer reduction once tensor time dominates
+            import os as _os
+            itc_mode = itc_mode or _os.environ.get("TIC_PEER_ITC_MODE") or None     # env: A/B measurement switch
+            self.itc_mode = itc_mode if itc_mode is not None else ("symmetric" if N < 4096 else "rowblock")
+            assert self.itc_mode in ("symmetric", "rowblock")
+            if self.itc_mode == "symmetric":
+                self._init_symmetric(b, N, group)
+            else:
+                self._init_rowblock(b, N, group)
+
+        def _init_symmetric(self, b, N, group):
+            world, rank, dev, Pe = self.world, self.rank, self.dev, self.Pe
             precise = N < 4096
             self.has_lo = precise and self.P is not None  # residuals exist only for embeddings projected on the device
             ybytes = 2 * b * Pe * 2
@@ -255,6 +322,51 @@ def _make_peer_head_plan():
             self.lse_ws = torch.zeros(int(capi_load().tic_itc_lse_rows_workspace_bytes(b)) // 4, dtype=F32, device=dev)
             self.sym = SymmetricItc(self.rb, self.cb, pg.exchange, self._lse_rows, b, world, rank, branches=self.br)
 
+        def _init_rowblock(self, b, N, group):
+            world, rank, dev, Pe = self.world, self.rank, self.dev, self.Pe
+            self.has_lo = False
+            off_y = 0
+            off_rinv = off_y + _up(2 * b * Pe * 2)
+            off_col = off_rinv + _up(b * 4)
+            off_acc = off_col + _up(N * 4)
+            self.pg = PeerGroup(off_acc + _up(N * Pe * 4), world, rank, dev, group)
+            pg = self.pg
+            e = lambda *s, dt=F32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
+            self.Y = pg.view(off_y, (2 * b, Pe), BF16)                    # [text rows ; image rows] (image half is pulled by peers)
+            self.Y_lo = e(2 * b, Pe, dt=BF16) if self.P is not None else None
+            self.V_all, self.rinv_v_all = e(N, Pe, dt=BF16), e(N)
+            col_all, dv_parts, acc_v_mine = e(world, N), e(world, b, Pe), e(b, Pe)
+            half = b * Pe * 2
+            pg.define_phase("emb", [(off_y + half, half, self.V_all, half), (off_rinv, b * 4, self.rinv_v_all, b * 4)])
+            pg.define_phase("col", [(off_col, N * 4, col_all, N * 4)])
+            pg.define_phase("dv", [(off_acc + rank * b * Pe * 4, b * Pe * 4, dv_parts, b * Pe * 4)])
+            blk = P.ItcPlan(b, N, Pe, dev, row_offset=rank * b, need_dv=True, precise=False)
+            blk.rinv_v = self.rinv_v_all
+            blk.acc_v = pg.view(off_acc, (N, Pe), F32)                  # published gradient contributions
+            blk.col_sum = pg.view(off_col, (N,), F32)                   # published column sums
+            rinv_pub = pg.view(off_rinv, (b,), F32)
+            plan = self
+
+            def publish_v_norm(V):
+                call("tic_row_rnorm_bf16", ptr(V), None, V.stride(0), b, Pe, ptr(rinv_pub), None, 0, P._stream())
+
+            def publish_col_sums():
+                call("tic_reduce_parts", ptr(blk.col_part), blk.ncp, N, ptr(blk.col_sum), P._stream())
+
+            def lse_loss_gathered(scale, loss_sums):
+                blk.lse_loss(scale, loss_sums, col_parts=col_all, n_col_parts=world)
+
+            def reduce_dv():
+                call("tic_reduce_parts", ptr(dv_parts), world, b * Pe, ptr(acc_v_mine), P._stream())
+                return acc_v_mine
+
+            blk.publish_v_norm, blk.publish_col_sums, blk.lse_loss_gathered, blk.reduce_dv = \
+                publish_v_norm, publish_col_sums, lse_loss_gathered, reduce_dv
+            blk.rinv_v_mine = lambda: rinv_pub
+            self.itc = self.rb = blk
+            self._keep = (col_all, dv_parts, acc_v_mine, rinv_pub, plan)
+            self.sym = RowBlockItc(blk, pg.exchange, b, world, rank, branches=self.br)
+
         def _lse_rows(self, rb, cb, scale, loss_sums):
             call("tic_itc_lse_rows", ptr(rb.row_part), ptr(cb.row_part), rb.nrp, self.B, ptr(rb.diag), float(scale),
                  ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), P._stream())
@@ -270,6 +382,8 @@ def _make_peer_head_plan():
         def _ops(self):
             b = self.B
             lo = self.has_lo
+            if self.itc_mode == "rowblock":
+                return dict(T=self.Y[:b], V=self.Y[b:], V_all=self.V_all)
             return dict(T=self.Y[:b], V=self.Y[b:], T_all=self.T_all, V_all=self.V_all,
                         T_lo=self.Y_lo[:b] if lo else None, V_lo=self.Y_lo[b:] if lo else None,
                         T_all_lo=self.T_all_lo, V_all_lo=self.V_all_lo)
