@@ -3,6 +3,7 @@
 //               the main and the ITM pass (mm_late.py:98-113,195-210; only ctx[:,0,:] is consumed, :111)
 //   aspect-att: tanh-scored 2-way softmax over the (scrambled) pooled pair (mm_late.py:115-131)
 //   gmu       : sigmoid gate of the raw concatenation (mm_late.py:133-144)
+#include <cstdlib>
 #include "common.cuh"
 #include "tic_ptx.cuh"
 
@@ -594,6 +595,19 @@ __global__ void gmu_gate_bwd_kernel(const __nv_bfloat16* __restrict__ X, int64_t
   if (dX) dX[r * lddx + c] = g * (tp[r * ldp + c] - vp[r * ldp + c]) * z * (1.f - z);
 }
 
+// tensor-core form of the two kernels above (attn_mma.cu); TIC_ATTN_V3=0 keeps the SIMT pipeline (A/B measurement switch)
+int attn_pool_fwd_mma(const void* xv, int64_t bstride, const float* kq, int64_t ldkq, int B, int npass, int Lv, float scale,
+                      void* xbar_b, void* xbar_lo, int64_t ld_xb, float* xbar_f, int64_t ld_xf, float* attn, int64_t ld_attn,
+                      cudaStream_t st);
+int attn_pool_bwd_mma(const void* xv, int64_t bstride, const float* attn, int64_t ld_attn, const float* dxbar, int64_t ld_dxb,
+                      const float* xbar_f, int64_t ld_xf, int B, int npass, int Lv, float scale, void* dkq, void* dkq_lo,
+                      int64_t ld_dkq, cudaStream_t st);
+static bool attn_v3() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIC_ATTN_V3"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 }  // namespace tic
 
 using namespace tic;
@@ -609,6 +623,13 @@ int tic_attn_pool_fwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
                 "tic_attn_pool_fwd: 16-byte aligned x_v rows / augmented kq (ld >= E+1) required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (xv_tok_stride == E && (xv_batch_stride & 7) == 0 && (ldkq & 3) == 0 && (reinterpret_cast<uintptr_t>(kq) & 15) == 0) {
+    if (attn_v3() && (ld_xb & 1) == 0 && (ld_xf & 1) == 0 && ((reinterpret_cast<uintptr_t>(xbar_f32) | reinterpret_cast<uintptr_t>(xbar_bf16) |
+                                                               reinterpret_cast<uintptr_t>(xbar_bf16_lo)) & 7) == 0) {
+      int rc = attn_pool_fwd_mma(xv, xv_batch_stride, static_cast<const float*>(kq), ldkq, B, npass, Lv, scale, xbar_bf16, xbar_bf16_lo,
+                                 ld_xb, xbar_f32, ld_xf, attn, ld_attn, st);
+      if (rc) set_error("tic_attn_pool_fwd: tensor-core kernel launch failed (%d)", rc);
+      return rc;
+    }
     const size_t sm2 = 128 + kApStages * kApChunkBytes + 16 * kApStages + sizeof(float) * (npass * Lv + npass * 16 + 8 * E);
     auto xb2 = static_cast<__nv_bfloat16*>(xbar_bf16);
     auto xl2 = static_cast<__nv_bfloat16*>(xbar_bf16_lo);
@@ -653,6 +674,12 @@ int tic_attn_pool_bwd(const void* xv, int64_t xv_batch_stride, int64_t xv_tok_st
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (xv_tok_stride == E && (xv_batch_stride & 7) == 0 && (ld_dxb & 3) == 0 && (ld_xf & 3) == 0 &&
       ((reinterpret_cast<uintptr_t>(dxbar) | reinterpret_cast<uintptr_t>(xbar_f32)) & 15) == 0) {
+    if (attn_v3() && (ld_dkq & 1) == 0 && ((reinterpret_cast<uintptr_t>(dkq_bf16) | reinterpret_cast<uintptr_t>(dkq_bf16_lo)) & 3) == 0) {
+      int rc = attn_pool_bwd_mma(xv, xv_batch_stride, attn, ld_attn, dxbar, ld_dxb, xbar_f32, ld_xf, B, npass, Lv, scale, dkq_bf16,
+                                 dkq_bf16_lo, ld_dkq, st);
+      if (rc) set_error("tic_attn_pool_bwd: tensor-core kernel launch failed (%d)", rc);
+      return rc;
+    }
     const size_t sm2 = 128 + kApStages * kApChunkBytes + 16 * kApStages + sizeof(float) * (8 * E + npass * 8 + npass * Lv);
     if (npass == 1) {
       auto k = attn_pool_bwd_v2_kernel<1>;
