@@ -452,8 +452,26 @@ def finalize_roofline(r, peaks):
         peak = peaks.get("hbm_gbs", 6650.0)
         src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"
     out = dict(r)
-    out.update(peak=peak, frac=r["achieved"] / peak, peak_source=src, traffic=r.get("traffic"))
+    key = out.pop("traffic_key", None)
+    traffic, tsrc = None, None
+    ent = _traffic_db().get(key) if key else None
+    if ent:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one committed `ncu --set full` capture
+        traffic, tsrc = ent.get("traffic_bytes"), "profiles/ncu_traffic.json[%s] (%s launch(es), ncu, bytes)" % (key, ent.get("launches", 1))
+    out.update(peak=peak, frac=r["achieved"] / peak, peak_source=src, traffic=traffic, traffic_source=tsrc)
     return out
+
+
+_TRAFFIC = None
+
+
+def _traffic_db():
+    global _TRAFFIC
+    if _TRAFFIC is None:
+        try:
+            _TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            _TRAFFIC = {}
+    return _TRAFFIC
 
 
 def time_kernel(fn, flush, iters=10):
@@ -485,15 +503,19 @@ def kernel_rooflines(P, plan, spec, dev_in, n_global, flush):
         d = it.P
         ldt, ldv = Yt.stride(0), Yv.stride(0)
         ms = time_kernel(lambda: it.fwd_tiles(Yt, ldt, Yv, ldv, plan.scale), flush)
+        shp = "%dx%d" % (B, d)
         ks.append(dict(kernel="tic_itc_fwd (tcgen05 similarity tiles + fused bidirectional softmax-CE)", bound="tensor",
-                       ms=ms, achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="2*B^2*d FLOP"))
+                       ms=ms, achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="2*B^2*d FLOP",
+                       traffic_key="itc_fwd_" + shp))
         ms = time_kernel(lambda: it.bwd_operands(Yt, ldt, Yv, ldv, plan.scale, 1.0 / (2 * B)), flush)
         ks.append(dict(kernel="tic_itc_bwd_g (tile recompute -> bf16 gradient operands)", bound="tensor", ms=ms,
                        achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s",
-                       algorithmic="recompute: 2*B^2*d executed FLOP, 0 algorithmic (reported as executed)"))
+                       algorithmic="recompute: 2*B^2*d executed FLOP, 0 algorithmic (reported as executed)",
+                       traffic_key="itc_bwd_" + shp))
         ms = time_kernel(lambda: it.grad_gemms(Yt, ldt, Yv, ldv), flush)
         ks.append(dict(kernel="tic_gemm_bf16 x2 (dT = GA*V, dV = GBT*T)", bound="tensor", ms=ms,
-                       achieved=4.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="4*B^2*d FLOP"))
+                       achieved=4.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="4*B^2*d FLOP",
+                       traffic_key="gemm_dtdv_" + shp))
     if spec["fusion"] == "attention":
         x_v = dev_in["x_v"]
         R_, Lv, Ea = plan.R, spec["Lv"], E + 8
@@ -503,18 +525,21 @@ def kernel_rooflines(P, plan, spec, dev_in, n_global, flush):
                                         Ea, B, npass, Lv, E, float(E) ** -0.5, plan.xbar_b.data_ptr(), plan.xbar_lo.data_ptr(),
                                         E, plan.xbar_f.data_ptr(), E, plan.attn.data_ptr(), Lv, st()), flush)
         ks.append(dict(kernel="tic_attn_pool_fwd (one streaming read of x_v, main+ITM pass)", bound="hbm", ms=ms,
-                       achieved=B * Lv * E * 2.0 / ms * 1e-6, unit="GB/s", algorithmic="B*Lv*E*2 bytes"))
+                       achieved=B * Lv * E * 2.0 / ms * 1e-6, unit="GB/s", algorithmic="B*Lv*E*2 bytes",
+                       traffic_key="attn_fwd_%d" % B))
         ms = time_kernel(lambda: P.call("tic_attn_pool_bwd", x_v.data_ptr(), x_v.stride(0), x_v.stride(1), plan.attn.data_ptr(),
                                         Lv, plan.dxbar.data_ptr(), E, plan.xbar_f.data_ptr(), E, B, npass, Lv, E,
                                         float(E) ** -0.5, plan.dkq.data_ptr(), plan.dkq_lo.data_ptr(), Ea, st()), flush)
         ks.append(dict(kernel="tic_attn_pool_bwd (second streaming read of x_v)", bound="hbm", ms=ms,
-                       achieved=B * Lv * E * 2.0 / ms * 1e-6, unit="GB/s", algorithmic="B*Lv*E*2 bytes"))
+                       achieved=B * Lv * E * 2.0 / ms * 1e-6, unit="GB/s", algorithmic="B*Lv*E*2 bytes",
+                       traffic_key="attn_bwd_%d" % B))
     if spec["fusion"] in ("concat",):
         R_, E2 = plan.R, 2 * E
         ms = time_kernel(lambda: P.gemm(plan.Xcat, E2, 0, plan.w["W_f"], E2, 0, plan.H, E, 0, R_, E, E2, bias=plan.w["b_f"],
                                         relu=True), flush)
         ks.append(dict(kernel="tic_gemm_bf16 (linear_fusion forward, bias+ReLU epilogue)", bound="tensor", ms=ms,
-                       achieved=2.0 * R_ * E * E2 / ms * 1e-9, unit="TFLOP/s", algorithmic="2*R*E*2E FLOP"))
+                       achieved=2.0 * R_ * E * E2 / ms * 1e-9, unit="TFLOP/s", algorithmic="2*R*E*2E FLOP",
+                       traffic_key="gemm_fusion_%dx%d" % (B, spec["P"] or 0)))
     if not ks:
         return None, []
     dom = max(ks, key=lambda k: k["ms"])
@@ -535,14 +560,16 @@ def scale_point(P, dev, flush, B=16384, d=768):
     it.run(T, V, scale, 1.0, sums, rsum, dT_f32=dT, dV_f32=dV)
     ks = []
     ms = time_kernel(lambda: it.fwd_tiles(T, ld, V, ld, scale), flush)
+    shp = "%dx%d" % (B, d)
     ks.append(dict(kernel="tic_itc_fwd", bound="tensor", ms=ms, achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s",
-                   algorithmic="2*B^2*d FLOP"))
+                   algorithmic="2*B^2*d FLOP", traffic_key="itc_fwd_" + shp))
     ms = time_kernel(lambda: it.bwd_operands(T, ld, V, ld, scale, 1.0 / (2 * B)), flush)
     ks.append(dict(kernel="tic_itc_bwd_g", bound="tensor", ms=ms, achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s",
-                   algorithmic="recompute: 2*B^2*d executed FLOP, 0 algorithmic (reported as executed)"))
+                   algorithmic="recompute: 2*B^2*d executed FLOP, 0 algorithmic (reported as executed)",
+                   traffic_key="itc_bwd_" + shp))
     ms = time_kernel(lambda: it.grad_gemms(T, ld, V, ld), flush)
     ks.append(dict(kernel="tic_gemm_bf16 x2 (dT, dV)", bound="tensor", ms=ms, achieved=4.0 * B * B * d / ms * 1e-9,
-                   unit="TFLOP/s", algorithmic="4*B^2*d FLOP"))
+                   unit="TFLOP/s", algorithmic="4*B^2*d FLOP", traffic_key="gemm_dtdv_" + shp))
     ms = time_kernel(lambda: it.run(T, V, scale, 1.0, sums, rsum, dT_f32=dT, dV_f32=dV), flush, iters=5)
     step = dict(kernel="whole ITC fwd+bwd step (norms, tiles, lse, recompute, 2 GEMMs, finalize)", bound="tensor", ms=ms,
                 achieved=6.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="6*B^2*d FLOP (recompute not counted)",
