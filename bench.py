@@ -31,7 +31,7 @@ import torch  # noqa: E402
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", type=str, default="c2")
     ap.add_argument("--impl", type=str, default="tic", choices=["tic", "reference"])
@@ -118,7 +118,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -128,6 +128,13 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
+
+    def wait_first(self, timeout_s=4.0):
+        """nvidia-smi takes ~1 s to come up (longer with 8 ranks starting at once): do not enter a sub-second timed
+        region before the sampler delivers."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout_s:
+            time.sleep(0.05)
 
     def stop(self):
         if self.proc is None:
@@ -335,6 +342,7 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        clocks.wait_first()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
