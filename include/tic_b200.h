@@ -92,7 +92,11 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
                 int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
                 float* col_part /* NULL: skip the column statistics (symmetric multi-GPU mode) */, float* diag,
                 float* logits_out, int64_t ld_logits, const float* ss_t_part, int n_ss_t, const float* ss_v_part, int n_ss_v,
-                void* stream);
+                const uint32_t* seg_ready, const uint32_t* seg_epoch, int seg_cols, int my_seg, void* stream);
+/* Consuming a gathered V as it lands (multi-GPU): seg_ready (NULL = V is complete) points at n_global/seg_cols device
+ * words; segment p (columns [p*seg_cols, (p+1)*seg_cols), written by a tic_peer_pull running beside this kernel) may be
+ * read once seg_ready[p] >= *seg_epoch.  Tiles are visited segment-major starting with my_seg (always ready); if seg_cols is
+ * not a multiple of the tile width the kernel waits for every segment before its first load instead. */
 /* Fused normalisation (small batches): when ss_t_part [n_ss_t][m_local] / ss_v_part [n_ss_v][n_global] — the per-tile row
  * sums of squares written by tic_gemm_bf16_rowss while it projected the embeddings — are given, the tiles derive
  * rinv = 1/sqrt(sum of partials) themselves and WRITE rinv_t / rinv_v for the kernels that follow; no norm kernel runs. */
@@ -272,6 +276,14 @@ int tic_peer_close(void* ptr);
 int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* ctr, int nseg,
                       const int64_t* src_off_host, const int64_t* bytes_host, void* const* dst_host,
                       const int64_t* dst_stride_host, void* stream);
+/* tic_peer_pull: the pull half alone (the ranks were ordered by the preceding tic_peer_exchange on the same stream or an
+ * ancestor of it): peer by peer starting with `rank`, and after peer p's ranges have landed ready[p] = ctr[0] (the epoch of
+ * that exchange) is published with release semantics — the consumer side of tic_itc_fwd(seg_ready = ready, seg_epoch = ctr)
+ * may run concurrently on another stream.  ready / tickets: `world` zero-initialised uint32 each, local device memory.
+ * max_blocks bounds the grid (0 = 148 blocks of 128 threads, 64 registers each) so the pull lives beside a persistent GEMM. */
+int tic_peer_pull(void* const* bases_host, int world, int rank, const uint32_t* ctr, uint32_t* ready, uint32_t* tickets, int nseg,
+                  const int64_t* src_off_host, const int64_t* bytes_host, void* const* dst_host, const int64_t* dst_stride_host,
+                  int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ _SIGS = {
     "tic_row_rnorm_bf16": ("ppliipplp", ctypes.c_int),
     "tic_itc_row_parts": ("i", ctypes.c_int),
     "tic_itc_col_parts": ("i", ctypes.c_int),
-    "tic_itc_fwd": ("pplpplppiiiiffpppplpipip", ctypes.c_int),
+    "tic_itc_fwd": ("pplpplppiiiiffpppplpipippiip", ctypes.c_int),
     "tic_reduce_parts": ("piipp", ctypes.c_int),
     "tic_itc_lse_loss": ("pipipiiifpppp", ctypes.c_int),
     "tic_itc_lse_rows_workspace_bytes": ("i", ctypes.c_int64),
@@ -38,6 +38,7 @@ _SIGS = {
     "tic_peer_open": ("pp", ctypes.c_int),
     "tic_peer_close": ("p", ctypes.c_int),
     "tic_peer_exchange": ("piilpippppp", ctypes.c_int),
+    "tic_peer_pull": ("piipppippppip", ctypes.c_int),
     "tic_itc_bwd_g": ("pplpplppppiiiffplplpppipifp", ctypes.c_int),
     "tic_itc_ds_operands": ("pliipppplpplp", ctypes.c_int),
     "tic_itc_grad_finalize": ("plpplppplpiiffplpplpip", ctypes.c_int),

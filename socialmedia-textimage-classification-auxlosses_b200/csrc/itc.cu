@@ -761,7 +761,8 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
                 float* rinv_v,
                 int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
                 float* col_part, float* diag, float* logits_out, int64_t ld_logits, const float* ss_t_part, int n_ss_t,
-                const float* ss_v_part, int n_ss_v, void* stream) {
+                const float* ss_v_part, int n_ss_v, const uint32_t* seg_ready, const uint32_t* seg_epoch, int seg_cols,
+                int my_seg, void* stream) {
   TIC_CHECK_ARG(T && V && rinv_t && rinv_v && row_part && diag, "tic_itc_fwd: null pointer");
   TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_fwd: empty problem");
   TIC_CHECK_ARG(row_offset >= 0 && row_offset + m_local <= n_global, "tic_itc_fwd: row block outside the global batch");
@@ -773,14 +774,24 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
   ItcFwdEpi::Params ep{rinv_t, rinv_v, ss_t_part, ss_v_part, n_ss_t, n_ss_v, scale * kLog2e, shift * kLog2e, scale, row_part, col_part, diag, logits_out, ld_logits,
                        row_offset};
   const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
+  // V arriving segment by segment (peer pull running beside this kernel): tiles go segment-major, local segment first
+  SegOrder so{nullptr, nullptr, 0, 0, 0};
+  const SegOrder* sop = nullptr;
+  if (seg_ready != nullptr) {
+    TIC_CHECK_ARG(seg_epoch && seg_cols > 0 && n_global % seg_cols == 0 && my_seg >= 0 && my_seg < n_global / seg_cols,
+                  "tic_itc_fwd: bad segment description (seg_cols=%d my_seg=%d n_global=%d)", seg_cols, my_seg, n_global);
+    const int bn = itc_bn(n_global);
+    so = SegOrder{seg_ready, seg_epoch, seg_cols % bn == 0 ? seg_cols / bn : 0, my_seg, n_global / seg_cols};
+    sop = &so;
+  }
   int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, ldt, V, ldv, m_local, n_global, P, ep,
-                                                                                        static_cast<cudaStream_t>(stream))
+                                                                                        static_cast<cudaStream_t>(stream), sop)
            : itc_bn(n_global) == kItcBN
                ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
-                                                                                P, ep, static_cast<cudaStream_t>(stream), 1)
+                                                                                P, ep, static_cast<cudaStream_t>(stream), 1, 0, sop)
                : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
                                                                                      n_global, P, ep,
-                                                                                     static_cast<cudaStream_t>(stream), 1);
+                                                                                     static_cast<cudaStream_t>(stream), 1, 0, sop);
   if (rc == -3) { set_error("tic_itc_fwd: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_fwd: launch failed"); return TIC_E_LAUNCH; }
   return rc;

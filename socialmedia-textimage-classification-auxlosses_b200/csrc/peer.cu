@@ -113,6 +113,48 @@ peer_exchange_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32
   }
 }
 
+// Pull WITHOUT a barrier (the barrier of the preceding tic_peer_exchange already ordered the ranks), peer by peer starting
+// with the rank itself: when the last block has copied peer p's ranges it publishes ready[p] = epoch (release, gpu scope).
+// A GEMM running beside this kernel consumes the segments as they land (SegOrder in tic_umma.cuh).
+// Register budget: this kernel must be able to co-reside with the persistent ITC tile kernel (320 threads x 168 registers
+// per SM leave 11.7 K registers) — otherwise the tile kernel, which waits for the segments, would starve it: 128 x 64.
+__global__ void __maxnreg__(64)
+peer_pull_kernel(PeerPtrs sym, int world, int rank, const uint32_t* __restrict__ ctr, uint32_t* __restrict__ ready,
+                 uint32_t* __restrict__ tickets, ExchangeArgs xa) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(ctr);
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int k = 0; k < world; ++k) {
+    int p = rank + k;
+    if (p >= world) p -= world;
+    for (int s = 0; s < xa.nseg; ++s) {
+      const ExchangeSeg sg = xa.seg[s];
+      const int64_t words = sg.bytes >> 4;
+      const uint4* src = reinterpret_cast<const uint4*>(sym.base[p] + sg.src_off);
+      uint4* dst = reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride);
+      int64_t i = tid;
+      for (; i + 3 * nthr < words; i += 4 * nthr) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_nc_na(src + i + u * nthr);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[i + u * nthr] = v[u];
+      }
+      for (; i < words; i += nthr) dst[i] = ld_nc_na(src + i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(tickets + p, 1u) == gridDim.x - 1) {
+        tickets[p] = 0u;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ready + p), "r"(epoch) : "memory");
+      }
+    }
+  }
+}
+
 }  // namespace tic
 
 using namespace tic;
@@ -196,6 +238,36 @@ int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag
   launch_k(peer_exchange_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), sym, world, rank, flag_off, ctr, xa,
                                                                            20ull * 1000ull * 1000ull * 1000ull);
   TIC_CHECK_LAUNCH("tic_peer_exchange");
+  return TIC_OK;
+}
+
+int tic_peer_pull(void* const* bases_host, int world, int rank, const uint32_t* ctr, uint32_t* ready, uint32_t* tickets, int nseg,
+                  const int64_t* src_off_host, const int64_t* bytes_host, void* const* dst_host, const int64_t* dst_stride_host,
+                  int max_blocks, void* stream) {
+  TIC_CHECK_ARG(bases_host && ctr && ready && tickets && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+                "tic_peer_pull: bad group (world=%d rank=%d)", world, rank);
+  TIC_CHECK_ARG(nseg >= 1 && nseg <= kMaxSeg, "tic_peer_pull: bad segment list");
+  PeerPtrs sym{};
+  for (int p = 0; p < world; ++p) {
+    TIC_CHECK_ARG(bases_host[p] != nullptr, "tic_peer_pull: rank %d has no mapped block", p);
+    sym.base[p] = static_cast<uint8_t*>(bases_host[p]);
+  }
+  ExchangeArgs xa{};
+  xa.nseg = nseg;
+  int64_t per_peer = 0;
+  for (int s = 0; s < nseg; ++s) {
+    TIC_CHECK_ARG((src_off_host[s] & 15) == 0 && (bytes_host[s] & 15) == 0 && (dst_stride_host[s] & 15) == 0 &&
+                      aligned16(dst_host[s]) && bytes_host[s] >= 0,
+                  "tic_peer_pull: segment %d is not 16-byte aligned", s);
+    xa.seg[s] = ExchangeSeg{src_off_host[s], bytes_host[s], static_cast<uint8_t*>(dst_host[s]), dst_stride_host[s]};
+    per_peer += bytes_host[s];
+  }
+  int grid = static_cast<int>((per_peer / 16 + 128 * 4 - 1) / (128 * 4));
+  if (max_blocks <= 0) max_blocks = 148;   // one small block per SM: enough loads in flight for NVLink beside a persistent GEMM
+  if (grid > max_blocks) grid = max_blocks;
+  if (grid < 1) grid = 1;
+  launch_k(peer_pull_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), sym, world, rank, ctr, ready, tickets, xa);
+  TIC_CHECK_LAUNCH("tic_peer_pull");
   return TIC_OK;
 }
 

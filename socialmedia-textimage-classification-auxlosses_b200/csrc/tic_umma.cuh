@@ -49,6 +49,30 @@ struct EpiCtx {
   uint8_t* scratch;    // kEpiScratchBytes of smem shared by the epilogue warps
 };
 
+// Optional tile order for a B operand that ARRIVES segment by segment (multi-GPU: the gathered embeddings are pulled from the
+// peers by a concurrent kernel): tiles are visited segment-major starting with the local segment, and the TMA producer waits
+// for a segment's ready word (>= *epoch, acquire) before its first load from it — the GEMM consumes the all-gather as it lands.
+constexpr int kSegFreeSms = 8;
+struct SegOrder {
+  const uint32_t* ready;   // [nseg] device words, nullptr = ordinary order / operand complete
+  const uint32_t* epoch;
+  int tiles_per_seg;       // N tiles per segment; 0 = layout not tile-aligned: wait for every segment up front
+  int my_seg;              // visited first (the pull copies it first: a local copy, no NVLink hop)
+  int nseg;
+};
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void seg_wait(const SegOrder& so, int seg, uint32_t epoch) {
+  uint32_t spins = 0;
+  while (static_cast<int32_t>(ld_acquire_gpu_u32(so.ready + seg) - epoch) < 0) {
+    if (++spins > (1u << 28)) { printf("tic: segment %d never became ready\n", seg); __trap(); }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // the pulled data is read by the TMA (async proxy) next
+}
+
 // Named barrier among the epilogue warps only (id 1); the producer / MMA warps never touch it.
 __device__ __forceinline__ void epi_bar_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
@@ -62,7 +86,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi, int CLUSTER = 
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int ksplit,
-                 int M, int N, int K, const __grid_constant__ typename Epi::Params ep) {
+                 int M, int N, int K, const __grid_constant__ typename Epi::Params ep, SegOrder so) {
   static_assert(CLUSTER == 1 || (CLUSTER == 2 && BN >= 128), "cluster multicast needs BN >= 128");
   using Cfg = UmmaCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
@@ -96,7 +120,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t crank = CLUSTER == 1 ? 0u : cluster_ctarank();
   const int worker = CLUSTER == 1 ? blockIdx.x : blockIdx.x / CLUSTER;
   const int nworkers = CLUSTER == 1 ? gridDim.x : gridDim.x / CLUSTER;
+  const bool seg_major = so.ready != nullptr && so.tiles_per_seg > 0;
   auto tile_of = [&](int item, int& m_blk, int& n_blk) {
+    if (seg_major) {   // segment-major, local segment first (ksplit == 1 in this mode)
+      const int per_seg = m_groups * so.tiles_per_seg;
+      const int sidx = item / per_seg, rem = item - sidx * per_seg;
+      int seg = so.my_seg + sidx;
+      if (seg >= so.nseg) seg -= so.nseg;
+      m_blk = (rem / so.tiles_per_seg) * CLUSTER + static_cast<int>(crank);
+      n_blk = seg * so.tiles_per_seg + rem % so.tiles_per_seg;
+      return;
+    }
     m_blk = (item / n_tiles) * CLUSTER + static_cast<int>(crank);
     n_blk = item % n_tiles;
   };
@@ -129,11 +163,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      int seg_ok = -1;
+      uint32_t seg_epoch = 0;
+      if (so.ready != nullptr) {
+        seg_epoch = *reinterpret_cast<const volatile uint32_t*>(so.epoch);
+        if (!seg_major)   // segments are not tile-aligned: the whole operand has to be there before the first load
+          for (int g = 0; g < so.nseg; ++g) seg_wait(so, g, seg_epoch);
+      }
       for (int w = worker; w < num_items; w += nworkers) {
         const int t = w / ksplit, ks = w - t * ksplit;
         int m_blk, n_blk;
         tile_of(t, m_blk, n_blk);
         const int m0 = m_blk * kBM, n0 = n_blk * BN;
+        if (seg_major) {
+          const int seg = n_blk / so.tiles_per_seg;
+          if (seg != seg_ok) { seg_wait(so, seg, seg_epoch); seg_ok = seg; }   // the local segment is copied first, but copied too
+        }
         const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / ksplit);
         const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / ksplit);
         for (int kt = kt_begin; kt < kt_end; ++kt) {
@@ -273,7 +318,8 @@ int device_sm_count();
 
 template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
 int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B, const void* B_lo, int64_t ldb, int M, int N,
-                     int K, const typename Epi::Params& ep, cudaStream_t stream, int ksplit = 1, int max_ctas = 0) {
+                     int K, const typename Epi::Params& ep, cudaStream_t stream, int ksplit = 1, int max_ctas = 0,
+                     const SegOrder* seg = nullptr) {
   using Cfg = UmmaCfg<BN>;
   if (M <= 0 || N <= 0 || K <= 0) return -1;
   CUtensorMap ta, tb, ta_lo, tb_lo;
@@ -303,15 +349,18 @@ int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B
   if (ksplit > total_kb) ksplit = total_kb;
   int grid = m_tiles * n_tiles * ksplit;
   int cap = max_ctas > 0 ? max_ctas : device_sm_count();
+  if (seg && seg->ready && cap > device_sm_count() - kSegFreeSms) cap = device_sm_count() - kSegFreeSms;
   if (grid > cap) grid = cap;
-  launch_k(kern, dim3(grid), dim3(64 + 32 * EPI_WARPS), Cfg::kSmemBytes, stream, ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep);
+  SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0};
+  if (so.ready && (ksplit != 1 || so.tiles_per_seg <= 0 || so.tiles_per_seg * so.nseg != n_tiles)) so.tiles_per_seg = 0;
+  launch_k(kern, dim3(grid), dim3(64 + 32 * EPI_WARPS), Cfg::kSmemBytes, stream, ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep, so);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 // Cluster (TMA multicast) launch: pairs of M-adjacent tiles share B. No split operands, no split-K.
 template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi>
 int launch_umma_gemm_cluster2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
-                              const typename Epi::Params& ep, cudaStream_t stream) {
+                              const typename Epi::Params& ep, cudaStream_t stream, const SegOrder* seg = nullptr) {
   using Cfg = UmmaCfg<BN>;
   if (M <= 0 || N <= 0 || K <= 0) return -1;
   CUtensorMap ta, tb, tb_half;
@@ -333,7 +382,10 @@ int launch_umma_gemm_cluster2(const void* A, int64_t lda, const void* B, int64_t
   }
   const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
   const int items = ((m_tiles + 1) / 2) * n_tiles;
-  int clusters = device_sm_count() / 2;
+  // Segment-consuming mode: leave kSegFreeSms SMs to the concurrent pull kernel.  Co-residency of its blocks with this
+  // kernel's CTAs (one per SM, ~all shared memory) is not something the hardware scheduler promises, and a pull that cannot
+  // be scheduled while the producers wait for its segments is a deadlock.
+  int clusters = (device_sm_count() - (seg && seg->ready ? kSegFreeSms : 0)) / 2;
   if (clusters > items) clusters = items;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
@@ -348,7 +400,9 @@ int launch_umma_gemm_cluster2(const void* A, int64_t lda, const void* B, int64_t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int split = 0, ksplit = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta, tb, tb_half, split, ksplit, M, N, K, ep);
+  SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0};
+  if (so.ready && (so.tiles_per_seg <= 0 || so.tiles_per_seg * so.nseg != n_tiles)) so.tiles_per_seg = 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta, tb, tb_half, split, ksplit, M, N, K, ep, so);
   return e == cudaSuccess ? 0 : -4;
 }
 

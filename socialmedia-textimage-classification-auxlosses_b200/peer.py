@@ -94,7 +94,9 @@ class RowBlockItc:
     4096 global negatives on, where recomputing the swapped tile block (SymmetricItc) would cost more tensor time than
     moving the gradient contributions:
 
-        exchange "emb"   V_all, rinv_v_all                          (text rows never leave their rank)
+        exchange "emb"   barrier + rinv_v_all; then V_all is pulled peer by peer on a side branch while the row-block tile
+                         kernel already runs: its TMA producer waits per segment (local segment first)  — the all-gather
+                         is consumed as it lands                       (text rows never leave their rank)
         row block        S[rows_r, :] -> row sums (complete), column partial sums [N] (published)
         exchange "col"   every rank's column sums [R, N] -> summed in rank order -> lse_col (identical on all ranks)
         row block        GA = G'[rows_r, :] * rinv_v ;  dT_r = GA V_all (local)
@@ -104,8 +106,13 @@ class RowBlockItc:
     blk implements the plan.ItcPlan piece interface (GA-shared mode); publish_v_norm / publish_col_sums / lse_loss_gathered
     / reduce_dv are the pieces that touch the published block."""
 
-    def __init__(self, blk, exchange, b_local: int, world: int, rank: int, branches=None):
-        self.blk, self.exchange = blk, exchange
+    def __init__(self, blk, exchange, b_local: int, world: int, rank: int, branches=None, pull=None, seg=None):
+        """pull(name): the barrier-free pull half of an exchange, issued on a side branch; seg: the (ready, epoch, seg_cols,
+        my_seg) description handed to fwd_tiles so that the tiles consume V_all segment by segment while it lands.  Without
+        `pull` the "emb" exchange gathers V_all itself (gloo/CPU stand-in)."""
+        self.blk, self.exchange, self.pull, self.seg = blk, exchange, pull, seg
+        import os as _os
+        self.overlap = _os.environ.get("TIC_PEER_OVERLAP", "1") != "0"
         self.b, self.world, self.rank, self.N = b_local, world, rank, b_local * world
         self.br = branches if branches is not None else _NoBranches()
 
@@ -120,8 +127,17 @@ class RowBlockItc:
             produce_t()
         blk.norm_t(T, ldt)                                      # local (+ normalised bf16 copy for the dV product)
         br.join("cb")
-        self.exchange("emb")
-        blk.fwd_tiles(T, ldt, V_all, V_all.stride(0), scale)
+        self.exchange("emb")                                    # barrier (+ inverse norms; + V_all when there is no pull)
+        if self.pull is not None and self.overlap:
+            with br("pull"):
+                self.pull("vall")                               # V_all lands peer by peer beside the tile kernel
+            blk.fwd_tiles(T, ldt, V_all, V_all.stride(0), scale, seg=self.seg)
+            br.join("pull")
+        elif self.pull is not None:                             # TIC_PEER_OVERLAP=0: pull, then tiles (A/B switch)
+            self.pull("vall")
+            blk.fwd_tiles(T, ldt, V_all, V_all.stride(0), scale)
+        else:
+            blk.fwd_tiles(T, ldt, V_all, V_all.stride(0), scale)
         blk.publish_col_sums()
         self.exchange("col")
         blk.lse_loss_gathered(scale, loss_sums)
@@ -233,6 +249,21 @@ class PeerGroup:
         self.capi.call("tic_peer_exchange", self._bases_c, self.world, self.rank, self.flag_off, self.ctr.data_ptr(), n, so, nb,
                        dst, ds, torch.cuda.current_stream().cuda_stream)
 
+    def define_pull(self, name: str, segs, max_blocks: int = 148):
+        n = len(segs)
+        ready = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
+        tickets = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
+        self._pulls = getattr(self, "_pulls", {})
+        self._pulls[name] = (n, (ctypes.c_int64 * n)(*[s[0] for s in segs]), (ctypes.c_int64 * n)(*[s[1] for s in segs]),
+                             (ctypes.c_void_p * n)(*[s[2].data_ptr() for s in segs]),
+                             (ctypes.c_int64 * n)(*[s[3] for s in segs]), ready, tickets, max_blocks, [s[2] for s in segs])
+        return ready
+
+    def pull(self, name: str):
+        n, so, nb, dst, ds, ready, tickets, mb, _keep = self._pulls[name]
+        self.capi.call("tic_peer_pull", self._bases_c, self.world, self.rank, self.ctr.data_ptr(), ready.data_ptr(),
+                       tickets.data_ptr(), n, so, nb, dst, ds, mb, torch.cuda.current_stream().cuda_stream)
+
     def close(self):
         for r, b in enumerate(self.bases):
             if r != self.rank and b:
@@ -337,7 +368,8 @@ def _make_peer_head_plan():
             self.V_all, self.rinv_v_all = e(N, Pe, dt=BF16), e(N)
             col_all, dv_parts, acc_v_mine = e(world, N), e(world, b, Pe), e(b, Pe)
             half = b * Pe * 2
-            pg.define_phase("emb", [(off_y + half, half, self.V_all, half), (off_rinv, b * 4, self.rinv_v_all, b * 4)])
+            pg.define_phase("emb", [(off_rinv, b * 4, self.rinv_v_all, b * 4)])
+            v_ready = pg.define_pull("vall", [(off_y + half, half, self.V_all, half)])
             pg.define_phase("col", [(off_col, N * 4, col_all, N * 4)])
             pg.define_phase("dv", [(off_acc + rank * b * Pe * 4, b * Pe * 4, dv_parts, b * Pe * 4)])
             blk = P.ItcPlan(b, N, Pe, dev, row_offset=rank * b, need_dv=True, precise=False)
@@ -365,7 +397,8 @@ def _make_peer_head_plan():
             blk.rinv_v_mine = lambda: rinv_pub
             self.itc = self.rb = blk
             self._keep = (col_all, dv_parts, acc_v_mine, rinv_pub, plan)
-            self.sym = RowBlockItc(blk, pg.exchange, b, world, rank, branches=self.br)
+            self.sym = RowBlockItc(blk, pg.exchange, b, world, rank, branches=self.br, pull=pg.pull,
+                                   seg=(v_ready, pg.ctr, b, rank))
 
         def _lse_rows(self, rb, cb, scale, loss_sums):
             call("tic_itc_lse_rows", ptr(rb.row_part), ptr(cb.row_part), rb.nrp, self.B, ptr(rb.diag), float(scale),

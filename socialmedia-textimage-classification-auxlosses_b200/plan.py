@@ -85,7 +85,7 @@ class ItcPlan:
     """ITC forward+backward for a row block of `m` text rows against `n` gathered image columns (single GPU: m == n)."""
 
     def __init__(self, m: int, n: int, P: int, device, row_offset: int = 0, materialize_logits: bool = False,
-                 need_dv: bool = True, precise: Optional[bool] = None, col_sums: bool = True):
+                 need_dv: bool = True, precise: Optional[bool] = None, col_sums: bool = True, splitk_grad: Optional[bool] = None):
         assert P % 8 == 0, "embedding width must be a multiple of 8 (16-byte TMA rows)"
         self.m, self.n, self.P, self.row_offset = m, n, P, row_offset
         # Split-precision gradient operands (bf16 hi+lo): with few negatives the bf16 rounding of the softmax
@@ -116,6 +116,9 @@ class ItcPlan:
         self.acc_v = torch.empty(n, P, dtype=F32, device=dev) if need_dv else None
         self.logits = torch.empty(m, n, dtype=F32, device=dev) if materialize_logits else None
         self.need_dv = need_dv
+        # dT = GA[m,n] V[n,P] with m << n (multi-GPU row block at small per-rank batch): the un-split GEMM has m/128 * P/64
+        # CTAs walking the whole K = n; fp32-atomic split-K fills the machine instead (nondeterministic summation order)
+        self.splitk_grad = (m <= 1024 and n >= 4 * m) if splitk_grad is None else bool(splitk_grad)
 
     # -- pieces (the distributed path interleaves collectives between them) --
     def norm_t(self, T, ldt, T_lo=None):
@@ -129,13 +132,16 @@ class ItcPlan:
         if not t_only:
             self.norm_v(V, ldv, V_lo=V_lo)
 
-    def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None, ss_t=None, ss_v=None):
+    def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None, ss_t=None, ss_v=None, seg=None):
         """ss_t / ss_v: row sum-of-squares partials from the projection GEMMs (gemm(row_ss=...)); the tiles then compute and
-        write rinv_t / rinv_v themselves and norm_t()/norm_v() are not needed."""
+        write rinv_t / rinv_v themselves and norm_t()/norm_v() are not needed.
+        seg = (ready, epoch, seg_cols, my_seg): V is being pulled from the peers by a concurrent kernel, segment p of
+        seg_cols columns is usable once ready[p] >= epoch[0]; the tiles are visited local-segment-first."""
+        sr, se, sc, ms = (ptr(seg[0]), ptr(seg[1]), int(seg[2]), int(seg[3])) if seg is not None else (None, None, 0, 0)
         call("tic_itc_fwd", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), self.m, self.n, self.P,
              self.row_offset, float(scale), float(scale), ptr(self.row_part), ptr(self.col_part), ptr(self.diag),
              ptr(self.logits), self.n if self.logits is not None else 0, ptr(ss_t), 0 if ss_t is None else ss_t.shape[0],
-             ptr(ss_v), 0 if ss_v is None else ss_v.shape[0], _stream())
+             ptr(ss_v), 0 if ss_v is None else ss_v.shape[0], sr, se, sc, ms, _stream())
 
     def lse_loss(self, scale, loss_sums, col_parts=None, n_col_parts=None):
         cp = self.col_part if col_parts is None else col_parts
@@ -158,6 +164,11 @@ class ItcPlan:
 
     def grad_gemm_t(self, V, ldv, V_lo=None):
         # dT_acc[m,P] = GA[m,n] * V[n,P]   (A K-major, B = V read MN-major: no transposed copy of V)
+        if self.splitk_grad:   # few output tiles, long K (a small row block against many gathered columns): split K over CTAs
+            self.acc_t.zero_()
+            gemm(self.GA, self.ld_ga, 0, V, ldv, 1, self.acc_t, self.P, 0, self.m, self.P, self.n, A_lo=self.GA_lo, B_lo=V_lo,
+                 accumulate=True)
+            return
         gemm(self.GA, self.ld_ga, 0, V, ldv, 1, self.acc_t, self.P, 0, self.m, self.P, self.n, A_lo=self.GA_lo, B_lo=V_lo)
 
     def grad_gemm_v(self, T, ldt, T_lo=None):
