@@ -192,6 +192,55 @@ def test_peer_exchange_single_rank_pulls_its_own_block():
         capi.call("tic_peer_free", p)
 
 
+def test_peer_pull_feeds_segment_waiting_tiles_single_rank():
+    """tic_peer_pull on a side stream + tic_itc_fwd(seg_ready=...) on the main stream, world == 1: the tile kernel's producer
+    waits for the ready word of the (single) segment, which the pull publishes after copying V out of the peer block; the
+    statistics equal those of the plain call on the same V."""
+    P, capi = _mods()
+    d = _dev()
+    B, Pd = 4096, 256
+    g = torch.Generator().manual_seed(5)
+    T = torch.randn(B, Pd, generator=g).to(torch.bfloat16).to(d)
+    V = (torch.randn(B, Pd, generator=g)).to(torch.bfloat16).to(d)
+    nbytes = B * Pd * 2
+    p = ctypes.c_void_p()
+    capi.call("tic_peer_alloc", nbytes + 256, ctypes.byref(p))
+    try:
+        from tic_b200.peer import _RawCuda
+        block = torch.as_tensor(_RawCuda(int(p.value), nbytes + 256), device=d)
+        block[:nbytes].view(torch.bfloat16).view(B, Pd).copy_(V)
+        bases = (ctypes.c_void_p * 1)(int(p.value))
+        ctr = torch.zeros(2, dtype=torch.int32, device=d)
+        z = (ctypes.c_int64 * 0)()
+        capi.call("tic_peer_exchange", bases, 1, 0, nbytes, ctr.data_ptr(), 0, z, z, (ctypes.c_void_p * 0)(), z,
+                  torch.cuda.current_stream().cuda_stream)           # the ordering exchange: epoch 1
+        ready, tickets = torch.zeros(1, dtype=torch.int32, device=d), torch.zeros(1, dtype=torch.int32, device=d)
+        V_all = torch.zeros(B, Pd, dtype=torch.bfloat16, device=d)
+        scale = math.exp(2.6592)
+        ref = P.ItcPlan(B, B, Pd, d)
+        ref.norms(T, Pd, V, Pd)
+        ref.fwd_tiles(T, Pd, V, Pd, scale)
+        it = P.ItcPlan(B, B, Pd, d)
+        it.norm_t(T, Pd)
+        it.rinv_v.copy_(ref.rinv_v)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        so, nb = (ctypes.c_int64 * 1)(0), (ctypes.c_int64 * 1)(nbytes)
+        dst, ds = (ctypes.c_void_p * 1)(V_all.data_ptr()), (ctypes.c_int64 * 1)(nbytes)
+        with torch.cuda.stream(side):
+            capi.call("tic_peer_pull", bases, 1, 0, ctr.data_ptr(), ready.data_ptr(), tickets.data_ptr(), 1, so, nb, dst, ds, 0,
+                      side.cuda_stream)
+        it.fwd_tiles(T, Pd, V_all, Pd, scale, seg=(ready, ctr, B, 0))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        assert int(ready[0]) == 1 and torch.equal(V_all.view(torch.int16), V.view(torch.int16))
+        assert _rel(it.row_part.sum(0), ref.row_part.sum(0)) < 1e-5
+        assert _rel(it.col_part.sum(0), ref.col_part.sum(0)) < 1e-5
+        assert _rel(it.diag, ref.diag) < 1e-6
+    finally:
+        capi.call("tic_peer_free", p)
+
+
 # ---------------------------------------------------------------------------------------------------- pipelined host entry point
 def test_host_pipeline_matches_synchronous_host_step():
     P, capi = _mods()

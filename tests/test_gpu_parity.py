@@ -377,6 +377,33 @@ def test_head_plan_vs_oracle(fusion, use_itm, B):
     assert abs(float(plan.out["loss"][0]) - l1) <= 1e-6 * abs(l1) + 1e-7
 
 
+@pytest.mark.parametrize("fusion,use_itm,B,C,Lv", [("concat", True, 1, 4, 2), ("concat", True, 2, 2, 2), ("attention", True, 1, 3, 197),
+                                                   ("attention", True, 3, 2, 5), ("gmu", True, 2, 3, 2), ("aspect-att", False, 1, 4, 2),
+                                                   ("concat", True, 257, 3, 2), ("attention", False, 130, 4, 33)])
+def test_head_plan_edge_shapes_vs_oracle(fusion, use_itm, B, C, Lv):
+    """Edge shapes of the domain: a single sample (ITM: every row is a match, mm_late.py:410-412; ITC of one pair: loss 0),
+    two samples (the only possible negative), ragged batches (not a multiple of any tile), 2/3/4 classes (config.py:18-48),
+    token counts that are not a multiple of the 16-token attention chunk."""
+    P = _plan_mod()
+    dev_in, ora_in = _make_head_case(B, C, 2, Lv, seed=17 * B + C)
+    p32 = R.init_params(C, seed=3)
+    plan = P.HeadPlan(B, C=C, fusion=fusion, use_itc=True, use_itm=use_itm, Lv=Lv)
+    plan.set_weights(p32)
+    if B == 1:
+        out = plan.step(dev_in)
+        torch.cuda.synchronize()
+        assert abs(float(out["loss"][2])) < 1e-6                    # clip_loss of a 1x1 logits matrix
+        if use_itm:
+            assert int(out["lbl_tim"][0]) == 1 and int(out["src_idx"][0]) == 0
+        assert torch.isfinite(out["out_cls"]).all() and torch.isfinite(out["loss"]).all()
+        ref = R.head_step(ora_in, {k: v for k, v in _bf16_params(p32).items()}, fusion_name=fusion, use_itc=True, use_itm=use_itm,
+                          beta_itc=0.1, beta_itm=0.1)
+        assert _rel(out["out_cls"], ref["out_cls"]) < REL
+        assert abs(float(out["loss"][0]) - float(ref["loss"])) <= REL * abs(float(ref["loss"]))
+        return
+    _check_head(plan, dev_in, ora_in, p32, fusion, use_itm)
+
+
 @pytest.mark.parametrize("fusion,B,Lv", [("attention", 1024, 197), ("concat", 2048, 2), ("gmu", 1024, 2)])
 def test_head_plan_single_bf16_operands_vs_oracle(fusion, B, Lv):
     """Opt-in fast mode (split_precision=False: plain bf16 intermediates in the fusion chain, not the default): losses
