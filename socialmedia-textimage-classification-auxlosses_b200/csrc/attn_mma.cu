@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t split_pack(float x0, float x1, int lo) {
 }
 
 struct A3Smem {
-  uint32_t ring, full0, empty0;
+  uint32_t ring, full0, empty0, pbar;
   uint8_t* ring_ptr;
   float* part;      // [2][8 warps][16 tok][8]
   float* vec;       // [NPASS][Lv]  scores (forward) / attention weights (backward)
@@ -69,6 +69,7 @@ __device__ __forceinline__ A3Smem a3_carve(uint8_t* raw) {
   s.ring_ptr = p;
   s.full0 = base + kA3Stages * kA3ChunkBytes;
   s.empty0 = s.full0 + 8 * kA3Stages;
+  s.pbar = s.empty0 + 8 * kA3Stages;      // "partial scores of a chunk are written": one arrival per consumer warp
   s.part = reinterpret_cast<float*>(p + kA3Stages * kA3ChunkBytes + 128);
   s.vec = s.part + 2 * kA3Warps * kA3Rows * 8;
   return s;
@@ -95,6 +96,7 @@ attn_pool_mma_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, cons
     reinterpret_cast<uint4*>(sm.ring_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kA3Stages; ++i) { mbar_init(sm.full0 + 8 * i, 1); mbar_init(sm.empty0 + 8 * i, kA3Warps); }
+    mbar_init(sm.pbar, kA3Warps);
     fence_mbar_init();
   }
   fence_proxy_async();
@@ -128,7 +130,7 @@ attn_pool_mma_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, cons
   const int jl = lane & 15;                            // ... and the token of the chunk
   const int ka = warp * kA3KSlice;                     // this warp's K slice (phase A) = feature columns (phase B)
   uint32_t it = 0;
-  int buf = 0;
+  int buf = 0;   // 3 partial-score buffers: a warp may run one chunk ahead of the slowest reader (split arrive / wait below)
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     // ---- per-sample setup: B fragments of Qm for my K slice (column n = g: query n>>1, hi/lo part n&1)
     uint32_t qb[6][2];
@@ -208,7 +210,8 @@ attn_pool_mma_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, cons
       float sc[4];
       phase_a(sm.ring + st * kA3ChunkBytes, sc);
       write_part(buf, sc);
-      a3_bar();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.pbar);
     }
     for (int c = 0; c < nchunks; ++c, ++it) {
       const uint32_t st = it % kA3Stages;
@@ -220,6 +223,14 @@ attn_pool_mma_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, cons
         const uint32_t st1 = (it + 1) % kA3Stages, ph1 = ((it + 1) / kA3Stages) & 1u;
         mbar_wait(sm.full0 + 8 * st1, ph1);
         phase_a(sm.ring + st1 * kA3ChunkBytes, sc_next);
+      }
+      // Split barrier on the partial scores: wait for chunk `it` (every warp arrived for it one chunk ago), THEN arrive for
+      // chunk it+1 — in this order a warp's arrival can never be counted into a phase an earlier chunk still needs.
+      mbar_wait(sm.pbar, it & 1u);
+      if (has_next) {
+        write_part(buf == 2 ? 0 : buf + 1, sc_next);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.pbar);
       }
       // ---- scores / weights of (token jl, query pl) of THIS chunk, identically in every warp
       const int jj = c * kA3Rows + jl;
@@ -282,9 +293,7 @@ attn_pool_mma_kernel(const __nv_bfloat16* __restrict__ xv, int64_t bstride, cons
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.empty0 + 8 * st);
-      if (has_next) write_part(buf ^ 1, sc_next);
-      a3_bar();
-      buf ^= 1;
+      buf = buf == 2 ? 0 : buf + 1;
     }
 
     // ---- per-sample epilogue: hi + lo rows, normalise, write out
