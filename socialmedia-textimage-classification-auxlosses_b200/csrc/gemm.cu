@@ -218,6 +218,16 @@ static int dispatch_major_cluster(const void* A, int64_t lda, int a_mn, const vo
   if (a_mn && !b_mn) return launch_umma_gemm_cluster2<BN, true, false, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
   return launch_umma_gemm_cluster2<BN, true, true, 4, StoreEpi>(A, lda, B, ldb, M, N, K, ep, st);
 }
+// Split-K GEMMs (weight gradients) run on side branches of the step beside the latency-critical chain; every CTA of this
+// kernel owns a whole SM (shared memory), so a split that fills the machine makes the critical kernels queue for SMs.
+// Measured on the c2 step (one multi-branch CUDA graph): 0.110 ms with split-K up to 148 CTAs, 0.098 ms capped at 64.
+// Small GEMMs (< 4 GFLOP) are therefore capped at 64 CTAs; large ones may fill the machine.  TIC_SPLITK_MAX_CTAS overrides.
+static int splitk_max_ctas(double flops) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIC_SPLITK_MAX_CTAS"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+  if (v > 0) return v;
+  return flops < 4e9 ? 64 : 1 << 30;
+}
 // TIC_GEMM_MULTICAST=0 disables the cluster variant (A/B measurement switch).
 static bool gemm_multicast() {
   static int v = -1;
@@ -288,6 +298,7 @@ static int gemm_impl(const void* A, const void* A_lo, int64_t lda, int a_mn, con
     for (int ks = 1; ks <= (accumulate ? 16 : 1); ks *= 2) {
       if (ks > total_kb) break;
       const int items = tiles * ks;
+      if (ks > 1 && items > splitk_max_ctas(2.0 * M * N * K)) break;
       const int waves = ceil_div(items, sms);
       const double t = waves * (ceil_div(total_kb, ks) * cyc_kb[i] + 1500.0 + 8.0 * bns[i] * (accumulate ? 2.0 : 1.0));
       if (t < best) { best = t; best_bn = bns[i]; best_ks = ks; }
