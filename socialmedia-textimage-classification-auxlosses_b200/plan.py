@@ -51,8 +51,9 @@ class _Branches:
     the current stream); `br.join(k)` makes the current stream wait for it.  Under CUDA-graph capture the branches become
     parallel paths of the graph — the small-batch step is a chain of latency-bound kernels, so width matters."""
 
-    def __init__(self, device, enabled=True):
+    def __init__(self, device, enabled=True, priority=None):
         self.dev, self.enabled, self.side = device, enabled, {}
+        self.priority = priority or {}     # branch key -> CUDA stream priority (-1 = high; default 0 = low)
 
     class _Ctx:
         def __init__(self, outer, k):
@@ -63,7 +64,7 @@ class _Branches:
             if not o.enabled:
                 return
             if self.k not in o.side:
-                o.side[self.k] = torch.cuda.Stream(device=o.dev)
+                o.side[self.k] = torch.cuda.Stream(device=o.dev, priority=o.priority.get(self.k, 0))
             s = o.side[self.k]
             s.wait_stream(torch.cuda.current_stream())
             self.cm = torch.cuda.stream(s)
@@ -256,8 +257,11 @@ class HeadPlan:
         self.w: Dict[str, torch.Tensor] = {}
         self.scale = math.exp(2.6592)
         self.parallel_streams = True
+        import os as _os
+        self.hi_priority_chains = _os.environ.get("TIC_HI_PRIORITY", "1") != "0"    # A/B measurement switch
         self._side = None
-        self.br = _Branches(self.dev, enabled=True)
+        self._hi0 = None
+        self.br = _Branches(self.dev, enabled=True, priority={"v": -1, "cb": -1} if self.hi_priority_chains else None)
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self):
@@ -479,12 +483,28 @@ class HeadPlan:
         The ITC chain and the fusion/heads chain are independent until the loss mix, so they are issued on two streams
         (fork/join with events; captured as parallel branches of one CUDA graph) — the small-batch step is latency-bound."""
         B, z, o = self.B, self.z, self.out
+        if self.parallel_streams and self.hi_priority_chains:
+            # the two latency-critical chains run on high-priority streams, the parameter-gradient branches on ordinary ones:
+            # when an SM frees up, the next kernel of a chain gets it before a split-K weight-gradient CTA does
+            caller = torch.cuda.current_stream()
+            if self._hi0 is None:
+                self._hi0 = torch.cuda.Stream(device=self.dev, priority=-1)
+            self._hi0.wait_stream(caller)
+            with torch.cuda.stream(self._hi0):
+                self._step_body(inp)
+            caller.wait_stream(self._hi0)
+            return o
+        self._step_body(inp)
+        return o
+
+    def _step_body(self, inp):
+        B, z, o = self.B, self.z, self.out
         s0 = torch.cuda.current_stream()
         self.zb.zero_()
         two = self.use_itc and self.fusion is not None and self.parallel_streams
         if two:
             if self._side is None:
-                self._side = torch.cuda.Stream(device=self.dev)
+                self._side = torch.cuda.Stream(device=self.dev, priority=-1 if self.hi_priority_chains else 0)
             s1 = self._side
             if self.itm_mode == 1:       # hard negatives read the materialised logits: sampling waits for the ITC tiles
                 self._itc_fwd(inp)
