@@ -292,7 +292,8 @@ def main():
 
     capi.call_hook = hook
     plan.step(dev_in)
-    launches_per_step = counter["n"] + 1  # + the accumulator memset
+    # + the accumulator memsets (small block on the chain, large block on a side branch)
+    launches_per_step = counter["n"] + 1 + (1 if getattr(plan, "_z_pending", False) else 0)
     capi.call_hook = None
     torch.cuda.synchronize()
 

@@ -131,6 +131,7 @@ def _make_dist_head_plan():
 
         def _itc_bwd(self, inp, dS=None):
             assert dS is None, "the sharded path implements the fused loss only"
+            self._join_zero()
             B, E, w, z, o = self.B, self.E, self.w, self.z, self.out
             Yt, Yv, Ytl, Yvl = self._itc_operands(inp)
             if self.P is not None:

@@ -436,6 +436,7 @@ def _make_peer_head_plan():
 
         def _itc_bwd(self, inp, dS=None):
             assert dS is None, "the sharded path implements the fused loss only"
+            self._join_zero()
             B, E, w, z, o, br = self.B, self.E, self.w, self.z, self.out, self.br
             br.enabled = self.parallel_streams
             if self.P is not None:

@@ -286,6 +286,11 @@ class HeadPlan:
         for k, n in sizes.items():
             self.z[k] = self.zb[off:off + n]
             off += n
+        # the first keys (loss sums, small-head gradients) are needed right away; the large weight-gradient accumulators only
+        # by the parameter-gradient branches and the final unpack: their memset runs on a side branch (_zero_accumulators)
+        n_small = sum(n for k, n in sizes.items() if k in ("losses", "itc_sums", "r_sum", "_pad", "dW_cls", "db_cls", "dW_tim",
+                                                           "db_tim", "db_f", "db_Q", "db_V", "db_gt", "db_gv", "dw_a", "db_a"))
+        self.zb_small, self.zb_big = self.zb[:n_small], self.zb[n_small:]
         self.out: Dict[str, torch.Tensor] = {"loss": e(4)}
         o = self.out
         if self.P is not None:
@@ -434,6 +439,7 @@ class HeadPlan:
 
     def _itc_bwd(self, inp, dS=None):
         """dS None: fused loss (tile recompute, g = beta_itc); else operands from the upstream gradient of the logits."""
+        self._join_zero()
         B, E, w, z, o, it = self.B, self.E, self.w, self.z, self.out, self.itc
         Yt, Yv, Ytl, Yvl = self._itc_operands(inp)
         ldt, ldv = Yt.stride(0), Yv.stride(0)
@@ -500,7 +506,7 @@ class HeadPlan:
     def _step_body(self, inp):
         B, z, o = self.B, self.z, self.out
         s0 = torch.cuda.current_stream()
-        self.zb.zero_()
+        self._zero_accumulators()
         two = self.use_itc and self.fusion is not None and self.parallel_streams
         if two:
             if self._side is None:
@@ -527,6 +533,22 @@ class HeadPlan:
              self.beta_itc if self.fusion is not None else 1.0, self.beta_itm, int(self.use_itc), int(self.use_itm),
              ptr(o["loss"]), _stream())
         return o
+
+    def _zero_accumulators(self):
+        self.zb_small.zero_()
+        if self.parallel_streams and self.zb_big.numel() > 0:
+            self.br.enabled = True
+            with self.br("z"):
+                self.zb_big.zero_()
+            self._z_pending = True
+        else:
+            self.zb_big.zero_()
+            self._z_pending = False
+
+    def _join_zero(self):
+        """call on a stream right before it first touches a large accumulator (weight gradients, d_xt_cls)"""
+        if getattr(self, "_z_pending", False):
+            self.br.join("z")
 
     def _lo(self, t):
         """the bf16 residual twin of an intermediate, or None when split precision is off for this plan"""
@@ -650,6 +672,7 @@ class HeadPlan:
         gemm(self.Hin, E2, 0, w["W_f"], E2, 0, self.H, E, 0, R, E, E2, bias=w["b_f"], relu=True, A_lo=self.Hin_lo)
 
     def _fusion_bwd(self, inp):
+        self._join_zero()      # the large accumulators (dW_*, d_xt_cls) are zero from here on
         B, E, R, w, z, o, st = self.B, self.E, self.R, self.w, self.z, self.out, _stream()
         E2 = 2 * E
         src = o["src_idx"] if self.use_itm else None
