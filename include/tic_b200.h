@@ -210,6 +210,12 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
                       const float* dlogits_ext /* NULL = fused losses; else upstream dL/dlogits [rows, 8] (autograd mode) */,
                       void* stream);
 
+/* The parameter-gradient half of tic_heads_fwd_bwd alone (dW/db of linear_cls and linear_tim from the dlogits that call left
+ * in `ws`): call tic_heads_fwd_bwd with dW_* = NULL and this on another stream so that it runs beside the input-gradient
+ * chain instead of inside it.  Accumulates (+=) with fp32 atomics into zero-initialised buffers. */
+int tic_heads_wgrad(const float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* dlogits, const uint8_t* keep,
+                    float keep_scale, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, void* stream);
+
 /* attention fusion, CLS-row collapse of mm_late.py:98-113,195-210 (exact algebra):
  *   q0 = fc_Q(x_t[:,0]);  kq = W_K^T q0;  c = <q0,b_K>;  s_j = (<kq, x_v[j]> + c) * E^-1/2;  a = softmax_j(s)
  *   xbar = sum_j a_j x_v[j];  ctx0 = W_V xbar + b_V.

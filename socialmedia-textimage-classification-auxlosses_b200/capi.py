@@ -51,6 +51,7 @@ _SIGS = {
     "tic_pack_cls_pairs": ("plpliipplppp", ctypes.c_int),
     "tic_unpack_cls_grad": ("plpliipplp", ctypes.c_int),
     "tic_heads_fwd_bwd": ("pliiiippppppppfffppppplplppppippp", ctypes.c_int),
+    "tic_heads_wgrad": ("pliiiippfppppp", ctypes.c_int),
     "tic_attn_pool_fwd": ("pllpliiiifpplplplp", ctypes.c_int),
     "tic_attn_pool_bwd": ("pllplplpliiiifpplp", ctypes.c_int),
     "tic_aspect_fwd": ("plpliippplpp", ctypes.c_int),

@@ -398,6 +398,18 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
   return TIC_OK;
 }
 
+int tic_heads_wgrad(const float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* dlogits, const uint8_t* keep,
+                    float keep_scale, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, void* stream) {
+  TIC_CHECK_ARG(H && dlogits && dW_cls && db_cls && B > 0 && E > 0 && C >= 1 && C <= kMaxClasses, "tic_heads_wgrad: bad arguments");
+  TIC_CHECK_ARG(!has_tim || (dW_tim && db_tim), "tic_heads_wgrad: ITM head pointers missing");
+  const int rpb = max(8, ceil_div(B, 128));
+  dim3 grid(ceil_div(E, 128), ceil_div(B, rpb), has_tim ? 2 : 1);
+  launch_k(heads_wgrad_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), H, ldh, B, E, C, dlogits, keep, keep_scale,
+           dW_cls, db_cls, dW_tim, db_tim, rpb);
+  TIC_CHECK_LAUNCH("tic_heads_wgrad");
+  return TIC_OK;
+}
+
 int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, void* stream) {
   TIC_CHECK_ARG(X && out && rows > 0 && cols > 0, "tic_colsum_bf16: bad arguments");
   const int rpb = max(8, ceil_div(rows, 128));

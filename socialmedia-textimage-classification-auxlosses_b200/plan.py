@@ -571,6 +571,7 @@ class HeadPlan:
         self.br.join("s")      # lbl_tim (heads) / src_idx (unpack) come from the sampler
         self._heads(inp, dH_f32=self.dHf if self.fusion == "aspect-att" else None)
         self._fusion_bwd(inp)
+        self.br.join("hw")
 
     def forward(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Autograd mode, forward half: logits_per_text (materialised), mm_features, out_cls, out_tim.  ITM decisions come
@@ -599,6 +600,7 @@ class HeadPlan:
                 dz[B:, :2].copy_(d_out_tim)
             self._heads(inp, dH_f32=self.dHf if self.fusion == "aspect-att" else None, dz_ext=dz)
             self._fusion_bwd(inp)
+            self.br.join("hw")
         if self.use_itc:
             if d_logits is None:
                 d_logits = torch.zeros(B, B, dtype=F32, device=self.dev)
@@ -629,13 +631,21 @@ class HeadPlan:
         if y_soft is None:   # autograd mode: the classification loss is the caller's
             y_soft = self.y_dummy
         no = forward_only
+        side = self.parallel_streams and not no      # dW/db of the two small heads run beside the input-gradient chain
+        wg = no or side
         call("tic_heads_fwd_bwd", ptr(self.H), E, B, E, self.C, int(self.use_itm), ptr(w["W_cls"]), ptr(w["b_cls"]),
              ptr(w["W_tim"]), ptr(w["b_tim"]), ptr(y_soft), ptr(inp.get("class_w")), ptr(o["lbl_tim"]),
              ptr(inp.get("keep")), float(inp.get("keep_scale", 1.0)), float(self.w_cls), float(self.beta_itm),
              ptr(o["out_cls"]), ptr(o.get("out_tim")), ptr(z["losses"]), None if no else ptr(self.dHb),
-             None if no else ptr(self._lo(self.dHb_lo)), E, None if no else ptr(dH_f32), E, None if no else ptr(z["dW_cls"]),
-             None if no else ptr(z["db_cls"]), None if no else ptr(z["dW_tim"]), None if no else ptr(z["db_tim"]), 1,
+             None if no else ptr(self._lo(self.dHb_lo)), E, None if no else ptr(dH_f32), E, None if wg else ptr(z["dW_cls"]),
+             None if wg else ptr(z["db_cls"]), None if wg else ptr(z["dW_tim"]), None if wg else ptr(z["db_tim"]), 1,
              ptr(self.heads_ws), ptr(dz_ext), _stream())
+        if side:
+            self.br.enabled = True
+            with self.br("hw"):
+                call("tic_heads_wgrad", ptr(self.H), E, B, E, self.C, int(self.use_itm), ptr(self.heads_ws), ptr(inp.get("keep")),
+                     float(inp.get("keep_scale", 1.0)), ptr(z["dW_cls"]), ptr(z["db_cls"]), ptr(z["dW_tim"]), ptr(z["db_tim"]),
+                     _stream())
 
     def _fusion_fwd(self, inp):
         B, E, R, w, o, st = self.B, self.E, self.R, self.w, self.out, _stream()
