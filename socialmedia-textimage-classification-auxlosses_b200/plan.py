@@ -258,7 +258,10 @@ class HeadPlan:
         self.scale = math.exp(2.6592)
         self.parallel_streams = True
         import os as _os
-        self.hi_priority_chains = _os.environ.get("TIC_HI_PRIORITY", "1") != "0"    # A/B measurement switch
+        # stream priorities only pay while the step is latency-bound (small batch); with persistent 148-CTA kernels they
+        # starve the concurrent side work instead (measured: c3 on 2 GPUs 0.331 -> 0.361 ms).  TIC_HI_PRIORITY=0/1 overrides.
+        _hp = _os.environ.get("TIC_HI_PRIORITY")
+        self.hi_priority_chains = (B <= 1024) if _hp is None else (_hp != "0")
         self._side = None
         self._hi0 = None
         self.br = _Branches(self.dev, enabled=True, priority={"v": -1, "cb": -1} if self.hi_priority_chains else None)
