@@ -92,6 +92,30 @@ def make_inputs(spec, seed=40, rank=0):
 BF16_KEYS = ("t_pool", "v_pool", "x_t", "x_v")
 
 
+def synthetic_params(num_labels, E=768, P=512, seed=40):
+    """Random-init weights of the head (nn.Linear-style U(-1/sqrt(in), 1/sqrt(in)); mm_late.py:71-89 + the two HF projection
+    layers, logit_scale = 2.6592) on numpy's legacy MT19937 stream.  bench.py's own generator: the GPU arm does not touch
+    oracle/ (the CPU legs use the oracle's own, which draws the same stream, so both arms see the same weights)."""
+    rs = np.random.RandomState(seed)
+
+    def lin(o, i, bias=True):
+        bound = 1.0 / math.sqrt(i)
+        w = torch.from_numpy(rs.uniform(-bound, bound, size=(o, i))).float()
+        b = torch.from_numpy(rs.uniform(-bound, bound, size=(o,))).float() if bias else None
+        return w, b
+
+    p = {}
+    if P is not None:
+        p["dual_encoder.visual_projection.weight"], _ = lin(P, E, False)
+        p["dual_encoder.text_projection.weight"], _ = lin(P, E, False)
+    p["dual_encoder.logit_scale"] = torch.tensor(2.6592)
+    for name, (o, i) in (("fc_Q", (E, E)), ("fc_K", (E, E)), ("fc_V", (E, E)), ("aspectattention", (1, E)),
+                         ("linear_fusion", (E, 2 * E)), ("linear_cls", (num_labels, E)), ("linear_tim", (2, E)),
+                         ("linear_iadds", (2, E)), ("linear_gmu_t", (2 * E, E)), ("linear_gmu_v", (2 * E, E))):
+        p[name + ".weight"], p[name + ".bias"] = lin(o, i)
+    return p
+
+
 def algorithmic_work(spec, n_global):
     """FLOPs / bytes per step per GPU as defined in SURVEY.md §8(d) (recompute is NOT counted)."""
     B, E = spec["B"], spec["E"]
@@ -257,7 +281,6 @@ def main():
 
     import tic_b200.plan as P
     from tic_b200 import capi
-    from oracle import restatement as R  # weights init only (test infrastructure is not on the timed path)
 
     B = spec["B"]
     host = make_inputs(spec, rank=rank)
@@ -279,7 +302,7 @@ def main():
             plan.Pe = spec["d"]
             plan.out["d_t_emb"] = torch.empty(B, spec["d"], device=dev)
             plan.out["d_v_emb"] = torch.empty(B, spec["d"], device=dev)
-    plan.set_weights(R.init_params(spec["C"], seed=40))
+    plan.set_weights(synthetic_params(spec["C"], seed=40))
 
     # ---- count launches of one step (kernels per C-ABI call are fixed)
     KPC = {"tic_itc_lse_loss": 2, "tic_heads_fwd_bwd": 1, "tic_ce_bidir_fwd": 2, "tic_gemm_rowss_parts": 0,

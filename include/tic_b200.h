@@ -63,6 +63,13 @@ int tic_gemm_rowss_parts(int N);
 int tic_gemm_bf16_rowss(const void* A, const void* A_lo, int64_t lda, int a_mn_major, const void* B, const void* B_lo,
                         int64_t ldb, int b_mn_major, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K,
                         float alpha, const float* bias, int relu, float* row_ss_part, void* stream);
+/* The launch shape tic_gemm_bf16 picks for a problem (no launch): tile width, fp32-atomic split-K factor (accumulate only) and
+ * CLUSTER split-K factor (1, 2 or 4): the CTAs of a thread-block cluster each take a K-slice of the same output tile and the
+ * partial tiles are folded through distributed shared memory before the ordinary epilogue — used for the small problems of
+ * the latency-bound small-batch step, where a CTA's k-loop rate, not the machine, bounds the kernel.  n_split_operands =
+ * number of operands passed as (hi, lo) pairs.  Cluster split-K is opt-in: TIC_CLUSTER_K=<CTA budget> enables it (measured: its
+ * fixed cost only pays from K >= ~2560 on, beyond the GEMMs of this path; see profiles/r01_cluster_splitk.md). */
+int tic_gemm_plan(int M, int N, int K, int n_split_operands, int accumulate, int* tile_n, int* ksplit, int* cluster_k);
 /* Reference-quality SIMT fp32-accumulate GEMM with the same semantics (debug / self-test only). */
 int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
                        int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu,
@@ -248,6 +255,27 @@ int tic_gmu_gate_fwd(const void* Xcat, int64_t ldx, const float* tp, const float
 int tic_gmu_gate_bwd(const void* Xcat, int64_t ldx, const float* tp, const float* vp, int64_t ldp, const float* dG,
                      int64_t lddg, int B, int E2, void* dtp_bf16, void* dvp_bf16, void* dtp_lo, void* dvp_lo, int64_t lddp,
                      float* dXcat_gate, int64_t lddx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ eval bookkeeping
+ * the per-batch tail of MMLate_Model.eval / compute_predictions (mm_late.py:594-612, 661-690) and
+ * utils.compute_metrics (utils.py:294-325) without a host synchronisation per batch.
+ * tic_eval_accumulate, one call per batch of B rows:
+ *   pred[i]   = first index of the maximum of logits[i, :C]   (torch.argmax(softmax(output), dim=1), mm_late.py:597-600)
+ *   target[i] = first index of the maximum of y_soft[i, :C]   (float one-hot labels, mm_late.py:601)  or  y_int[i]
+ *   preds_out[i], targets_out[i] (int64, the caller passes the write position inside its epoch-long arrays),
+ *   state: uint64 words [C*C confusion matrix, row = target, col = pred | correct | rows | batches | scratch]
+ *          (tic_eval_state_words(C) words, zero at the start of an epoch),
+ *   sums (fp32[2], zero at the start of an epoch): sums[0] += batch_loss[0] (optional, device scalar: the reference
+ *   averages per-batch losses, :594,615), sums[1] += 100 * correct_in_batch / B (per-batch accuracy, :607-608,616).
+ * tic_metrics_from_confusion: out6 = f1_weighted, f1_macro, precision_weighted, precision_macro, recall_weighted,
+ *   recall_macro with torchmetrics-0.11 multiclass semantics (0 where a denominator is 0; `macro` skips classes with
+ *   tp+fp+fn == 0).  torchmetrics is a third-party dependency pinned in timrel-env.yml:120 and absent here: parity
+ *   against it is unpinned; the restatement (oracle/restatement.py:metrics_from_confusion) is checked against sklearn. */
+int tic_eval_state_words(int C);
+int tic_eval_accumulate(const float* logits, int64_t ldl, const float* y_soft, int64_t ldy, const int64_t* y_int, int B, int C,
+                        const float* batch_loss, int64_t* preds_out, int64_t* targets_out, void* state, float* sums,
+                        void* stream);
+int tic_metrics_from_confusion(const void* state, int C, float* out6, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ utilities */
 int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream);

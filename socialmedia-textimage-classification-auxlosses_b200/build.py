@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libtic_b200.so")
 SELFTEST = os.path.join(OUT, "selftest")
-LIB_SOURCES = ["gemm.cu", "itc.cu", "heads.cu", "itm.cu", "fusion.cu", "ce.cu", "peer.cu", "attn_mma.cu"]
+LIB_SOURCES = ["gemm.cu", "itc.cu", "heads.cu", "itm.cu", "fusion.cu", "ce.cu", "peer.cu", "attn_mma.cu", "eval.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default"]
 

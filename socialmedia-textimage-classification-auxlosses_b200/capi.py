@@ -21,6 +21,7 @@ _SIGS = {
     "tic_sm_count": ("", ctypes.c_int),
     "tic_gemm_bf16": ("pplipplippliiiifpiip", ctypes.c_int),
     "tic_gemm_rowss_parts": ("i", ctypes.c_int),
+    "tic_gemm_plan": ("iiiiippp", ctypes.c_int),
     "tic_gemm_bf16_rowss": ("pplipplippliiiifpipp", ctypes.c_int),
     "tic_gemm_bf16_simt": ("pliplipliiiifpip", ctypes.c_int),
     "tic_row_rnorm_bf16": ("ppliipplp", ctypes.c_int),
@@ -62,6 +63,9 @@ _SIGS = {
     "tic_cast_bf16_to_f32": ("plpliip", ctypes.c_int),
     "tic_colsum_bf16": ("pliipp", ctypes.c_int),
     "tic_loss_mix": ("ppiffiipp", ctypes.c_int),
+    "tic_eval_state_words": ("i", ctypes.c_int),
+    "tic_eval_accumulate": ("plplpiipppppp", ctypes.c_int),
+    "tic_metrics_from_confusion": ("pipp", ctypes.c_int),
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float}
 

@@ -110,11 +110,21 @@ struct StoreEpi {
     int accumulate;   // D += result with fp32 atomics (D holds the initial value); required for split-K
     float* row_ss_part;   // optional [n_tiles][M]: per-tile sum of squares of each output row (fused L2-norm statistics)
   };
+  // bias of this tile's columns -> shared memory (double-buffered by tile parity), before the accumulator is waited for
+  template <int BN>
+  __device__ static void prefetch(const Params& p, EpiCtx& cx) {
+    if (p.bias == nullptr || cx.ks != 0) return;   // CTA-uniform
+    float* sbias = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * BN;
+    for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) sbias[j] = (cx.n0 + j < cx.N) ? __ldg(p.bias + cx.n0 + j) : 0.f;
+    epi_bar_sync(cx.epi_threads);
+  }
   template <int BN>
   __device__ static void tile(const Params& p, const EpiCtx& cx) {
     const int lane = threadIdx.x & 31;
     const int row = cx.m0 + cx.quad * 32 + lane;
     const int cols_per_part = BN / cx.nparts;
+    const float* sbias = reinterpret_cast<const float*>(cx.scratch) + (cx.iter & 1) * BN;
+    const bool add_bias = p.bias != nullptr && cx.ks == 0;
     const bool vec_ok = p.d_bf16 ? ((p.ldd & 7) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0)
                                  : ((p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
     float ss = 0.f;
@@ -131,7 +141,7 @@ struct StoreEpi {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float x = p.alpha * __uint_as_float(v[j]);
-        if (p.bias != nullptr && cx.ks == 0 && col0 + j < cx.N) x += __ldg(p.bias + col0 + j);
+        if (add_bias) x += sbias[cl + j];
         if (p.relu) x = fmaxf(x, 0.f);
         f[j] = x;
         if (col0 + j < cx.N) ss = fmaf(x, x, ss);
@@ -198,9 +208,23 @@ struct StoreEpi {
   }
 };
 
+// cluster split-K variants (kc = 2 | 4): see the KC comment in tic_umma.cuh
+template <int BN, int KC>
+static int dispatch_major_kc(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
+                             int b_mn, int M, int N, int K, const StoreEpi::Params& ep, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_umma_gemm_kc<BN, false, false, 4, StoreEpi, KC>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
+  if (!a_mn && b_mn) return launch_umma_gemm_kc<BN, false, true, 4, StoreEpi, KC>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
+  if (a_mn && !b_mn) return launch_umma_gemm_kc<BN, true, false, 4, StoreEpi, KC>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
+  return launch_umma_gemm_kc<BN, true, true, 4, StoreEpi, KC>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st);
+}
+
 template <int BN>
 static int dispatch_major(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
-                          int b_mn, int M, int N, int K, const StoreEpi::Params& ep, cudaStream_t st, int ksplit) {
+                          int b_mn, int M, int N, int K, const StoreEpi::Params& ep, cudaStream_t st, int ksplit, int kc = 1) {
+  if constexpr (BN <= 128) {
+    if (kc == 4) return dispatch_major_kc<BN, 4>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st);
+    if (kc == 2) return dispatch_major_kc<BN, 2>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st);
+  }
   if (!a_mn && !b_mn) return launch_umma_gemm<BN, false, false, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st, ksplit);
   if (!a_mn && b_mn) return launch_umma_gemm<BN, false, true, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st, ksplit);
   if (a_mn && !b_mn) return launch_umma_gemm<BN, true, false, 4, StoreEpi>(A, A_lo, lda, B, B_lo, ldb, M, N, K, ep, st, ksplit);
@@ -262,6 +286,36 @@ __global__ void simt_gemm_kernel(const __nv_bfloat16* A, int64_t lda, int a_mn, 
   }
 }
 
+
+// Tile width / split-K / cluster split-K of one GEMM call (also exported as tic_gemm_plan so tests can see the choice).
+static void gemm_config(int M, int N, int K, int n_split_operands, int accumulate, bool rowss, int& best_bn, int& best_ks, int& kc) {
+  const int sms = device_sm_count();
+  const int m_tiles = ceil_div(M, kBM);
+  const int total_kb = ceil_div(K, kBK) * (1 + n_split_operands);
+  // Tile width / split-K by a small cost model: waves x (k-blocks x cycles-per-k-block(BN) + fixed + epilogue(BN)).
+  // Narrow tiles are shared-memory-bandwidth bound (A is re-read per N tile), wide ones leave SMs idle on small problems;
+  // split-K (only when the caller lets us accumulate atomically) fills the machine for long-K weight-gradient GEMMs.
+  static const int bns[3] = {256, 128, 64};
+  static const double cyc_kb[3] = {520.0, 300.0, 200.0};
+  best_bn = 128; best_ks = 1;
+  double best = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int tiles = m_tiles * ceil_div(N, bns[i]);
+    for (int ks = 1; ks <= (accumulate ? 16 : 1); ks *= 2) {
+      if (ks > total_kb) break;
+      const int items = tiles * ks;
+      if (ks > 1 && items > splitk_max_ctas(2.0 * M * N * K)) break;
+      const int waves = ceil_div(items, sms);
+      const double t = waves * (ceil_div(total_kb, ks) * cyc_kb[i] + 1500.0 + 8.0 * bns[i] * (accumulate ? 2.0 : 1.0));
+      if (t < best) { best = t; best_bn = bns[i]; best_ks = ks; }
+    }
+  }
+  if (rowss) { best_bn = kRowSsBN; best_ks = 1; }   // the partial layout [ceil(N/64)][M] is part of the ABI
+  // Cluster split-K for the small (single-wave) problems whose result needs a real epilogue (no atomics): K over 2 or 4 SMs.
+  kc = 1;
+  if (!accumulate && best_ks == 1 && best_bn <= 128) kc = pick_cluster_k(m_tiles * ceil_div(N, best_bn), total_kb);
+}
+
 }  // namespace tic
 
 using namespace tic;
@@ -285,33 +339,15 @@ static int gemm_impl(const void* A, const void* A_lo, int64_t lda, int a_mn, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int sms = device_sm_count();
   const int m_tiles = ceil_div(M, kBM);
-  const int total_kb = ceil_div(K, kBK) * (1 + (A_lo ? 1 : 0) + (B_lo ? 1 : 0));
-  // Tile width / split-K by a small cost model: waves x (k-blocks x cycles-per-k-block(BN) + fixed + epilogue(BN)).
-  // Narrow tiles are shared-memory-bandwidth bound (A is re-read per N tile), wide ones leave SMs idle on small problems;
-  // split-K (only when the caller lets us accumulate atomically) fills the machine for long-K weight-gradient GEMMs.
-  static const int bns[3] = {256, 128, 64};
-  static const double cyc_kb[3] = {520.0, 300.0, 200.0};
-  int best_bn = 128, best_ks = 1;
-  double best = 1e30;
-  for (int i = 0; i < 3; ++i) {
-    const int tiles = m_tiles * ceil_div(N, bns[i]);
-    for (int ks = 1; ks <= (accumulate ? 16 : 1); ks *= 2) {
-      if (ks > total_kb) break;
-      const int items = tiles * ks;
-      if (ks > 1 && items > splitk_max_ctas(2.0 * M * N * K)) break;
-      const int waves = ceil_div(items, sms);
-      const double t = waves * (ceil_div(total_kb, ks) * cyc_kb[i] + 1500.0 + 8.0 * bns[i] * (accumulate ? 2.0 : 1.0));
-      if (t < best) { best = t; best_bn = bns[i]; best_ks = ks; }
-    }
-  }
-  if (row_ss_part) { best_bn = kRowSsBN; best_ks = 1; }   // the partial layout [ceil(N/64)][M] is part of the ABI
+  int best_bn, best_ks, kc;
+  gemm_config(M, N, K, (A_lo ? 1 : 0) + (B_lo ? 1 : 0), accumulate, row_ss_part != nullptr, best_bn, best_ks, kc);
   int rc;
   const bool cluster = gemm_multicast() && !A_lo && !B_lo && best_ks == 1 && best_bn == 256 && m_tiles >= 16 &&
                        static_cast<int64_t>(m_tiles) * ceil_div(N, best_bn) >= 2 * sms;
   if (cluster) rc = dispatch_major_cluster<256>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
   else if (best_bn == 256) rc = dispatch_major<256>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
-  else if (best_bn == 128) rc = dispatch_major<128>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
-  else rc = dispatch_major<64>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
+  else if (best_bn == 128) rc = dispatch_major<128>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks, kc);
+  else rc = dispatch_major<64>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks, kc);
   if (rc == -3) { set_error("tic_gemm_bf16: cudaFuncSetAttribute(max dynamic smem) failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_gemm_bf16: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return TIC_E_LAUNCH; }
   return rc;
@@ -325,6 +361,13 @@ int tic_gemm_bf16(const void* A, const void* A_lo, int64_t lda, int a_mn, const 
 }
 
 int tic_gemm_rowss_parts(int N) { return ceil_div(N, kRowSsBN); }
+
+int tic_gemm_plan(int M, int N, int K, int n_split_operands, int accumulate, int* tile_n, int* ksplit, int* cluster_k) {
+  TIC_CHECK_ARG(M > 0 && N > 0 && K > 0 && n_split_operands >= 0 && n_split_operands <= 2 && tile_n && ksplit && cluster_k,
+                "tic_gemm_plan: bad arguments");
+  gemm_config(M, N, K, n_split_operands, accumulate, false, *tile_n, *ksplit, *cluster_k);
+  return TIC_OK;
+}
 
 int tic_gemm_bf16_rowss(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
                         int b_mn, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha,

@@ -19,6 +19,13 @@ constexpr int kItcBN = 256;        // wide tiles: best tensor-pipe efficiency at
 constexpr int kItcBNSmall = 64;    // narrow tiles below kItcSmallN columns: 4x more CTAs for the latency-bound small batch
 constexpr int kItcSmallN = 2048;
 inline int itc_bn(int n_global) { return n_global <= kItcSmallN ? kItcBNSmall : kItcBN; }
+// cluster split-K factor of the narrow-tile (small batch) similarity kernels; not combined with segment-consuming mode
+inline int itc_small_kc(int m_local, int n_global, int P, const void* T_lo, const void* V_lo, const SegOrder* sop) {
+  if (sop != nullptr) return 1;
+  const int tiles = ceil_div(m_local, kBM) * ceil_div(n_global, kItcBNSmall);
+  const int total_kb = ceil_div(P, kBK) * (1 + (T_lo ? 1 : 0) + (V_lo ? 1 : 0));
+  return pick_cluster_k(tiles, total_kb);
+}
 // TIC_ITC_MULTICAST=0 disables the 2-CTA TMA-multicast variant (A/B measurement switch, not a fallback).
 inline bool itc_multicast() {
   static int v = -1;
@@ -99,13 +106,13 @@ struct ItcFwdEpi {
     int64_t ld_logits;
     int row_offset;
   };
+  // column norms of this tile -> shared memory, this thread's row norm -> cx.pre[0]; runs while the MMAs of the tile are in flight
   template <int BN>
-  __device__ static void tile(const Params& p, const EpiCtx& cx) {
+  __device__ static void prefetch(const Params& p, EpiCtx& cx) {
     const int lane = threadIdx.x & 31;
     const int row = cx.m0 + cx.quad * 32 + lane;
     const bool valid_row = row < cx.M;
     float* sb = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * BN;   // rinv_v of this tile (double-buffered)
-    float* scol = reinterpret_cast<float*>(cx.scratch) + 2 * BN;             // [4 quads][BN] partial column sums
     for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) {
       float b = 0.f;
       if (cx.n0 + j < cx.N) {
@@ -132,6 +139,16 @@ struct ItcFwdEpi {
         rt = p.rinv_t[row];
       }
     }
+    cx.pre[0] = rt;
+  }
+  template <int BN>
+  __device__ static void tile(const Params& p, const EpiCtx& cx) {
+    const int lane = threadIdx.x & 31;
+    const int row = cx.m0 + cx.quad * 32 + lane;
+    const bool valid_row = row < cx.M;
+    const float* sb = reinterpret_cast<const float*>(cx.scratch) + (cx.iter & 1) * BN;   // rinv_v of this tile (prefetch)
+    float* scol = reinterpret_cast<float*>(cx.scratch) + 2 * BN;                         // [4 quads][BN] partial column sums
+    const float rt = cx.pre[0];
     const float rt2 = rt * p.scale_log2e;
     const float negshift = valid_row ? -p.shift_log2e : -INFINITY;
     const int gcol = p.row_offset + row;  // column holding this row's positive
@@ -241,8 +258,10 @@ struct ItcBwdEpi {
     int tma_store;       // GA leaves through shared memory + TMA 32x32 tile stores (full lines) instead of 16-byte pieces
     alignas(64) CUtensorMap tmap_ga;
   };
+  // per-column vectors of this tile -> shared memory, this thread's row norm / row lse -> cx.pre[0..1]; runs while the MMAs of
+  // the tile are in flight (small batch: lse comes from up to 64 forward partials per row and column — a long load chain)
   template <int BN>
-  __device__ static void tile(const Params& p, const EpiCtx& cx) {
+  __device__ static void prefetch(const Params& p, EpiCtx& cx) {
     const int lane = threadIdx.x & 31;
     const int row = cx.m0 + cx.quad * 32 + lane;
     const bool valid_row = row < cx.M;
@@ -280,6 +299,18 @@ struct ItcBwdEpi {
         lr = __ldg(p.lse_row + row) * kLog2e;
       }
     }
+    cx.pre[0] = rt;
+    cx.pre[1] = lr;
+  }
+  template <int BN>
+  __device__ static void tile(const Params& p, const EpiCtx& cx) {
+    const int lane = threadIdx.x & 31;
+    const int row = cx.m0 + cx.quad * 32 + lane;
+    const bool valid_row = row < cx.M;
+    const float* sb = reinterpret_cast<const float*>(cx.scratch) + (cx.iter & 1) * 3 * BN;  // filled by prefetch
+    const float* sl = sb + BN;
+    const float* sg = sb + 2 * BN;
+    const float rt = cx.pre[0], lr = cx.pre[1];
     const float rt2 = rt * p.scale_log2e;
     const int cols_per_part = BN / cx.nparts;
     const bool vec_ok = (p.ld_ga & 7) == 0;
@@ -789,9 +820,15 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
            : itc_bn(n_global) == kItcBN
                ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
                                                                                 P, ep, static_cast<cudaStream_t>(stream), 1, 0, sop)
-               : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
-                                                                                     n_global, P, ep,
-                                                                                     static_cast<cudaStream_t>(stream), 1, 0, sop);
+               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, sop) == 4
+                   ? launch_umma_gemm_kc<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi, 4>(
+                         T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, static_cast<cudaStream_t>(stream))
+               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, sop) == 2
+                   ? launch_umma_gemm_kc<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi, 2>(
+                         T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, static_cast<cudaStream_t>(stream))
+                   : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
+                                                                                         n_global, P, ep,
+                                                                                         static_cast<cudaStream_t>(stream), 1, 0, sop);
   if (rc == -3) { set_error("tic_itc_fwd: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_fwd: launch failed"); return TIC_E_LAUNCH; }
   return rc;
@@ -856,9 +893,15 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
            : itc_bn(n_global) == kItcBN
                ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
                                                                                 P, ep, static_cast<cudaStream_t>(stream), 1)
-               : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
-                                                                                     n_global, P, ep,
-                                                                                     static_cast<cudaStream_t>(stream), 1);
+               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, nullptr) == 4
+                   ? launch_umma_gemm_kc<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi, 4>(
+                         T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, static_cast<cudaStream_t>(stream))
+               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, nullptr) == 2
+                   ? launch_umma_gemm_kc<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi, 2>(
+                         T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, static_cast<cudaStream_t>(stream))
+                   : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
+                                                                                         n_global, P, ep,
+                                                                                         static_cast<cudaStream_t>(stream), 1);
   if (rc == -3) { set_error("tic_itc_bwd_g: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_bwd_g: launch failed"); return TIC_E_LAUNCH; }
   return rc;

@@ -47,6 +47,7 @@ struct EpiCtx {
   int iter;             // tiles already processed by this CTA (for double-buffering the scratch)
   int ks, ksplit;       // split-K: this work item covers K-slice ks of ksplit (epilogue must accumulate atomically)
   uint8_t* scratch;    // kEpiScratchBytes of smem shared by the epilogue warps
+  float pre[4];        // per-thread values loaded by Epi::prefetch for Epi::tile (row norms, row lse)
 };
 
 // Optional tile order for a B operand that ARRIVES segment by segment (multi-GPU: the gathered embeddings are pulled from the
@@ -82,16 +83,29 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
 // of it and TMA-multicasts it into both CTAs' shared memory (operand traffic from L2 per tile drops by 1/3 for 128x256
 // tiles; the K=768 similarity tiles are L2-bandwidth-bound otherwise).  Stage release is a multicast tcgen05.commit to
 // the `empty` barrier of both CTAs.  In that mode tmap_b_lo holds the half-height box map of B (no split operands).
-template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi, int CLUSTER = 1>
+//
+// KC > 1: CLUSTER SPLIT-K.  The KC CTAs of a cluster work on the SAME output tile, CTA r on K-slice r, each into its own
+// TMEM accumulator; the non-leaders then push their fp32 partial tiles into the leader's shared memory (DSMEM stores into
+// the operand ring, which is idle once the leader's MMAs have completed), the leader folds them into its TMEM accumulator
+// and runs the ordinary epilogue.  Why: a CTA's k-loop runs at ~0.28 us per 64-deep k-block whatever the number of CTAs
+// (measured, scripts/gemm_rate.py: 16 and 144 CTAs take the same time), so the small-batch GEMMs of the c2 step — 8..48
+// tiles of 12..24 k-blocks on a 148-SM machine — are shortened by spreading K over idle SMs, and unlike the fp32-atomic
+// split-K this works for every epilogue (bias / ReLU / bf16 output, the ITC softmax epilogues).  One tile per cluster
+// (grid = tiles * KC, not persistent): the reduce buffer is used once, so there is no reuse handshake.
+template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi, int CLUSTER = 1, int KC = 1>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int ksplit,
-                 int M, int N, int K, const __grid_constant__ typename Epi::Params ep, SegOrder so) {
+                 int M, int N, int K, const __grid_constant__ typename Epi::Params ep, SegOrder so, int stages_rt = 0) {
   static_assert(CLUSTER == 1 || (CLUSTER == 2 && BN >= 128), "cluster multicast needs BN >= 128");
   using Cfg = UmmaCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
+  constexpr int kMaxStages = Cfg::kStages;
+  const int STAGES = (stages_rt > 0 && stages_rt < kMaxStages) ? stages_rt : kMaxStages;   // probe: shallower ring / less smem
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps must cover the 4 TMEM lane quadrants");
   static_assert(BN % 64 == 0 && BN <= 256, "BN in {64,128,192,256}");
+  static_assert(KC == 1 || CLUSTER == 1, "cluster split-K and B-multicast pairs are exclusive");
+  static_assert(KC == 1 || KC == 2 || KC == 4, "cluster split-K over 2 or 4 CTAs");
+  static_assert((KC - 1) * kBM * BN * 4 <= kMaxStages * Cfg::kStageBytes, "split-K partial tiles must fit in the operand ring");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -102,6 +116,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t red_full = bar_base + 8u * (2 * STAGES + 5);   // leader: every non-leader epilogue warp has delivered
+  const uint32_t red_go = bar_base + 8u * (2 * STAGES + 6);     // non-leader: the leader's operand ring is free
   uint8_t* scratch = smem_gen + STAGES * Cfg::kStageBytes + 256;
 
   const int warp = threadIdx.x >> 5;
@@ -116,10 +132,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int total_kb = num_kb * nseg;
   // work item = (tile, K-slice); in cluster mode an item is a PAIR of M-adjacent tiles, one per CTA of the cluster
   const int m_groups = (m_tiles + CLUSTER - 1) / CLUSTER;
-  const int num_items = (CLUSTER == 1 ? num_tiles : m_groups * n_tiles) * ksplit;
+  const int num_items = KC > 1 ? num_tiles : (CLUSTER == 1 ? num_tiles : m_groups * n_tiles) * ksplit;
   const uint32_t crank = CLUSTER == 1 ? 0u : cluster_ctarank();
-  const int worker = CLUSTER == 1 ? blockIdx.x : blockIdx.x / CLUSTER;
-  const int nworkers = CLUSTER == 1 ? gridDim.x : gridDim.x / CLUSTER;
+  const uint32_t krank = KC == 1 ? 0u : cluster_ctarank();        // K-slice of this CTA in cluster split-K mode
+  const int kslices = KC > 1 ? KC : ksplit;
+  const int worker = (CLUSTER == 1 && KC == 1) ? blockIdx.x : blockIdx.x / (CLUSTER * KC);
+  const int nworkers = (CLUSTER == 1 && KC == 1) ? gridDim.x : gridDim.x / (CLUSTER * KC);
+  // work item -> (tile, K-slice): split-K items enumerate the slices, cluster split-K takes the slice from the CTA rank
+  auto item_of = [&](int w, int& t, int& ks) {
+    if constexpr (KC > 1) { t = w; ks = static_cast<int>(krank); }
+    else { t = w / ksplit; ks = w - t * ksplit; }
+  };
   const bool seg_major = so.ready != nullptr && so.tiles_per_seg > 0;
   auto tile_of = [&](int item, int& m_blk, int& n_blk) {
     if (seg_major) {   // segment-major, local segment first (ksplit == 1 in this mode)
@@ -148,17 +171,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EPI_WARPS);
     }
+    if constexpr (KC > 1) {
+      mbar_init(red_full, (KC - 1) * EPI_WARPS);
+      mbar_init(red_go, 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   if constexpr (CLUSTER > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote commit
+  if constexpr (KC > 1) { if (!(split & 32)) cluster_sync_all(); }   // (bit 5 of `split`: timing probe without the cluster syncs)
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   pdl_wait();      // prologue done (barriers, TMEM, descriptors); from here on global memory of the predecessors is read
 
-  if (warp == 0) {
+  if (split & 64) {
+    // timing probe: prologue + teardown only
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
@@ -171,7 +201,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int g = 0; g < so.nseg; ++g) seg_wait(so, g, seg_epoch);
       }
       for (int w = worker; w < num_items; w += nworkers) {
-        const int t = w / ksplit, ks = w - t * ksplit;
+        int t, ks;
+        item_of(w, t, ks);
         int m_blk, n_blk;
         tile_of(t, m_blk, n_blk);
         const int m0 = m_blk * kBM, n0 = n_blk * BN;
@@ -179,8 +210,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int seg = n_blk / so.tiles_per_seg;
           if (seg != seg_ok) { seg_wait(so, seg, seg_epoch); seg_ok = seg; }   // the local segment is copied first, but copied too
         }
-        const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / ksplit);
-        const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / ksplit);
+        const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / kslices);
+        const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / kslices);
         for (int kt = kt_begin; kt < kt_end; ++kt) {
           const int seg = kt / num_kb, kb = kt - seg * num_kb;
           const bool a_lo = (seg == 1) && (split & 1);
@@ -235,9 +266,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       for (int w = worker; w < num_items; w += nworkers) {
-        const int ks = w % ksplit;
-        const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / ksplit);
-        const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / ksplit);
+        int t_unused, ks;
+        item_of(w, t_unused, ks);
+        const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / kslices);
+        const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / kslices);
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -273,14 +305,73 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t aph = 0;
     cx.iter = 0;
     for (int w = worker; w < num_items; w += nworkers) {
-      const int t = w / ksplit;
-      cx.ks = w - t * ksplit; cx.ksplit = ksplit;
+      int t;
+      item_of(w, t, cx.ks);
+      cx.ksplit = ksplit;
+      if constexpr (KC > 1) { cx.ks = 0; cx.ksplit = 1; }   // the leader's epilogue sees the complete K sum
       tile_of(t, cx.m_blk, cx.n_blk);
       cx.m0 = cx.m_blk * kBM; cx.n0 = cx.n_blk * BN;
+      // Everything the epilogue reads from global memory that does not depend on the accumulator (bias, norms, softmax
+      // statistics) is fetched BEFORE waiting for the MMAs, so its latency hides behind the k-loop: measured on a one-tile
+      // GEMM (scripts/gemm_rate.py probes) the epilogue was 3.9 us of an 8.2 us launch, most of it exposed load latency.
+      if (cx.m0 < M && (KC == 1 || krank == 0)) Epi::template prefetch<BN>(ep, cx);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       cx.tmem_acc = tmem_base + as * BN;
-      if (cx.m0 < M) Epi::template tile<BN>(ep, cx);   // the odd tail tile of a cluster pair has no rows
+      if constexpr (KC > 1) {
+        // ---- cluster split-K reduction through distributed shared memory (one tile per cluster)
+        // partial tile of non-leader r: fp32 [BN columns][128 rows] at ring offset (r-1) * 128*BN*4 of the LEADER
+        constexpr uint32_t kPartBytes = kBM * BN * 4;
+        constexpr int kColsPerPart = BN / (EPI_WARPS / 4);
+        const int quad = warp & 3, part = (warp - 2) >> 2;
+        const uint32_t trow = cx.tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
+        const uint32_t row_off = static_cast<uint32_t>(quad * 32 + lane) * 4u;
+        if (split & 16) {                        // timing probe: no reduction at all (results are wrong by design)
+          if (krank == 0 && cx.m0 < M) Epi::template tile<BN>(ep, cx);
+        } else if (krank != 0) {
+          mbar_wait_cluster(red_go, 0);          // the leader's MMAs are done reading its ring
+          const uint32_t dst = mapa_cluster(smem_base, 0) + (krank - 1) * kPartBytes + row_off;
+#pragma unroll 1
+          for (int c = 0; c < kColsPerPart / 32; ++c) {
+            const int cl = part * kColsPerPart + c * 32;
+            uint32_t v[32];
+            tmem_ld_32x32(trow + cl, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st_cluster_f32(dst + static_cast<uint32_t>(cl + j) * (kBM * 4u), v[j]);
+          }
+          fence_acq_rel_cluster();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_cluster(red_full, 0));
+        } else {
+          if (cx.epi_tid == 0) {                 // tfull observed: this CTA's MMAs have completed, its ring is free
+#pragma unroll
+            for (uint32_t r = 1; r < KC; ++r) mbar_arrive_remote(mapa_cluster(red_go, r));
+          }
+          mbar_wait_cluster(red_full, 0);
+#pragma unroll 1
+          for (int c = 0; c < kColsPerPart / 32; ++c) {
+            const int cl = part * kColsPerPart + c * 32;
+            uint32_t v[32];
+            tmem_ld_32x32(trow + cl, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (uint32_t r = 0; r + 1 < KC; ++r) {
+              const float* src = reinterpret_cast<const float*>(smem_gen + r * kPartBytes + row_off);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + src[(cl + j) * kBM]);
+            }
+            tmem_st_32x32(trow + cl, v);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          epi_bar_sync(32 * EPI_WARPS);          // every epilogue warp may read any column of the folded accumulator
+          tc_fence_after();
+          if (cx.m0 < M) Epi::template tile<BN>(ep, cx);
+        }
+      } else {
+        if (cx.m0 < M && !(split & 128)) Epi::template tile<BN>(ep, cx);   // the odd tail tile of a cluster pair has no rows
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -293,6 +384,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if constexpr (CLUSTER > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it
+  if constexpr (KC > 1) { if (!(split & 32)) cluster_sync_all(); }   // no CTA exits while a peer may still write into / signal it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -336,7 +428,10 @@ int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B
   if ((rc = map_b(&tb, B))) return rc;
   if ((rc = map_a(&ta_lo, A_lo ? A_lo : A))) return rc;
   if ((rc = map_b(&tb_lo, B_lo ? B_lo : B))) return rc;
-  const int split = (A_lo ? 1 : 0) | (B_lo ? 2 : 0);
+  int split = (A_lo ? 1 : 0) | (B_lo ? 2 : 0);
+  int stages_rt = 0;
+  { const char* e = getenv("TIC_KC_PROBE"); if (e) split |= (atoi(e) & 15) << 4; }
+  { const char* e = getenv("TIC_GEMM_STAGES"); if (e) stages_rt = atoi(e); }
   auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI_WARPS, Epi>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
@@ -353,8 +448,74 @@ int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B
   if (grid > cap) grid = cap;
   SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0};
   if (so.ready && (ksplit != 1 || so.tiles_per_seg <= 0 || so.tiles_per_seg * so.nseg != n_tiles)) so.tiles_per_seg = 0;
-  launch_k(kern, dim3(grid), dim3(64 + 32 * EPI_WARPS), Cfg::kSmemBytes, stream, ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep, so);
+  size_t smem = Cfg::kSmemBytes;
+  if (stages_rt > 0 && stages_rt < Cfg::kStages) smem -= static_cast<size_t>(Cfg::kStages - stages_rt) * Cfg::kStageBytes;
+  launch_k(kern, dim3(grid), dim3(64 + 32 * EPI_WARPS), smem, stream, ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep, so, stages_rt);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// Cluster split-K launch (KC CTAs per output tile, reduction through DSMEM; see the kernel comment).  One cluster per tile.
+template <int BN, bool A_MN, bool B_MN, int EPI_WARPS, class Epi, int KC>
+int launch_umma_gemm_kc(const void* A, const void* A_lo, int64_t lda, const void* B, const void* B_lo, int64_t ldb, int M, int N,
+                        int K, const typename Epi::Params& ep, cudaStream_t stream) {
+  using Cfg = UmmaCfg<BN>;
+  if (M <= 0 || N <= 0 || K <= 0) return -1;
+  CUtensorMap ta, tb, ta_lo, tb_lo;
+  auto map_a = [&](CUtensorMap* t, const void* p) {
+    return !A_MN ? make_tmap_bf16_2d(t, p, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM)
+                 : make_tmap_bf16_2d(t, p, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, kBK);
+  };
+  auto map_b = [&](CUtensorMap* t, const void* p) {
+    return !B_MN ? make_tmap_bf16_2d(t, p, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, BN)
+                 : make_tmap_bf16_2d(t, p, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, kBK);
+  };
+  int rc;
+  if ((rc = map_a(&ta, A))) return rc;
+  if ((rc = map_b(&tb, B))) return rc;
+  if ((rc = map_a(&ta_lo, A_lo ? A_lo : A))) return rc;
+  if ((rc = map_b(&tb_lo, B_lo ? B_lo : B))) return rc;
+  int split = (A_lo ? 1 : 0) | (B_lo ? 2 : 0);
+  { static int probe = -1; if (probe < 0) { const char* e = getenv("TIC_KC_PROBE"); probe = e ? atoi(e) : 0; } split |= (probe & 3) << 4; }
+  const int total_kb = ((K + kBK - 1) / kBK) * (1 + (A_lo ? 1 : 0) + (B_lo ? 1 : 0));
+  if (total_kb < KC) return -1;   // every CTA of the cluster needs at least one k-block (its accumulator must be defined)
+  auto kern = umma_gemm_kernel<BN, A_MN, B_MN, EPI_WARPS, Epi, 1, KC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return -3;
+    attr_set = true;
+  }
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(m_tiles * n_tiles * KC);
+  cfg.blockDim = dim3(64 + 32 * EPI_WARPS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = KC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  SegOrder so{nullptr, nullptr, 0, 0, 0};
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta_lo, tb, tb_lo, split, 1, M, N, K, ep, so, 0);
+  return e == cudaSuccess ? 0 : -4;
+}
+
+// Largest cluster split-K factor (4, 2 or 1) for a problem of `tiles` output tiles and `total_kb` k-blocks: every CTA keeps
+// at least `min_kb` k-blocks and the launch stays within a CTA budget.  OFF unless TIC_CLUSTER_K=<CTA budget> is set (read
+// at every call): measured on B200 (scripts/gemm_rate.py, profiles/r01_cluster_splitk.md) the k-loop does shrink by the
+// split factor (0.28 us per k-block per CTA), but a cluster launch costs +1.4 us, its two cluster barriers +0.5 us and the
+// DSMEM fold +3.5 us, so it only wins from ~40 k-blocks per tile on (K >= 2560) — none of the GEMMs of the c2 step (12-24).
+inline int pick_cluster_k(int tiles, int total_kb, int min_kb = 3) {
+  const char* e = getenv("TIC_CLUSTER_K");
+  const int budget = e ? atoi(e) : 0;
+  if (budget <= 0) return 1;
+  for (int kc = 4; kc >= 2; kc /= 2)
+    if (tiles * kc <= budget && total_kb >= kc * min_kb) return kc;
+  return 1;
 }
 
 // Cluster (TMA multicast) launch: pairs of M-adjacent tiles share B. No split operands, no split-K.
@@ -402,7 +563,7 @@ int launch_umma_gemm_cluster2(const void* A, int64_t lda, const void* B, int64_t
   int split = 0, ksplit = 1;
   SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0};
   if (so.ready && (so.tiles_per_seg <= 0 || so.tiles_per_seg * so.nseg != n_tiles)) so.tiles_per_seg = 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta, tb, tb_half, split, ksplit, M, N, K, ep, so);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta, tb, tb_half, split, ksplit, M, N, K, ep, so, 0);
   return e == cudaSuccess ? 0 : -4;
 }
 

@@ -264,6 +264,12 @@ class HeadPlan:
         self.hi_priority_chains = (B <= 1024) if _hp is None else (_hp != "0")
         self._side = None
         self._hi0 = None
+        self._ev_heads = None
+        # TIC_STEP_TAIL bit 0: small memset on a side branch, bit 1: loss mix issued before the backward (A/B switch).
+        # Measured on the c2 graph (scripts/timeline.py --plain-only, 400 replays): 0 -> 92.2 us, 1 -> 96.4 us (a memset node
+        # joined into both chains costs more than the ~2 us it takes at the head), 2 -> 90.3 us, 3 -> 92.7 us.  Default 2.
+        _tail = int(_os.environ.get("TIC_STEP_TAIL", "2"))
+        self._defer_small_zero, self._early_mix = bool(_tail & 1), bool(_tail & 2)
         self.br = _Branches(self.dev, enabled=True, priority={"v": -1, "cb": -1} if self.hi_priority_chains else None)
 
     # ------------------------------------------------------------------ buffers
@@ -431,6 +437,7 @@ class HeadPlan:
         br.join("v")
         it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl, ss_t=self.ss_t if fused_norm else None,
                      ss_v=self.ss_v if fused_norm else None)
+        self._join_small_zero()        # itc_sums / r_sum live in the small zeroed block
         if with_loss:
             if it.can_inline_lse:      # small batch: the backward derives lse itself; the loss runs on a side branch
                 with br("l"):
@@ -522,23 +529,55 @@ class HeadPlan:
                 self._fusion_chain(inp)
             if self.itm_mode != 1:
                 self._itc_fwd(inp)
+            mixed = self._loss_mix_early()
             self._itc_bwd(inp)
             s0.wait_stream(s1)
         else:
+            mixed = False
             if self.use_itc:
                 self._itc_fwd(inp)
             if self.fusion is not None:
                 self._fusion_chain(inp)
+            elif self.use_itc:
+                mixed = self._loss_mix_early()
             if self.use_itc:
                 self._itc_bwd(inp)
-        self.br.join("l")      # ITC loss terms (side branch when the backward derives lse inline)
-        call("tic_loss_mix", ptr(z["losses"]), ptr(z["itc_sums"]), getattr(self, "n_global", B),
-             self.beta_itc if self.fusion is not None else 1.0, self.beta_itm, int(self.use_itc), int(self.use_itm),
-             ptr(o["loss"]), _stream())
+        self.br.join("l")      # ITC loss terms (+ the early loss mix) on their side branch
+        if not mixed:
+            self._loss_mix()
         return o
 
+    def _loss_mix(self):
+        z, o = self.z, self.out
+        call("tic_loss_mix", ptr(z["losses"]), ptr(z["itc_sums"]), getattr(self, "n_global", self.B),
+             self.beta_itc if self.fusion is not None else 1.0, self.beta_itm, int(self.use_itc), int(self.use_itm),
+             ptr(o["loss"]), _stream())
+
+    def _loss_mix_early(self):
+        """The mixed loss depends on the forward halves only (heads' loss sums, ITC lse sums): issue it on the `l` side branch
+        as soon as both are there instead of after the backward of both chains, where it was one more serialised ~3 us
+        launch at the tail of the step.  Base single-GPU plan only (the multi-GPU plans finish their lse sums elsewhere)."""
+        if not (self._early_mix and self.parallel_streams and self.use_itc and self.itc.can_inline_lse
+                and type(self)._itc_fwd is HeadPlan._itc_fwd):
+            return False
+        self.br.enabled = True
+        with self.br("l"):          # same side stream as lse_loss: ordered after it
+            if self.fusion is not None:
+                torch.cuda.current_stream().wait_event(self._ev_heads)
+            self._loss_mix()
+        return True
+
     def _zero_accumulators(self):
-        self.zb_small.zero_()
+        # The small block (loss sums, small-head gradients) is first touched by lse_loss / heads, several kernels into the
+        # step: its memset leaves the head of both chains too (base plan only: the multi-GPU plans touch it earlier).
+        self._zs_pending = False
+        if self.parallel_streams and self._defer_small_zero and type(self)._itc_fwd is HeadPlan._itc_fwd:
+            self.br.enabled = True
+            with self.br("zs"):
+                self.zb_small.zero_()
+            self._zs_pending = True
+        else:
+            self.zb_small.zero_()
         if self.parallel_streams and self.zb_big.numel() > 0:
             self.br.enabled = True
             with self.br("z"):
@@ -552,6 +591,11 @@ class HeadPlan:
         """call on a stream right before it first touches a large accumulator (weight gradients, d_xt_cls)"""
         if getattr(self, "_z_pending", False):
             self.br.join("z")
+
+    def _join_small_zero(self):
+        """call on a stream right before it first touches the small accumulator block (loss sums, small-head gradients)"""
+        if getattr(self, "_zs_pending", False):
+            self.br.join("zs")
 
     def _lo(self, t):
         """the bf16 residual twin of an intermediate, or None when split precision is off for this plan"""
@@ -572,7 +616,11 @@ class HeadPlan:
                 self._sample_itm(inp)
         self._fusion_fwd(inp)
         self.br.join("s")      # lbl_tim (heads) / src_idx (unpack) come from the sampler
+        self._join_small_zero()
         self._heads(inp, dH_f32=self.dHf if self.fusion == "aspect-att" else None)
+        if self._early_mix:    # the loss mix needs the heads' loss sums only: it does not wait for the backward (see _loss_mix_early)
+            self._ev_heads = torch.cuda.Event()
+            self._ev_heads.record(torch.cuda.current_stream())
         self._fusion_bwd(inp)
         self.br.join("hw")
 
