@@ -39,6 +39,13 @@ extern "C" {
 const char* tic_last_error_string(void);
 int tic_version(void);
 int tic_sm_count(void);
+/* Programmatic dependent launch for the launches this THREAD makes next: 1 = every kernel is launched with the
+ * programmatic-stream-serialization attribute (its prologue may overlap the tail of its predecessor in the stream; all
+ * kernels of the library call griddepcontrol.launch_dependents / .wait), 0 = ordinary stream order, -1 = follow the TIC_PDL
+ * environment variable (default off).  Returns the previous mode.  Lets a caller turn it on for the kernels of a
+ * latency-critical chain only: on the multi-branch small-batch step, early-launched CTAs of side-branch kernels (one CTA
+ * per SM) otherwise take SMs from the chains. */
+int tic_set_pdl(int mode);
 
 /* ------------------------------------------------------------------------------------------------ GEMM
  * D[m,n] = alpha * sum_k A(m,k) * B(n,k) (+ bias[n]) (relu)   bf16 operands, fp32 accumulate (tcgen05 / TMEM).
@@ -282,6 +289,8 @@ int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, 
 int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream);
 /* dst[r, c] (+)= column sums etc. are done by GEMMs; bias gradient: db[n] = sum_m dY[m,n] (bf16 in, fp32 out). */
 int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, void* stream);
+/* Same for a split-precision (hi, lo) pair of identical layout in ONE launch (X_lo may be NULL). */
+int tic_colsum_bf16_pair(const void* X, const void* X_lo, int64_t ldx, int rows, int cols, float* out, void* stream);
 /* out[0] = (1-bi-bm)*losses[0] + bi*0.5*(itc[0]+itc[1])/B + bm*losses[1]  (mm_late.py:473-487);
  * out[1..3] = L_cls, L_itc, L_itm.  out has 4 floats. */
 int tic_loss_mix(const float* losses, const float* itc_sums, int n_global, float beta_itc, float beta_itm,

@@ -342,3 +342,57 @@ def init_params(num_labels: int, E: int = 768, P: Optional[int] = 512, seed: int
                          ("linear_iadds", (2, E)), ("linear_gmu_t", (2 * E, E)), ("linear_gmu_v", (2 * E, E))):
         p[name + ".weight"], p[name + ".bias"] = lin(o, i)
     return p
+
+
+# ------------------------------------------------------------------------------------------------ eval bookkeeping (§8 f-4)
+def eval_batch(output: torch.Tensor, label: torch.Tensor):
+    """models/mm_late.py:596-608 (single-label branch): pred = argmax(softmax(output)), target = argmax(label) of the float
+    one-hot labels, accuracy of this batch in percent.  Returns (pred int64 [B], target int64 [B], accuracy float)."""
+    pred = torch.argmax(torch.softmax(output.double(), dim=1), dim=1)
+    target = torch.argmax(label, dim=1)
+    return pred, target, float((pred == target).double().mean()) * 100.0
+
+
+def confusion_matrix(pred: np.ndarray, target: np.ndarray, C: int) -> np.ndarray:
+    """conf[t, p] = number of samples with target t predicted as p (the statistic every torchmetrics score below reduces)."""
+    conf = np.zeros((C, C), dtype=np.int64)
+    np.add.at(conf, (np.asarray(target, dtype=np.int64), np.asarray(pred, dtype=np.int64)), 1)
+    return conf
+
+
+def metrics_from_confusion(conf: np.ndarray) -> Dict[str, float]:
+    """models/utils.py:294-325 compute_metrics, single-label branch: F1 / precision / recall, `weighted` and `macro`, as
+    torchmetrics==0.11.0 (timrel-env.yml:120) computes them for task="multiclass".  torchmetrics is a third-party dependency
+    that is NOT in the reference tree and NOT installed here, so this restates its published algorithm
+    (functional/classification/{f_beta,precision_recall}.py: per-class tp/fp/fn from the confusion matrix, _safe_divide -> 0
+    where the denominator is 0, _adjust_weights_safe_divide: `weighted` weighs classes by support tp+fn; `macro` averages the
+    classes with tp+fp+fn > 0).  PARITY UNPINNED against torchmetrics itself; tests pin it against scikit-learn where the
+    semantics coincide (every class present)."""
+    conf = np.asarray(conf, dtype=np.float64)
+    tp = np.diag(conf)
+    fn = conf.sum(axis=1) - tp
+    fp = conf.sum(axis=0) - tp
+
+    def sdiv(a, b):
+        out = np.zeros_like(a)
+        np.divide(a, b, out=out, where=b != 0)
+        return out
+
+    prec, rec, f1 = sdiv(tp, tp + fp), sdiv(tp, tp + fn), sdiv(2 * tp, 2 * tp + fp + fn)
+    w_sup = tp + fn
+    w_mac = ((tp + fp + fn) > 0).astype(np.float64)
+
+    def avg(score, w):
+        return float((score * w).sum() / w.sum()) if w.sum() > 0 else 0.0
+
+    return {"f1_weighted": avg(f1, w_sup), "f1_macro": avg(f1, w_mac), "precision_weighted": avg(prec, w_sup),
+            "precision_macro": avg(prec, w_mac), "recall_weighted": avg(rec, w_sup), "recall_macro": avg(rec, w_mac)}
+
+
+def compute_metrics(res: Dict, num_classes: int) -> Dict[str, list]:
+    """models/utils.py:294-325: {"metric": [six names, "loss"], "result": [...]} from an eval() result dict."""
+    pred = torch.as_tensor(res["predictions"]).cpu().numpy()
+    tgt = torch.as_tensor(res["labels"]).cpu().numpy()
+    m = metrics_from_confusion(confusion_matrix(pred, tgt, num_classes))
+    m["loss"] = res["loss"]
+    return {"metric": list(m.keys()), "result": list(m.values())}

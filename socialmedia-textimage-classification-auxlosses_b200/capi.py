@@ -19,6 +19,7 @@ _SIGS = {
     "tic_last_error_string": ("", ctypes.c_char_p),
     "tic_version": ("", ctypes.c_int),
     "tic_sm_count": ("", ctypes.c_int),
+    "tic_set_pdl": ("i", ctypes.c_int),
     "tic_gemm_bf16": ("pplipplippliiiifpiip", ctypes.c_int),
     "tic_gemm_rowss_parts": ("i", ctypes.c_int),
     "tic_gemm_plan": ("iiiiippp", ctypes.c_int),
@@ -62,6 +63,7 @@ _SIGS = {
     "tic_cast_f32_to_bf16": ("plpliip", ctypes.c_int),
     "tic_cast_bf16_to_f32": ("plpliip", ctypes.c_int),
     "tic_colsum_bf16": ("pliipp", ctypes.c_int),
+    "tic_colsum_bf16_pair": ("ppliipp", ctypes.c_int),
     "tic_loss_mix": ("ppiffiipp", ctypes.c_int),
     "tic_eval_state_words": ("i", ctypes.c_int),
     "tic_eval_accumulate": ("plplpiipppppp", ctypes.c_int),

@@ -16,10 +16,17 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local int g_pdl_override = -1;   // tic_set_pdl: -1 = follow TIC_PDL, 0 / 1 = force for this thread's next launches
 bool pdl_enabled() {
+  if (g_pdl_override >= 0) return g_pdl_override == 1;
   static int v = -1;
   if (v < 0) { const char* e = getenv("TIC_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
+}
+int set_pdl_override(int mode) {
+  const int prev = g_pdl_override;
+  g_pdl_override = mode < 0 ? -1 : (mode ? 1 : 0);
+  return prev;
 }
 
 TmapEncoder::EncodeFn TmapEncoder::get() {
@@ -325,6 +332,7 @@ extern "C" {
 const char* tic_last_error_string(void) { return g_err; }
 int tic_version(void) { return 100; }
 int tic_sm_count(void) { return device_sm_count(); }
+int tic_set_pdl(int mode) { return set_pdl_override(mode); }
 
 static int gemm_impl(const void* A, const void* A_lo, int64_t lda, int a_mn, const void* B, const void* B_lo, int64_t ldb,
                      int b_mn, void* D, void* D_lo, int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias,

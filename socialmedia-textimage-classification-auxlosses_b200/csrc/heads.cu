@@ -291,8 +291,8 @@ __global__ void heads_wgrad_kernel(const float* __restrict__ H, int64_t ldh, int
 }
 
 // out[n] += sum_m X[m,n]  (bf16 in) — bias gradients of the fusion / projection linears.
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, int rows, int cols, float* __restrict__ out,
-                                   int rows_per_blk) {
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ X_lo, int64_t ldx, int rows,
+                                   int cols, float* __restrict__ out, int rows_per_blk) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,6 +300,8 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t 
   const int rb = blockIdx.y * rows_per_blk, re = min(rb + rows_per_blk, rows);
   float s = 0.f;
   for (int r = rb; r < re; ++r) s += __bfloat162float(X[static_cast<int64_t>(r) * ldx + n]);
+  if (X_lo != nullptr)   // residual twin of a split-precision operand: one launch sums the pair
+    for (int r = rb; r < re; ++r) s += __bfloat162float(X_lo[static_cast<int64_t>(r) * ldx + n]);
   atomicAdd(out + n, s);
 }
 
@@ -410,14 +412,17 @@ int tic_heads_wgrad(const float* H, int64_t ldh, int B, int E, int C, int has_ti
   return TIC_OK;
 }
 
-int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, void* stream) {
+int tic_colsum_bf16_pair(const void* X, const void* X_lo, int64_t ldx, int rows, int cols, float* out, void* stream) {
   TIC_CHECK_ARG(X && out && rows > 0 && cols > 0, "tic_colsum_bf16: bad arguments");
   const int rpb = max(8, ceil_div(rows, 128));
   dim3 grid(ceil_div(cols, 128), ceil_div(rows, rpb));
-  launch_k(colsum_bf16_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(X), ldx, rows, cols,
-                                                                          out, rpb);
+  launch_k(colsum_bf16_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(X),
+           static_cast<const __nv_bfloat16*>(X_lo), ldx, rows, cols, out, rpb);
   TIC_CHECK_LAUNCH("tic_colsum_bf16");
   return TIC_OK;
+}
+int tic_colsum_bf16(const void* X, int64_t ldx, int rows, int cols, float* out, void* stream) {
+  return tic_colsum_bf16_pair(X, nullptr, ldx, rows, cols, out, stream);
 }
 
 int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream) {

@@ -177,6 +177,42 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_mbar_init();
   }
+  // one k-block of operands -> ring stage s (issued by the producer lane only)
+  auto load_stage = [&](int kt, int m0, int n0, int s) {
+    const int seg = kt / num_kb, kb = kt - seg * num_kb;
+    const bool a_lo = (seg == 1) && (split & 1);
+    const bool b_lo = (seg >= 1) && !a_lo;
+    const CUtensorMap* ta = a_lo ? &tmap_a_lo : &tmap_a;
+    const CUtensorMap* tb = b_lo ? &tmap_b_lo : &tmap_b;
+    const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+    const uint32_t sb = sa + kABytes;
+    mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
+    const int k0 = kb * kBK;
+    if constexpr (!A_MN) {
+      tma_load_2d(sa, ta, full_bar(s), k0, m0);
+    } else {
+      tma_load_2d(sa, ta, full_bar(s), m0, k0);
+      tma_load_2d(sa + 8192, ta, full_bar(s), m0 + 64, k0);
+    }
+    if constexpr (CLUSTER == 2) {
+      // my half of the shared B tile, multicast into both CTAs of the pair
+      if constexpr (!B_MN) {
+        tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tmap_b_lo, full_bar(s), k0, n0 + static_cast<int>(crank) * (BN / 2),
+                       uint16_t(3));
+      } else {
+#pragma unroll
+        for (int i = 0; i < BN / 128; ++i) {
+          const int bi = static_cast<int>(crank) * (BN / 128) + i;
+          tma_load_2d_mc(sb + bi * 8192, tb, full_bar(s), n0 + bi * 64, k0, uint16_t(3));
+        }
+      }
+    } else if constexpr (!B_MN) {
+      tma_load_2d(sb, tb, full_bar(s), k0, n0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, tb, full_bar(s), n0 + i * 64, k0);
+    }
+  };
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -213,40 +249,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / kslices);
         const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / kslices);
         for (int kt = kt_begin; kt < kt_end; ++kt) {
-          const int seg = kt / num_kb, kb = kt - seg * num_kb;
-          const bool a_lo = (seg == 1) && (split & 1);
-          const bool b_lo = (seg >= 1) && !a_lo;
-          const CUtensorMap* ta = a_lo ? &tmap_a_lo : &tmap_a;
-          const CUtensorMap* tb = b_lo ? &tmap_b_lo : &tmap_b;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          const uint32_t sb = sa + kABytes;
-          mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
-          const int k0 = kb * kBK;
-          if constexpr (!A_MN) {
-            tma_load_2d(sa, ta, full_bar(s), k0, m0);
-          } else {
-            tma_load_2d(sa, ta, full_bar(s), m0, k0);
-            tma_load_2d(sa + 8192, ta, full_bar(s), m0 + 64, k0);
-          }
-          if constexpr (CLUSTER == 2) {
-            // my half of the shared B tile, multicast into both CTAs of the pair
-            if constexpr (!B_MN) {
-              tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tmap_b_lo, full_bar(s), k0, n0 + static_cast<int>(crank) * (BN / 2),
-                             uint16_t(3));
-            } else {
-#pragma unroll
-              for (int i = 0; i < BN / 128; ++i) {
-                const int bi = static_cast<int>(crank) * (BN / 128) + i;
-                tma_load_2d_mc(sb + bi * 8192, tb, full_bar(s), n0 + bi * 64, k0, uint16_t(3));
-              }
-            }
-          } else if constexpr (!B_MN) {
-            tma_load_2d(sb, tb, full_bar(s), k0, n0);
-          } else {
-#pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, tb, full_bar(s), n0 + i * 64, k0);
-          }
+          load_stage(kt, m0, n0, s);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }

@@ -216,7 +216,8 @@ class MMLate_Model(object):
     """mm_late.py:298-739: trainer wrapper.  Data loading is out of scope of this path: pass
     DataLoaders yielding the reference's batch dict (input_ids, attention_mask, pixel_values, labels, data_id)."""
 
-    def __init__(self, config, txt_model_name, img_model_name, fusion_name, multilabel=False, model=None, device=None):
+    def __init__(self, config, txt_model_name, img_model_name, fusion_name, multilabel=False, model=None, device=None,
+                 itm_rng="numpy"):
         self.batch_size, self.num_labels, self.multilabel = config.batch_size, config.num_labels, multilabel
         self.use_clip_loss, self.beta_itc = config.use_clip_loss, config.beta_itc
         self.use_tim_loss, self.beta_itm = config.use_tim_loss, config.beta_itm
@@ -231,6 +232,10 @@ class MMLate_Model(object):
                                                               config.dropout, fusion_name=fusion_name)
         self.model.to(self.device)
         self.softmax, self.sigmoid = nn.Softmax(dim=1), nn.Sigmoid()
+        # "numpy": ITM decisions replay the reference's global numpy stream (seed-exact CLI parity); "device": drawn and applied
+        # on the GPU by one kernel, no host loop in the training step
+        self.itm_rng = itm_rng
+        self.last_eval = None
 
     def load_saved_model(self, model_path):
         self.model.load_state_dict(torch.load(model_path))
@@ -259,13 +264,32 @@ class MMLate_Model(object):
                 DataLoader(mk(val, y_val, "val"), batch_size=self.batch_size, shuffle=False),
                 DataLoader(mk(test, y_te, "test"), batch_size=self.batch_size, shuffle=False), class_weights, None)
 
-    def prepare_itm_inputs(self, ids, mask, return_src=False):
-        """mm_late.py:389-414 — consumes the GLOBAL numpy stream exactly like the reference (coin, then pick, per row), then
-        performs all row copies with the device gather kernel.  Returns fresh tensors (tim_ids, tim_mask, lbl_tim), plus
-        the source rows when return_src=True (so forward() need not re-derive them)."""
+    def prepare_itm_inputs(self, ids, mask, return_src=False, rng="numpy", generator=None):
+        """mm_late.py:389-414.  rng="numpy" (default, seed-exact with the reference CLI): consumes the GLOBAL numpy stream
+        exactly like the reference (coin, then pick, per row), then performs all row copies with the device gather kernel.
+        rng="device" (SURVEY §8 f-2): no host loop and no host->device copy at all — the two uniforms per row come from
+        torch's CUDA generator (`generator`, default the global one) and ONE kernel applies the same rule (swap iff
+        u_coin < 0.5; uniform pick over the other B-1 rows) and gathers ids and mask.  Same distribution, different stream.
+        Returns fresh tensors (tim_ids, tim_mask, lbl_tim), plus the source rows when return_src=True (so forward() need not
+        re-derive them)."""
         if not ids.is_cuda:
             raise capi.TicError("prepare_itm_inputs needs CUDA tensors: this package has no CPU path")
         B = ids.shape[0]
+        if rng == "device":
+            dev = ids.device
+            ids_c, mask_c = ids.contiguous(), mask.contiguous()
+            if ids_c.dtype != mask_c.dtype or ids_c.shape != mask_c.shape:
+                raise ValueError("ids and mask must share dtype and shape")
+            u = torch.rand(2, B, device=dev, generator=generator)
+            tim_ids, tim_mask = torch.empty_like(ids_c), torch.empty_like(mask_c)   # never aliases its inputs (:391-392)
+            lbl_tim = torch.empty(B, dtype=torch.int64, device=dev)
+            src_d = torch.empty(B, dtype=torch.int32, device=dev)
+            capi.call("tic_itm_sample_gather", u[0].data_ptr(), u[1].data_ptr(), B, 0, None, 0, ids_c.data_ptr(), mask_c.data_ptr(),
+                      ids_c.stride(0) * ids_c.element_size(), tim_ids.data_ptr(), tim_mask.data_ptr(), lbl_tim.data_ptr(),
+                      src_d.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            return (tim_ids, tim_mask, lbl_tim, src_d) if return_src else (tim_ids, tim_mask, lbl_tim)
+        if rng != "numpy":
+            raise ValueError("rng must be 'numpy' or 'device'")
         swap, src = _decisions_from_numpy_stream(B)
         dev = ids.device
         ids_c, mask_c = ids.contiguous(), mask.contiguous()
@@ -311,10 +335,7 @@ class MMLate_Model(object):
                 ids, mask, pixel_values = self._batch(batch)
                 label = batch["labels"].to(self.device)
                 optimizer.zero_grad()
-                tim_inputs, lbl_tim = None, None
-                if self.use_tim_loss:
-                    tim_ids, tim_mask, lbl_tim, src = self.prepare_itm_inputs(ids, mask, return_src=True)
-                    tim_inputs = (tim_ids, tim_mask, src)
+                tim_inputs, lbl_tim = self._itm_inputs(ids, mask)
                 output, logits_per_text, output_tim, _, _ = self.model(ids, mask, pixel_values, tim_inputs=tim_inputs,
                                                                        iadds_task=self.use_iadds_loss)
                 label = label.type_as(output)
@@ -335,35 +356,75 @@ class MMLate_Model(object):
             logger.info("{} saved".format(model_path))
         return res_val, res_te
 
+    def _itm_inputs(self, ids, mask):
+        """(tim_inputs, lbl_tim) for one batch, or (None, None); the reference samples ITM negatives in eval, prediction and
+        feature extraction too (mm_late.py:567,669,719)."""
+        if not self.use_tim_loss:
+            return None, None
+        tim_ids, tim_mask, lbl_tim, src = self.prepare_itm_inputs(ids, mask, return_src=True, rng=self.itm_rng)
+        return (tim_ids, tim_mask, src), lbl_tim
+
     def eval(self, dataloader, loss_fn, tim_loss_fn=None, iadds_loss_fn=None):
-        """mm_late.py:534-638 — returns {data_id, loss, predictions, labels}."""
-        eval_loss, eval_acc, predictions, labels, data_ids = [], [], [], [], []
+        """mm_late.py:534-638 — returns {data_id, loss, predictions, labels}.  Predictions, targets, the loss sum and the
+        confusion matrix are accumulated on the device (eval.EvalAccumulator): one host synchronisation per
+        epoch instead of two per batch; `self.last_eval` keeps the accumulator (confusion matrix, device-side metrics)."""
+        from .eval import EvalAccumulator
+        if self.multilabel:
+            raise NotImplementedError("multilabel evaluation belongs to the unreachable task 10 of the reference (config.py:10)")
         self.model.eval()
+        try:
+            capacity = len(dataloader.dataset)
+        except (TypeError, AttributeError):
+            capacity = len(dataloader) * self.batch_size
+        acc = EvalAccumulator(self.num_labels, capacity, device=self.device)
         for batch in dataloader:
             ids, mask, pixel_values = self._batch(batch)
             label = batch["labels"].to(self.device)
             data_id = batch["data_id"].to(self.device)
             with torch.no_grad():
-                tim_inputs, lbl_tim = None, None
-                if self.use_tim_loss:   # the reference samples ITM negatives in eval too (mm_late.py:567)
-                    tim_ids, tim_mask, lbl_tim, src = self.prepare_itm_inputs(ids, mask, return_src=True)
-                    tim_inputs = (tim_ids, tim_mask, src)
+                tim_inputs, lbl_tim = self._itm_inputs(ids, mask)
                 output, logits_per_text, output_tim, _, _ = self.model(ids, mask, pixel_values, tim_inputs=tim_inputs,
                                                                        iadds_task=self.use_iadds_loss)
                 label = label.type_as(output)
                 loss = self._loss(loss_fn, tim_loss_fn, output, label, logits_per_text, output_tim, lbl_tim)
-            eval_loss.append(loss.item())
-            if not self.multilabel:
-                pred = torch.argmax(self.softmax(output), dim=1)
-                target = torch.argmax(label, dim=1)
+            acc.update(output, label, loss=loss, data_id=data_id)
+        res = acc.result()
+        self.last_eval = acc
+        logger.info("loss: %.4f acc: %.4f", res["loss"], res["accuracy"])
+        return {"data_id": res.get("data_id"), "loss": res["loss"], "predictions": res["predictions"], "labels": res["labels"]}
+
+    def compute_predictions(self, dataloader):
+        """mm_late.py:640-701 — {data_id, predictions}.  (The reference unpacks 4 of the model's 5 outputs at :674 and would
+        raise; SURVEY §9: keep the method, fix the unpack.)"""
+        self.model.eval()
+        predictions, data_ids = [], []
+        for batch in dataloader:
+            ids, mask, pixel_values = self._batch(batch)
+            data_id = batch["data_id"].to(self.device)
+            with torch.no_grad():
+                tim_inputs, _ = self._itm_inputs(ids, mask)
+                output, _, _, _, _ = self.model(ids, mask, pixel_values, tim_inputs=tim_inputs, iadds_task=self.use_iadds_loss)
+            if self.multilabel:
+                pred = torch.round(self.sigmoid(output))
             else:
-                pred, target = torch.round(self.sigmoid(output)), label
-            eval_acc.append((pred == target).float().mean().item() * 100)
-            predictions += pred
-            labels += target
-            data_ids += data_id
-        return {"data_id": torch.stack(data_ids), "loss": float(np.mean(eval_loss)), "predictions": torch.stack(predictions),
-                "labels": torch.stack(labels)}
+                pred = torch.argmax(self.softmax(output), dim=1)
+            predictions.append(pred)
+            data_ids.append(data_id)
+        return {"data_id": torch.cat(data_ids), "predictions": torch.cat(predictions)}
+
+    def extract_features(self, dataloader):
+        """mm_late.py:703-739 — (mm_features [N, 768], argmax labels [N])."""
+        self.model.eval()
+        features, labels = [], []
+        for batch in dataloader:
+            ids, mask, pixel_values = self._batch(batch)
+            label = batch["labels"].to(self.device)
+            with torch.no_grad():
+                tim_inputs, _ = self._itm_inputs(ids, mask)
+                _, _, _, _, mm_feats = self.model(ids, mask, pixel_values, tim_inputs=tim_inputs, iadds_task=self.use_iadds_loss)
+            features.append(mm_feats)
+            labels.append(torch.argmax(label, dim=1))
+        return torch.cat(features), torch.cat(labels)
 
 
 def _decisions_from_numpy_stream(B):

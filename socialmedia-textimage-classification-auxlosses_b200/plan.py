@@ -54,6 +54,7 @@ class _Branches:
     def __init__(self, device, enabled=True, priority=None):
         self.dev, self.enabled, self.side = device, enabled, {}
         self.priority = priority or {}     # branch key -> CUDA stream priority (-1 = high; default 0 = low)
+        self.pdl_chains = False
 
     class _Ctx:
         def __init__(self, outer, k):
@@ -69,9 +70,16 @@ class _Branches:
             s.wait_stream(torch.cuda.current_stream())
             self.cm = torch.cuda.stream(s)
             self.cm.__enter__()
+            # programmatic dependent launch follows the latency-critical chains only (HeadPlan.pdl_chains): a side branch
+            # launches its kernels in ordinary stream order, a high-priority branch inherits the chain's mode
+            self.prev_pdl = None
+            if o.pdl_chains:
+                self.prev_pdl = capi.load().tic_set_pdl(1 if o.priority.get(self.k, 0) < 0 else 0)
 
         def __exit__(self, *a):
             if self.o.enabled:
+                if self.prev_pdl is not None:
+                    capi.load().tic_set_pdl(self.prev_pdl)
                 self.cm.__exit__(*a)
 
     def __call__(self, k):
@@ -265,6 +273,9 @@ class HeadPlan:
         self._side = None
         self._hi0 = None
         self._ev_heads = None
+        # programmatic dependent launch on the kernels of the latency-critical chains only (TIC_PDL_CHAINS=1; needs the
+        # high-priority-chain mode): see _Branches and tic_set_pdl
+        self.pdl_chains = _os.environ.get("TIC_PDL_CHAINS", "0") == "1"
         # TIC_STEP_TAIL bit 0: small memset on a side branch, bit 1: loss mix issued before the backward (A/B switch).
         # Measured on the c2 graph (scripts/timeline.py --plain-only, 400 replays): 0 -> 92.2 us, 1 -> 96.4 us (a memset node
         # joined into both chains costs more than the ~2 us it takes at the head), 2 -> 90.3 us, 3 -> 92.7 us.  Default 2.
@@ -506,8 +517,14 @@ class HeadPlan:
             if self._hi0 is None:
                 self._hi0 = torch.cuda.Stream(device=self.dev, priority=-1)
             self._hi0.wait_stream(caller)
-            with torch.cuda.stream(self._hi0):
-                self._step_body(inp)
+            self.br.pdl_chains = self.pdl_chains
+            prev = capi.load().tic_set_pdl(1) if self.pdl_chains else None
+            try:
+                with torch.cuda.stream(self._hi0):
+                    self._step_body(inp)
+            finally:
+                if prev is not None:
+                    capi.load().tic_set_pdl(prev)
             caller.wait_stream(self._hi0)
             return o
         self._step_body(inp)
@@ -751,9 +768,7 @@ class HeadPlan:
         br = self.br
         br.enabled = self.parallel_streams
         with br("f"):   # parameter gradients of linear_fusion run beside the input-gradient chain
-            call("tic_colsum_bf16", ptr(dH), E, R, E, ptr(z["db_f"]), _stream())
-            if dHl is not None:
-                call("tic_colsum_bf16", ptr(dHl), E, R, E, ptr(z["db_f"]), _stream())
+            call("tic_colsum_bf16_pair", ptr(dH), ptr(dHl), E, R, E, ptr(z["db_f"]), _stream())     # hi + lo in one launch
             gemm(dH, E, 1, Hin, E2, 1, o["dW_f"], E2, 0, E, E2, R, A_lo=dHl, B_lo=Hin_lo, accumulate=True)           # dW_f = dH^T Hin
         if self.fusion == "concat":
             gemm(dH, E, 0, w["W_f"], E2, 1, self.dXt, E, 0, R, E, E, A_lo=dHl)                      # dX_text = dH W_f[:, :E]
@@ -762,9 +777,7 @@ class HeadPlan:
             Ea, Lv = E + 8, self.Lv
             gemm(dH, E, 0, w["W_f"], E2, 1, self.dXt, E, 0, R, E, E, A_lo=dHl)
             gemm(dH, E, 0, w["W_f"].data_ptr() + 2 * E, E2, 1, self.dctx, E, 1, R, E, E, A_lo=dHl, D_lo=lo(self.dctx_lo))
-            call("tic_colsum_bf16", ptr(self.dctx), E, R, E, ptr(z["db_V"]), st)
-            if self.split:
-                call("tic_colsum_bf16", ptr(self.dctx_lo), E, R, E, ptr(z["db_V"]), st)
+            call("tic_colsum_bf16_pair", ptr(self.dctx), ptr(lo(self.dctx_lo)), E, R, E, ptr(z["db_V"]), st)
             gemm(self.dctx, E, 1, self.xbar_b, E, 1, o["dW_V"], E, 0, E, E, R, A_lo=lo(self.dctx_lo), B_lo=lo(self.xbar_lo), accumulate=True)
             gemm(self.dctx, E, 0, w["W_V"], E, 1, self.dxbar, E, 0, R, E, E, A_lo=lo(self.dctx_lo))
             call("tic_attn_pool_bwd", ptr(x_v), x_v.stride(0), x_v.stride(1), ptr(self.attn), Lv, ptr(self.dxbar), E,
@@ -772,9 +785,7 @@ class HeadPlan:
                  Ea, st)
             gemm(self.dkq, Ea, 0, w["W_Kaug"], Ea, 0, self.dq0, E, 1, R, E, Ea, A_lo=lo(self.dkq_lo), D_lo=lo(self.dq0_lo))
             gemm(self.q0, E, 1, self.dkq, Ea, 1, self.dWK_aug, Ea, 0, E, Ea, R, A_lo=lo(self.q0_lo), B_lo=lo(self.dkq_lo), accumulate=True)  # [dW_K|db_K]
-            call("tic_colsum_bf16", ptr(self.dq0), E, R, E, ptr(z["db_Q"]), st)
-            if self.split:
-                call("tic_colsum_bf16", ptr(self.dq0_lo), E, R, E, ptr(z["db_Q"]), st)
+            call("tic_colsum_bf16_pair", ptr(self.dq0), ptr(lo(self.dq0_lo)), E, R, E, ptr(z["db_Q"]), st)
             gemm(self.dq0, E, 1, X, E2, 1, o["dW_Q"], E, 0, E, E, R, A_lo=lo(self.dq0_lo), accumulate=True)
             gemm(self.dq0, E, 0, w["W_Q"], E, 1, self.dXt2, E, 0, R, E, E, A_lo=lo(self.dq0_lo))
             call("tic_unpack_cls_grad", ptr(self.dXt), E, ptr(self.dXt2), E, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
@@ -782,10 +793,8 @@ class HeadPlan:
             gemm(dH, E, 0, w["W_f"], E2, 1, self.dG, E2, 0, R, E2, E, A_lo=dHl)                     # dG = dH W_f
             call("tic_gmu_gate_bwd", ptr(X), E2, ptr(self.tp), ptr(self.vp), E2, ptr(self.dG), E2, R, E2, ptr(self.dtp),
                  ptr(self.dvp), ptr(lo(self.dtp_lo)), ptr(lo(self.dvp_lo)), E2, ptr(self.dXg), E2, st)
-            for buf, acc in ((self.dtp, "db_gt"), (lo(self.dtp_lo), "db_gt"), (self.dvp, "db_gv"), (lo(self.dvp_lo), "db_gv")):
-                if buf is None:
-                    continue
-                call("tic_colsum_bf16", ptr(buf), E2, R, E2, ptr(z[acc]), st)
+            call("tic_colsum_bf16_pair", ptr(self.dtp), ptr(lo(self.dtp_lo)), E2, R, E2, ptr(z["db_gt"]), st)
+            call("tic_colsum_bf16_pair", ptr(self.dvp), ptr(lo(self.dvp_lo)), E2, R, E2, ptr(z["db_gv"]), st)
             gemm(self.dtp, E2, 1, X, E2, 1, o["dW_gt"], E, 0, E2, E, R, A_lo=lo(self.dtp_lo), accumulate=True)
             gemm(self.dvp, E2, 1, X.data_ptr() + 2 * E, E2, 1, o["dW_gv"], E, 0, E2, E, R, A_lo=lo(self.dvp_lo), accumulate=True)
             gemm(self.dtp, E2, 0, w["W_gt"], E, 1, self.dXt2, E, 0, R, E, E2, A_lo=lo(self.dtp_lo))

@@ -1,5 +1,6 @@
 """Mirror of the functions of the reference's models/utils.py that sit on the hot path: `contrastive_loss`, `clip_loss`
-(utils.py:225-231) and `get_optimizer_params` (utils.py:280-292).  `clip_loss` runs the hand-written bidirectional
+(utils.py:225-231) and `get_optimizer_params` (utils.py:280-292); `compute_metrics` / `agg_metrics_val` (utils.py:294-336)
+are the device-side versions of tic_b200.eval, imported lazily below.  `clip_loss` runs the hand-written bidirectional
 softmax-CE kernels (csrc/ce.cu) through the C ABI and is differentiable (torch.autograd.Function)."""
 import torch
 
@@ -62,3 +63,15 @@ def get_optimizer_params(named_parameters, weight_decay, lr, verbose=False):
         if param.requires_grad:
             params["params"].append(param)
     return [params]
+
+
+def compute_metrics(res, num_classes, multi_label=False):
+    """models/utils.py:294-325 (see tic_b200.eval.compute_metrics: confusion matrix + six scores on the device)."""
+    from .eval import compute_metrics as _cm
+    return _cm(res, num_classes, multi_label=multi_label)
+
+
+def agg_metrics_val(res_val, metric_names, num_labels):
+    """models/utils.py:327-336."""
+    from .eval import agg_metrics_val as _agg
+    return _agg(res_val, metric_names, num_labels)

@@ -55,3 +55,24 @@ def test_missing_library_fails_loudly(monkeypatch, lib_path):
     monkeypatch.setattr(capi, "LIB_PATH", "/nonexistent/libtic_b200.so")
     with pytest.raises(capi.TicError):
         capi.load()
+
+
+def test_gemm_plan_and_eval_state_without_gpu(lib_path, monkeypatch):
+    """Launch-shape selection is host arithmetic: observable without a device.  Cluster split-K is opt-in (TIC_CLUSTER_K)."""
+    from tic_b200 import capi
+    lib = capi.load()
+
+    def plan(M, N, K, ns=0, acc=0):
+        bn, ks, kc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        capi.call("tic_gemm_plan", M, N, K, ns, acc, ctypes.byref(bn), ctypes.byref(ks), ctypes.byref(kc))
+        return bn.value, ks.value, kc.value
+
+    monkeypatch.delenv("TIC_CLUSTER_K", raising=False)
+    assert plan(256, 512, 768) == (64, 1, 1)                  # default: no cluster split-K
+    assert plan(512, 768, 4096, 0, 1)[1] > 1                  # long-K weight-gradient GEMM: fp32-atomic split-K
+    monkeypatch.setenv("TIC_CLUSTER_K", "96")
+    assert plan(256, 512, 768) == (64, 1, 4) and plan(512, 768, 1536) == (64, 1, 2)
+    assert plan(4096, 4096, 4096)[2] == 1
+    assert lib.tic_eval_state_words(4) == 20 and lib.tic_eval_state_words(0) < 0
+    with pytest.raises(capi.TicError):
+        capi.call("tic_eval_accumulate", None, 4, None, 0, None, 8, 4, None, None, None, None, None, None)
