@@ -318,9 +318,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // Everything the epilogue reads from global memory that does not depend on the accumulator (bias, norms, softmax
       // statistics) is fetched BEFORE waiting for the MMAs, so its latency hides behind the k-loop: measured on a one-tile
       // GEMM (scripts/gemm_rate.py probes) the epilogue was 3.9 us of an 8.2 us launch, most of it exposed load latency.
-      if (cx.m0 < M && (KC == 1 || krank == 0)) Epi::template prefetch<BN>(ep, cx);
+      // Only for the FIRST tile of a CTA, though: there the epilogue warps would otherwise idle through the whole k-loop.  On
+      // the later tiles of a persistent CTA the epilogue is the busy side (the MMAs run a tile ahead) and the early placement
+      // measured slower (ITC forward at 16384x768: 0.306 -> 0.391 ms), so those keep the loads after the wait.
+      const bool have_rows = cx.m0 < M && (KC == 1 || krank == 0);
+      const bool early = cx.iter == 0;
+      if (have_rows && early) Epi::template prefetch<BN>(ep, cx);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
+      if (have_rows && !early) Epi::template prefetch<BN>(ep, cx);
       cx.tmem_acc = tmem_base + as * BN;
       if constexpr (KC > 1) {
         // ---- cluster split-K reduction through distributed shared memory (one tile per cluster)
