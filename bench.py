@@ -247,6 +247,33 @@ def cpu_reference_run(spec, steps, warmup, budget_s, threads=None):
     return B / (ms / 1e3), ms, "%s, %d timed steps, fp32 torch CPU" % (note, len(times)), threads
 
 
+# ------------------------------------------------------------------------------------------------ stdout hygiene
+class _QuietStdout:
+    """Rank 0 must print ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its version
+    banner there when NCCL_DEBUG is set by the environment): while the benchmark runs, fd 1 points at stderr; `emit` puts it
+    back and prints the line."""
+
+    def __init__(self):
+        self.saved = None
+        try:
+            sys.stdout.flush()
+            self.saved = os.dup(1)
+            os.dup2(2, 1)
+        except OSError:
+            self.saved = None
+
+    def emit(self, line):
+        sys.stdout.flush()
+        if self.saved is not None:
+            try:
+                os.dup2(self.saved, 1)
+                os.close(self.saved)
+            except OSError:
+                pass
+            self.saved = None
+        print(line, flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse_args()
@@ -271,6 +298,7 @@ def main():
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    out = _QuietStdout()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -387,7 +415,7 @@ def main():
     if args.profile:
         if rank == 0:
             clocks.stop()
-            print(json.dumps(dict(base, value=value, ms_per_step=ms_per_step, profile_run=True)))
+            out.emit(json.dumps(dict(base, value=value, ms_per_step=ms_per_step, profile_run=True)))
         return
     # ---- end-to-end: HOST buffers in, loss out, through the public host-facing API.
     # (1) synchronous: every call = pinned arena -> H2D -> step -> D2H losses -> host sync; L2 flushed outside the brackets.
@@ -469,7 +497,7 @@ def main():
         val, ms, sample, threads = cpu_reference_run(spec, 1000, 1, args.cpu_seconds)
         line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
                                 "ms_per_step": ms}
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -99,12 +99,9 @@ def compute_metrics(res: Dict, num_classes: int, multi_label: bool = False) -> D
     pred, tgt = res["predictions"], res["labels"]
     if not pred.is_cuda:
         raise capi.TicError("compute_metrics needs CUDA tensors: this package has no CPU path")
-    acc = EvalAccumulator(num_classes, 1, device=pred.device)
+    acc = EvalAccumulator(num_classes, max(int(pred.numel()), 1), device=pred.device)
     # predictions are already class ids: feed them as one-hot "logits" of a single pass over the whole epoch
-    onehot = torch.nn.functional.one_hot(pred.to(torch.int64), num_classes).to(torch.float32)
-    acc.preds = torch.empty(pred.numel(), dtype=torch.int64, device=pred.device)
-    acc.targets = torch.empty(pred.numel(), dtype=torch.int64, device=pred.device)
-    acc.capacity = pred.numel()
+    onehot = torch.nn.functional.one_hot(pred.to(torch.int64).reshape(-1), num_classes).to(torch.float32)
     acc.update(onehot, tgt.to(torch.int64).reshape(-1))
     vals = acc.metrics_device().tolist()
     return {"metric": METRIC_NAMES + ["loss"], "result": vals + [res["loss"]]}
