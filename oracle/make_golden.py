@@ -6,6 +6,9 @@ What is recorded
   itm_stream.npz      MMLate_Model.prepare_itm_inputs (mm_late.py:389-414) on the global numpy stream for
                       (seed, B) in {(40,8), (30,16), (123,256), (0,2), (7,1)}: labels, gathered ids/mask, source rows.
   clip_loss.npz       utils.clip_loss (utils.py:225-231) values + autograd gradients on seeded matrices.
+  mm_early_tail.npz   the encoder-free tail of the early-fusion models: ViLT.get_logits_per_text
+                      (mm_early.py:96-103) + utils.clip_loss with autograd gradients w.r.t. both embeddings and logit_scale,
+                      and MMEarly_Model.prepare_itm_inputs (mm_early.py:262-293) on the numpy stream.
   head_<fusion>.npz   MM_Model.forward (mm_late.py:148-193) end to end through tiny random-init encoders, eval mode,
                       plus the reference loss code (run_mm_late.py:85,97; mm_late.py:473-487) and autograd:
                       captured encoder outputs (= the head's inputs), head outputs, losses, gradients of every head
@@ -178,9 +181,42 @@ def gen_head(ns, fusion, use_itm, B=4, C=4, Lt=12, seed=40):
     print(name, "loss", float(loss), "size KB", os.path.getsize(os.path.join(GOLD, name)) // 1024)
 
 
+def gen_mm_early(ns):
+    out = {}
+    for seed, B, d in ((0, 8, 768), (1, 33, 64), (2, 48, 256)):
+        g = torch.Generator().manual_seed(seed)
+        T = torch.randn(B, d, generator=g).requires_grad_(True)
+        V = (torch.randn(B, d, generator=g) + 0.3 * T.detach()).requires_grad_(True)
+        W = torch.randn(B, B, generator=g)
+        ls = torch.tensor(2.6592, requires_grad=True)
+        S = ref_shims.ref_early_logits(ns, T, V, ls)                       # mm_early.py:96-103
+        closs = ns.utils.clip_loss(S)                                      # utils.py:228-231 (mm_early.py:367-368)
+        (closs + 1e-3 * (S * W).sum()).backward()
+        key = "b%d_d%d" % (B, d)
+        for k, v in (("T", T), ("V", V), ("W", W), ("S", S), ("clip_loss", closs), ("dT", T.grad), ("dV", V.grad),
+                     ("dls", ls.grad)):
+            out[key + "_" + k] = v.detach().numpy()
+    for seed, B in ((40, 8), (30, 16), (7, 1)):
+        L = 6
+        ids = (torch.arange(B * L).view(B, L) * 7 + 3) % 1000
+        mask = ((torch.arange(B * L).view(B, L) % 5) != 0).long()
+        tt = (torch.arange(B * L).view(B, L) % 2)
+        np.random.seed(seed)
+        tim_ids, tim_mask, tim_tt, lbl = ref_shims.ref_early_prepare_itm_inputs(ns, ids, mask, tt)   # mm_early.py:262-293
+        key = "s%d_b%d" % (seed, B)
+        for k, v in (("ids", ids), ("mask", mask), ("tt", tt), ("tim_ids", tim_ids), ("tim_mask", tim_mask), ("tim_tt", tim_tt),
+                     ("lbl", lbl)):
+            out[key + "_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, "mm_early_tail.npz"), **out)
+    print("mm_early_tail: clip_loss", float(out["b8_d768_clip_loss"]), "lbl", out["s40_b8_lbl"].tolist())
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ns = ref_shims.load_reference(small_encoders=True)
+    gen_mm_early(ref_shims.load_reference_early())
+    if "--only-early" in sys.argv:
+        return
     gen_itm_stream(ns)
     gen_clip_loss(ns)
     for fusion, itm in (("concat", True), ("attention", True), ("gmu", True), ("aspect-att", False), ("concat", False)):

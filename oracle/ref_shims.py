@@ -103,6 +103,59 @@ def load_reference(small_encoders: bool = True):
     return ns
 
 
+def load_reference_early():
+    """Adds `ns.mm_early` (models/mm_early.py) to the namespace of load_reference().  Extra shim (v): the module imports
+    `lxmert_scripts.{modeling_frcnn,utils,processing_image}` (mm_early.py:10-12), a package that is NOT in the reference
+    tree: stub modules with placeholder classes — only the encoder-free tail is ever called here
+    (ViLT.get_logits_per_text :96-103, MMEarly_Model.prepare_itm_inputs :262-293)."""
+    ns = load_reference()
+    if getattr(ns, "mm_early", None) is not None:
+        return ns
+    stubs = {"lxmert_scripts": {}, "lxmert_scripts.modeling_frcnn": {"GeneralizedRCNN": type("GeneralizedRCNN", (), {})},
+             "lxmert_scripts.utils": {"Config": type("Config", (), {})},
+             "lxmert_scripts.processing_image": {"Preprocess": type("Preprocess", (), {})}}
+    added = []
+    for name, attrs in stubs.items():
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            added.append(name)
+    saved_path, saved_cwd = list(sys.path), os.getcwd()
+    names = ("config", "utils", "datasets", "mm_early", "text_processing")
+    saved_mods = {k: sys.modules.get(k) for k in names}
+    try:
+        os.chdir(REF_MODELS)
+        sys.path.insert(0, REF_PREPROC)
+        sys.path.insert(0, REF_MODELS)
+        for k in names:
+            sys.modules.pop(k, None)
+        sys.modules["config"], sys.modules["utils"] = ns.config, ns.utils     # the already-shimmed modules (config.T, torchmetrics)
+        import mm_early as ref_mm_early  # noqa: E402
+    finally:
+        os.chdir(saved_cwd)
+        sys.path[:] = saved_path
+        for k, v in saved_mods.items():
+            if v is not None:
+                sys.modules[k] = v
+            else:
+                sys.modules.pop(k, None)
+        for name in added:
+            sys.modules.pop(name, None)
+    ns.mm_early = ref_mm_early
+    return ns
+
+
+def ref_early_logits(ns, text_embeds, image_embeds, logit_scale):
+    """models/mm_early.py:96-103 (ViLT.get_logits_per_text), called unbound on a dummy self that owns `logit_scale`."""
+    return ns.mm_early.ViLT.get_logits_per_text(types.SimpleNamespace(logit_scale=logit_scale), text_embeds, image_embeds)
+
+
+def ref_early_prepare_itm_inputs(ns, ids, mask, token_type_ids):
+    """models/mm_early.py:262-293, called unbound on a dummy self. Consumes np.random global state."""
+    return ns.mm_early.MMEarly_Model.prepare_itm_inputs(types.SimpleNamespace(), ids, mask, token_type_ids)
+
+
 def ref_prepare_itm_inputs(ns, ids, mask):
     """models/mm_late.py:389-414, called unbound on a dummy self (it uses no attributes). Consumes np.random global state."""
     dummy = types.SimpleNamespace()

@@ -123,6 +123,28 @@ def test_mm_early_get_logits_per_text_and_gradients(B, d):
     assert abs(float(ls.grad) - float(l.grad)) / max(abs(float(l.grad)), 1e-6) < 1e-3
 
 
+@pytest.mark.parametrize("B,d", [(8, 768), (33, 64), (48, 256)])
+def test_mm_early_tail_vs_reference_golden(golden_dir, B, d):
+    """Against values and gradients recorded from the UNMODIFIED reference (ViLT.get_logits_per_text + utils.clip_loss,
+    tests/golden/mm_early_tail.npz by oracle/make_golden.py), same loss as the fixture: clip_loss(S) + 1e-3 * <S, W>."""
+    from tic_b200.mm_early import get_logits_per_text, itc_loss
+    from tic_b200.utils import clip_loss
+    gd = dict(np.load(os.path.join(golden_dir, "mm_early_tail.npz")))
+    key = "b%d_d%d_" % (B, d)
+    T = torch.tensor(gd[key + "T"], device=DEV, requires_grad=True)
+    V = torch.tensor(gd[key + "V"], device=DEV, requires_grad=True)
+    ls = torch.tensor(2.6592, device=DEV, requires_grad=True)
+    S = get_logits_per_text(T, V, ls)
+    closs = clip_loss(S)
+    (closs + 1e-3 * (S * torch.tensor(gd[key + "W"], device=DEV)).sum()).backward()
+    assert _rel(S, torch.tensor(gd[key + "S"])) < 1e-3
+    assert abs(float(closs) - float(gd[key + "clip_loss"])) / float(gd[key + "clip_loss"]) < 1e-3
+    assert _rel(T.grad, torch.tensor(gd[key + "dT"])) < 1e-3 and _rel(V.grad, torch.tensor(gd[key + "dV"])) < 1e-3
+    assert abs(float(ls.grad) - float(gd[key + "dls"])) / abs(float(gd[key + "dls"])) < 1e-3
+    fused = itc_loss(T.detach(), V.detach(), ls.detach())
+    assert abs(float(fused) - float(gd[key + "clip_loss"])) / float(gd[key + "clip_loss"]) < 1e-3
+
+
 @pytest.mark.parametrize("B,d", [(8, 768), (256, 768), (1000, 256), (4096, 768)])
 def test_mm_early_fused_itc_loss(B, d):
     from tic_b200.mm_early import itc_loss

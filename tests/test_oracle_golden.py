@@ -158,3 +158,35 @@ def test_det_exp_accuracy_and_hard_sampler_properties():
     S2[np.arange(4), (np.arange(4) + 1) % 4] = 10.0
     lbl, src = R.itm_sample_hard(S2, np.zeros(4, np.float32), np.array([0.0, 0.3, 0.6, 0.999], np.float32))
     assert src.tolist() == [1, 2, 3, 0]
+
+
+# ---------------------------------------------------------------------------------------------------- mm_early tail (§8 f-3)
+@pytest.mark.parametrize("B,d", [(8, 768), (33, 64), (48, 256)])
+def test_mm_early_logits_and_gradients_match_reference(golden_dir, B, d):
+    """ViLT.get_logits_per_text (mm_early.py:96-103) + utils.clip_loss, recorded from the unmodified reference."""
+    g = _load(golden_dir, "mm_early_tail")
+    key = "b%d_d%d_" % (B, d)
+    T = torch.tensor(g[key + "T"], requires_grad=True)
+    V = torch.tensor(g[key + "V"], requires_grad=True)
+    ls = torch.tensor(2.6592, requires_grad=True)
+    S = R.itc_logits(T, V, ls)
+    closs = R.clip_loss(S)
+    (closs + 1e-3 * (S * torch.tensor(g[key + "W"])).sum()).backward()
+    np.testing.assert_allclose(S.detach().numpy(), g[key + "S"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(closs.detach().numpy(), g[key + "clip_loss"], rtol=1e-5)
+    np.testing.assert_allclose(T.grad.numpy(), g[key + "dT"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(V.grad.numpy(), g[key + "dV"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(ls.grad.numpy(), g[key + "dls"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("seed,B", [(40, 8), (30, 16), (7, 1)])
+def test_mm_early_itm_stream_matches_reference(golden_dir, seed, B):
+    """MMEarly_Model.prepare_itm_inputs (mm_early.py:262-293): the late-fusion rule plus token_type_ids, same numpy stream."""
+    g = _load(golden_dir, "mm_early_tail")
+    key = "s%d_b%d_" % (seed, B)
+    swap, src = R.itm_decisions_from_stream(B, np.random.RandomState(seed))
+    assert np.array_equal((~swap).astype(np.int64), g[key + "lbl"])
+    for name in ("ids", "mask", "tt"):
+        assert np.array_equal(R.gather_rows(torch.from_numpy(g[key + name]), src).numpy(), g[key + "tim_" + name])
+    late = _load(golden_dir, "itm_stream")      # the two wrappers consume the stream identically
+    assert np.array_equal(g[key + "lbl"], late["s%d_b%d_lbl" % (seed, B)])

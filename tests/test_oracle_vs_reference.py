@@ -60,3 +60,41 @@ def test_itc_logits_live_hf(ns):
                          R.project(out.vision_model_output.pooler_output, de.visual_projection.weight), de.logit_scale)
     assert torch.allclose(out.logits_per_text, S, rtol=1e-5, atol=1e-6)
     assert torch.allclose(out.loss, R.clip_loss(S), rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------- mm_early tail (§8 f-3)
+@pytest.fixture(scope="module")
+def ns_early():
+    return ref_shims.load_reference_early()
+
+
+@pytest.mark.parametrize("B,d", [(2, 768), (17, 768), (64, 128)])
+def test_mm_early_get_logits_per_text_live(ns_early, B, d):
+    """ViLT / Lxmert.get_logits_per_text (mm_early.py:96-103, 165-172) == the restatement, values and autograd gradients."""
+    g = torch.Generator().manual_seed(B + d)
+    T0, V0 = torch.randn(B, d, generator=g), torch.randn(B, d, generator=g)
+    outs = []
+    for fn in (lambda T, V, ls: ref_shims.ref_early_logits(ns_early, T, V, ls), R.itc_logits):
+        T, V = T0.clone().requires_grad_(True), V0.clone().requires_grad_(True)
+        ls = torch.tensor(2.6592, requires_grad=True)
+        S = fn(T, V, ls)
+        ns_early.utils.clip_loss(S).backward()
+        outs.append((S.detach(), T.grad, V.grad, ls.grad))
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    lx = ns_early.mm_early.Lxmert.get_logits_per_text
+    import types as _t
+    S2 = lx(_t.SimpleNamespace(logit_scale=torch.tensor(2.6592)), T0, V0)
+    assert torch.allclose(S2, outs[0][0], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed,B", [(0, 3), (11, 8), (40, 300)])
+def test_mm_early_prepare_itm_inputs_live(ns_early, seed, B):
+    ids = torch.arange(B * 4).view(B, 4)
+    mask, tt = (ids % 3 != 0).long(), ids % 2
+    np.random.seed(seed)
+    a, b, c, l = ref_shims.ref_early_prepare_itm_inputs(ns_early, ids, mask, tt)
+    swap, src = R.itm_decisions_from_stream(B, np.random.RandomState(seed))
+    assert torch.equal(l, torch.from_numpy((~swap).astype(np.int64)))
+    assert torch.equal(a, R.gather_rows(ids, src)) and torch.equal(b, R.gather_rows(mask, src)) and torch.equal(c, R.gather_rows(tt, src))
+    assert a.data_ptr() != ids.data_ptr()        # fresh clones (mm_early.py:265-267)
