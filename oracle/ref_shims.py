@@ -156,6 +156,32 @@ def ref_early_prepare_itm_inputs(ns, ids, mask, token_type_ids):
     return ns.mm_early.MMEarly_Model.prepare_itm_inputs(types.SimpleNamespace(), ids, mask, token_type_ids)
 
 
+def ref_eval(ns, outputs, labels, loss_fn):
+    """models/mm_late.py:534-638 (MMLate_Model.eval) run UNBOUND on a dummy trainer whose model replays the given per-batch
+    logits (no encoders, no aux losses): returns the reference's {data_id, loss, predictions, labels} for the eval bookkeeping."""
+    import torch
+    import torch.nn as nn
+    it = iter(outputs)
+
+    class _Model:
+        def eval(self):
+            return self
+
+        def __call__(self, ids, mask, pixel_values, tim_inputs=None, iadds_task=False):
+            return next(it), None, None, None, None
+
+    dummy = types.SimpleNamespace(model=_Model(), cnn=False, use_tim_loss=False, use_clip_loss=False, use_iadds_loss=False,
+                                  use_loss_correction=False, multilabel=False, softmax=nn.Softmax(dim=1), sigmoid=nn.Sigmoid(),
+                                  beta_itc=0.0, beta_itm=0.0, beta_iadds=0.0)
+    batches, n0 = [], 0
+    for out, lab in zip(outputs, labels):
+        B = out.shape[0]
+        batches.append({"input_ids": torch.zeros(B, 1, 4, dtype=torch.long), "attention_mask": torch.ones(B, 1, 4, dtype=torch.long),
+                        "pixel_values": torch.zeros(B, 1, 3, 2, 2), "labels": lab, "data_id": torch.arange(n0, n0 + B)})
+        n0 += B
+    return ns.mm_late.MMLate_Model.eval(dummy, batches, loss_fn)
+
+
 def ref_prepare_itm_inputs(ns, ids, mask):
     """models/mm_late.py:389-414, called unbound on a dummy self (it uses no attributes). Consumes np.random global state."""
     dummy = types.SimpleNamespace()

@@ -10,7 +10,8 @@ Pinning: the reference ships no tests / golden vectors for this path (SURVEY.md 
 pinned against the reference's own code run in the build container under the shims of oracle/ref_shims.py
 (tests/test_oracle_vs_reference.py) and against fixtures generated from it by oracle/make_golden.py
 (tests/golden/*.npz).  The similarity-weighted hard-negative sampler (itm_sample_hard) is an extension named only
-by BASELINE.json: its parity is UNPINNED by the reference — the spec is this file.
+by BASELINE.json: its parity is UNPINNED by the reference — the spec is this file.  metrics_from_confusion restates
+torchmetrics==0.11.0 (third-party, absent here): PARITY UNPINNED against torchmetrics, pinned against scikit-learn.
 
 Floating point is torch CPU (fp32 or fp64, chosen by the dtype of the inputs); integer / RNG work is numpy.
 """
@@ -351,6 +352,18 @@ def eval_batch(output: torch.Tensor, label: torch.Tensor):
     pred = torch.argmax(torch.softmax(output.double(), dim=1), dim=1)
     target = torch.argmax(label, dim=1)
     return pred, target, float((pred == target).double().mean()) * 100.0
+
+
+def eval_epoch(outputs, labels, losses) -> Dict:
+    """models/mm_late.py:544-636: the per-batch loop of MMLate_Model.eval on given per-batch logits / float one-hot labels /
+    batch losses: loss = mean of the batch losses (:594,615), accuracy = mean of the per-batch accuracies (:607-608,616 — a short
+    last batch weighs as much as a full one), predictions / labels concatenated in order (:610-611,623,628)."""
+    preds, tgts, accs = [], [], []
+    for out, lab in zip(outputs, labels):
+        p, t, a = eval_batch(out, lab)
+        preds.append(p); tgts.append(t); accs.append(a)
+    return {"loss": float(np.mean([float(l) for l in losses])), "accuracy": float(np.mean(accs)),
+            "predictions": torch.cat(preds), "labels": torch.cat(tgts)}
 
 
 def confusion_matrix(pred: np.ndarray, target: np.ndarray, C: int) -> np.ndarray:

@@ -98,3 +98,21 @@ def test_mm_early_prepare_itm_inputs_live(ns_early, seed, B):
     assert torch.equal(l, torch.from_numpy((~swap).astype(np.int64)))
     assert torch.equal(a, R.gather_rows(ids, src)) and torch.equal(b, R.gather_rows(mask, src)) and torch.equal(c, R.gather_rows(tt, src))
     assert a.data_ptr() != ids.data_ptr()        # fresh clones (mm_early.py:265-267)
+
+
+# ---------------------------------------------------------------------------------------------------- eval bookkeeping (§8 f-4)
+@pytest.mark.parametrize("C,sizes", [(4, [8, 8, 3]), (2, [5]), (3, [16, 16, 16, 1])])
+def test_eval_loop_live(ns, C, sizes, capsys):
+    """MMLate_Model.eval (mm_late.py:534-638), run unbound on replayed logits, == R.eval_epoch: predictions, labels, mean batch loss."""
+    g = torch.Generator().manual_seed(C + sum(sizes))
+    outs = [torch.randn(B, C, generator=g) for B in sizes]
+    labs = [torch.eye(C)[torch.randint(0, C, (B,), generator=g)] for B in sizes]
+    loss_fn = torch.nn.CrossEntropyLoss(weight=torch.rand(C, generator=g) + 0.5)
+    ref = ref_shims.ref_eval(ns, outs, labs, loss_fn)
+    mine = R.eval_epoch(outs, labs, [loss_fn(o, l) for o, l in zip(outs, labs)])
+    assert torch.equal(ref["predictions"], mine["predictions"]) and torch.equal(ref["labels"], mine["labels"])
+    assert abs(float(ref["loss"]) - mine["loss"]) < 1e-6
+    assert torch.equal(ref["data_id"], torch.arange(sum(sizes)))
+    printed = capsys.readouterr().out          # the reference prints "loss: … acc: …" (mm_late.py:618): pin the accuracy too
+    acc = float(printed.split("acc:")[1].split()[0])
+    assert abs(acc - mine["accuracy"]) < 1e-3
