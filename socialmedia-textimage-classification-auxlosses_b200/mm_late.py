@@ -343,14 +343,19 @@ class MMLate_Model(object):
                 loss.backward()
                 optimizer.step()
                 optimizer.zero_grad()
+            write = epoch % 2 == 0 or epoch == epochs - 1          # mm_late.py:511,523: every 2nd epoch and the last one
             if val_dataloader is not None:
                 r = self.eval(val_dataloader, loss_fn, tim_loss_fn=tim_loss_fn, iadds_loss_fn=iadds_loss_fn)
                 r["epoch"] = epoch
                 res_val.append(r)
+                if val_filename is not None and write:
+                    self._write_metrics(res_val, val_filename)
             if te_dataloader is not None:
                 r = self.eval(te_dataloader, loss_fn, tim_loss_fn=tim_loss_fn, iadds_loss_fn=iadds_loss_fn)
                 r["epoch"] = epoch
                 res_te.append(r)
+                if te_filename is not None and write:
+                    self._write_metrics(res_te, te_filename)
         if model_path is not None:
             torch.save(self.model.state_dict(), model_path)
             logger.info("{} saved".format(model_path))
@@ -363,6 +368,14 @@ class MMLate_Model(object):
             return None, None
         tim_ids, tim_mask, lbl_tim, src = self.prepare_itm_inputs(ids, mask, return_src=True, rng=self.itm_rng)
         return (tim_ids, tim_mask, src), lbl_tim
+
+    def _write_metrics(self, results, filename):
+        """mm_late.py:511-527: one column per epoch (utils.agg_metrics_val over config.metric_names) -> CSV."""
+        import pandas as pd
+        from .config import metric_names
+        from .eval import agg_metrics_val
+        pd.DataFrame(agg_metrics_val(results, metric_names, self.num_labels)).to_csv(filename, index=False)
+        logger.info("{} saved!".format(filename))
 
     def eval(self, dataloader, loss_fn, tim_loss_fn=None, iadds_loss_fn=None):
         """mm_late.py:534-638 — returns {data_id, loss, predictions, labels}.  Predictions, targets, the loss sum and the

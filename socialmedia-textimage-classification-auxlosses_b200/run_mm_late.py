@@ -41,6 +41,9 @@ def build_parser():
     parser.add_argument("--load_saved_model", action="store_true", help="load saved model")
     parser.add_argument("--save_preds", action="store_true", help="eval test")
     parser.add_argument("--use_saved_features", action="store_true", help="use preprocessed features")
+    # not in the reference: where the ITM coin flips / picks are drawn.  "numpy" replays the reference's global numpy stream
+    # (seed-exact with the reference CLI); "device" draws and applies them on the GPU in one kernel
+    parser.add_argument("--itm_rng", type=str, choices=["numpy", "device"], default="numpy", help="ITM sampling stream")
     return parser
 
 
@@ -51,6 +54,33 @@ def output_names(args, cfg, results_dir):
                                                  args.seed, cfg.loss_str, nsamples_str)
     model_path = results_dir + stem + "net.pth" if (args.save_model or args.load_saved_model) else None
     return model_path, results_dir + stem + "metrics_val.csv", results_dir + stem + "metrics_test.csv"
+
+
+def aux_names(args, cfg, results_dir):
+    """run_mm_late.py:124-126,148-162,178-187: prediction / metric files of --save_preds, --eval_txt_test, --load_saved_model."""
+    nsamples_str = "" if args.nsamples == -1 else "N" + str(args.nsamples) + "_"
+    stem = results_dir + "{}-{}-{}_task{}_seed{}_{}_{}".format(args.txt_model_name, args.img_model_name, args.fusion_name,
+                                                                  args.task, args.seed, cfg.loss_str, nsamples_str)
+    return {"preds": stem + "preds.csv", "preds_txt": stem + "preds_txt.csv", "metrics_txt": stem + "metrics_txt.csv",
+            "preds_lm": stem + "preds_lm.csv", "metrics_lm": stem + "metrics_lm.csv"}
+
+
+def save_predictions(predictions, filename):
+    """run_mm_late.py:119-123: data_id / label / prediction columns."""
+    import pandas as pd
+    pd.DataFrame(data={"data_id": predictions["data_id"].tolist(), "label": predictions["labels"].tolist(),
+                       "prediction": predictions["predictions"].tolist()}).to_csv(filename, index=False)
+    logger.info("{} saved".format(filename))
+
+
+def save_metrics(predictions, num_labels, filename):
+    """run_mm_late.py:141-152,179-187: utils.compute_metrics -> CSV (the confusion matrix and the six scores are computed on the
+    device).  The reference passes `multilabel=` to a function whose keyword is `multi_label` and raises on the
+    --load_saved_model path; the call here is the intended one."""
+    import pandas as pd
+    from .utils import compute_metrics
+    pd.DataFrame(compute_metrics(predictions, num_labels)).to_csv(filename, index=False)
+    logger.info("{} saved".format(filename))
 
 
 def main(argv=None):
@@ -70,7 +100,8 @@ def main(argv=None):
                                                args.testing, args.use_clip_loss, args.use_tim_loss, args.beta_itc,
                                                args.beta_itm, args.nsamples, args.seed))
     cfg = Config(args)
-    mm_model = MMLate_Model(cfg, args.txt_model_name, args.img_model_name, args.fusion_name, multilabel=cfg.multilabel)
+    mm_model = MMLate_Model(cfg, args.txt_model_name, args.img_model_name, args.fusion_name, multilabel=cfg.multilabel,
+                            itm_rng=args.itm_rng)
     train_loader, val_loader, test_loader, weight, txt_te_loader = mm_model.load_data(
         cfg.data, cfg.img_fmt, testing=args.testing, nsamples=args.nsamples, saved_features=args.use_saved_features,
         task_name=cfg.task_name, eval_txt_test=args.eval_txt_test)
@@ -82,10 +113,21 @@ def main(argv=None):
         logger.info("Training")
         mm_model.train(train_loader, val_loader, args.epochs, loss_fn, cfg.lr, cfg.weight_decay, tim_loss_fn=tim_loss_fn,
                        te_dataloader=test_loader, model_path=model_path, val_filename=val_filename, te_filename=te_filename)
-    else:
+        names = aux_names(args, cfg, results_dir)
+        if args.save_preds:                                       # run_mm_late.py:117-127
+            save_predictions(mm_model.eval(test_loader, loss_fn, tim_loss_fn=tim_loss_fn), names["preds"])
+        if args.eval_txt_test and txt_te_loader is not None:      # run_mm_late.py:128-153
+            logger.info("Evaluate and compute metrics (txt test)")
+            predictions = mm_model.eval(txt_te_loader, loss_fn, tim_loss_fn=tim_loss_fn)
+            save_predictions(predictions, names["preds_txt"])
+            save_metrics(predictions, cfg.num_labels, names["metrics_txt"])
+    else:                                                         # run_mm_late.py:156-187
         mm_model.load_saved_model(model_path)
-        logger.info("Evaluate (test)")
-        mm_model.eval(test_loader, loss_fn, tim_loss_fn=tim_loss_fn)
+        logger.info("Evaluate and compute metrics (test)")
+        names = aux_names(args, cfg, results_dir)
+        predictions = mm_model.eval(test_loader, loss_fn, tim_loss_fn=tim_loss_fn)
+        save_predictions(predictions, names["preds_lm"])
+        save_metrics(predictions, cfg.num_labels, names["metrics_lm"])
     logger.info("Done!")
 
 
