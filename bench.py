@@ -7,7 +7,8 @@ A "step" is one pass of the hot path (forward, losses, backward) over one batch 
 Workloads (BASELINE.json `configs`):
   c2  (default, configs[1]) BERT-base + ViT-B/16 late concat fusion + ITC + ITM, batch 256 per GPU, E=768, P=512, bf16
   c3  ITC only, synthetic d=768 embeddings, 4096 rows per GPU against the global batch (32k at 8 GPUs)
-  c4  attention fusion (128 text tokens x 197 patches) + ITC + ITM, batch 4096 per GPU
+  c4  attention fusion (128 text tokens x 197 patches) + ITC + ITM with similarity-weighted HARD-NEGATIVE mining,
+      batch 4096 per GPU (configs[3])
   itc:<B>x<d>  ITC only sweep point (c5)
 One JSON line is printed by rank 0 (see the task contract for the keys).
 """
@@ -52,8 +53,9 @@ def workload_spec(name, world):
         return dict(workload="c2: concat fusion + ITC + ITM, B=256/GPU, E=768, P=512, C=4", B=256, E=E, P=512, C=4,
                     fusion="concat", use_itc=True, use_itm=True, Lt=128, Lv=197)
     if name == "c4":
-        return dict(workload="c4: attention fusion (128x197 tokens) + ITC + ITM, B=4096/GPU, E=768, P=512, C=4", B=4096, E=E,
-                    P=512, C=4, fusion="attention", use_itc=True, use_itm=True, Lt=128, Lv=197)
+        return dict(workload="c4: attention fusion (128x197 tokens) + ITC + ITM with hard-negative mining (similarity-weighted "
+                             "multinomial sampling from the ITC tiles + pair gather), B=4096/GPU, E=768, P=512, C=4", B=4096,
+                    E=E, P=512, C=4, fusion="attention", use_itc=True, use_itm=True, Lt=128, Lv=197, itm_mode="hard")
     if name == "c3":
         return dict(workload="c3: ITC only, d=768, 4096 rows/GPU vs global batch", B=4096, E=E, P=None, d=768, C=4, fusion=None,
                     use_itc=True, use_itm=False, Lt=0, Lv=0)
@@ -188,23 +190,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
-def cpu_reference_run(spec, steps, warmup, budget_s, threads=None):
+def cpu_reference_run(spec, steps, warmup, budget_s, threads=None, world=1, min_timed_s=2.0):
     """The reference's CPU implementation of the path (oracle restatement of models/mm_late.py + utils.clip_loss, pinned
-    against the unmodified reference), fp32, all host threads.  Returns (samples/s, ms/step, sample description)."""
+    against the unmodified reference), fp32, all host threads, on the GLOBAL batch of the GPU arm (B per GPU x world: ITC
+    is O(B^2), so a per-GPU batch would be a different problem).  At least max(warmup, 10) untimed steps, then at least
+    `steps` timed steps AND `min_timed_s` seconds, all within `budget_s`.  Returns (samples/s, ms/step, sample, threads)."""
     from oracle import restatement as R
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    B = spec["B"]
-    note = "full batch B=%d" % B
+    B_full = spec["B"] * world
+    B = B_full
+    note = "full global batch B=%d" % B
     if spec["fusion"] is None and B > 8192:
         B = 8192
-        note = "B=8192 of %d rows (ITC is O(B^2): throughput at the full size is lower)" % spec["B"]
+        note = "B=8192 of %d rows (ITC is O(B^2): CPU throughput at the full size is LOWER than this sample's)" % B_full
     if spec["fusion"] == "attention" and B > 256:
         B = 256
-        note = "B=256 of %d samples (attention fusion is per-sample; ITC part is O(B^2))" % spec["B"]
+        note = "B=256 of %d samples (attention fusion is per-sample; the ITC part is O(B^2): throughput at the full size is lower)" % B_full
+    if spec["fusion"] == "concat" and B > 2048:
+        B = 2048
+        note = "B=2048 of %d samples" % B_full
     s2 = dict(spec, B=B)
     inp = make_inputs(s2)
     inp = {k: (v.to(torch.bfloat16).float() if k in BF16_KEYS else v) for k, v in inp.items()}
+    hard = spec.get("itm_mode") == "hard"
     if spec["fusion"] is None:
         ls = torch.tensor(2.6592, requires_grad=True)
 
@@ -216,7 +225,8 @@ def cpu_reference_run(spec, steps, warmup, budget_s, threads=None):
             return float(loss.detach())
     else:
         p = {k: v.clone().requires_grad_(True) for k, v in R.init_params(spec["C"], seed=40).items()}
-        lbl, src = R.itm_sample_uniform(inp["u_coin"].numpy(), inp["u_pick"].numpy())
+        u_coin, u_pick = inp["u_coin"].numpy(), inp["u_pick"].numpy()
+        lbl, src = R.itm_sample_uniform(u_coin, u_pick)
         base = dict(inp)
         if spec["fusion"] == "attention":
             base["x_t"] = inp["x_t"].expand(B, 1, spec["E"])  # literal reference attention needs all Lt rows; use collapse
@@ -225,26 +235,40 @@ def cpu_reference_run(spec, steps, warmup, budget_s, threads=None):
             cur = dict(base)
             cur["x_t"] = base["x_t"].clone().requires_grad_(True)
             cur["t_pool"] = base["t_pool"].clone().requires_grad_(True)
-            # mm_late.py:389-414 host loop + row copies are part of the path
-            tim_ids, tim_mask, _ = R.prepare_itm_inputs_stream(inp["ids"], inp["mask"], np.random.RandomState(0))
-            cur["lbl_tim"], cur["src_idx"] = torch.from_numpy(lbl), torch.from_numpy(src)
+            if hard:   # similarity-weighted negatives: sample from this step's logits (oracle spec), then gather ids / mask
+                with torch.no_grad():
+                    S = R.itc_logits(R.project(cur["t_pool"], p["dual_encoder.text_projection.weight"]),
+                                     R.project(base["v_pool"], p["dual_encoder.visual_projection.weight"]),
+                                     p["dual_encoder.logit_scale"])
+                l_, s_ = R.itm_sample_hard(S.numpy(), u_coin, u_pick, ref=float(np.float32(math.exp(2.6592))))
+                idx = torch.from_numpy(s_)
+                _tim = (inp["ids"][idx].clone(), inp["mask"][idx].clone())
+                cur["lbl_tim"], cur["src_idx"] = torch.from_numpy(l_), idx
+            else:      # mm_late.py:389-414 host loop + row copies are part of the path
+                R.prepare_itm_inputs_stream(inp["ids"], inp["mask"], np.random.RandomState(0))
+                cur["lbl_tim"], cur["src_idx"] = torch.from_numpy(lbl), torch.from_numpy(src)
             for v in p.values():
                 v.grad = None
             out = R.head_step(cur, p, fusion_name=spec["fusion"], use_itc=True, use_itm=spec["use_itm"])
             out["loss"].backward()
             return float(out["loss"].detach())
-    for _ in range(max(1, min(warmup, 2))):
-        step()
-    times = []
     t_begin = time.perf_counter()
-    for _ in range(steps):
+    n_warm = 0
+    while n_warm < max(warmup, 10) and (n_warm < 2 or time.perf_counter() - t_begin < 0.25 * budget_s):
+        step()
+        n_warm += 1
+    times = []
+    t_timed = time.perf_counter()
+    while True:
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_begin > budget_s:
+        el = time.perf_counter() - t_timed
+        if (len(times) >= steps and el >= min_timed_s) or time.perf_counter() - t_begin > budget_s:
             break
     ms = 1e3 * float(np.median(times))
-    return B / (ms / 1e3), ms, "%s, %d timed steps, fp32 torch CPU" % (note, len(times)), threads
+    return B / (ms / 1e3), ms, "%s, %d warm-up + %d timed steps (%.1f s), median, fp32 torch CPU" % (
+        note, n_warm, len(times), sum(times)), threads
 
 
 # ------------------------------------------------------------------------------------------------ stdout hygiene
@@ -290,7 +314,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        val, ms, sample, threads = cpu_reference_run(spec, max(args.steps, 3), args.warmup, 150.0)
+        val, ms, sample, threads = cpu_reference_run(spec, max(args.steps, 3), args.warmup, 150.0, world=world)
         line = dict(base, impl="reference", value=val, ms_per_step=ms, dtype="f32", gpu_launches=0,
                     cpu_baseline={"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
                     e2e={"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
@@ -324,18 +348,26 @@ def main():
                             use_itm=spec["use_itm"], Lv=spec["Lv"], device=dev)
     else:
         plan = P.HeadPlan(B, E=spec["E"], P=spec["P"], C=spec["C"], fusion=spec["fusion"], use_itc=spec["use_itc"],
-                          use_itm=spec["use_itm"], Lv=max(spec["Lv"], 1), device=dev)
+                          use_itm=spec["use_itm"], Lv=max(spec["Lv"], 1), device=dev, itm_mode=spec.get("itm_mode", "uniform"))
         if spec["P"] is None:
             plan.itc = P.ItcPlan(B, B, spec["d"], dev)
+            plan.itc.scale_dev = plan.scale_t
             plan.Pe = spec["d"]
             plan.out["d_t_emb"] = torch.empty(B, spec["d"], device=dev)
             plan.out["d_v_emb"] = torch.empty(B, spec["d"], device=dev)
-    plan.set_weights(synthetic_params(spec["C"], seed=40))
+    # fp32 MASTER weights resident on the device; the step itself (first node of the captured graph) refreshes the bf16
+    # working copies and exp(logit_scale) from them, so the timed step is a training step's forward+backward, not a step on
+    # pre-cast constants.  (Multi-GPU plans take a snapshot: set_weights.)
+    master = {k: v.to(dev) for k, v in synthetic_params(spec["C"], seed=40).items()}
+    if world == 1:
+        plan.bind_params(master, live=True)
+    else:
+        plan.set_weights(master)
 
     # ---- count launches of one step (kernels per C-ABI call are fixed)
     KPC = {"tic_itc_lse_loss": 2, "tic_heads_fwd_bwd": 1, "tic_ce_bidir_fwd": 2, "tic_gemm_rowss_parts": 0,
            "tic_itc_row_parts": 0, "tic_itc_col_parts": 0}
-    KPC.update({"tic_peer_alloc": 0, "tic_peer_export": 0, "tic_peer_open": 0, "tic_peer_close": 0})
+    KPC.update({"tic_peer_alloc": 0, "tic_peer_export": 0, "tic_peer_open": 0, "tic_peer_close": 0, "tic_gemm_plan": 0})
     counter = {"n": 0}
 
     def hook(name):
@@ -465,8 +497,18 @@ def main():
             e2e_ms, e2e_mode = pipe_ms, "pipelined, 2 slots: H2D of step k+1 overlaps step k; 160 MiB L2 flush inside the timed region"
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- the drop-in API itself (c2, one GPU): MM_Model.head() -> the reference's loss code -> loss.backward()
+    dropin = None
+    if world == 1 and args.workload == "c2":
+        dropin = dropin_leg(spec, host, dev, master, flush, args.steps)
+    # ---- multi-GPU: the global ITC loss of the peer-memory step against an NCCL all-gather + plain torch fp32 evaluation
+    check = global_loss_check(plan, dist, dev, n_global) if (world > 1 and spec["use_itc"]) else None
+
     # ---- per-kernel timing of the dominant kernels (live, CUDA events on the launching stream, L2 flushed)
     roof, kernels = kernel_rooflines(P, plan, spec, dev_in, n_global, flush)
+    if world > 1 and hasattr(plan, "pg"):
+        kernels += exchange_points(plan, flush)
+    hbm_points = hbm_kernel_points(P, dev, flush) if world == 1 else None
     # the default workload (B=256) is launch-latency-bound: also time the same ITC kernels where a roofline applies
     at_scale = None
     if world == 1 and spec["B"] < 4096 and spec["use_itc"] and not args.no_scale_point:
@@ -484,7 +526,15 @@ def main():
     line = dict(base, value=value, ms_per_step=ms_per_step, dtype="bf16", gpu_launches=launches_per_step * args.steps,
                 clocks=clk, e2e={"value": n_global / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
                                  "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes,
-                                 "loss": loss_host, "mode": e2e_mode, "sync_ms_per_step": e2e_sync_ms})
+                                 "loss": loss_host, "mode": e2e_mode, "sync_ms_per_step": e2e_sync_ms,
+                                 "returns": "the 4 loss scalars only (mix, cls, itc, itm): gradients and outputs stay on the "
+                                            "device for a device-side optimiser"})
+    if dropin is not None:
+        line["e2e_dropin"] = dropin
+    if check is not None:
+        line["global_loss_check"] = check
+    if hbm_points is not None:
+        line["kernels_hbm_4096"] = [finalize_roofline(k, peaks) for k in hbm_points]
     line["config"].update({"l2": "flushed between timed steps (256 MiB write)", "cuda_graph": bool(use_graph),
                            "launches_per_step": launches_per_step, "loss": float(plan.out["loss"][0])})
     line["roofline"] = finalize_roofline(roof, peaks)
@@ -494,7 +544,8 @@ def main():
                                      "step": finalize_roofline(at_scale["step"], peaks),
                                      "kernels": [finalize_roofline(k, peaks) for k in at_scale["kernels"]]}
     if not args.no_cpu_baseline:
-        val, ms, sample, threads = cpu_reference_run(spec, 1000, 1, args.cpu_seconds)
+        val, ms, sample, threads = cpu_reference_run(spec, 20, 10, args.cpu_seconds + 8.0, world=world,
+                                                     min_timed_s=args.cpu_seconds)
         line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
                                 "ms_per_step": ms}
     out.emit(json.dumps(line))
@@ -505,6 +556,11 @@ def main():
 def finalize_roofline(r, peaks):
     if r is None:
         return None
+    if r["bound"] == "nvlink":
+        out = dict(r)
+        out.update(peak=900.0, frac=r["achieved"] / 900.0, peak_source="NVLink 5 via NVSwitch: 900 GB/s per direction per GPU (nominal)",
+                   traffic=None, traffic_source=None)
+        return out
     if r["bound"] == "tensor":
         peak = peaks.get("bf16_tflops", 1590.0)
         src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if "bf16_tflops" in peaks else "fallback 1590"
@@ -576,6 +632,21 @@ def kernel_rooflines(P, plan, spec, dev_in, n_global, flush):
         ks.append(dict(kernel="tic_gemm_bf16 x2 (dT = GA*V, dV = GBT*T)", bound="tensor", ms=ms,
                        achieved=4.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="4*B^2*d FLOP",
                        traffic_key="gemm_dtdv_" + shp))
+    if spec["use_itc"] and getattr(plan, "itc_mode", None) == "rowblock":
+        # multi-GPU row block (this rank's m = B rows against the n_global gathered columns): the rank-local tensor kernels
+        blk, T, V_all = plan.rb, plan.Y[:B], plan.V_all
+        d, ldt, ldv = blk.P, plan.Y.stride(0), plan.V_all.stride(0)
+        shp = "%dx%dx%d" % (B, n_global, d)
+        ms = time_kernel(lambda: blk.fwd_tiles(T, ldt, V_all, ldv, plan.scale), flush)
+        ks.append(dict(kernel="tic_itc_fwd row block %s (per rank)" % shp, bound="tensor", ms=ms,
+                       achieved=2.0 * B * n_global * d / ms * 1e-9, unit="TFLOP/s", algorithmic="2*m*N*d FLOP per rank"))
+        ms = time_kernel(lambda: blk.bwd_operands(T, ldt, V_all, ldv, plan.scale, 1.0 / (2 * n_global)), flush)
+        ks.append(dict(kernel="tic_itc_bwd_g row block %s (per rank)" % shp, bound="tensor", ms=ms,
+                       achieved=2.0 * B * n_global * d / ms * 1e-9, unit="TFLOP/s",
+                       algorithmic="recompute: 2*m*N*d executed FLOP per rank, 0 algorithmic (reported as executed)"))
+        ms = time_kernel(lambda: (blk.grad_gemm_t(V_all, ldv), blk.grad_gemm_v(T, ldt)), flush)
+        ks.append(dict(kernel="tic_gemm_bf16 x2 row block %s (dT_r = GA*V_all, dV contributions = GA^T*That_r)" % shp, bound="tensor",
+                       ms=ms, achieved=4.0 * B * n_global * d / ms * 1e-9, unit="TFLOP/s", algorithmic="4*m*N*d FLOP per rank"))
     if spec["fusion"] == "attention":
         x_v = dev_in["x_v"]
         R_, Lv, Ea = plan.R, spec["Lv"], E + 8
@@ -604,6 +675,179 @@ def kernel_rooflines(P, plan, spec, dev_in, n_global, flush):
         return None, []
     dom = max(ks, key=lambda k: k["ms"])
     return dom, ks
+
+
+def dropin_leg(spec, host, dev, master, flush, steps):
+    """The reference-facing API timed the way the reference's loop drives it (models/mm_late.py:459-490): HOST encoder outputs
+    -> device -> MM_Model.head() (autograd Function over the HeadPlan) -> nn.CrossEntropyLoss / clip_loss / ITM CE ->
+    loss.backward() -> loss.item().  No CUDA graph, torch's autograd and allocator in the loop: this is what a user who only
+    swaps the import gets; `value` / `e2e` are what the fused plan API gets."""
+    import torch.nn as nn
+    from tic_b200.mm_late import MM_Model
+    from tic_b200.utils import clip_loss
+    B, E, C = spec["B"], spec["E"], spec["C"]
+
+    class _Stub(nn.Module):   # the three non-tower parameters of the HF dual encoder (the towers are outside this path)
+        def __init__(self):
+            super().__init__()
+            self.visual_projection = nn.Linear(E, spec["P"], bias=False)
+            self.text_projection = nn.Linear(E, spec["P"], bias=False)
+            self.logit_scale = nn.Parameter(torch.tensor(2.6592))
+
+    model = MM_Model(C, "bert", "vit", 0.0, fusion_name=spec["fusion"], dual_encoder=_Stub())
+    sd = model.state_dict()
+    for k, v in master.items():
+        if k in sd:
+            sd[k].copy_(v)
+    model = model.to(dev).train()
+    loss_fn, tim_loss_fn = nn.CrossEntropyLoss(), nn.CrossEntropyLoss()
+    pinned = {k: v.to(torch.bfloat16 if k in BF16_KEYS else v.dtype).pin_memory() for k, v in host.items()
+              if k in ("x_t", "x_v", "t_pool", "v_pool", "y_soft", "u_coin", "u_pick")}
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+
+    def step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        x_t = d["x_t"].float().requires_grad_(True)
+        t_pool = d["t_pool"].float().requires_grad_(True)
+        lbl = (d["u_coin"] >= 0.5).long()                         # uniform rule on the device (no host loop)
+        k = torch.clamp((d["u_pick"] * (B - 1)).floor().long(), max=B - 2)
+        i = torch.arange(B, device=dev)
+        src = torch.where(lbl == 1, i, torch.where(k < i, k, k + 1)).to(torch.int32)
+        model.zero_grad(set_to_none=True)
+        out_cls, logits, out_tim, _ = model.head(x_t, d["x_v"].float(), t_pool, d["v_pool"].float(), tim_src=src)
+        loss = 0.8 * loss_fn(out_cls, d["y_soft"]) + 0.1 * clip_loss(logits) + 0.1 * tim_loss_fn(out_tim, lbl)
+        loss.backward()
+        return float(loss.item())
+
+    for _ in range(5):
+        loss = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    n = max(steps, 10)
+    for kk in range(n):
+        flush.fill_(float(kk))
+        torch.cuda.synchronize()
+        e0.record()
+        loss = step()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / n
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "loss": loss, "api": "tic_b200.mm_late.MM_Model.head() + nn.CrossEntropyLoss / tic_b200.utils.clip_loss + "
+                                 "loss.backward() (eager autograd, no CUDA graph; mm_late.py:459-490)"}
+
+
+def global_loss_check(plan, dist, dev, n_global):
+    """SCALE correctness: the ITC loss of the multi-GPU step (own peer-memory kernels) against NCCL all_gather of the ranks'
+    projected embeddings + a plain torch fp32 (TF32 off) clip_loss on the global matrix, row-chunked.  Raises on > 1e-3."""
+    b = plan.B
+    Yt = plan.Y[:b].float() + (plan.Y_lo[:b].float() if getattr(plan, "has_lo", False) else 0)
+    Yv = plan.Y[b:].float() + (plan.Y_lo[b:].float() if getattr(plan, "has_lo", False) else 0)
+    world = dist.get_world_size()
+    Ta = [torch.empty_like(Yt) for _ in range(world)]
+    Va = [torch.empty_like(Yv) for _ in range(world)]
+    dist.all_gather(Ta, Yt.contiguous())
+    dist.all_gather(Va, Yv.contiguous())
+    T, V = torch.cat(Ta), torch.cat(Va)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        Tn, Vn = torch.nn.functional.normalize(T, dim=1), torch.nn.functional.normalize(V, dim=1)
+        s = float(plan.scale)
+        N = T.shape[0]
+        diag = s * (Tn * Vn).sum(1)
+        lse_r = torch.empty(N, device=dev)
+        col_m = torch.full((N,), -float("inf"), device=dev)
+        col_s = torch.zeros(N, device=dev)
+        for i in range(0, N, 4096):
+            S = s * Tn[i:i + 4096] @ Vn.t()
+            lse_r[i:i + 4096] = torch.logsumexp(S, 1)
+            m = torch.maximum(col_m, S.max(0).values)
+            col_s = col_s * torch.exp(col_m - m) + torch.exp(S - m).sum(0)
+            col_m = m
+        ref = float(0.5 * ((lse_r - diag).mean() + (col_m + torch.log(col_s) - diag).mean()))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    got = float(plan.global_loss()[2]) if hasattr(plan, "global_loss") else float("nan")
+    rel = abs(got - ref) / max(abs(ref), 1e-12)
+    out = {"itc_loss_global": got, "itc_loss_nccl_allgather_torch_fp32": ref, "rel_err": rel, "tolerance": 1e-3,
+           "n_global": n_global}
+    if not rel < 1e-3:
+        raise SystemExit("multi-GPU ITC loss differs from the all-gathered fp32 evaluation: %r" % out)
+    return out
+
+
+def exchange_points(plan, flush):
+    """Peer-exchange kernels timed alone (all ranks call in lock step): barrier + pull over NVLink; achieved = bytes this
+    rank pulls from REMOTE peers / time (the local segment is an HBM copy)."""
+    pg = plan.pg
+    ks = []
+    for name, ph in pg._phases.items():
+        n, so, nb, dst, ds, _keep = ph
+        remote = sum(int(nb[i]) for i in range(n)) * (pg.world - 1)
+        ms = time_kernel(lambda: pg.exchange(name), flush, iters=10)
+        ks.append(dict(kernel="tic_peer_exchange[%s] (system-scope flag barrier + pull of %d range(s) from %d peers)" % (name, n, pg.world - 1),
+                       bound="nvlink", ms=ms, achieved=remote / ms * 1e-6 if remote else 0.0, unit="GB/s",
+                       algorithmic="%d bytes pulled from remote peers per rank" % remote))
+    return ks
+
+
+def hbm_kernel_points(P, dev, flush, B=4096, Lt=128):
+    """The HBM-bound kernels north_star names, at the c4 batch size (4096), timed alone (CUDA events, L2 flushed):
+    materialised clip_loss forward/backward (models/utils.py:225-231; BASELINE.md target 12*B^2 bytes -> 31 us) and the ITM
+    sampler + pair gather (mm_late.py:389-414: ids and mask rows, int64 x 128 tokens)."""
+    st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    g = torch.Generator().manual_seed(7)
+    S = (torch.randn(B, B, generator=g) * 3).to(dev)
+    dS = torch.empty_like(S)
+    lse_r, lse_c = torch.empty(B, device=dev), torch.empty(B, device=dev)
+    loss, gl = torch.zeros(1, device=dev), torch.ones(1, device=dev)
+    ws = torch.empty(int(P.capi.load().tic_ce_bidir_workspace_bytes(B)), dtype=torch.uint8, device=dev)
+    ks = []
+    ms_f = time_kernel(lambda: P.call("tic_ce_bidir_fwd", S.data_ptr(), B, B, lse_r.data_ptr(), lse_c.data_ptr(), loss.data_ptr(),
+                                      ws.data_ptr(), st()), flush)
+    ks.append(dict(kernel="tic_ce_bidir_fwd (materialised clip_loss: one read of S)", bound="hbm", ms=ms_f,
+                   achieved=4.0 * B * B / ms_f * 1e-6, unit="GB/s", algorithmic="4*B^2 bytes (S read once)", traffic_key="ce_fwd_%d" % B))
+    ms_b = time_kernel(lambda: P.call("tic_ce_bidir_bwd", S.data_ptr(), B, B, lse_r.data_ptr(), lse_c.data_ptr(), gl.data_ptr(),
+                                      dS.data_ptr(), B, st()), flush)
+    ks.append(dict(kernel="tic_ce_bidir_bwd (one read of S, one write of dS)", bound="hbm", ms=ms_b,
+                   achieved=8.0 * B * B / ms_b * 1e-6, unit="GB/s", algorithmic="8*B^2 bytes", traffic_key="ce_bwd_%d" % B,
+                   fwd_plus_bwd_us=(ms_f + ms_b) * 1e3, baseline_md_target_us_for_12B2_bytes=12.0 * B * B / 6455.6e9 * 1e6))
+    ids = torch.randint(0, 30000, (B, Lt), generator=g).to(dev)
+    mask = torch.ones(B, Lt, dtype=torch.int64, device=dev)
+    t_ids, t_mask = torch.empty_like(ids), torch.empty_like(mask)
+    uc, up = torch.rand(B, generator=g).to(dev), torch.rand(B, generator=g).to(dev)
+    lbl, src = torch.empty(B, dtype=torch.int64, device=dev), torch.empty(B, dtype=torch.int32, device=dev)
+    rb = Lt * 8
+    ms = time_kernel(lambda: P.call("tic_itm_sample_gather", uc.data_ptr(), up.data_ptr(), B, 0, None, 0, 0.0, None, ids.data_ptr(),
+                                    mask.data_ptr(), rb, t_ids.data_ptr(), t_mask.data_ptr(), lbl.data_ptr(), src.data_ptr(), st()),
+                     flush)
+    ks.append(dict(kernel="tic_itm_sample_gather (uniform rule + gather of ids and mask, one launch)", bound="hbm", ms=ms,
+                   achieved=4.0 * B * rb / ms * 1e-6, unit="GB/s", algorithmic="2 row sets x (read + write) x B x 1024 bytes",
+                   traffic_key="itm_sample_gather_%d" % B))
+    ms = time_kernel(lambda: P.call("tic_gather_rows", ids.data_ptr(), rb, t_ids.data_ptr(), rb, rb, src.data_ptr(), B, st()), flush)
+    ks.append(dict(kernel="tic_gather_rows (one row set, 1024-byte rows)", bound="hbm", ms=ms, achieved=2.0 * B * rb / ms * 1e-6,
+                   unit="GB/s", algorithmic="(read + write) x B x 1024 bytes", traffic_key="gather_rows_%d" % B))
+    # hard-negative sampler, tile-stream form, P=512: weight sums ride on the forward tiles; locate; pick tiles
+    d = 512
+    T = torch.randn(B, d, generator=g).to(torch.bfloat16).to(dev)
+    V = (torch.randn(B, d, generator=g) + 0.3 * T.float().cpu()).to(torch.bfloat16).to(dev)
+    sc = math.exp(2.6592)
+    it0, it1 = P.ItcPlan(B, B, d, dev), P.ItcPlan(B, B, d, dev, hard=True)
+    for it in (it0, it1):
+        it.norms(T, d, V, d)
+    ms0 = time_kernel(lambda: it0.fwd_tiles(T, d, V, d, sc), flush)
+    ms1 = time_kernel(lambda: it1.fwd_tiles(T, d, V, d, sc), flush)
+    msl = time_kernel(lambda: it1.hard_locate(uc, up, lbl, src), flush)
+    msp = time_kernel(lambda: it1.hard_pick(T, d, V, d, sc, src), flush)
+    ks.append(dict(kernel="hard-negative sampler, tile-stream form (weight sums in tic_itc_fwd + tic_itm_hard_locate + tic_itc_pick)",
+                   bound="hbm", ms=(ms1 - ms0) + msl + msp, achieved=(2.0 * B * it1.nrp * 8 + 20.0 * B) / ((ms1 - ms0) + msl + msp) * 1e-6,
+                   unit="GB/s", algorithmic="8 bytes per (row, part) written + read, 20 bytes per row; S itself never reaches HBM",
+                   fwd_tiles_plain_us=ms0 * 1e3, fwd_tiles_with_weight_sums_us=ms1 * 1e3, locate_us=msl * 1e3, pick_tiles_us=msp * 1e3,
+                   materialised_alternative_bytes=8.0 * B * B))
+    return ks
 
 
 def scale_point(P, dev, flush, B=16384, d=768):

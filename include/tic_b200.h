@@ -77,7 +77,8 @@ int tic_gemm_bf16_rowss(const void* A, const void* A_lo, int64_t lda, int a_mn_m
  * number of operands passed as (hi, lo) pairs.  Cluster split-K is opt-in: TIC_CLUSTER_K=<CTA budget> enables it (measured: its
  * fixed cost only pays from K >= ~2560 on, beyond the GEMMs of this path; see profiles/r01_cluster_splitk.md). */
 int tic_gemm_plan(int M, int N, int K, int n_split_operands, int accumulate, int* tile_n, int* ksplit, int* cluster_k);
-/* Reference-quality SIMT fp32-accumulate GEMM with the same semantics (debug / self-test only). */
+/* TEST-ONLY: reference-quality SIMT fp32-accumulate GEMM with the same semantics.  Called by csrc/selftest.cu and the GPU
+ * tests as the in-library cross-check of the tcgen05 path; no product code path calls it. */
 int tic_gemm_bf16_simt(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
                        int64_t ldd, int d_dtype, int M, int N, int K, float alpha, const float* bias, int relu,
                        void* stream);
@@ -106,7 +107,24 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
                 int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
                 float* col_part /* NULL: skip the column statistics (symmetric multi-GPU mode) */, float* diag,
                 float* logits_out, int64_t ld_logits, const float* ss_t_part, int n_ss_t, const float* ss_v_part, int n_ss_v,
-                const uint32_t* seg_ready, const uint32_t* seg_epoch, int seg_cols, int my_seg, void* stream);
+                const uint32_t* seg_ready, const uint32_t* seg_epoch, int seg_cols, int my_seg,
+                const float* scale_dev /* optional DEVICE scalar exp(logit_scale): overrides scale and shift */,
+                void* qpart /* optional uint64 [tic_itc_row_parts(n_global)][m_local]: hard-negative weight sums, see below */,
+                void* stream);
+/* Trainable temperature: logit_scale is a parameter of the reference model (mm_late.py:59-69 keeps it trainable; HF :272
+ * applies exp()).  Every ITC entry point takes `scale_dev`, a DEVICE pointer to exp(logit_scale) (written by
+ * tic_refresh_weights at the head of the step); when it is non-NULL it replaces the host `scale` / `shift` arguments, so
+ * a step captured into a CUDA graph follows the optimiser's updates of logit_scale without re-capture.
+ * Hard-negative sampling without a materialised S (a-5', tile-stream form; spec oracle/restatement.py:itm_sample_hard with
+ * ref = shift): with `qpart` the forward tiles also write, per row and per column part (part p = the columns the row
+ * partial row_part[p] covers), the integer sum of q_ij = trunc(det_exp(min(S_ij - shift, 0)) * 2^40), j != positive.
+ * tic_itm_hard_locate turns these sums and the row's uniform into (part, residual target); tic_itc_pick recomputes the
+ * tiles (bit-identical accumulators: same operands, shapes and k order) and walks the located part:
+ * src = first column whose running weight exceeds the residual.  Traffic: 8 bytes per (row, part) instead of 4*B bytes per row. */
+int tic_itc_pick(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv, const float* rinv_t,
+                 const float* rinv_v, int m_local, int n_global, int P, int row_offset, float scale, float shift,
+                 const float* scale_dev, const int32_t* loc_part, const void* loc_res /* uint64 [m_local] */,
+                 int32_t* src_idx /* only located rows are written */, void* stream);
 /* Consuming a gathered V as it lands (multi-GPU): seg_ready (NULL = V is complete) points at n_global/seg_cols device
  * words; segment p (columns [p*seg_cols, (p+1)*seg_cols), written by a tic_peer_pull running beside this kernel) may be
  * read once seg_ready[p] >= *seg_epoch.  Tiles are visited segment-major starting with my_seg (always ready); if seg_cols is
@@ -122,7 +140,7 @@ int tic_reduce_parts(const float* part, int nparts, int n, float* out, void* str
  * partials with tic_reduce_parts, all-reduce(SUM) the result across ranks, then call this with n_col_parts = 1. */
 int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, const float* diag,
                      int m_local, int n_global, int row_offset, float shift, float* lse_row, float* lse_col,
-                     float* loss_sums, void* stream);
+                     float* loss_sums, const float* scale_dev /* optional: shift = *scale_dev */, void* stream);
 /* Symmetric (peer-memory) multi-GPU mode: rank r runs tic_itc_fwd twice — on its row block S[rows_r, :] and, with the
  * operands swapped, on S^T[cols_r, :] (col_part = NULL in both) — so BOTH softmax directions are complete row statistics on
  * the rank that owns them and no cross-rank reduction exists.  This call turns the two sets of row partials into
@@ -131,7 +149,7 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
  * workspace: tic_itc_lse_rows_workspace_bytes(m) bytes, zero-initialised once (self-resetting). utils.py:225-231. */
 int64_t tic_itc_lse_rows_workspace_bytes(int m);
 int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift, float* lse_a,
-                     float* lse_b, float* loss_sums, void* workspace, void* stream);
+                     float* lse_b, float* loss_sums, void* workspace, const float* scale_dev, void* stream);
 /* Recompute S tiles and emit the bf16 gradient operands (g = dLoss/d(clip_loss), B = n_global):
  *   Gp[i,j] = g/(2B) * (exp(S-lse_row[i]) + exp(S-lse_col[j]))      (the -I/B diagonal is applied in fp32 later)
  *   GA [m_local, ld_ga ] row-major:  Gp[i,j] * rinv_v[j]            (A operand of dT = GA * V)
@@ -144,7 +162,7 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale,
                   float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo /* optional residuals */,
                   void* GBT_lo, const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, float shift,
-                  void* stream);
+                  const float* scale_dev, void* stream);
 /* Inline statistics (small batches): when row_part / col_part (the partials written by tic_itc_fwd) are given, the kernel
  * derives lse_row / lse_col = shift + log(sum of partials) itself (same expression as tic_itc_lse_loss) and the matching
  * lse pointer may be NULL — tic_itc_lse_loss then only produces the loss and runs beside the backward, not before it. */
@@ -162,7 +180,7 @@ int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const
                           float diag_coef, float* dX_f32, int64_t ld_df, void* dX_bf16, void* dX_bf16_lo, int64_t ld_db,
                           float* r_sum /* [1], atomically accumulated */,
                           int acc_div_rinv /* 1: acc rows carry an extra factor rinv[row] (GA-shared mode, see tic_itc_bwd_g) */,
-                          void* stream);
+                          const float* scale_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ clip_loss on a given matrix
  * utils.py:225-231 on a materialised similarity S [B,B] fp32: loss = (CE(S, I) + CE(S^T, I)) / 2.
@@ -177,18 +195,27 @@ int tic_ce_bidir_bwd(const float* S, int64_t lds, int B, const float* lse_row, c
 /* ------------------------------------------------------------------------------------------------ ITM sampling + gather
  * mm_late.py:389-414 (prepare_itm_inputs).  Row i is swapped iff u_coin[i] < 0.5 (label 0), else kept (label 1);
  * B == 1 keeps everything.  Uniform mode: k = min(floor(u_pick[i]*(B-1)), B-2), src = k < i ? k : k+1.
- * Hard mode: src ~ Multinomial(w), w[j] = exp(S[i,j]-max_j S[i,:]) for j != i, by inverse CDF on fixed-point
- * (2^30) weights with a bit-reproducible exp (see oracle/restatement.py: det_exp_f32).
+ * Hard mode (extension named by BASELINE.json only): src ~ Multinomial(w), w[j] = exp(S[i,j] - ref) for j != i with a FIXED
+ * reference ref >= max S (hard_ref, or *hard_ref_dev when given: the step passes exp(logit_scale)), by inverse CDF on
+ * fixed-point (2^40) weights with a bit-reproducible exp (oracle/restatement.py: det_exp_f32, itm_sample_hard).  This
+ * entry point is the materialised-S form (S = logits_per_text of the drop-in API); the fused step uses the tile-stream
+ * form (tic_itc_fwd(qpart) -> tic_itm_hard_locate -> tic_itc_pick), which computes the same indices without S in memory.
  * Gathers nrowsets row-major byte matrices: dst_k[i,:] = src_k[src[i],:]  (ids, mask; any row_bytes).
  * labels int64 [B], src_idx int32 [B]. */
-int tic_itm_sample(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds,
-                   int64_t* labels, int32_t* src_idx, void* stream);
+int tic_itm_sample(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds, float hard_ref,
+                   const float* hard_ref_dev, int64_t* labels, int32_t* src_idx, void* stream);
+/* Middle step of the tile-stream form: per row, label (as above, with the row's global index row_offset + i), default
+ * source (the row itself, or the uniform pick when every weight is zero), the part p with
+ * sum_{p' < p} qpart[p'][i] <= target < sum_{p' <= p} qpart[p'][i] and the residual target - sum_{p' < p} (uint64);
+ * loc_part = -1 for rows with nothing to pick.  target = floor(trunc(u_pick * 2^24) * total / 2^24). */
+int tic_itm_hard_locate(const float* u_coin, const float* u_pick, int m_local, int n_global, int row_offset, const void* qpart,
+                        int n_parts, int64_t* labels, int32_t* src_idx, int32_t* loc_part, void* loc_res, void* stream);
 int tic_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int64_t row_bytes,
                     const int32_t* src_idx, int rows, void* stream);
 /* Fused: sample + gather of ids and mask in one launch (the mm_late.py:396-409 loop). */
-int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds,
-                          const void* ids, const void* mask, int64_t row_bytes, void* tim_ids, void* tim_mask,
-                          int64_t* labels, int32_t* src_idx, void* stream);
+int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds, float hard_ref,
+                          const float* hard_ref_dev, const void* ids, const void* mask, int64_t row_bytes, void* tim_ids,
+                          void* tim_mask, int64_t* labels, int32_t* src_idx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ fusion heads
  * Pack the CLS rows for linear_fusion (torch.cat at mm_late.py:94,111,141):
@@ -285,6 +312,13 @@ int tic_eval_accumulate(const float* logits, int64_t ldl, const float* y_soft, i
 int tic_metrics_from_confusion(const void* state, int C, float* out6, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ utilities */
+/* Head of a captured TRAINING step: refresh the bf16 working copies of up to 8 fp32 master weight matrices (the optimiser
+ * updates the masters in place between replays; models/utils.py:280-292 selects them) and scale_out[0] = exp(*logit_scale)
+ * (HF :272; values outside (0, 40] are clamped to 40 and *status = 1, sticky) in ONE launch.  The *_host arrays are HOST
+ * arrays of n entries; matrix i is [rows, cols] fp32 with leading dimension lds[i], written as bf16 with ldd[i]. */
+int tic_refresh_weights(int n, const float* const* src_host, void* const* dst_host, const int64_t* lds_host,
+                        const int64_t* ldd_host, const int* rows_host, const int* cols_host, const float* logit_scale,
+                        float* scale_out, uint32_t* status, void* stream);
 int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream);
 int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream);
 /* dst[r, c] (+)= column sums etc. are done by GEMMs; bias gradient: db[n] = sum_m dY[m,n] (bf16 in, fp32 out). */

@@ -244,12 +244,27 @@ def det_exp_f32(x: np.ndarray) -> np.ndarray:
     return np.ldexp(y, n.astype(np.int32)).astype(np.float32)
 
 
-def itm_sample_hard(S: np.ndarray, u_coin: np.ndarray, u_pick: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+HARD_FIXED_POINT_BITS = 40
+
+
+def hard_qweights(row: np.ndarray, ref, i: int) -> np.ndarray:
+    """Fixed-point weights of one similarity row: q_j = trunc(det_exp(min(S[i,j] - ref, 0)) * 2^40), q_i = 0 (uint64)."""
+    x = np.minimum(np.asarray(row, dtype=np.float32) - np.float32(ref), np.float32(0.0)).astype(np.float32)
+    q = (det_exp_f32(x) * np.float32(2.0 ** HARD_FIXED_POINT_BITS)).astype(np.uint64)
+    q[i] = 0
+    return q
+
+
+def itm_sample_hard(S: np.ndarray, u_coin: np.ndarray, u_pick: np.ndarray, ref=None) -> Tuple[np.ndarray, np.ndarray]:
     """Similarity-weighted hard-negative sampling (extension; ALBEF convention: weights = softmax(S[i,:]) with the
-    positive zeroed), made order-independent by fixed-point weights:
-        q_j = trunc(det_exp(S[i,j] - max_j S[i,:]) * 2^30), q_i = 0;  total = sum q
+    positive zeroed), made order-independent by fixed-point weights against a FIXED reference `ref` >= max S (the
+    product passes exp(logit_scale), the upper bound of the logits and the shift of its softmax statistics; default here:
+    the fp32 maximum of S), so that the weights of a row can be summed tile by tile, in any order, without knowing the
+    row maximum first:
+        q_j = trunc(det_exp(min(S[i,j] - ref, 0)) * 2^40) (uint64), q_i = 0;  total = sum_j q_j
         U = trunc(u_pick * 2^24); target = U*(total>>24) + ((U*(total & (2^24-1))) >> 24)   (= floor(U*total / 2^24))
-        src = first j with inclusive-cumsum(q)_j > target.   total == 0 falls back to the uniform rule."""
+        src = first j with inclusive-cumsum(q)_j > target.   total == 0 falls back to the uniform rule.
+    Rows are swapped iff u_coin < 0.5 exactly as in the uniform rule (mm_late.py:396-399)."""
     S = np.asarray(S, dtype=np.float32)
     u_coin = np.asarray(u_coin, dtype=np.float32)
     u_pick = np.asarray(u_pick, dtype=np.float32)
@@ -257,25 +272,25 @@ def itm_sample_hard(S: np.ndarray, u_coin: np.ndarray, u_pick: np.ndarray) -> Tu
     labels_u, src_u = itm_sample_uniform(u_coin, u_pick)
     if B <= 1:
         return labels_u, src_u
+    ref = np.float32(S.max()) if ref is None else np.float32(ref)
     src = src_u.copy()
     for i in np.nonzero(labels_u == 0)[0]:
-        row = S[i]
-        w = det_exp_f32(row - row.max())
-        q = (w * np.float32(2.0 ** 30)).astype(np.uint64)
-        q[i] = 0
-        total = int(q.sum())
+        q = hard_qweights(S[i], ref, int(i))
+        total = int(q.sum(dtype=np.uint64))
         if total == 0:
             continue
         U = int(np.float32(u_pick[i]) * np.float32(16777216.0))
         target = U * (total >> 24) + ((U * (total & 0xFFFFFF)) >> 24)
-        c = np.cumsum(q)
-        src[i] = int(np.searchsorted(c, target, side="right"))
+        c = np.cumsum(q, dtype=np.uint64)
+        src[i] = int(np.searchsorted(c, np.uint64(target), side="right"))
     return labels_u, src
 
 
 def gather_rows(x, src):
     """mm_late.py:403-404 as one gather: out[i] = x[src[i]]."""
-    return x[torch.as_tensor(np.asarray(src), dtype=torch.long)]
+    if torch.is_tensor(src):
+        return x[src.to(device=x.device, dtype=torch.long)]
+    return x[torch.as_tensor(np.asarray(src), dtype=torch.long, device=x.device)]
 
 
 # ---------------------------------------------------------------------------------------------------- full head

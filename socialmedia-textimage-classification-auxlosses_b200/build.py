@@ -51,9 +51,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
             if verbose and out.strip():
                 print(out)
-        _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+        # the SHARED CUDA runtime (libcudart.so.12: torch's copy when torch is already loaded, else the toolkit's through the
+        # rpath): the library carries no private runtime instance and none of the static runtime's symbol strings
+        _run([nvcc, "-shared", "-cudart", "shared", "-o", LIB] + objs +
+             ["-Xlinker", "-rpath,/usr/local/cuda/lib64", "-ldl", "-lrt", "-lpthread"])
         _run([nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "selftest.cu"), "-o", SELFTEST, "-L" + OUT, "-ltic_b200",
-                                    "-Xlinker", "-rpath," + "$ORIGIN"])
+                                    "-cudart", "shared", "-Xlinker", "-rpath," + "$ORIGIN", "-Xlinker", "-rpath,/usr/local/cuda/lib64"])
     return LIB
 
 

@@ -28,11 +28,12 @@ _SIGS = {
     "tic_row_rnorm_bf16": ("ppliipplp", ctypes.c_int),
     "tic_itc_row_parts": ("i", ctypes.c_int),
     "tic_itc_col_parts": ("i", ctypes.c_int),
-    "tic_itc_fwd": ("pplpplppiiiiffpppplpipippiip", ctypes.c_int),
+    "tic_itc_fwd": ("pplpplppiiiiffpppplpipippiippp", ctypes.c_int),
+    "tic_itc_pick": ("pplpplppiiiiffppppp", ctypes.c_int),
     "tic_reduce_parts": ("piipp", ctypes.c_int),
-    "tic_itc_lse_loss": ("pipipiiifpppp", ctypes.c_int),
+    "tic_itc_lse_loss": ("pipipiiifppppp", ctypes.c_int),
     "tic_itc_lse_rows_workspace_bytes": ("i", ctypes.c_int64),
-    "tic_itc_lse_rows": ("ppiipfppppp", ctypes.c_int),
+    "tic_itc_lse_rows": ("ppiipfpppppp", ctypes.c_int),
     "tic_peer_handle_bytes": ("", ctypes.c_int),
     "tic_peer_alloc": ("lp", ctypes.c_int),
     "tic_peer_free": ("p", ctypes.c_int),
@@ -41,15 +42,16 @@ _SIGS = {
     "tic_peer_close": ("p", ctypes.c_int),
     "tic_peer_exchange": ("piilpippppp", ctypes.c_int),
     "tic_peer_pull": ("piipppippppip", ctypes.c_int),
-    "tic_itc_bwd_g": ("pplpplppppiiiffplplpppipifp", ctypes.c_int),
+    "tic_itc_bwd_g": ("pplpplppppiiiffplplpppipifpp", ctypes.c_int),
     "tic_itc_ds_operands": ("pliipppplpplp", ctypes.c_int),
-    "tic_itc_grad_finalize": ("plpplppplpiiffplpplpip", ctypes.c_int),
+    "tic_itc_grad_finalize": ("plpplppplpiiffplpplpipp", ctypes.c_int),
     "tic_ce_bidir_workspace_bytes": ("i", ctypes.c_int64),
     "tic_ce_bidir_fwd": ("plippppp", ctypes.c_int),
     "tic_ce_bidir_bwd": ("plipppplp", ctypes.c_int),
-    "tic_itm_sample": ("ppiiplppp", ctypes.c_int),
+    "tic_itm_sample": ("ppiiplfpppp", ctypes.c_int),
+    "tic_itm_hard_locate": ("ppiiipippppp", ctypes.c_int),
     "tic_gather_rows": ("plpllpip", ctypes.c_int),
-    "tic_itm_sample_gather": ("ppiiplpplppppp", ctypes.c_int),
+    "tic_itm_sample_gather": ("ppiiplfppplppppp", ctypes.c_int),
     "tic_pack_cls_pairs": ("plpliipplppp", ctypes.c_int),
     "tic_unpack_cls_grad": ("plpliipplp", ctypes.c_int),
     "tic_heads_fwd_bwd": ("pliiiippppppppfffppppplplppppippp", ctypes.c_int),
@@ -60,6 +62,7 @@ _SIGS = {
     "tic_aspect_bwd": ("plpliippplpplplppp", ctypes.c_int),
     "tic_gmu_gate_fwd": ("plppliipplp", ctypes.c_int),
     "tic_gmu_gate_bwd": ("plpplpliipppplplp", ctypes.c_int),
+    "tic_refresh_weights": ("ipppppppppp", ctypes.c_int),
     "tic_cast_f32_to_bf16": ("plpliip", ctypes.c_int),
     "tic_cast_bf16_to_f32": ("plpliip", ctypes.c_int),
     "tic_colsum_bf16": ("pliipp", ctypes.c_int),

@@ -314,6 +314,58 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, int64_t lds, _
   const int64_t r = idx / cols, c = idx % cols;
   d[r * ldd + c] = __float2bfloat16_rn(s[r * lds + c]);
 }
+// Multi-tensor weight refresh: up to kMaxRefresh fp32 master matrices -> their bf16 working copies in ONE launch
+// (blockIdx.y = matrix; 4 elements per thread when the row geometry allows 16-byte loads), plus scale = exp(logit_scale)
+// by thread 0.  This is the first node of a captured training step: the optimiser updates the fp32 parameters in place,
+// the next replay of the same graph sees them (and the trainable logit_scale, models/mm_late.py:59-69) through this kernel.
+constexpr int kMaxRefresh = 8;
+struct RefreshDesc {
+  const float* src;
+  __nv_bfloat16* dst;
+  int64_t lds, ldd;
+  int rows, cols;
+};
+struct RefreshArgs {
+  RefreshDesc d[kMaxRefresh];
+  int n;
+  const float* logit_scale;   // optional device scalar (dual_encoder.logit_scale)
+  float* scale_out;           // [1] exp(logit_scale), clamped to (0, 40]
+  uint32_t* status;           // [1] sticky: 1 if logit_scale left the supported range (exp > 40 or not finite)
+};
+__global__ void __launch_bounds__(256) refresh_weights_kernel(RefreshArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && a.logit_scale != nullptr) {
+    float sc = expf(*a.logit_scale);
+    if (!(sc > 0.f) || !(sc <= 40.f)) {   // fixed-shift softmax statistics need exp(-2*scale) to stay normal in fp32
+      if (a.status) *a.status = 1u;
+      sc = 40.f;
+    }
+    *a.scale_out = sc;
+  }
+  if (static_cast<int>(blockIdx.y) >= a.n) return;
+  const RefreshDesc d = a.d[blockIdx.y];
+  const bool vec = (d.cols & 3) == 0 && (d.lds & 3) == 0 && (d.ldd & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(d.dst) & 7) == 0);
+  if (vec) {
+    const int64_t n4 = static_cast<int64_t>(d.rows) * (d.cols >> 2);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t r = i / (d.cols >> 2), c = (i - r * (d.cols >> 2)) << 2;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(d.src + r * d.lds + c));
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(d.dst + r * d.ldd + c) = u;
+    }
+  } else {
+    const int64_t n = static_cast<int64_t>(d.rows) * d.cols;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t r = i / d.cols, c = i - r * d.cols;
+      d.dst[r * d.ldd + c] = __float2bfloat16_rn(d.src[r * d.lds + c]);
+    }
+  }
+}
+
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, int64_t lds, float* __restrict__ d, int64_t ldd,
                                      int rows, int cols) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
@@ -439,6 +491,33 @@ int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, 
   launch_k(cast_bf16_f32_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(src), lds, dst, ldd, rows, cols);
   TIC_CHECK_LAUNCH("tic_cast_bf16_to_f32");
+  return TIC_OK;
+}
+
+int tic_refresh_weights(int n, const float* const* src_host, void* const* dst_host, const int64_t* lds_host, const int64_t* ldd_host,
+                        const int* rows_host, const int* cols_host, const float* logit_scale, float* scale_out, uint32_t* status,
+                        void* stream) {
+  TIC_CHECK_ARG(n >= 0 && n <= kMaxRefresh, "tic_refresh_weights: at most %d matrices per call", kMaxRefresh);
+  TIC_CHECK_ARG(n > 0 || logit_scale, "tic_refresh_weights: nothing to do");
+  TIC_CHECK_ARG(!logit_scale || scale_out, "tic_refresh_weights: scale_out is NULL");
+  RefreshArgs a{};
+  a.n = n;
+  a.logit_scale = logit_scale;
+  a.scale_out = scale_out;
+  a.status = status;
+  int64_t most = 1;
+  for (int i = 0; i < n; ++i) {
+    TIC_CHECK_ARG(src_host[i] && dst_host[i] && rows_host[i] > 0 && cols_host[i] > 0, "tic_refresh_weights: bad matrix %d", i);
+    a.d[i] = RefreshDesc{src_host[i], static_cast<__nv_bfloat16*>(dst_host[i]), lds_host[i], ldd_host[i], rows_host[i], cols_host[i]};
+    const int64_t e = static_cast<int64_t>(rows_host[i]) * cols_host[i];
+    if (e > most) most = e;
+  }
+  // ~2 vectors per thread for the largest matrix; smaller matrices leave their surplus blocks idle (they exit at once)
+  int gx = static_cast<int>((most / 4 + 511) / 512);
+  if (gx < 1) gx = 1;
+  if (gx > 592) gx = 592;
+  launch_k(refresh_weights_kernel, dim3(gx, n > 0 ? n : 1), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
+  TIC_CHECK_LAUNCH("tic_refresh_weights");
   return TIC_OK;
 }
 

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "tic_umma.cuh"
+#include "itm_rule.cuh"
 
 namespace tic {
 
@@ -99,12 +100,16 @@ struct ItcFwdEpi {
     float scale_log2e;   // scale * log2(e)
     float shift_log2e;   // shift * log2(e)
     float scale;
+    float shift;
     float* row_part;     // [n_tiles * nparts][M]
     float* col_part;     // [m_tiles][N]
     float* diag;         // [M]
     float* logits;       // optional [M, ld_logits]
     int64_t ld_logits;
     int row_offset;
+    const float* scale_dev;     // optional DEVICE scalar exp(logit_scale): overrides scale and shift (a trainable logit_scale
+                                // reaches a captured step by pointer, never as a launch-time constant)
+    unsigned long long* qpart;  // optional [n_tiles * nparts][M]: per-part integer sums of the hard-negative sampling weights
   };
   // column norms of this tile -> shared memory, this thread's row norm -> cx.pre[0]; runs while the MMAs of the tile are in flight
   template <int BN>
@@ -140,6 +145,10 @@ struct ItcFwdEpi {
       }
     }
     cx.pre[0] = rt;
+    float sc = p.scale, sh = p.shift;
+    if (p.scale_dev != nullptr) { sc = __ldg(p.scale_dev); sh = sc; }
+    cx.pre[1] = sc;
+    cx.pre[2] = sh;
   }
   template <int BN>
   __device__ static void tile(const Params& p, const EpiCtx& cx) {
@@ -149,8 +158,11 @@ struct ItcFwdEpi {
     const float* sb = reinterpret_cast<const float*>(cx.scratch) + (cx.iter & 1) * BN;   // rinv_v of this tile (prefetch)
     float* scol = reinterpret_cast<float*>(cx.scratch) + 2 * BN;                         // [4 quads][BN] partial column sums
     const float rt = cx.pre[0];
-    const float rt2 = rt * p.scale_log2e;
-    const float negshift = valid_row ? -p.shift_log2e : -INFINITY;
+    const float sc = cx.pre[1], sh = cx.pre[2];                      // scale, shift (host constants or the device scalar)
+    const float scale_log2e = sc * kLog2e, shift_log2e = sh * kLog2e;
+    const float rt2 = rt * scale_log2e;
+    const float negshift = valid_row ? -shift_log2e : -INFINITY;
+    unsigned long long qsum = 0;
     const int gcol = p.row_offset + row;  // column holding this row's positive
     const int cols_per_part = BN / cx.nparts;
     float rowsum = 0.f;
@@ -169,7 +181,7 @@ struct ItcFwdEpi {
       for (int j = 0; j < 32; ++j) v[j] = vn[j];
       if (c + 1 < nchunk && col0 + 32 < cx.N) tmem_ld_32x32(trow + cl + 32, vn);   // prefetch the next 32 columns
       float e[32];
-      if (col0 + 32 <= cx.N && p.logits == nullptr) {
+      if (col0 + 32 <= cx.N && p.logits == nullptr && p.qpart == nullptr) {
         // fast path (interior tile, logits not materialised): 1 FMUL + 1 FFMA + 1 MUFU + 1 FADD per element.
         // invalid rows carry negshift = -inf, so their exp is exactly 0 and they drop out of the column sums.
 #pragma unroll
@@ -188,20 +200,23 @@ struct ItcFwdEpi {
           float dv = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j == gcol) dv = __uint_as_float(v[j]) * rt * sb[cl + j] * p.scale;
+            if (col0 + j == gcol) dv = itc_logit(__uint_as_float(v[j]), rt, sb[cl + j], sc);
           p.diag[row] = dv;
         }
       } else {
-        // generic path: edge tiles (column tail) and materialised logits (drop-in API / hard-negative sampling)
+        // generic path: edge tiles (column tail), materialised logits (drop-in API) and the hard-negative weight sums.
+        // The logit is formed by itc_logit() — the expression the pick tiles repeat bit for bit.
         float dsel = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float cosv = __uint_as_float(v[j]) * rt * sb[cl + j];       // cosine similarity
+          const float cosv = __fmul_rn(__fmul_rn(__uint_as_float(v[j]), rt), sb[cl + j]);   // cosine similarity
+          const float sij = __fmul_rn(cosv, sc);                                            // == itc_logit(...)
           const bool ok = valid_row && (col0 + j < cx.N);
-          e[j] = ok ? exp2f(fmaf(cosv, p.scale_log2e, -p.shift_log2e)) : 0.f;
+          e[j] = ok ? exp2f(fmaf(cosv, scale_log2e, -shift_log2e)) : 0.f;
           rowsum += e[j];
-          if (col0 + j == gcol) dsel = cosv * p.scale;
-          v[j] = __float_as_uint(cosv * p.scale);
+          if (col0 + j == gcol) dsel = sij;
+          else if (p.qpart != nullptr && ok) qsum += hard_qweight(sij, sh);
+          v[j] = __float_as_uint(sij);
         }
         if (valid_row && gcol >= col0 && gcol < col0 + 32) p.diag[row] = dsel;
         if (p.logits != nullptr && valid_row) {
@@ -224,12 +239,86 @@ struct ItcFwdEpi {
       }
     }
     if (valid_row) p.row_part[static_cast<int64_t>(cx.n_blk * cx.nparts + cx.part) * cx.M + row] = rowsum;
+    if (p.qpart != nullptr && valid_row) p.qpart[static_cast<int64_t>(cx.n_blk * cx.nparts + cx.part) * cx.M + row] = qsum;
     if (p.col_part == nullptr) return;
     epi_bar_sync(cx.epi_threads);
     for (int j = cx.epi_tid; j < BN; j += cx.epi_threads)
       if (cx.n0 + j < cx.N)
         p.col_part[static_cast<int64_t>(cx.m_blk) * cx.N + cx.n0 + j] =
             (scol[j] + scol[BN + j]) + (scol[2 * BN + j] + scol[3 * BN + j]);
+  }
+};
+
+// ------------------------------------------------------------------ hard-negative pick epilogue
+// Third step of the tile-stream hard-negative sampler (SURVEY.md a-5', BASELINE north_star "fused hard-negative
+// multinomial-sampling"): the forward tiles summed the integer sampling weights per (row, column part), tic_itm_hard_locate
+// turned each row's uniform into (part, residual target); these tiles recompute S and walk the ONE located part of every
+// mismatch row: src = first column whose running weight sum exceeds the residual.  S never exists in HBM; what the sampler
+// reads instead is 8 bytes per (row, part).  Recomputed accumulators are bit-identical (same operands, same UMMA shapes,
+// same k order), and the logit / weight expressions are the shared itc_logit() / hard_qweight().
+struct ItcPickEpi {
+  struct Params {
+    const float* rinv_t;
+    const float* rinv_v;
+    float scale, shift;
+    const float* scale_dev;
+    int row_offset;
+    const int32_t* loc_part;               // [M] part holding the row's target, -1 = nothing to pick
+    const unsigned long long* loc_res;     // [M] target minus the weight of the parts before it
+    int32_t* src_idx;                      // [M] out (only located rows are written)
+  };
+  template <int BN>
+  __device__ static void prefetch(const Params& p, EpiCtx& cx) {
+    const int lane = threadIdx.x & 31;
+    const int row = cx.m0 + cx.quad * 32 + lane;
+    float* sb = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * BN;
+    for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) sb[j] = (cx.n0 + j < cx.N) ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
+    epi_bar_sync(cx.epi_threads);
+    const bool valid_row = row < cx.M;
+    cx.pre[0] = valid_row ? __ldg(p.rinv_t + row) : 0.f;
+    float sc = p.scale, sh = p.shift;
+    if (p.scale_dev != nullptr) { sc = __ldg(p.scale_dev); sh = sc; }
+    cx.pre[1] = sc;
+    cx.pre[2] = sh;
+    const int lp = valid_row ? __ldg(p.loc_part + row) : -1;
+    cx.pre[3] = __int_as_float(lp);
+    const unsigned long long res = lp >= 0 ? __ldg(p.loc_res + row) : 0ull;
+    cx.pre[4] = __uint_as_float(static_cast<uint32_t>(res));
+    cx.pre[5] = __uint_as_float(static_cast<uint32_t>(res >> 32));
+  }
+  template <int BN>
+  __device__ static void tile(const Params& p, const EpiCtx& cx) {
+    const int lane = threadIdx.x & 31;
+    const int row = cx.m0 + cx.quad * 32 + lane;
+    const int cols_per_part = BN / cx.nparts;
+    const bool mine = __float_as_int(cx.pre[3]) == cx.n_blk * cx.nparts + cx.part;
+    if (!__any_sync(0xffffffffu, mine)) return;          // warp-uniform: no row of this warp has its target in this part
+    const float* sb = reinterpret_cast<const float*>(cx.scratch) + (cx.iter & 1) * BN;
+    const float rt = cx.pre[0], sc = cx.pre[1], sh = cx.pre[2];
+    const unsigned long long res = static_cast<unsigned long long>(__float_as_uint(cx.pre[4])) |
+                                   (static_cast<unsigned long long>(__float_as_uint(cx.pre[5])) << 32);
+    const int gcol = p.row_offset + row;
+    const uint32_t trow = cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16);
+    unsigned long long run = 0;
+    int found = -1;
+#pragma unroll 1
+    for (int c = 0; c < cols_per_part / 32; ++c) {
+      const int cl = cx.part * cols_per_part + c * 32;
+      const int col0 = cx.n0 + cl;
+      if (col0 >= cx.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(trow + cl, v);
+      tmem_ld_wait();
+      if (mine && found < 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < cx.N && col != gcol) run += hard_qweight(itc_logit(__uint_as_float(v[j]), rt, sb[cl + j], sc), sh);
+          if (found < 0 && run > res) found = col;
+        }
+      }
+    }
+    if (mine && found >= 0) p.src_idx[row] = found;
   }
 };
 
@@ -256,6 +345,7 @@ struct ItcBwdEpi {
     float shift_log2e;   // common offset of the factored form below (keeps 2^(lr-off), 2^(off-lc) in fp32 range)
     int factored;        // fast path: ONE ex2 per element (host enables it for scale <= 20)
     int tma_store;       // GA leaves through shared memory + TMA 32x32 tile stores (full lines) instead of 16-byte pieces
+    const float* scale_dev;   // optional DEVICE scalar exp(logit_scale): overrides scale_log2e / shift / shift_log2e / factored
     alignas(64) CUtensorMap tmap_ga;
   };
   // per-column vectors of this tile -> shared memory, this thread's row norm / row lse -> cx.pre[0..1]; runs while the MMAs of
@@ -268,6 +358,13 @@ struct ItcBwdEpi {
     float* sb = reinterpret_cast<float*>(cx.scratch) + (cx.iter & 1) * 3 * BN;  // rinv_v | -lse_col*log2e | gscale*rinv_v
     float* sl = sb + BN;
     float* sg = sb + 2 * BN;
+    float scale_log2e = p.scale_log2e, shift = p.shift, shift_log2e = p.shift_log2e;
+    int factored = p.factored;
+    if (p.scale_dev != nullptr) {
+      const float sc = __ldg(p.scale_dev);
+      scale_log2e = sc * kLog2e; shift = sc; shift_log2e = scale_log2e;
+      factored = p.factored && sc <= 20.f;
+    }
     for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) {
       const bool ok = cx.n0 + j < cx.N;
       const float b = ok ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
@@ -277,14 +374,14 @@ struct ItcBwdEpi {
         if (p.col_part != nullptr) {
           float cs = 0.f;
           for (int q = 0; q < p.n_col_parts; ++q) cs += __ldg(p.col_part + static_cast<int64_t>(q) * cx.N + cx.n0 + j);
-          lc = p.shift + logf(cs);
+          lc = shift + logf(cs);
         } else {
           lc = __ldg(p.lse_col + cx.n0 + j);
         }
       }
       // factored fast path:  e^{S-lse_row} + e^{S-lse_col} = e1 * (1 + Er_i * Ec_j),  e1 = 2^(s2 - lr),
       //   Er_i = 2^(lr - off), Ec_j = 2^(off - lc)  ->  GA = e1 * (g_j + Er_i * (Ec_j g_j)),  g_j = gscale * rinv_v[j]
-      sl[j] = p.factored ? (ok ? exp2f(p.shift_log2e - lc * kLog2e) * b * p.gscale : 0.f) : lc * kLog2e;
+      sl[j] = factored ? (ok ? exp2f(shift_log2e - lc * kLog2e) * b * p.gscale : 0.f) : lc * kLog2e;
       sg[j] = b * p.gscale;
     }
     epi_bar_sync(cx.epi_threads);
@@ -294,13 +391,16 @@ struct ItcBwdEpi {
       if (p.row_part != nullptr) {
         float rs = 0.f;
         for (int q = 0; q < p.n_row_parts; ++q) rs += __ldg(p.row_part + static_cast<int64_t>(q) * cx.M + row);
-        lr = (p.shift + logf(rs)) * kLog2e;
+        lr = (shift + logf(rs)) * kLog2e;
       } else {
         lr = __ldg(p.lse_row + row) * kLog2e;
       }
     }
     cx.pre[0] = rt;
     cx.pre[1] = lr;
+    cx.pre[2] = scale_log2e;
+    cx.pre[3] = shift_log2e;
+    cx.pre[4] = __int_as_float(factored);
   }
   template <int BN>
   __device__ static void tile(const Params& p, const EpiCtx& cx) {
@@ -311,7 +411,9 @@ struct ItcBwdEpi {
     const float* sl = sb + BN;
     const float* sg = sb + 2 * BN;
     const float rt = cx.pre[0], lr = cx.pre[1];
-    const float rt2 = rt * p.scale_log2e;
+    const float scale_log2e = cx.pre[2], shift_log2e = cx.pre[3];
+    const bool factored = __float_as_int(cx.pre[4]) != 0;
+    const float rt2 = rt * scale_log2e;
     const int cols_per_part = BN / cx.nparts;
     const bool vec_ok = (p.ld_ga & 7) == 0;
     const uint32_t trow = cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16);
@@ -329,10 +431,10 @@ struct ItcBwdEpi {
       for (int j = 0; j < 32; ++j) v[j] = vn[j];
       if (c + 1 < nchunk && col0 + 32 < cx.N) tmem_ld_32x32(trow + cl + 32, vn);   // prefetch the next 32 columns
       float ga[32];
-      if (col0 + 32 <= cx.N && p.GBT == nullptr && p.factored) {
+      if (col0 + 32 <= cx.N && p.GBT == nullptr && factored) {
         // fast path (interior tile, no transposed operand): FMUL, FFMA, MUFU, FFMA, FMUL per element — the XU pipe (16 ex2
         // per clock per SM) is what bounds this epilogue, so the second exponential is replaced by the factored form.
-        const float er = valid_row ? exp2f(lr - p.shift_log2e) : 0.f;
+        const float er = valid_row ? exp2f(lr - shift_log2e) : 0.f;
         const float nlr = valid_row ? -lr : -INFINITY;
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -363,9 +465,9 @@ struct ItcBwdEpi {
       __nv_bfloat16* gbt_lo = (p.GBT && p.GBT_lo) ? p.GBT_lo + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float s2 = __uint_as_float(v[j]) * rt * sb[cl + j] * p.scale_log2e;  // S * log2e
-        if (p.factored) {   // (edge tile of the factored mode; GBT is NULL there) sl = Ec_j * g_j, sg = g_j
-          ga[j] = exp2f(s2 - lr) * fmaf(exp2f(lr - p.shift_log2e), sl[cl + j], sg[cl + j]);
+        const float s2 = __uint_as_float(v[j]) * rt * sb[cl + j] * scale_log2e;  // S * log2e
+        if (factored) {   // (edge tile of the factored mode; GBT is NULL there) sl = Ec_j * g_j, sg = g_j
+          ga[j] = exp2f(s2 - lr) * fmaf(exp2f(lr - shift_log2e), sl[cl + j], sg[cl + j]);
           continue;
         }
         const float pr = p.gscale * (exp2f(s2 - lr) + exp2f(s2 - sl[cl + j]));
@@ -497,9 +599,11 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int nparts, 
 
 // Multi-block: fixed-order sum of the per-tile partials -> lse vectors (thread t owns row t and column t).
 __global__ void itc_lse_kernel(const float* __restrict__ row_part, int nrp, const float* __restrict__ col_part, int ncp, int M,
-                               int N, float shift, float* __restrict__ lse_row, float* __restrict__ lse_col) {
+                               int N, float shift, const float* __restrict__ scale_dev, float* __restrict__ lse_row,
+                               float* __restrict__ lse_col) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
+  if (scale_dev != nullptr) shift = __ldg(scale_dev);
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < N) {
     float s = 0.f;
@@ -542,10 +646,12 @@ __global__ void itc_loss_kernel(const float* __restrict__ lse_row, const float* 
 // swapped block S^T[cols_r, :].  blockIdx.y selects the direction; lse = shift + log(sum of the per-tile partials);
 // the loss terms sum_i (lse_i - diag_i) are reduced in a fixed order (block partials, last block adds them up).
 __global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int nparts, int m,
-                                    const float* __restrict__ diag, float shift, float* __restrict__ lse_a,
-                                    float* __restrict__ lse_b, float* __restrict__ loss_sums, float* __restrict__ ws) {
+                                    const float* __restrict__ diag, float shift, const float* __restrict__ scale_dev,
+                                    float* __restrict__ lse_a, float* __restrict__ lse_b, float* __restrict__ loss_sums,
+                                    float* __restrict__ ws) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
+  if (scale_dev != nullptr) shift = __ldg(scale_dev);
   const int dir = blockIdx.y;
   const float* part = dir == 0 ? part_a : part_b;
   float* lse = dir == 0 ? lse_a : lse_b;
@@ -588,9 +694,10 @@ __global__ void itc_grad_finalize_kernel(const float* __restrict__ acc, int64_t 
                                          int64_t ldxo, const float* __restrict__ rinv_o, int rows, int P, float scale,
                                          float diag_coef, float* __restrict__ dXf, int64_t ld_df,
                                          __nv_bfloat16* __restrict__ dXb, __nv_bfloat16* __restrict__ dXb_lo, int64_t ld_db,
-                                         float* __restrict__ r_sum, int acc_div_rinv) {
+                                         float* __restrict__ r_sum, int acc_div_rinv, const float* __restrict__ scale_dev) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
+  if (scale_dev != nullptr) scale = __ldg(scale_dev);
   const int warp_in_blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp_in_blk;
   __shared__ float sblk[32];
@@ -658,9 +765,11 @@ itc_grad_finalize_vec_kernel(const float* __restrict__ acc, int64_t ld_acc, cons
                              const __nv_bfloat16* __restrict__ Xo, const __nv_bfloat16* __restrict__ Xo_lo, int64_t ldxo,
                              const float* __restrict__ rinv_o, int rows, int P, float scale, float diag_coef,
                              float* __restrict__ dXf, int64_t ld_df, __nv_bfloat16* __restrict__ dXb,
-                             __nv_bfloat16* __restrict__ dXb_lo, int64_t ld_db, float* __restrict__ r_sum, int acc_div_rinv) {
+                             __nv_bfloat16* __restrict__ dXb_lo, int64_t ld_db, float* __restrict__ r_sum, int acc_div_rinv,
+                             const float* __restrict__ scale_dev) {
   pdl_trigger();
   pdl_wait();
+  if (scale_dev != nullptr) scale = __ldg(scale_dev);
   constexpr int MAXC = 4;
   const int warp_in_blk = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp_in_blk;
@@ -793,17 +902,18 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
                 int m_local, int n_global, int P, int row_offset, float scale, float shift, float* row_part,
                 float* col_part, float* diag, float* logits_out, int64_t ld_logits, const float* ss_t_part, int n_ss_t,
                 const float* ss_v_part, int n_ss_v, const uint32_t* seg_ready, const uint32_t* seg_epoch, int seg_cols,
-                int my_seg, void* stream) {
+                int my_seg, const float* scale_dev, void* qpart, void* stream) {
   TIC_CHECK_ARG(T && V && rinv_t && rinv_v && row_part && diag, "tic_itc_fwd: null pointer");
   TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_fwd: empty problem");
   TIC_CHECK_ARG(row_offset >= 0 && row_offset + m_local <= n_global, "tic_itc_fwd: row block outside the global batch");
-  if (!(scale > 0.f) || scale > 40.f || shift < scale) {
+  if (scale_dev == nullptr && (!(scale > 0.f) || scale > 40.f || shift < scale)) {
     set_error("tic_itc_fwd: scale=%g shift=%g outside the supported range (0 < scale <= 40, shift >= scale)", scale, shift);
     return TIC_E_RANGE;
   }
   TIC_CHECK_ARG((!ss_t_part || n_ss_t > 0) && (!ss_v_part || n_ss_v > 0), "tic_itc_fwd: empty sum-of-squares partial list");
-  ItcFwdEpi::Params ep{rinv_t, rinv_v, ss_t_part, ss_v_part, n_ss_t, n_ss_v, scale * kLog2e, shift * kLog2e, scale, row_part, col_part, diag, logits_out, ld_logits,
-                       row_offset};
+  ItcFwdEpi::Params ep{rinv_t, rinv_v, ss_t_part, ss_v_part, n_ss_t, n_ss_v, scale * kLog2e, shift * kLog2e, scale, shift,
+                       row_part, col_part, diag, logits_out, ld_logits, row_offset, scale_dev,
+                       static_cast<unsigned long long*>(qpart)};
   const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
   // V arriving segment by segment (peer pull running beside this kernel): tiles go segment-major, local segment first
   SegOrder so{nullptr, nullptr, 0, 0, 0};
@@ -820,10 +930,10 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
            : itc_bn(n_global) == kItcBN
                ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
                                                                                 P, ep, static_cast<cudaStream_t>(stream), 1, 0, sop)
-               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, sop) == 4
+               : (qpart == nullptr && itc_small_kc(m_local, n_global, P, T_lo, V_lo, sop) == 4)   // (pick tiles recompute without KC)
                    ? launch_umma_gemm_kc<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi, 4>(
                          T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, static_cast<cudaStream_t>(stream))
-               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, sop) == 2
+               : (qpart == nullptr && itc_small_kc(m_local, n_global, P, T_lo, V_lo, sop) == 2)
                    ? launch_umma_gemm_kc<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi, 2>(
                          T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, static_cast<cudaStream_t>(stream))
                    : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcFwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
@@ -831,6 +941,26 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
                                                                                          static_cast<cudaStream_t>(stream), 1, 0, sop);
   if (rc == -3) { set_error("tic_itc_fwd: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_fwd: launch failed"); return TIC_E_LAUNCH; }
+  return rc;
+}
+
+int tic_itc_pick(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv, const float* rinv_t,
+                 const float* rinv_v, int m_local, int n_global, int P, int row_offset, float scale, float shift,
+                 const float* scale_dev, const int32_t* loc_part, const void* loc_res, int32_t* src_idx, void* stream) {
+  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && loc_part && loc_res && src_idx, "tic_itc_pick: null pointer");
+  TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_pick: empty problem");
+  ItcPickEpi::Params ep{rinv_t, rinv_v, scale, shift, scale_dev, row_offset, loc_part,
+                        static_cast<const unsigned long long*>(loc_res), src_idx};
+  // the SAME tile shapes as tic_itc_fwd picks for this problem: the recomputed accumulators must be bit-identical
+  const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcPickEpi>(T, ldt, V, ldv, m_local, n_global, P, ep, st)
+           : itc_bn(n_global) == kItcBN
+               ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcPickEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, st, 1)
+               : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcPickEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep,
+                                                                                     st, 1);
+  if (rc == -3) { set_error("tic_itc_pick: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
+  if (rc == -4) { set_error("tic_itc_pick: launch failed"); return TIC_E_LAUNCH; }
   return rc;
 }
 
@@ -843,13 +973,13 @@ int tic_reduce_parts(const float* part, int nparts, int n, float* out, void* str
 
 int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, const float* diag,
                      int m_local, int n_global, int row_offset, float shift, float* lse_row, float* lse_col,
-                     float* loss_sums, void* stream) {
+                     float* loss_sums, const float* scale_dev, void* stream) {
   TIC_CHECK_ARG(row_part && col_part && diag && lse_row && lse_col && loss_sums && n_row_parts > 0 && n_col_parts > 0,
                 "tic_itc_lse_loss: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int mx = m_local > n_global ? m_local : n_global;
   launch_k(itc_lse_kernel, dim3(ceil_div(mx, 256)), dim3(256), 0, st, row_part, n_row_parts, col_part, n_col_parts, m_local, n_global, shift,
-                                                     lse_row, lse_col);
+           scale_dev, lse_row, lse_col);
   launch_k(itc_loss_kernel, dim3(1), dim3(1024), 0, st, lse_row, lse_col, diag, m_local, row_offset, loss_sums);
   TIC_CHECK_LAUNCH("tic_itc_lse_loss");
   return TIC_OK;
@@ -858,12 +988,12 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
 int64_t tic_itc_lse_rows_workspace_bytes(int m) { return static_cast<int64_t>(2 + 2 * ceil_div(m, 256)) * 4; }
 
 int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift, float* lse_a,
-                     float* lse_b, float* loss_sums, void* workspace, void* stream) {
+                     float* lse_b, float* loss_sums, void* workspace, const float* scale_dev, void* stream) {
   TIC_CHECK_ARG(part_a && part_b && diag && lse_a && lse_b && loss_sums && workspace && n_parts > 0 && m > 0,
                 "tic_itc_lse_rows: bad arguments");
   dim3 grid(ceil_div(m, 256), 2);
-  launch_k(itc_lse_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), part_a, part_b, n_parts, m, diag, shift, lse_a, lse_b,
-                                                                          loss_sums, static_cast<float*>(workspace));
+  launch_k(itc_lse_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), part_a, part_b, n_parts, m, diag, shift,
+           scale_dev, lse_a, lse_b, loss_sums, static_cast<float*>(workspace));
   TIC_CHECK_LAUNCH("tic_itc_lse_rows");
   return TIC_OK;
 }
@@ -872,7 +1002,7 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
                   const float* rinv_t, const float* rinv_v,
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale, float gscale,
                   void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo, void* GBT_lo, const float* row_part,
-                  int n_row_parts, const float* col_part, int n_col_parts, float shift, void* stream) {
+                  int n_row_parts, const float* col_part, int n_col_parts, float shift, const float* scale_dev, void* stream) {
   TIC_CHECK_ARG(T && V && rinv_t && rinv_v && GA, "tic_itc_bwd_g: null pointer");
   TIC_CHECK_ARG((lse_row || (row_part && n_row_parts > 0)) && (lse_col || (col_part && n_col_parts > 0)),
                 "tic_itc_bwd_g: need lse_row/lse_col or the forward partials");
@@ -880,7 +1010,7 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
   ItcBwdEpi::Params ep{rinv_t, rinv_v, lse_row, lse_col, scale * kLog2e, gscale, static_cast<__nv_bfloat16*>(GA), ld_ga,
                        static_cast<__nv_bfloat16*>(GBT), ld_gbt, static_cast<__nv_bfloat16*>(GA_lo),
                        static_cast<__nv_bfloat16*>(GBT_lo), row_part, col_part, n_row_parts, n_col_parts, shift,
-                       scale * kLog2e, (scale <= 20.f && GBT == nullptr) ? 1 : 0, 0, {}};
+                       scale * kLog2e, ((scale_dev != nullptr || scale <= 20.f) && GBT == nullptr) ? 1 : 0, 0, scale_dev, {}};
   if (GA_lo == nullptr && GBT == nullptr && (ld_ga & 7) == 0 && aligned16(GA) && itc_tma_store()) {
     int trc = make_tmap_bf16_store32(&ep.tmap_ga, GA, static_cast<uint64_t>(n_global), static_cast<uint64_t>(m_local),
                                      static_cast<uint64_t>(ld_ga));
@@ -910,7 +1040,7 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
 int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const void* X_lo, int64_t ldx, const float* rinv,
                           const void* Xo, const void* Xo_lo, int64_t ldxo, const float* rinv_o, int rows, int P, float scale, float diag_coef, float* dX_f32,
                           int64_t ld_df, void* dX_bf16, void* dX_bf16_lo, int64_t ld_db, float* r_sum, int acc_div_rinv,
-                          void* stream) {
+                          const float* scale_dev, void* stream) {
   TIC_CHECK_ARG(acc && X && rinv && rows > 0 && P > 0, "tic_itc_grad_finalize: bad arguments");
   TIC_CHECK_ARG(dX_f32 || dX_bf16, "tic_itc_grad_finalize: no output requested");
   const bool vec = (P & 7) == 0 && P <= 1024 && (ld_acc & 3) == 0 && (ldx & 7) == 0 && (ldxo & 7) == 0 && (ld_df & 3) == 0 &&
@@ -922,7 +1052,7 @@ int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const
       acc, ld_acc, static_cast<const __nv_bfloat16*>(X), static_cast<const __nv_bfloat16*>(X_lo), ldx, rinv,
       static_cast<const __nv_bfloat16*>(Xo), static_cast<const __nv_bfloat16*>(Xo_lo), ldxo, rinv_o,
       rows, P, scale, diag_coef, dX_f32, ld_df, static_cast<__nv_bfloat16*>(dX_bf16), static_cast<__nv_bfloat16*>(dX_bf16_lo), ld_db,
-      r_sum, acc_div_rinv);
+      r_sum, acc_div_rinv, scale_dev);
   TIC_CHECK_LAUNCH("tic_itc_grad_finalize");
   return TIC_OK;
 }

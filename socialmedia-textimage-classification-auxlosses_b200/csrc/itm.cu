@@ -12,22 +12,6 @@
 
 namespace tic {
 
-__device__ __forceinline__ float det_exp(float x) {
-  // mirrored op-for-op by oracle/restatement.py:det_exp_f32 — no FMA contraction, no library transcendental
-  x = fmaxf(x, -80.0f);
-  const float n = rintf(__fmul_rn(x, 1.44269504088896341f));
-  float r = __fsub_rn(x, __fmul_rn(n, 0.693359375f));
-  r = __fsub_rn(r, __fmul_rn(n, -2.12194440e-4f));
-  float p = 1.9875691500e-4f;
-  p = __fadd_rn(__fmul_rn(p, r), 1.3981999507e-3f);
-  p = __fadd_rn(__fmul_rn(p, r), 8.3334519073e-3f);
-  p = __fadd_rn(__fmul_rn(p, r), 4.1665795894e-2f);
-  p = __fadd_rn(__fmul_rn(p, r), 1.6666665459e-1f);
-  p = __fadd_rn(__fmul_rn(p, r), 5.0000001201e-1f);
-  const float y = __fadd_rn(__fadd_rn(__fmul_rn(p, __fmul_rn(r, r)), r), 1.0f);
-  return __int_as_float(__float_as_int(y) + (static_cast<int>(n) << 23));  // exact scaling by 2^n (result stays normal)
-}
-
 __global__ void itm_sample_uniform_kernel(const float* __restrict__ u_coin, const float* __restrict__ u_pick, int B,
                                           int64_t* __restrict__ labels, int32_t* __restrict__ src_idx) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
@@ -40,16 +24,16 @@ __global__ void itm_sample_uniform_kernel(const float* __restrict__ u_coin, cons
   src_idx[i] = s;
 }
 
-__device__ __forceinline__ unsigned long long qweight(float s, float mx) {
-  return static_cast<unsigned long long>(__fmul_rn(det_exp(__fsub_rn(s, mx)), 1073741824.0f));
-}
-
-// One 256-thread block per row; thread t owns the contiguous column chunk [t*chunk, (t+1)*chunk).
+// One 256-thread block per row; thread t owns the contiguous column chunk [t*chunk, (t+1)*chunk).  Materialised-S form of the
+// hard-negative sampler (drop-in batch sizes, where logits_per_text exists anyway); the fused step uses the tile-stream
+// form instead (tic_itc_fwd(qpart) -> tic_itm_hard_locate -> tic_itc_pick), which never needs S in memory.
 __global__ void __launch_bounds__(256) itm_sample_hard_kernel(const float* __restrict__ u_coin, const float* __restrict__ u_pick,
-                                                              int B, const float* __restrict__ S, int64_t lds,
+                                                              int B, const float* __restrict__ S, int64_t lds, float ref,
+                                                              const float* __restrict__ ref_dev,
                                                               int64_t* __restrict__ labels, int32_t* __restrict__ src_idx) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
+  if (ref_dev != nullptr) ref = __ldg(ref_dev);
   const int i = blockIdx.x, t = threadIdx.x;
   int label, src;
   uniform_rule(u_coin, u_pick, B, i, label, src);
@@ -57,24 +41,15 @@ __global__ void __launch_bounds__(256) itm_sample_hard_kernel(const float* __res
     if (t == 0) { labels[i] = 1; src_idx[i] = i; }
     return;
   }
-  __shared__ float smax[8];
   __shared__ unsigned long long ssum[256];
   __shared__ int sres;
   const float* row = S + static_cast<int64_t>(i) * lds;
-  float mx = -INFINITY;
-  for (int j = t; j < B; j += 256) mx = fmaxf(mx, row[j]);
-  mx = warp_max(mx);
-  if ((t & 31) == 0) smax[t >> 5] = mx;
   if (t == 0) sres = -1;
-  __syncthreads();
-  mx = smax[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, smax[w]);
   const int chunk = (B + 255) / 256;
   const int j0 = t * chunk, j1 = min(j0 + chunk, B);
   unsigned long long local = 0;
   for (int j = j0; j < j1; ++j)
-    if (j != i) local += qweight(row[j], mx);
+    if (j != i) local += hard_qweight(row[j], ref);
   ssum[t] = local;
   __syncthreads();
   // exclusive prefix of the 256 chunk sums (integer => order independent); 256 adds per thread is negligible
@@ -85,12 +60,11 @@ __global__ void __launch_bounds__(256) itm_sample_hard_kernel(const float* __res
     total += s;
   }
   if (total != 0) {
-    const unsigned long long U = static_cast<unsigned long long>(__fmul_rn(u_pick[i], 16777216.0f));
-    const unsigned long long target = U * (total >> 24) + ((U * (total & 0xFFFFFFull)) >> 24);
+    const unsigned long long target = hard_target(u_pick[i], total);
     if (local != 0 && target >= excl && target < excl + local) {
       unsigned long long c = excl;
       for (int j = j0; j < j1; ++j) {
-        if (j != i) c += qweight(row[j], mx);
+        if (j != i) c += hard_qweight(row[j], ref);
         if (c > target) { sres = j; break; }
       }
     }
@@ -99,6 +73,65 @@ __global__ void __launch_bounds__(256) itm_sample_hard_kernel(const float* __res
   if (t == 0) {
     labels[i] = 0;
     src_idx[i] = (total != 0 && sres >= 0) ? sres : src;
+  }
+}
+
+// Tile-stream form, middle step: the similarity tiles (tic_itc_fwd with qpart) left, for every row, the integer weight sum
+// of each column part; one warp per row turns them into (part holding the target, residual target inside that part).
+// Also writes the row's label and its default source (itself, or the uniform pick when every weight is zero);
+// tic_itc_pick then overwrites src_idx of the located rows.
+__global__ void __launch_bounds__(256) itm_hard_locate_kernel(const float* __restrict__ u_coin, const float* __restrict__ u_pick,
+                                                              int m_local, int n_global, int row_offset,
+                                                              const unsigned long long* __restrict__ qpart, int n_parts,
+                                                              int64_t* __restrict__ labels, int32_t* __restrict__ src_idx,
+                                                              int32_t* __restrict__ loc_part,
+                                                              unsigned long long* __restrict__ loc_res) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= m_local) return;
+  int label = 1, src = row_offset + r;
+  if (n_global > 1 && u_coin[r] < 0.5f) {     // the uniform rule with this row's GLOBAL index (itm_rule.cuh: uniform_rule)
+    label = 0;
+    int k = static_cast<int>(floorf(__fmul_rn(u_pick[r], static_cast<float>(n_global - 1))));
+    k = min(k, n_global - 2);
+    src = k < row_offset + r ? k : k + 1;
+  }
+  int part = -1;
+  unsigned long long res = 0;
+  if (label == 0) {
+    unsigned long long tot = 0;
+    for (int p = lane; p < n_parts; p += 32) tot += qpart[static_cast<int64_t>(p) * m_local + r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (tot != 0) {
+      const unsigned long long target = hard_target(u_pick[r], tot);
+      unsigned long long run = 0;      // weights of the parts before the current group of 32
+      for (int p0 = 0; p0 < n_parts && part < 0; p0 += 32) {
+        const int p = p0 + lane;
+        const unsigned long long q = p < n_parts ? qpart[static_cast<int64_t>(p) * m_local + r] : 0ull;
+        unsigned long long inc = q;    // inclusive scan over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += up;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, run + inc > target);
+        if (hit != 0) {
+          const int l = __ffs(hit) - 1;
+          part = p0 + l;
+          const unsigned long long before = run + __shfl_sync(0xffffffffu, inc - q, l);
+          res = target - before;
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+  }
+  if (lane == 0) {
+    labels[r] = label;
+    src_idx[r] = src;
+    loc_part[r] = part;
+    loc_res[r] = res;
   }
 }
 
@@ -138,15 +171,15 @@ using namespace tic;
 
 extern "C" {
 
-int tic_itm_sample(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds, int64_t* labels,
-                   int32_t* src_idx, void* stream) {
+int tic_itm_sample(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds, float hard_ref,
+                   const float* hard_ref_dev, int64_t* labels, int32_t* src_idx, void* stream) {
   TIC_CHECK_ARG(u_coin && u_pick && labels && src_idx && B > 0, "tic_itm_sample: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == TIC_ITM_UNIFORM) {
     launch_k(itm_sample_uniform_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, st, u_coin, u_pick, B, labels, src_idx);
   } else if (mode == TIC_ITM_HARD) {
     TIC_CHECK_ARG(S != nullptr && lds >= B, "tic_itm_sample: hard mode needs the similarity matrix");
-    launch_k(itm_sample_hard_kernel, dim3(B), dim3(256), 0, st, u_coin, u_pick, B, S, lds, labels, src_idx);
+    launch_k(itm_sample_hard_kernel, dim3(B), dim3(256), 0, st, u_coin, u_pick, B, S, lds, hard_ref, hard_ref_dev, labels, src_idx);
   } else {
     set_error("tic_itm_sample: unknown mode %d", mode);
     return TIC_E_ARG;
@@ -167,7 +200,7 @@ int tic_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t
 }
 
 int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int mode, const float* S, int64_t lds,
-                          const void* ids, const void* mask, int64_t row_bytes, void* tim_ids, void* tim_mask,
+                          float hard_ref, const float* hard_ref_dev, const void* ids, const void* mask, int64_t row_bytes, void* tim_ids, void* tim_mask,
                           int64_t* labels, int32_t* src_idx, void* stream) {
   TIC_CHECK_ARG(u_coin && u_pick && ids && mask && tim_ids && tim_mask && labels && src_idx && B > 0 && row_bytes > 0,
                 "tic_itm_sample_gather: bad arguments");
@@ -178,13 +211,25 @@ int tic_itm_sample_gather(const float* u_coin, const float* u_pick, int B, int m
                                              static_cast<const uint8_t*>(mask), static_cast<uint8_t*>(tim_mask), row_bytes,
                                              row_bytes, row_bytes, nullptr, B, u_coin, u_pick, labels, src_idx);
   } else {
-    int rc = tic_itm_sample(u_coin, u_pick, B, mode, S, lds, labels, src_idx, stream);
+    int rc = tic_itm_sample(u_coin, u_pick, B, mode, S, lds, hard_ref, hard_ref_dev, labels, src_idx, stream);
     if (rc) return rc;
     launch_k(gather_rows_kernel, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(ids), static_cast<uint8_t*>(tim_ids),
                                              static_cast<const uint8_t*>(mask), static_cast<uint8_t*>(tim_mask), row_bytes,
                                              row_bytes, row_bytes, src_idx, B, nullptr, nullptr, nullptr, nullptr);
   }
   TIC_CHECK_LAUNCH("tic_itm_sample_gather");
+  return TIC_OK;
+}
+
+int tic_itm_hard_locate(const float* u_coin, const float* u_pick, int m_local, int n_global, int row_offset, const void* qpart,
+                        int n_parts, int64_t* labels, int32_t* src_idx, int32_t* loc_part, void* loc_res, void* stream) {
+  TIC_CHECK_ARG(u_coin && u_pick && qpart && labels && src_idx && loc_part && loc_res && m_local > 0 && n_parts > 0 &&
+                    row_offset >= 0 && row_offset + m_local <= n_global,
+                "tic_itm_hard_locate: bad arguments");
+  launch_k(itm_hard_locate_kernel, dim3(ceil_div(m_local, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), u_coin, u_pick,
+           m_local, n_global, row_offset, static_cast<const unsigned long long*>(qpart), n_parts, labels, src_idx, loc_part,
+           static_cast<unsigned long long*>(loc_res));
+  TIC_CHECK_LAUNCH("tic_itm_hard_locate");
   return TIC_OK;
 }
 

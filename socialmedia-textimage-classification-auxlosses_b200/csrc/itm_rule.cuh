@@ -16,4 +16,40 @@ __device__ __forceinline__ void uniform_rule(const float* u_coin, const float* u
   }
 }
 
+// Bit-reproducible fp32 exp for x <= 0, mirrored op-for-op by oracle/restatement.py:det_exp_f32 — every step is a single
+// IEEE-754 round-to-nearest operation (no FMA contraction, no library transcendental).
+__device__ __forceinline__ float det_exp(float x) {
+  x = fmaxf(x, -80.0f);
+  const float n = rintf(__fmul_rn(x, 1.44269504088896341f));
+  float r = __fsub_rn(x, __fmul_rn(n, 0.693359375f));
+  r = __fsub_rn(r, __fmul_rn(n, -2.12194440e-4f));
+  float p = 1.9875691500e-4f;
+  p = __fadd_rn(__fmul_rn(p, r), 1.3981999507e-3f);
+  p = __fadd_rn(__fmul_rn(p, r), 8.3334519073e-3f);
+  p = __fadd_rn(__fmul_rn(p, r), 4.1665795894e-2f);
+  p = __fadd_rn(__fmul_rn(p, r), 1.6666665459e-1f);
+  p = __fadd_rn(__fmul_rn(p, r), 5.0000001201e-1f);
+  const float y = __fadd_rn(__fadd_rn(__fmul_rn(p, __fmul_rn(r, r)), r), 1.0f);
+  return __int_as_float(__float_as_int(y) + (static_cast<int>(n) << 23));  // exact scaling by 2^n (result stays normal)
+}
+
+// Hard-negative sampling weight of one logit against the FIXED reference `ref` >= max S (oracle/restatement.py:
+// hard_qweights): q = trunc(det_exp(min(s - ref, 0)) * 2^40).  Integer weights make every prefix sum associative, the fixed
+// reference lets the similarity tiles sum them in any order without knowing the row maximum first.
+__device__ __forceinline__ unsigned long long hard_qweight(float s, float ref) {
+  return static_cast<unsigned long long>(__fmul_rn(det_exp(fminf(__fsub_rn(s, ref), 0.0f)), 1099511627776.0f));
+}
+// target = floor(U * total / 2^24), U = trunc(u_pick * 2^24)  (no 128-bit product needed: total < 2^60)
+__device__ __forceinline__ unsigned long long hard_target(float u_pick, unsigned long long total) {
+  const unsigned long long U = static_cast<unsigned long long>(__fmul_rn(u_pick, 16777216.0f));
+  return U * (total >> 24) + ((U * (total & 0xFFFFFFull)) >> 24);
+}
+
+// One similarity logit from a tensor-core accumulator value (raw <t_i, v_j>), the two inverse norms and the scale.  The
+// forward tiles (when they materialise logits or sum hard-negative weights) and the pick tiles use THIS expression, so
+// that a recomputed tile reproduces the logits bit for bit.
+__device__ __forceinline__ float itc_logit(float acc, float rinv_t, float rinv_v, float scale) {
+  return __fmul_rn(__fmul_rn(__fmul_rn(acc, rinv_t), rinv_v), scale);
+}
+
 }  // namespace tic

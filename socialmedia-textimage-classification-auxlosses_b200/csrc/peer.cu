@@ -40,9 +40,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ uint4 ld_nc_na(const uint4* p) {   // streaming 16-byte load (peer memory: never re-read)
+// Streaming 16-byte load of a peer-published payload.  NOT `.nc`: the remote ranks write these blocks while this kernel is
+// already resident (it spins on their flags), and PTX only allows the non-coherent path for data that is read-only for the
+// kernel's whole lifetime.  A relaxed system-scope load after the ld.acquire.sys of the flag is ordered by that acquire and
+// is served from the point of coherence; L1::no_allocate keeps the never-re-read payload out of L1.
+__device__ __forceinline__ uint4 ld_nc_na(const uint4* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  asm volatile("ld.relaxed.sys.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 

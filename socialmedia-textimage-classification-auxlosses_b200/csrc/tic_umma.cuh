@@ -47,7 +47,7 @@ struct EpiCtx {
   int iter;             // tiles already processed by this CTA (for double-buffering the scratch)
   int ks, ksplit;       // split-K: this work item covers K-slice ks of ksplit (epilogue must accumulate atomically)
   uint8_t* scratch;    // kEpiScratchBytes of smem shared by the epilogue warps
-  float pre[4];        // per-thread values loaded by Epi::prefetch for Epi::tile (row norms, row lse)
+  float pre[8];        // per-thread values loaded by Epi::prefetch for Epi::tile (row norms, row lse, logit scale)
 };
 
 // Optional tile order for a B operand that ARRIVES segment by segment (multi-GPU: the gathered embeddings are pulled from the

@@ -36,6 +36,28 @@ def _plan(B, d, dev, logits):
     return _PLANS[key]
 
 
+def _device_scale(logit_scale, dev):
+    """exp(logit_scale) as a device scalar (clamped to (0, 40] by the library, status word sticky): no host read"""
+    ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    sc = torch.empty(1, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("tic_refresh_weights", 0, None, None, None, None, None, None, ptr(ls), ptr(sc), ptr(status), _stream())
+    return sc
+
+
+def _enter(it):
+    """The forward activations (inverse norms, partial sums) live in the shape-keyed plan: stamp the forward so that a
+    backward which follows ANOTHER forward on the same plan fails loudly instead of differentiating the wrong buffers."""
+    it.generation = getattr(it, "generation", 0) + 1
+    return it.generation
+
+
+def _check_generation(it, gen):
+    if getattr(it, "generation", 0) != gen:
+        raise RuntimeError("tic_b200.mm_early: another forward with the same (B, d) ran between this forward and its backward; "
+                           "the saved activations are gone (call backward before the next forward of the same shape)")
+
+
 def _split(x):
     """fp32 [B, d] -> contiguous bf16 (hi, lo) with hi + lo == x to ~16 mantissa bits"""
     x = x.detach().to(torch.float32).contiguous()
@@ -59,16 +81,20 @@ class _LogitsFn(torch.autograd.Function):
         it = _plan(B, d, text_embeds.device, True)
         T, Tl = _split(text_embeds)
         V, Vl = _split(image_embeds)
-        scale = float(torch.exp(logit_scale.detach().float()))
+        scale = 0.0                                  # unused: the kernels read the device scalar
+        it.scale_dev = sc = _device_scale(logit_scale, T.device)
+        ctx.gen = _enter(it)
         it.norms(T, d, V, d, T_lo=Tl, V_lo=Vl)
         it.fwd_tiles(T, d, V, d, scale, T_lo=Tl, V_lo=Vl)
-        ctx.it, ctx.ops, ctx.scale = it, (T, Tl, V, Vl), scale
+        ctx.it, ctx.ops, ctx.scale, ctx.sc = it, (T, Tl, V, Vl), scale, sc
         ctx.dtypes = (text_embeds.dtype, image_embeds.dtype, logit_scale.dtype)
         return it.logits.clone().to(text_embeds.dtype)
 
     @staticmethod
     def backward(ctx, dS):
         it, (T, Tl, V, Vl), scale = ctx.it, ctx.ops, ctx.scale
+        _check_generation(it, ctx.gen)
+        it.scale_dev = ctx.sc
         B, d = T.shape
         dev = T.device
         dS = dS.detach().to(torch.float32).contiguous()
@@ -103,18 +129,22 @@ class _ItcLossFn(torch.autograd.Function):
         V, Vl = _split(image_embeds)
         if not lo:            # >= 4096 negatives: the embeddings are consumed as single bf16 — the residual K-segments are
             Tl = Vl = None    # skipped where tensor time matters; below that, (hi, lo) pairs keep fp32 inputs intact
-        scale = float(torch.exp(logit_scale.detach().float()))
+        scale = 0.0                                  # unused: the kernels read the device scalar
+        it.scale_dev = sc = _device_scale(logit_scale, T.device)
+        ctx.gen = _enter(it)
         sums = torch.zeros(2, dtype=torch.float32, device=T.device)
         it.norms(T, d, V, d, T_lo=Tl, V_lo=Vl)
         it.fwd_tiles(T, d, V, d, scale, T_lo=Tl, V_lo=Vl)
         it.lse_loss(scale, sums)
-        ctx.it, ctx.ops, ctx.scale = it, (T, Tl, V, Vl), scale
+        ctx.it, ctx.ops, ctx.scale, ctx.sc = it, (T, Tl, V, Vl), scale, sc
         ctx.dtypes = (text_embeds.dtype, image_embeds.dtype, logit_scale.dtype)
         return (0.5 * sums.sum() / B).to(text_embeds.dtype)
 
     @staticmethod
     def backward(ctx, g):
         it, (T, Tl, V, Vl), scale = ctx.it, ctx.ops, ctx.scale
+        _check_generation(it, ctx.gen)
+        it.scale_dev = ctx.sc
         B, d = T.shape
         dev = T.device
         gf = float(g)          # upstream scalar (one host read; the fused HeadPlan path has none)
@@ -152,7 +182,7 @@ def prepare_itm_inputs(ids, mask, token_type_ids, rng="numpy", generator=None):
     src = torch.empty(B, dtype=torch.int32, device=dev)
     if rng == "device":
         u = torch.rand(2, B, device=dev, generator=generator)
-        call("tic_itm_sample", u[0].data_ptr(), u[1].data_ptr(), B, 0, None, 0, lbl.data_ptr(), src.data_ptr(), st)
+        call("tic_itm_sample", u[0].data_ptr(), u[1].data_ptr(), B, 0, None, 0, 0.0, None, lbl.data_ptr(), src.data_ptr(), st)
     elif rng == "numpy":
         from .mm_late import _decisions_from_numpy_stream
         swap, s_np = _decisions_from_numpy_stream(B)

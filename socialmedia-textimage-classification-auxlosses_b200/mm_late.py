@@ -69,9 +69,14 @@ class _HeadFn(torch.autograd.Function):
         bf = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()  # noqa: E731
         inp = {"x_t": bf(x_t), "x_v": bf(x_v), "t_pool": bf(t_pool), "v_pool": bf(v_pool)}
         inp.update(aux)
-        plan.set_weights(dict(zip(HEAD_PARAM_ORDER, params)))
+        # The plan reads the parameters through pointers (HeadPlan.bind_params): bound once per parameter storage; every
+        # forward then refreshes the bf16 working copies and exp(logit_scale) on the device — no host synchronisation.
+        key = tuple(p.data_ptr() for p in params)
+        if getattr(plan, "_bound_key", None) != key:
+            plan.bind_params(dict(zip(HEAD_PARAM_ORDER, params)), live=True)
+            plan._bound_key = key
         out = plan.forward(inp)
-        ctx.plan, ctx.inp = plan, inp
+        ctx.plan, ctx.inp, ctx.generation = plan, inp, plan.generation
         ctx.shapes = (x_t.shape, x_v.shape, x_t.dtype, t_pool.dtype, [p.dtype for p in params])
         out_tim = out["out_tim"].clone() if plan.use_itm else torch.zeros(0, device=dev)
         res = (out["out_cls"].clone(), out["logits_per_text"].clone(), out_tim, out["mm_features"].clone())
@@ -82,11 +87,11 @@ class _HeadFn(torch.autograd.Function):
     def backward(ctx, d_cls, d_logits, d_tim, _d_mm):
         plan = ctx.plan
         xt_shape, xv_shape, xt_dtype, tp_dtype, pdtypes = ctx.shapes
-        o = plan.backward(ctx.inp, d_cls, d_logits, d_tim if plan.use_itm else None)
+        # the activations live in the plan's buffers: a second forward on the same plan before this backward is an error
+        o = plan.backward(ctx.inp, d_cls, d_logits, d_tim if plan.use_itm else None, generation=ctx.generation)
         d_x_t = None
-        if "d_xt_cls" in o:
-            d_x_t = torch.zeros(xt_shape, dtype=xt_dtype, device=plan.dev)
-            d_x_t[:, 0, :] = o["d_xt_cls"].to(xt_dtype)   # every fusion variant reads only the CLS row of x_t
+        if "d_xt_cls" in o:   # x_t arrives as its CLS row only ([B,1,E], sliced by MM_Model.head)
+            d_x_t = o["d_xt_cls"].to(xt_dtype).reshape(xt_shape).clone()
         d_tp = o["d_t_pool"].clone()
         if "d_t_pool_fusion" in o:
             d_tp = d_tp + o["d_t_pool_fusion"]
@@ -183,7 +188,9 @@ class MM_Model(nn.Module):
         if self.training and p > 0:
             aux["keep"] = (torch.rand(B, fixed_feat_size, device=x_t.device) >= p).to(torch.uint8)
             aux["keep_scale"] = 1.0 / (1.0 - p)
-        out_cls, logits, out_tim, mm = _HeadFn.apply(plan, aux, x_t, x_v, x_t_pool, x_v_pool, *self._head_params())
+        # every fusion variant reads only the CLS row of x_t (mm_late.py:94,111,141): slice here, so that the cast to bf16 and
+        # the gradient handed back to autograd are [B,1,E] instead of [B,Lt,E]
+        out_cls, logits, out_tim, mm = _HeadFn.apply(plan, aux, x_t[:, :1], x_v, x_t_pool, x_v_pool, *self._head_params())
         return out_cls, logits, (out_tim if use_itm else None), mm
 
     # ---------------------------------------------------------------- reference surface
@@ -284,7 +291,7 @@ class MMLate_Model(object):
             tim_ids, tim_mask = torch.empty_like(ids_c), torch.empty_like(mask_c)   # never aliases its inputs (:391-392)
             lbl_tim = torch.empty(B, dtype=torch.int64, device=dev)
             src_d = torch.empty(B, dtype=torch.int32, device=dev)
-            capi.call("tic_itm_sample_gather", u[0].data_ptr(), u[1].data_ptr(), B, 0, None, 0, ids_c.data_ptr(), mask_c.data_ptr(),
+            capi.call("tic_itm_sample_gather", u[0].data_ptr(), u[1].data_ptr(), B, 0, None, 0, 0.0, None, ids_c.data_ptr(), mask_c.data_ptr(),
                       ids_c.stride(0) * ids_c.element_size(), tim_ids.data_ptr(), tim_mask.data_ptr(), lbl_tim.data_ptr(),
                       src_d.data_ptr(), torch.cuda.current_stream().cuda_stream)
             return (tim_ids, tim_mask, lbl_tim, src_d) if return_src else (tim_ids, tim_mask, lbl_tim)

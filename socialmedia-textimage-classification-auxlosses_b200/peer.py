@@ -402,7 +402,7 @@ def _make_peer_head_plan():
 
         def _lse_rows(self, rb, cb, scale, loss_sums):
             call("tic_itc_lse_rows", ptr(rb.row_part), ptr(cb.row_part), rb.nrp, self.B, ptr(rb.diag), float(scale),
-                 ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), P._stream())
+                 ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), None, P._stream())
 
         def _heads(self, inp, dH_f32=None, forward_only=False, dz_ext=None):
             saved = self.beta_itm

@@ -10,6 +10,7 @@ for device memory and streams.
   HeadPlan  everything models/mm_late.py does after the encoders return (MM_Model.forward :155-193, the loss mix
             :473-487) for fusion in {concat, attention, gmu, aspect-att}, with ITM sampling/gather (:389-414).
 """
+import ctypes
 import math
 from typing import Dict, Optional
 
@@ -94,9 +95,13 @@ class ItcPlan:
     """ITC forward+backward for a row block of `m` text rows against `n` gathered image columns (single GPU: m == n)."""
 
     def __init__(self, m: int, n: int, P: int, device, row_offset: int = 0, materialize_logits: bool = False,
-                 need_dv: bool = True, precise: Optional[bool] = None, col_sums: bool = True, splitk_grad: Optional[bool] = None):
+                 need_dv: bool = True, precise: Optional[bool] = None, col_sums: bool = True, splitk_grad: Optional[bool] = None,
+                 hard: bool = False):
         assert P % 8 == 0, "embedding width must be a multiple of 8 (16-byte TMA rows)"
         self.m, self.n, self.P, self.row_offset = m, n, P, row_offset
+        # device scalar exp(logit_scale) (HeadPlan: written by tic_refresh_weights at the head of the step); None = the host
+        # floats passed to the methods below are used
+        self.scale_dev = None
         # Split-precision gradient operands (bf16 hi+lo): with few negatives the bf16 rounding of the softmax
         # probabilities does not average out; from ~4k columns on it does and the second K-segment is skipped.
         self.precise = (n < 4096) if precise is None else bool(precise)
@@ -125,6 +130,10 @@ class ItcPlan:
         self.acc_v = torch.empty(n, P, dtype=F32, device=dev) if need_dv else None
         self.logits = torch.empty(m, n, dtype=F32, device=dev) if materialize_logits else None
         self.need_dv = need_dv
+        # hard-negative sampling in tile-stream form (a-5'): per (row, column part) integer weight sums + the located part
+        self.qpart = torch.empty(self.nrp, m, dtype=torch.int64, device=dev) if hard else None
+        self.loc_part = torch.empty(m, dtype=torch.int32, device=dev) if hard else None
+        self.loc_res = torch.empty(m, dtype=torch.int64, device=dev) if hard else None
         # dT = GA[m,n] V[n,P] with m << n (multi-GPU row block at small per-rank batch): the un-split GEMM has m/128 * P/64
         # CTAs walking the whole K = n; fp32-atomic split-K fills the machine instead (nondeterministic summation order)
         self.splitk_grad = (m <= 1024 and n >= 4 * m) if splitk_grad is None else bool(splitk_grad)
@@ -150,13 +159,24 @@ class ItcPlan:
         call("tic_itc_fwd", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), self.m, self.n, self.P,
              self.row_offset, float(scale), float(scale), ptr(self.row_part), ptr(self.col_part), ptr(self.diag),
              ptr(self.logits), self.n if self.logits is not None else 0, ptr(ss_t), 0 if ss_t is None else ss_t.shape[0],
-             ptr(ss_v), 0 if ss_v is None else ss_v.shape[0], sr, se, sc, ms, _stream())
+             ptr(ss_v), 0 if ss_v is None else ss_v.shape[0], sr, se, sc, ms, ptr(self.scale_dev), ptr(self.qpart), _stream())
+
+    def hard_locate(self, u_coin, u_pick, labels, src_idx):
+        """labels / default sources for every row + (part, residual) of each mismatch row from the weight sums of fwd_tiles"""
+        call("tic_itm_hard_locate", ptr(u_coin), ptr(u_pick), self.m, self.n, self.row_offset, ptr(self.qpart), self.nrp,
+             ptr(labels), ptr(src_idx), ptr(self.loc_part), ptr(self.loc_res), _stream())
+
+    def hard_pick(self, T, ldt, V, ldv, scale, src_idx, T_lo=None, V_lo=None):
+        """tile recompute: src_idx of the located rows (same operands and tile shapes as fwd_tiles -> identical logits)"""
+        call("tic_itc_pick", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), self.m, self.n,
+             self.P, self.row_offset, float(scale), float(scale), ptr(self.scale_dev), ptr(self.loc_part), ptr(self.loc_res),
+             ptr(src_idx), _stream())
 
     def lse_loss(self, scale, loss_sums, col_parts=None, n_col_parts=None):
         cp = self.col_part if col_parts is None else col_parts
         ncp = self.ncp if n_col_parts is None else n_col_parts
         call("tic_itc_lse_loss", ptr(self.row_part), self.nrp, ptr(cp), ncp, ptr(self.diag), self.m, self.n,
-             self.row_offset, float(scale), ptr(self.lse_row), ptr(self.lse_col), ptr(loss_sums), _stream())
+             self.row_offset, float(scale), ptr(self.lse_row), ptr(self.lse_col), ptr(loss_sums), ptr(self.scale_dev), _stream())
 
     def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None, inline_lse=False):
         """inline_lse: derive lse_row/lse_col inside the kernel from the forward partials (few partials = small batch), so
@@ -165,7 +185,8 @@ class ItcPlan:
         cp = (ptr(self.col_part), self.ncp) if inline_lse else (None, 0)
         call("tic_itc_bwd_g", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), ptr(self.lse_row),
              ptr(self.lse_col), self.m, self.n, self.P, float(scale), float(gscale), ptr(self.GA), self.ld_ga,
-             ptr(self.GBT), self.ld_gbt, ptr(self.GA_lo), ptr(self.GBT_lo), rp[0], rp[1], cp[0], cp[1], float(scale), _stream())
+             ptr(self.GBT), self.ld_gbt, ptr(self.GA_lo), ptr(self.GBT_lo), rp[0], rp[1], cp[0], cp[1], float(scale),
+             ptr(self.scale_dev), _stream())
 
     @property
     def can_inline_lse(self):
@@ -199,14 +220,14 @@ class ItcPlan:
         call("tic_itc_grad_finalize", ptr(self.acc_t), self.P, ptr(T), ptr(T_lo), ldt, ptr(self.rinv_t), ptr(V_diag),
              ptr(V_diag_lo), ldv,
              ptr(rinv_v_diag), self.m, self.P, float(scale), float(diag_coef), ptr(dT_f32), self.P, ptr(dT_bf16), ptr(dT_lo),
-             self.P, ptr(r_sum), 0, _stream())
+             self.P, ptr(r_sum), 0, ptr(self.scale_dev), _stream())
 
     def finalize_v(self, acc_v, V, ldv, rinv_v, T_diag, ldt, rinv_t_diag, rows, scale, diag_coef, dV_f32, dV_bf16,
                    dV_lo=None, V_lo=None, T_diag_lo=None):
         call("tic_itc_grad_finalize", ptr(acc_v), self.P, ptr(V), ptr(V_lo), ldv, ptr(rinv_v), ptr(T_diag), ptr(T_diag_lo),
              ldt, ptr(rinv_t_diag),
              rows, self.P, float(scale), float(diag_coef), ptr(dV_f32), self.P, ptr(dV_bf16), ptr(dV_lo), self.P, None,
-             1 if self.shared_ga else 0, _stream())
+             1 if self.shared_ga else 0, ptr(self.scale_dev), _stream())
 
     # -- single-GPU convenience: full forward + backward --
     def run(self, T, V, scale, g, loss_sums, r_sum, dT_f32=None, dT_bf16=None, dV_f32=None, dV_bf16=None):
@@ -258,12 +279,22 @@ class HeadPlan:
         else:
             self.w_cls = 1.0 - (self.beta_itc + self.beta_itm)
             self.g_itc = self.beta_itc
-        if self.itm_mode == 1 and use_itc:
-            materialize_logits = True
-        self.itc = ItcPlan(B, B, self.Pe, self.dev, materialize_logits=materialize_logits) if use_itc else None
+        if self.itm_mode == 1 and not (use_itc and self.use_itm):
+            raise ValueError("itm_mode='hard' samples negatives from the ITC similarities: it needs use_itc and use_itm")
+        self.itc = ItcPlan(B, B, self.Pe, self.dev, materialize_logits=materialize_logits,
+                           hard=self.itm_mode == 1) if use_itc else None
         self._alloc()
         self.w: Dict[str, torch.Tensor] = {}
-        self.scale = math.exp(2.6592)
+        self.scale = math.exp(2.6592)            # host copy of exp(logit_scale): informational once weights are bound
+        # exp(logit_scale) as a DEVICE scalar: every ITC kernel of this plan reads it through a pointer, so a captured step
+        # follows a trainable logit_scale (mm_late.py:59-69); scale_status != 0 if it ever left (0, 40]
+        self.scale_t = torch.full((1,), self.scale, dtype=F32, device=self.dev)
+        self.scale_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        if self.itc is not None:
+            self.itc.scale_dev = self.scale_t
+        self.live_weights = False                # bind_params(live=True): the bf16 working copies are refreshed inside step()
+        self._refresh_groups = {}
+        self.generation = 0                      # autograd mode: bumped by forward(); backward() checks it (see mm_late._HeadFn)
         self.parallel_streams = True
         import os as _os
         # stream priorities only pay while the step is latency-bound (small batch); with persistent 148-CTA kernels they
@@ -369,44 +400,86 @@ class HeadPlan:
             o["dW_gv"], o["db_gv"] = self.z["dW_gv"].view(2 * E, E), self.z["db_gv"]
 
     # ------------------------------------------------------------------ weights
-    def set_weights(self, p: Dict[str, torch.Tensor]):
-        """p: fp32 tensors under the reference's state-dict names (mm_late.py:59-89).  Builds the bf16 working copies
-        consumed by the tensor-core GEMMs (one cast kernel per matrix) and reads logit_scale (one host sync)."""
+    def bind_params(self, p: Dict[str, torch.Tensor], live: bool = True):
+        """p: fp32 tensors under the reference's state-dict names (mm_late.py:59-89).  The plan keeps POINTERS to them: the
+        small fp32 layers are read in place, the large matrices get bf16 working copies that ONE multi-tensor kernel per chain
+        (tic_refresh_weights) rewrites from the masters — together with exp(logit_scale) — at the head of every step() when
+        live=True.  An optimiser that updates the parameters in place between replays of a captured step is therefore seen
+        by the next replay: the captured step is a training step.  Tensors that are not fp32 / contiguous / on the plan's
+        device are copied once (and are then NOT live: rebind after changing them).  No host synchronisation."""
         E, dev = self.E, self.dev
         w = self.w
+        self._masters = {}
 
-        def cast(name, src, cols_pad=None):
-            src = src.detach().to(device=dev, dtype=F32).contiguous()
-            rows, cols = src.shape
-            ld = cols if cols_pad is None else cols_pad
-            if name not in w or w[name].shape != (rows, ld):
-                w[name] = torch.zeros(rows, ld, dtype=BF16, device=dev)
-            call("tic_cast_f32_to_bf16", ptr(src), cols, ptr(w[name]), ld, rows, cols, _stream())
+        def master(src):
+            return src.detach().to(device=dev, dtype=F32).contiguous()
+
+        groups = {"itc": [], "fusion": []}
+
+        def cast(group, name, src, cols_pad=None, dst_col=0):
+            m = master(src)
+            if m.dim() == 1:
+                m = m.reshape(-1, 1)
+            rows, cols = m.shape
+            if dst_col == 0:
+                ld = cols if cols_pad is None else cols_pad
+                if name not in w or w[name].shape != (rows, ld):
+                    w[name] = torch.zeros(rows, ld, dtype=BF16, device=dev)
+            dst = w[name]
+            self._masters[name + "@%d" % dst_col] = m
+            groups[group].append((m.data_ptr(), dst.data_ptr() + 2 * dst_col, m.stride(0), dst.stride(0), rows, cols))
 
         def keep(name, src):
-            w[name] = src.detach().to(device=dev, dtype=F32).contiguous()
+            w[name] = master(src)
 
-        self.scale = float(torch.exp(p["dual_encoder.logit_scale"].detach().float()).item())
+        self._logit_scale = master(p["dual_encoder.logit_scale"]).reshape(1)
         if self.P is not None:
-            cast("W_t", p["dual_encoder.text_projection.weight"])
-            cast("W_v", p["dual_encoder.visual_projection.weight"])
-        if self.fusion is None:
+            cast("itc", "W_t", p["dual_encoder.text_projection.weight"])
+            cast("itc", "W_v", p["dual_encoder.visual_projection.weight"])
+        if self.fusion is not None:
+            keep("W_cls", p["linear_cls.weight"]); keep("b_cls", p["linear_cls.bias"])
+            keep("W_tim", p["linear_tim.weight"]); keep("b_tim", p["linear_tim.bias"])
+            if self.fusion == "aspect-att":
+                keep("w_a", p["aspectattention.weight"].reshape(-1)); keep("b_a", p["aspectattention.bias"].reshape(-1))
+            else:
+                cast("fusion", "W_f", p["linear_fusion.weight"]); keep("b_f", p["linear_fusion.bias"])
+            if self.fusion == "attention":
+                cast("fusion", "W_Q", p["fc_Q.weight"]); keep("b_Q", p["fc_Q.bias"])
+                cast("fusion", "W_V", p["fc_V.weight"]); keep("b_V", p["fc_V.bias"])
+                cast("fusion", "W_Kaug", p["fc_K.weight"], cols_pad=E + 8)  # [W_K | b_K | 0..]: column E carries <q0, b_K>
+                cast("fusion", "W_Kaug", p["fc_K.bias"], dst_col=E)
+            if self.fusion == "gmu":
+                cast("fusion", "W_gt", p["linear_gmu_t.weight"]); keep("b_gt", p["linear_gmu_t.bias"])
+                cast("fusion", "W_gv", p["linear_gmu_v.weight"]); keep("b_gv", p["linear_gmu_v.bias"])
+        self._refresh_groups = {}
+        for g, items in groups.items():
+            n = len(items)
+            if n == 0 and g != "itc":
+                continue
+            self._refresh_groups[g] = (n, (ctypes.c_void_p * max(n, 1))(*[i[0] for i in items]),
+                                       (ctypes.c_void_p * max(n, 1))(*[i[1] for i in items]),
+                                       (ctypes.c_int64 * max(n, 1))(*[i[2] for i in items]),
+                                       (ctypes.c_int64 * max(n, 1))(*[i[3] for i in items]),
+                                       (ctypes.c_int * max(n, 1))(*[i[4] for i in items]),
+                                       (ctypes.c_int * max(n, 1))(*[i[5] for i in items]))
+        self.live_weights = bool(live)
+        self._refresh("itc", force=True)
+        self._refresh("fusion", force=True)
+
+    def _refresh(self, group, force=False):
+        """fp32 masters -> bf16 working copies of one chain's matrices (+ exp(logit_scale) with the ITC group): one launch"""
+        if not (force or self.live_weights) or group not in self._refresh_groups:
             return
-        keep("W_cls", p["linear_cls.weight"]); keep("b_cls", p["linear_cls.bias"])
-        keep("W_tim", p["linear_tim.weight"]); keep("b_tim", p["linear_tim.bias"])
-        if self.fusion == "aspect-att":
-            keep("w_a", p["aspectattention.weight"].reshape(-1)); keep("b_a", p["aspectattention.bias"].reshape(-1))
-            return
-        cast("W_f", p["linear_fusion.weight"]); keep("b_f", p["linear_fusion.bias"])
-        if self.fusion == "attention":
-            cast("W_Q", p["fc_Q.weight"]); keep("b_Q", p["fc_Q.bias"])
-            cast("W_V", p["fc_V.weight"]); keep("b_V", p["fc_V.bias"])
-            cast("W_Kaug", p["fc_K.weight"], cols_pad=E + 8)  # [W_K | b_K | 0..]: column E carries <q0, b_K>
-            bk = p["fc_K.bias"].detach().to(device=dev, dtype=F32).reshape(E, 1).contiguous()
-            call("tic_cast_f32_to_bf16", ptr(bk), 1, w["W_Kaug"].data_ptr() + 2 * E, E + 8, E, 1, _stream())
-        if self.fusion == "gmu":
-            cast("W_gt", p["linear_gmu_t.weight"]); keep("b_gt", p["linear_gmu_t.bias"])
-            cast("W_gv", p["linear_gmu_v.weight"]); keep("b_gv", p["linear_gmu_v.bias"])
+        n, src, dst, lds, ldd, rows, cols = self._refresh_groups[group]
+        with_scale = group == "itc"
+        call("tic_refresh_weights", n, src, dst, lds, ldd, rows, cols, ptr(self._logit_scale) if with_scale else None,
+             ptr(self.scale_t) if with_scale else None, ptr(self.scale_status) if with_scale else None, _stream())
+
+    def set_weights(self, p: Dict[str, torch.Tensor]):
+        """Snapshot form of bind_params: casts once, now; step() does not refresh.  Also reads exp(logit_scale) back into
+        `self.scale` (one host synchronisation, outside any step) for callers that want the value on the host."""
+        self.bind_params(p, live=False)
+        self.scale = float(self.scale_t.item())
 
     # ------------------------------------------------------------------ phases
     # fused mode   : step()                      = itc_fwd, fusion_fwd, heads (losses fused), loss mix, fusion_bwd, itc_bwd
@@ -427,6 +500,7 @@ class HeadPlan:
         ldt, ldv = Yt.stride(0), Yv.stride(0)
         br = self.br
         br.enabled = self.parallel_streams
+        self._refresh("itc")                              # live weights: W_t / W_v working copies + exp(logit_scale)
         fused_norm = self.P is not None and B <= 1024     # small batch: norm statistics ride on the projection GEMMs
         if fused_norm and getattr(self, "ss_t", None) is None:
             nss = capi.load().tic_gemm_rowss_parts(self.P)
@@ -624,6 +698,7 @@ class HeadPlan:
         return self.use_itm and self.itm_mode == 0 and "src_idx" not in inp and inp.get("u_coin") is not None
 
     def _fusion_chain(self, inp):
+        self._refresh("fusion")
         if self.use_itm:
             if self._inline_rule(inp):
                 self.br.enabled = self.parallel_streams
@@ -640,23 +715,33 @@ class HeadPlan:
             self._ev_heads.record(torch.cuda.current_stream())
         self._fusion_bwd(inp)
         self.br.join("hw")
+        self.br.join("g")
 
     def forward(self, inp: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Autograd mode, forward half: logits_per_text (materialised), mm_features, out_cls, out_tim.  ITM decisions come
         from the caller (`lbl_tim`, `src_idx`) exactly as the reference passes `tim_inputs`."""
         assert self.itc is None or self.itc.logits is not None, "autograd mode needs materialize_logits=True"
+        self.generation += 1
         self.zb.zero_()
         if self.use_itc:
             self._itc_fwd(inp, with_loss=False)
         if self.fusion is not None:
+            self._refresh("fusion")
             if self.use_itm:
                 self._sample_itm(inp)
             self._fusion_fwd(inp)
             self._heads(inp, forward_only=True)
         return self.out
 
-    def backward(self, inp, d_out_cls=None, d_logits=None, d_out_tim=None) -> Dict[str, torch.Tensor]:
-        """Autograd mode, backward half: upstream gradients of the three outputs -> gradients of inputs and parameters."""
+    def backward(self, inp, d_out_cls=None, d_logits=None, d_out_tim=None, generation=None) -> Dict[str, torch.Tensor]:
+        """Autograd mode, backward half: upstream gradients of the three outputs -> gradients of inputs and parameters.
+        The forward activations live in this plan's buffers: `generation` (the value of self.generation right after the
+        matching forward()) makes a backward that follows ANOTHER forward on the same plan fail loudly instead of
+        differentiating the wrong activations."""
+        if generation is not None and generation != self.generation:
+            raise RuntimeError("HeadPlan.backward: the plan ran another forward (generation %d) after the one being "
+                               "differentiated (%d); its activations are gone.  Use one plan per in-flight forward."
+                               % (self.generation, generation))
         B, C = self.B, self.C
         self.zb.zero_()
         if self.fusion is not None:
@@ -681,16 +766,29 @@ class HeadPlan:
             o["lbl_tim"].copy_(inp["lbl_tim"])
             o["src_idx"].copy_(inp["src_idx"].to(torch.int32))
             return
-        S = self.itc.logits if (self.itm_mode == 1 and self.itc is not None) else None
-        if inp.get("ids") is not None:
-            ids, mask = inp["ids"], inp["mask"]
-            if "tim_ids" not in o:
-                o["tim_ids"], o["tim_mask"] = torch.empty_like(ids), torch.empty_like(mask)
-            call("tic_itm_sample_gather", ptr(inp["u_coin"]), ptr(inp["u_pick"]), B, self.itm_mode, ptr(S), B, ptr(ids),
+        ids, mask = inp.get("ids"), inp.get("mask")
+        if ids is not None and "tim_ids" not in o:
+            o["tim_ids"], o["tim_mask"] = torch.empty_like(ids), torch.empty_like(mask)
+        if self.itm_mode == 1:
+            # hard negatives, tile-stream form: the forward tiles left per-part weight sums; locate the part of every
+            # mismatch row's target, then recompute the tiles and walk that part (csrc/itc.cu: ItcPickEpi)
+            it = self.itc
+            Yt, Yv, Ytl, Yvl = self._itc_operands(inp)
+            it.hard_locate(inp["u_coin"], inp["u_pick"], o["lbl_tim"], o["src_idx"])
+            it.hard_pick(Yt, Yt.stride(0), Yv, Yv.stride(0), self.scale, o["src_idx"], T_lo=Ytl, V_lo=Yvl)
+            if ids is not None:   # the gathered ids / mask feed nothing downstream here (no second encoder pass): side branch
+                self.br.enabled = self.parallel_streams
+                with self.br("g"):
+                    for s_, d_ in ((ids, o["tim_ids"]), (mask, o["tim_mask"])):
+                        call("tic_gather_rows", ptr(s_), s_.stride(0) * s_.element_size(), ptr(d_),
+                             d_.stride(0) * d_.element_size(), s_.shape[1] * s_.element_size(), ptr(o["src_idx"]), B, _stream())
+            return
+        if ids is not None:
+            call("tic_itm_sample_gather", ptr(inp["u_coin"]), ptr(inp["u_pick"]), B, 0, None, 0, 0.0, None, ptr(ids),
                  ptr(mask), ids.stride(0) * ids.element_size(), ptr(o["tim_ids"]), ptr(o["tim_mask"]), ptr(o["lbl_tim"]),
                  ptr(o["src_idx"]), st)
         else:
-            call("tic_itm_sample", ptr(inp["u_coin"]), ptr(inp["u_pick"]), B, self.itm_mode, ptr(S), B, ptr(o["lbl_tim"]),
+            call("tic_itm_sample", ptr(inp["u_coin"]), ptr(inp["u_pick"]), B, 0, None, 0, 0.0, None, ptr(o["lbl_tim"]),
                  ptr(o["src_idx"]), st)
 
     def _heads(self, inp, dH_f32=None, forward_only=False, dz_ext=None):

@@ -106,7 +106,7 @@ def test_itc_lse_rows_matches_oracle():
     for _ in range(2):   # twice: the workspace ticket must reset itself
         sums.zero_()
         capi.call("tic_itc_lse_rows", pad.data_ptr(), pbd.data_ptr(), nparts, m, dd.data_ptr(), shift,
-                  la.data_ptr(), lb.data_ptr(), sums.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                  la.data_ptr(), lb.data_ptr(), sums.data_ptr(), ws.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         ra, rb = shift + torch.log(pa.double().sum(0)), shift + torch.log(pb.double().sum(0))
         assert _rel(la, ra) < 1e-6 and _rel(lb, rb) < 1e-6

@@ -228,7 +228,7 @@ def test_itm_replays_reference_stream(golden_dir, seed, B):
     lbl = torch.empty(B, dtype=torch.int64, device=_dev())
     sidx = torch.empty(B, dtype=torch.int32, device=_dev())
     uc, up = torch.tensor(u_coin, device=_dev()), torch.tensor(u_pick, device=_dev())
-    capi.call("tic_itm_sample_gather", uc.data_ptr(), up.data_ptr(), B, 0, None, 0, ids.data_ptr(), mask.data_ptr(),
+    capi.call("tic_itm_sample_gather", uc.data_ptr(), up.data_ptr(), B, 0, None, 0, 0.0, None, ids.data_ptr(), mask.data_ptr(),
               ids.stride(0) * 8, tim_ids.data_ptr(), tim_mask.data_ptr(), lbl.data_ptr(), sidx.data_ptr(),
               torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
@@ -248,16 +248,26 @@ def test_itm_sampler_bit_exact(B, mode):
     if mode == "uniform":
         lbl_o, src_o = R.itm_sample_uniform(u_coin, u_pick)
     else:
-        lbl_o, src_o = R.itm_sample_hard(S, u_coin, u_pick)
+        # fixed reference >= max S (the product passes exp(logit_scale)); once as a host float, once as a device scalar
+        ref = np.float32(S.max() + 0.5)
+        lbl_o, src_o = R.itm_sample_hard(S, u_coin, u_pick, ref=ref)
     lbl = torch.empty(B, dtype=torch.int64, device=_dev())
     sidx = torch.empty(B, dtype=torch.int32, device=_dev())
     Sd = torch.tensor(S, device=_dev())
     uc, up = torch.tensor(u_coin, device=_dev()), torch.tensor(u_pick, device=_dev())
-    capi.call("tic_itm_sample", uc.data_ptr(), up.data_ptr(), B, 0 if mode == "uniform" else 1, Sd.data_ptr(), B, lbl.data_ptr(), sidx.data_ptr(),
-              torch.cuda.current_stream().cuda_stream)
+    ref_h = float(ref) if mode == "hard" else 0.0
+    capi.call("tic_itm_sample", uc.data_ptr(), up.data_ptr(), B, 0 if mode == "uniform" else 1, Sd.data_ptr(), B, ref_h, None,
+              lbl.data_ptr(), sidx.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(lbl.cpu().numpy(), lbl_o)
     assert np.array_equal(sidx.cpu().numpy().astype(np.int64), src_o)
+    if mode == "hard":
+        ref_d = torch.tensor([ref], dtype=torch.float32, device=_dev())
+        sidx.zero_()
+        capi.call("tic_itm_sample", uc.data_ptr(), up.data_ptr(), B, 1, Sd.data_ptr(), B, -1.0, ref_d.data_ptr(),
+                  lbl.data_ptr(), sidx.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(sidx.cpu().numpy().astype(np.int64), src_o)
     # gathered rows (generic byte rows, odd width -> scalar path; 16-byte width -> vector path)
     for width in (5, 16):
         x = torch.arange(B * width, dtype=torch.uint8, device=_dev()).view(B, width)
@@ -300,16 +310,19 @@ def _bf16_params(p):
     return out
 
 
-def _check_head(plan, dev_in, ora_in, p32, fusion, use_itm, tol=REL):
+def _check_head(plan, dev_in, ora_in, p32, fusion, use_itm, tol=REL, odev="cpu"):
+    """odev: where the fp64 oracle runs.  "cpu" for the small cases; "cuda" for BASELINE-size cases (the oracle is plain
+    torch code — in fp64 on the GPU it is the same arithmetic, minutes faster, and still independent of libtic_b200)."""
     out = plan.step(dev_in)
     torch.cuda.synchronize()
-    pd = {k: v.clone().requires_grad_(True) for k, v in _bf16_params(p32).items()}
+    pd = {k: v.to(odev).clone().requires_grad_(True) for k, v in _bf16_params(p32).items()}
+    ora_in = {k: (v.to(odev) if torch.is_tensor(v) else v) for k, v in ora_in.items()}
     for k in ("x_t", "t_pool"):
         ora_in[k] = ora_in[k].clone().requires_grad_(True)
     # ReLU sits on a discontinuity of the gradient: a pre-activation within rounding distance of 0 may land on the other
     # side in the bf16-operand path.  The oracle therefore differentiates with the CUDA path's 0/1 mask, and the test
     # checks separately that every disagreement with the oracle's own mask is such a near-zero pre-activation.
-    Hm = (plan.H > 0).cpu()
+    Hm = (plan.H > 0).to(odev)
     masks = {"main": Hm[:plan.B], "tim": Hm[plan.B:] if use_itm else None}
     ref = R.head_step(ora_in, pd, fusion_name=fusion, use_itc=True, use_itm=use_itm, beta_itc=0.1, beta_itm=0.1,
                       relu_masks=masks)
@@ -330,8 +343,8 @@ def _check_head(plan, dev_in, ora_in, p32, fusion, use_itm, tol=REL):
     if use_itm:
         errs["loss_itm"] = abs(float(out["loss"][3]) - float(ref["loss_itm"])) / abs(float(ref["loss_itm"]))
         errs["out_tim"] = _rel(out["out_tim"], ref["out_tim"])
-        assert np.array_equal(out["lbl_tim"].cpu().numpy(), ora_in["lbl_tim"].numpy())
-        assert np.array_equal(out["src_idx"].cpu().numpy().astype(np.int64), ora_in["src_idx"].numpy())
+        assert np.array_equal(out["lbl_tim"].cpu().numpy(), ora_in["lbl_tim"].cpu().numpy())
+        assert np.array_equal(out["src_idx"].cpu().numpy().astype(np.int64), ora_in["src_idx"].cpu().numpy())
     names = {"dW_t": "dual_encoder.text_projection.weight", "dW_v": "dual_encoder.visual_projection.weight",
              "dW_cls": "linear_cls.weight", "db_cls": "linear_cls.bias", "dW_tim": "linear_tim.weight",
              "db_tim": "linear_tim.bias", "dW_f": "linear_fusion.weight", "db_f": "linear_fusion.bias",
@@ -351,6 +364,11 @@ def _check_head(plan, dev_in, ora_in, p32, fusion, use_itm, tol=REL):
     d_tpool = out["d_t_pool"].double().cpu()
     if "d_t_pool_fusion" in out:
         d_tpool = d_tpool + out["d_t_pool_fusion"].double().cpu()
+    # per-ROW relative check of the two logit outputs (max-norm over the whole tensor can hide a bad row)
+    for k in ("out_cls", "out_tim"):
+        if k in out and (k != "out_tim" or use_itm):
+            g_, r_ = out[k].double().cpu(), ref[k].detach().double().cpu()
+            errs[k + "_rowrel"] = float(((g_ - r_).abs().amax(1) / r_.abs().amax(1).clamp_min(1e-3)).max())
     errs["d_t_pool"] = _rel(d_tpool, ora_in["t_pool"].grad)
     if "d_xt_cls" in out:
         errs["d_xt_cls"] = _rel(out["d_xt_cls"], ora_in["x_t"].grad[:, 0, :])
