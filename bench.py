@@ -664,7 +664,13 @@ def kernel_rooflines(P, plan, spec, dev_in, n_global, flush):
         ks.append(dict(kernel="tic_attn_pool_bwd (second streaming read of x_v)", bound="hbm", ms=ms,
                        achieved=B * Lv * E * 2.0 / ms * 1e-6, unit="GB/s", algorithmic="B*Lv*E*2 bytes",
                        traffic_key="attn_bwd_%d" % B))
-    if spec["fusion"] in ("concat",):
+    if spec["fusion"] in ("concat",) and getattr(plan, "pairwise", False):
+        E2, x_t = 2 * E, dev_in["x_t"]
+        ms = time_kernel(lambda: P.gemm(x_t, x_t.stride(0), 0, plan.w["W_f"], E2, 0, plan.Pt, E, 0, B, E, E), flush)
+        ks.append(dict(kernel="tic_gemm_bf16 (linear_fusion, text half Pt = x_t W_f[:, :E]^T; the image half runs beside it)",
+                       bound="tensor", ms=ms, achieved=2.0 * B * E * E / ms * 1e-9, unit="TFLOP/s", algorithmic="2*B*E*E FLOP",
+                       traffic_key="gemm_fusion_half_%d" % B))
+    elif spec["fusion"] in ("concat",):
         R_, E2 = plan.R, 2 * E
         ms = time_kernel(lambda: P.gemm(plan.Xcat, E2, 0, plan.w["W_f"], E2, 0, plan.H, E, 0, R_, E, E2, bias=plan.w["b_f"],
                                         relu=True), flush)

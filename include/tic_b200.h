@@ -163,6 +163,17 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
                   float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo /* optional residuals */,
                   void* GBT_lo, const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, float shift,
                   const float* scale_dev, void* stream);
+/* Fused forward + backward tiles for the small-batch step (at most 8 tiles of 128 x 64: tic_itc_fused_small_ok): ONE launch
+ * = tic_itc_fwd (same outputs: partials, diag, inverse norms, optional logits / qpart) followed, after a cluster-wide
+ * barrier, by tic_itc_bwd_g with the inline statistics — the S tiles stay in TMEM in between, the second k-loop and one
+ * launch leave the critical chain of the step (HF :268-273 + utils.py:225-231 forward, and the gradient operands). */
+int tic_itc_fused_small_ok(int m_local, int n_global);
+int tic_itc_fwd_bwd_small(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv,
+                          float* rinv_t, float* rinv_v, int m_local, int n_global, int P, int row_offset, float scale,
+                          float* row_part, float* col_part, float* diag, float* logits_out, int64_t ld_logits,
+                          const float* ss_t_part, int n_ss_t, const float* ss_v_part, int n_ss_v, const float* scale_dev,
+                          void* qpart, float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo,
+                          void* GBT_lo, void* stream);
 /* Inline statistics (small batches): when row_part / col_part (the partials written by tic_itc_fwd) are given, the kernel
  * derives lse_row / lse_col = shift + log(sum of partials) itself (same expression as tic_itc_lse_loss) and the matching
  * lse pointer may be NULL — tic_itc_lse_loss then only produces the loss and runs beside the backward, not before it. */
@@ -242,14 +253,24 @@ int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, const float* dX2 /* opt
  * c_tim*dL_tim/dH, already multiplied by the ReLU mask (H > 0).  dW/db are accumulated (+=) in fp32 with atomics
  * into zero-initialised buffers.  losses[0] += L_cls, losses[1] += L_tim (unweighted). keep (uint8 dropout mask
  * [B,E], may be NULL) and keep_scale = 1/(1-p) reproduce nn.Dropout on the classifier branch only. */
-int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* W_cls,
+int tic_heads_fwd_bwd(float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* W_cls,
                       const float* b_cls, const float* W_tim, const float* b_tim, const float* y_soft,
                       const float* class_w, const int64_t* lbl_tim, const uint8_t* keep, float keep_scale, float c_cls,
                       float c_tim, float* logits_cls, float* logits_tim, float* losses, void* dH_bf16, void* dH_bf16_lo, int64_t ld_dhb,
                       float* dH_f32 /* optional */, int64_t ld_dhf, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask,
                       float* ws /* [rows * 8] floats scratch (dlogits) */,
                       const float* dlogits_ext /* NULL = fused losses; else upstream dL/dlogits [rows, 8] (autograd mode) */,
+                      const float* Pt, const float* Pv, int64_t ldp, const int32_t* src_idx /* pairwise form, see below */,
                       void* stream);
+/* Pairwise form of concat fusion (mm_late.py:92-96 with the ITM pairs of :170-181): linear_fusion([x_t | x_v]) =
+ * x_t W_f[:, :E]^T + (x_v W_f[:, E:]^T + b_f).  With Pt = text halves and Pv = image halves (+ bias), fp32 [B, ldp], the
+ * kernel above builds H itself — H[i] = relu(Pt[i] + Pv[i]), H[B+i] = relu(Pt[src_idx[i]] + Pv[i]) — and STORES it (H is an
+ * output then): every sample is projected once, no packed [2B, 2E] operand exists, the fusion GEMM does half the FLOPs.
+ * tic_fusion_pair_grad is its backward: from dH [2B, E] (bf16 hi + optional lo)
+ *   dPv[i] = dH[i] + dH[B+i],   dPt[k] = dH[k] + sum_{i: src_idx[i] == k} dH[B+i]      (bf16 hi + optional lo, [B, ldo])
+ * without atomics (the inverse of the gather is found by scanning src_idx; fixed summation order). */
+int tic_fusion_pair_grad(const void* dH, const void* dH_lo, int64_t ld, int B, int E, int has_tim, const int32_t* src_idx,
+                         void* dPt, void* dPt_lo, void* dPv, void* dPv_lo, int64_t ldo, void* stream);
 
 /* The parameter-gradient half of tic_heads_fwd_bwd alone (dW/db of linear_cls and linear_tim from the dlogits that call left
  * in `ws`): call tic_heads_fwd_bwd with dW_* = NULL and this on another stream so that it runs beside the input-gradient

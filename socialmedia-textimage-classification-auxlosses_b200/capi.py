@@ -29,6 +29,8 @@ _SIGS = {
     "tic_itc_row_parts": ("i", ctypes.c_int),
     "tic_itc_col_parts": ("i", ctypes.c_int),
     "tic_itc_fwd": ("pplpplppiiiiffpppplpipippiippp", ctypes.c_int),
+    "tic_itc_fused_small_ok": ("ii", ctypes.c_int),
+    "tic_itc_fwd_bwd_small": ("pplpplppiiiifpppplpipippfplplppp", ctypes.c_int),
     "tic_itc_pick": ("pplpplppiiiiffppppp", ctypes.c_int),
     "tic_reduce_parts": ("piipp", ctypes.c_int),
     "tic_itc_lse_loss": ("pipipiiifppppp", ctypes.c_int),
@@ -54,7 +56,8 @@ _SIGS = {
     "tic_itm_sample_gather": ("ppiiplfppplppppp", ctypes.c_int),
     "tic_pack_cls_pairs": ("plpliipplppp", ctypes.c_int),
     "tic_unpack_cls_grad": ("plpliipplp", ctypes.c_int),
-    "tic_heads_fwd_bwd": ("pliiiippppppppfffppppplplppppippp", ctypes.c_int),
+    "tic_heads_fwd_bwd": ("pliiiippppppppfffppppplplppppipppplpp", ctypes.c_int),
+    "tic_fusion_pair_grad": ("ppliiippppplp", ctypes.c_int),
     "tic_heads_wgrad": ("pliiiippfppppp", ctypes.c_int),
     "tic_attn_pool_fwd": ("pllpliiiifpplplplp", ctypes.c_int),
     "tic_attn_pool_bwd": ("pllplplpliiiifpplp", ctypes.c_int),

@@ -66,7 +66,12 @@ __global__ void unpack_accum_kernel(const float* __restrict__ dX, int64_t ldd, c
 
 // ------------------------------------------------------------------ heads: logits, losses, dlogits, dH
 // One warp per row of H. rows [0,B) feed linear_cls (+ dropout keep mask), rows [B,2B) feed linear_tim.
-__global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int B, int E, int C, int has_tim,
+//
+// Pairwise form of concat fusion (Pt != nullptr): linear_fusion([x_t | x_v]) = x_t W_f[:, :E]^T + (x_v W_f[:, E:]^T + b), so the
+// two halves are projected ONCE per sample (Pt = text half, Pv = image half + bias, fp32 [B, E]) and the fused vector of the
+// ITM pair (text of sample src[i], image of sample i; mm_late.py:170-181) is relu(Pt[src[i]] + Pv[i]) — no packed [2B, 2E]
+// operand, half the fusion FLOPs.  The kernel then builds its row of H itself (and stores it: mm_features / weight gradients).
+__global__ void heads_rows_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C, int has_tim,
                                   const float* __restrict__ W_cls, const float* __restrict__ b_cls,
                                   const float* __restrict__ W_tim, const float* __restrict__ b_tim,
                                   const float* __restrict__ y_soft, const float* __restrict__ class_w,
@@ -75,7 +80,8 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
                                   float* __restrict__ losses, float* __restrict__ dlogits /* [rows, kMaxClasses] */,
                                   const float* __restrict__ dz_ext /* upstream dL/dlogits or nullptr (fused losses) */,
                                   __nv_bfloat16* __restrict__ dHb, __nv_bfloat16* __restrict__ dHb_lo, int64_t ld_dhb,
-                                  float* __restrict__ dHf, int64_t ld_dhf, int relu_mask) {
+                                  float* __restrict__ dHf, int64_t ld_dhf, int relu_mask, const float* __restrict__ Pt,
+                                  const float* __restrict__ Pv, int64_t ldp, const int32_t* __restrict__ src) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
   const int rows = has_tim ? 2 * B : B;
@@ -89,16 +95,31 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
     const int nc = is_cls ? C : 2;
     const float* W = is_cls ? W_cls : W_tim;
     const float* bias = is_cls ? b_cls : b_tim;
-    const float* h = H + static_cast<int64_t>(r) * ldh;
+    float* h = H + static_cast<int64_t>(r) * ldh;
     const uint8_t* kp = (is_cls && keep) ? keep + static_cast<int64_t>(i) * E : nullptr;
     float z[kMaxClasses];
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c) z[c] = 0.f;
     // 16-byte path: every lane owns 4 consecutive features per 128-wide chunk (6 independent iterations at E = 768)
-    const bool vec = (E & 3) == 0 && (ldh & 3) == 0 && (ld_dhb & 3) == 0 && (ld_dhf & 3) == 0 &&
+    const bool vec = (E & 3) == 0 && (ldh & 3) == 0 && (ld_dhb & 3) == 0 && (ld_dhf & 3) == 0 && (ldp & 3) == 0 &&
                      ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W_cls) | reinterpret_cast<uintptr_t>(W_tim) |
-                       reinterpret_cast<uintptr_t>(dHf) | reinterpret_cast<uintptr_t>(keep)) & 15) == 0 &&
+                       reinterpret_cast<uintptr_t>(dHf) | reinterpret_cast<uintptr_t>(keep) | reinterpret_cast<uintptr_t>(Pt) |
+                       reinterpret_cast<uintptr_t>(Pv)) & 15) == 0 &&
                      ((reinterpret_cast<uintptr_t>(dHb) | reinterpret_cast<uintptr_t>(dHb_lo)) & 7) == 0;
+    if (Pt != nullptr) {   // pairwise form: this row of H = relu(Pt[text row] + Pv[image row]); every lane re-reads only its own stores
+      const float* pt = Pt + static_cast<int64_t>(is_cls ? i : src[i]) * ldp;
+      const float* pv = Pv + static_cast<int64_t>(i) * ldp;
+      if (vec) {
+#pragma unroll 2
+        for (int k = lane * 4; k < E; k += 128) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(pt + k)), b = __ldg(reinterpret_cast<const float4*>(pv + k));
+          *reinterpret_cast<float4*>(h + k) = make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f),
+                                                          fmaxf(a.w + b.w, 0.f));
+        }
+      } else {
+        for (int k = lane; k < E; k += 32) h[k] = fmaxf(__ldg(pt + k) + __ldg(pv + k), 0.f);
+      }
+    }
     if (vec) {
 #pragma unroll 2
       for (int k = lane * 4; k < E; k += 128) {
@@ -235,6 +256,90 @@ __global__ void heads_rows_kernel(const float* __restrict__ H, int64_t ldh, int 
     if (lane == 0) {
       if (a != 0.f) atomicAdd(losses + 0, a);
       if (b != 0.f) atomicAdd(losses + 1, b);
+    }
+  }
+}
+
+// Backward of the pairwise form: gradients w.r.t. the two projected halves from dH [2B, E] (bf16 hi + lo):
+//   dPv[i] = dH[i] + dH[B+i]                                  (image half of sample i feeds its main row and its ITM row)
+//   dPt[k] = dH[k] + sum over {i : src[i] == k} of dH[B+i]    (text half of sample k feeds its main row and every ITM row that drew it)
+// One warp per sample; the inverse of the gather is found by scanning src (ballot over 32 candidates per step): no atomics,
+// fixed summation order, nothing to zero.  Outputs are bf16 (hi, lo) pairs: A operands of the dX / dW GEMMs.
+__global__ void __launch_bounds__(256) fusion_pair_grad_kernel(const __nv_bfloat16* __restrict__ dH, const __nv_bfloat16* __restrict__ dH_lo,
+                                                               int64_t ld, int B, int E, int has_tim, const int32_t* __restrict__ src,
+                                                               __nv_bfloat16* __restrict__ dPt, __nv_bfloat16* __restrict__ dPt_lo,
+                                                               __nv_bfloat16* __restrict__ dPv, __nv_bfloat16* __restrict__ dPv_lo,
+                                                               int64_t ldo) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int MAXC = 4;                         // E <= 1024: 8 consecutive features per lane per 256-wide chunk
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= B) return;
+  auto ld8 = [&](const __nv_bfloat16* base, const __nv_bfloat16* base_lo, int row, int c, float (&f)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(row) * ld + c));
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(hh[q]); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
+    if (base_lo != nullptr) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base_lo + static_cast<int64_t>(row) * ld + c));
+      const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(hl[q]); f[2 * q] += t.x; f[2 * q + 1] += t.y; }
+    }
+  };
+  auto st8 = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, int row, int c, float (&g)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]); u.z = pack_bf16x2(g[4], g[5]); u.w = pack_bf16x2(g[6], g[7]);
+    *reinterpret_cast<uint4*>(hi + static_cast<int64_t>(row) * ldo + c) = u;
+    if (lo != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] -= __bfloat162float(__float2bfloat16_rn(g[j]));
+      u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]); u.z = pack_bf16x2(g[4], g[5]); u.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(lo + static_cast<int64_t>(row) * ldo + c) = u;
+    }
+  };
+  float at[MAXC][8], av[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < E) {
+      ld8(dH, dH_lo, k, col, at[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) av[c][j] = at[c][j];
+      if (has_tim) {
+        float t[8];
+        ld8(dH, dH_lo, B + k, col, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) av[c][j] += t[j];
+      }
+    }
+  }
+  if (has_tim) {
+    for (int j0 = 0; j0 < B; j0 += 32) {
+      const int j = j0 + lane;
+      unsigned hit = __ballot_sync(0xffffffffu, j < B && __ldg(src + j) == k);
+      while (hit != 0) {                       // ascending j: a fixed summation order
+        const int jj = j0 + __ffs(hit) - 1;
+        hit &= hit - 1;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          const int col = c * 256 + lane * 8;
+          if (col < E) {
+            float t[8];
+            ld8(dH, dH_lo, B + jj, col, t);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) at[c][q] += t[q];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < E) {
+      st8(dPt, dPt_lo, k, col, at[c]);
+      st8(dPv, dPv_lo, k, col, av[c]);
     }
   }
 }
@@ -425,12 +530,28 @@ int tic_unpack_cls_grad(const float* dXcat, int64_t ldd, const float* dX2, int64
   return TIC_OK;
 }
 
-int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* W_cls, const float* b_cls,
+int tic_fusion_pair_grad(const void* dH, const void* dH_lo, int64_t ld, int B, int E, int has_tim, const int32_t* src_idx, void* dPt,
+                         void* dPt_lo, void* dPv, void* dPv_lo, int64_t ldo, void* stream) {
+  TIC_CHECK_ARG(dH && dPt && dPv && B > 0 && E > 0 && (!has_tim || src_idx), "tic_fusion_pair_grad: bad arguments");
+  TIC_CHECK_ARG((E & 7) == 0 && E <= 1024 && (ld & 7) == 0 && (ldo & 7) == 0 && aligned16(dH) && aligned16(dH_lo) && aligned16(dPt) &&
+                    aligned16(dPt_lo) && aligned16(dPv) && aligned16(dPv_lo),
+                "tic_fusion_pair_grad: E must be a multiple of 8 (<= 1024), rows 16-byte aligned");
+  launch_k(fusion_pair_grad_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+           static_cast<const __nv_bfloat16*>(dH), static_cast<const __nv_bfloat16*>(dH_lo), ld, B, E, has_tim, src_idx,
+           static_cast<__nv_bfloat16*>(dPt), static_cast<__nv_bfloat16*>(dPt_lo), static_cast<__nv_bfloat16*>(dPv),
+           static_cast<__nv_bfloat16*>(dPv_lo), ldo);
+  TIC_CHECK_LAUNCH("tic_fusion_pair_grad");
+  return TIC_OK;
+}
+
+int tic_heads_fwd_bwd(float* H, int64_t ldh, int B, int E, int C, int has_tim, const float* W_cls, const float* b_cls,
                       const float* W_tim, const float* b_tim, const float* y_soft, const float* class_w,
                       const int64_t* lbl_tim, const uint8_t* keep, float keep_scale, float c_cls, float c_tim,
                       float* logits_cls, float* logits_tim, float* losses, void* dH_bf16, void* dH_bf16_lo, int64_t ld_dhb, float* dH_f32,
-                      int64_t ld_dhf, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask, float* ws, const float* dlogits_ext, void* stream) {
+                      int64_t ld_dhf, float* dW_cls, float* db_cls, float* dW_tim, float* db_tim, int relu_mask, float* ws, const float* dlogits_ext,
+                      const float* Pt, const float* Pv, int64_t ldp, const int32_t* src_idx, void* stream) {
   TIC_CHECK_ARG(H && W_cls && b_cls && y_soft && logits_cls && losses && ws, "tic_heads_fwd_bwd: null pointer");
+  TIC_CHECK_ARG((Pt == nullptr) == (Pv == nullptr) && (!Pt || !has_tim || src_idx), "tic_heads_fwd_bwd: pairwise form needs Pt, Pv (and src_idx with ITM)");
   TIC_CHECK_ARG(B > 0 && E > 0 && C >= 1 && C <= kMaxClasses, "tic_heads_fwd_bwd: need 1 <= C <= %d", kMaxClasses);
   TIC_CHECK_ARG(!has_tim || (W_tim && b_tim && lbl_tim && logits_tim), "tic_heads_fwd_bwd: ITM head pointers missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -440,7 +561,7 @@ int tic_heads_fwd_bwd(const float* H, int64_t ldh, int B, int E, int C, int has_
                                                         lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses,
                                                         dlogits, dlogits_ext, static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb,
                                                         dH_f32, ld_dhf,
-                                                        relu_mask);
+                                                        relu_mask, Pt, Pv, ldp, src_idx);
   if (dW_cls && db_cls) {
     const int rpb = max(8, ceil_div(B, 128));
     const int heads = (has_tim && dW_tim && db_tim) ? 2 : 1;

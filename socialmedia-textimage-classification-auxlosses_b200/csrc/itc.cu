@@ -349,9 +349,12 @@ struct ItcBwdEpi {
     alignas(64) CUtensorMap tmap_ga;
   };
   // per-column vectors of this tile -> shared memory, this thread's row norm / row lse -> cx.pre[0..1]; runs while the MMAs of
-  // the tile are in flight (small batch: lse comes from up to 64 forward partials per row and column — a long load chain)
-  template <int BN>
+  // the tile are in flight (small batch: lse comes from up to 64 forward partials per row and column — a long load chain).
+  // COH: the statistics were written by OTHER CTAs of this very kernel (fused forward+backward, below): they must not be
+  // read through the non-coherent path (ld.global.nc is only defined for data that is read-only during the kernel).
+  template <int BN, bool COH = false>
   __device__ static void prefetch(const Params& p, EpiCtx& cx) {
+    auto ldf = [](const float* q) { return COH ? __ldcg(q) : __ldg(q); };
     const int lane = threadIdx.x & 31;
     const int row = cx.m0 + cx.quad * 32 + lane;
     const bool valid_row = row < cx.M;
@@ -367,16 +370,16 @@ struct ItcBwdEpi {
     }
     for (int j = cx.epi_tid; j < BN; j += cx.epi_threads) {
       const bool ok = cx.n0 + j < cx.N;
-      const float b = ok ? __ldg(p.rinv_v + cx.n0 + j) : 0.f;
+      const float b = ok ? ldf(p.rinv_v + cx.n0 + j) : 0.f;
       sb[j] = b;
       float lc = 0.f;
       if (ok) {
         if (p.col_part != nullptr) {
           float cs = 0.f;
-          for (int q = 0; q < p.n_col_parts; ++q) cs += __ldg(p.col_part + static_cast<int64_t>(q) * cx.N + cx.n0 + j);
+          for (int q = 0; q < p.n_col_parts; ++q) cs += ldf(p.col_part + static_cast<int64_t>(q) * cx.N + cx.n0 + j);
           lc = shift + logf(cs);
         } else {
-          lc = __ldg(p.lse_col + cx.n0 + j);
+          lc = ldf(p.lse_col + cx.n0 + j);
         }
       }
       // factored fast path:  e^{S-lse_row} + e^{S-lse_col} = e1 * (1 + Er_i * Ec_j),  e1 = 2^(s2 - lr),
@@ -385,15 +388,15 @@ struct ItcBwdEpi {
       sg[j] = b * p.gscale;
     }
     epi_bar_sync(cx.epi_threads);
-    const float rt = valid_row ? __ldg(p.rinv_t + row) : 0.f;
+    const float rt = valid_row ? ldf(p.rinv_t + row) : 0.f;
     float lr = 0.f;
     if (valid_row) {
       if (p.row_part != nullptr) {
         float rs = 0.f;
-        for (int q = 0; q < p.n_row_parts; ++q) rs += __ldg(p.row_part + static_cast<int64_t>(q) * cx.M + row);
+        for (int q = 0; q < p.n_row_parts; ++q) rs += ldf(p.row_part + static_cast<int64_t>(q) * cx.M + row);
         lr = (shift + logf(rs)) * kLog2e;
       } else {
-        lr = __ldg(p.lse_row + row) * kLog2e;
+        lr = ldf(p.lse_row + row) * kLog2e;
       }
     }
     cx.pre[0] = rt;
@@ -544,6 +547,124 @@ struct ItcBwdEpi {
     }
   }
 };
+
+// ------------------------------------------------------------------ fused forward + backward tiles (small batch)
+// The small-batch step is a chain of latency-bound launches; forward tiles and gradient-operand tiles are two of them and
+// each runs the SAME k-loop over the same operands.  When the whole similarity matrix is at most 8 tiles of 128 x 64
+// (B <= 256 on one GPU) one thread-block CLUSTER computes it: every CTA keeps its S tile in TMEM, runs the forward
+// epilogue (row / column partial sums, positives, inverse norms, optional logits / hard-negative weight sums), the
+// cluster meets at ONE barrier (release/acquire at cluster scope: the partial sums every CTA wrote to global memory are
+// visible), and the backward epilogue derives lse_row / lse_col from those partials and emits the gradient operands from
+// the accumulator that is still in TMEM.  One launch and one k-loop less on the critical chain of the step.
+template <int BN>
+__global__ void __launch_bounds__(64 + 32 * kItcEpiWarps, 1)
+itc_fused_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
+                       const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int M,
+                       int N, int K, const __grid_constant__ ItcFwdEpi::Params fp, const __grid_constant__ ItcBwdEpi::Params bp) {
+  using Cfg = UmmaCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * Cfg::kStageBytes;
+  auto full_bar = [&](int st) { return bar_base + 8u * st; };
+  auto empty_bar = [&](int st) { return bar_base + 8u * (STAGES + st); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* scratch = smem_gen + STAGES * Cfg::kStageBytes + 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int m_blk = blockIdx.x / n_tiles, n_blk = blockIdx.x % n_tiles;   // one tile per CTA, the grid is one cluster
+  const int num_kb = (K + kBK - 1) / kBK;
+  const int nseg = 1 + (split & 1) + ((split >> 1) & 1);
+  const int total_kb = num_kb * nseg;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (split & 1) tma_prefetch_desc(&tmap_a_lo);
+    if (split & 2) tma_prefetch_desc(&tmap_b_lo);
+    for (int st = 0; st < STAGES; ++st) { mbar_init(full_bar(st), 1); mbar_init(empty_bar(st), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  pdl_wait();
+  const int m0 = m_blk * kBM, n0 = n_blk * BN;
+  EpiCtx cx;
+  if (warp == 0) {
+    if (lane == 0) {     // ---- TMA producer (same segment order as umma_gemm_kernel: hi*hi, lo*hi, hi*lo)
+      int st = 0;
+      uint32_t ph = 0;
+      for (int kt = 0; kt < total_kb; ++kt) {
+        mbar_wait(empty_bar(st), ph ^ 1u);
+        const int seg = kt / num_kb, kb = kt - seg * num_kb;
+        const bool a_lo = (seg == 1) && (split & 1);
+        const bool b_lo = (seg >= 1) && !a_lo;
+        const uint32_t sa = smem_base + st * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(full_bar(st), Cfg::kStageBytes);
+        tma_load_2d(sa, a_lo ? &tmap_a_lo : &tmap_a, full_bar(st), kb * kBK, m0);
+        tma_load_2d(sa + kABytes, b_lo ? &tmap_b_lo : &tmap_b, full_bar(st), kb * kBK, n0);
+        if (++st == STAGES) { st = 0; ph ^= 1u; }
+      }
+      pdl_trigger();
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {     // ---- MMA issuer
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, false, false);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(full_bar(st), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + st * Cfg::kStageBytes;
+        const uint64_t da = umma_smem_desc_sw128(sa, 16u, 1024u);
+        const uint64_t db = umma_smem_desc_sw128(sa + kABytes, 16u, 1024u);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k)
+          umma_bf16(tmem_base, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(empty_bar(st));
+        if (++st == STAGES) { st = 0; ph ^= 1u; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {               // ---- epilogue, phase 1: forward statistics
+    cx.M = M; cx.N = N;
+    cx.quad = warp & 3;
+    cx.part = (warp - 2) >> 2;
+    cx.nparts = kItcEpiWarps / 4;
+    cx.epi_tid = threadIdx.x - 64;
+    cx.epi_threads = 32 * kItcEpiWarps;
+    cx.scratch = scratch;
+    cx.iter = 0;
+    cx.ks = 0; cx.ksplit = 1;
+    cx.m_blk = m_blk; cx.n_blk = n_blk; cx.m0 = m0; cx.n0 = n0;
+    cx.tmem_acc = tmem_base;
+    ItcFwdEpi::template prefetch<BN>(fp, cx);
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    ItcFwdEpi::template tile<BN>(fp, cx);
+    tc_fence_before();
+  }
+  __syncwarp();
+  cluster_sync_all();    // every CTA's partial sums / inverse norms are in global memory and visible cluster-wide
+  if (warp >= 2) {       // ---- epilogue, phase 2: gradient operands from the accumulator still in TMEM
+    tc_fence_after();
+    cx.iter = 1;         // the other half of the double-buffered epilogue scratch
+    ItcBwdEpi::template prefetch<BN, true>(bp, cx);
+    ItcBwdEpi::template tile<BN>(bp, cx);
+    tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
 
 // ------------------------------------------------------------------ small HBM-bound kernels
 // rinv[i] = 1/||X[i,:]||  — one warp per row, 16-byte loads when aligned.
@@ -1035,6 +1156,74 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
   if (rc == -3) { set_error("tic_itc_bwd_g: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_bwd_g: launch failed"); return TIC_E_LAUNCH; }
   return rc;
+}
+
+int tic_itc_fused_small_ok(int m_local, int n_global) {
+  return itc_bn(n_global) == kItcBNSmall && ceil_div(m_local, kBM) * ceil_div(n_global, kItcBNSmall) <= 8 ? 1 : 0;
+}
+
+int tic_itc_fwd_bwd_small(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv, float* rinv_t,
+                          float* rinv_v, int m_local, int n_global, int P, int row_offset, float scale, float* row_part,
+                          float* col_part, float* diag, float* logits_out, int64_t ld_logits, const float* ss_t_part, int n_ss_t,
+                          const float* ss_v_part, int n_ss_v, const float* scale_dev, void* qpart, float gscale, void* GA,
+                          int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo, void* GBT_lo, void* stream) {
+  TIC_CHECK_ARG(T && V && rinv_t && rinv_v && row_part && col_part && diag && GA, "tic_itc_fwd_bwd_small: null pointer");
+  TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0 && row_offset >= 0 && row_offset + m_local <= n_global,
+                "tic_itc_fwd_bwd_small: bad problem");
+  TIC_CHECK_ARG(tic_itc_fused_small_ok(m_local, n_global), "tic_itc_fwd_bwd_small: more than 8 tiles of 128x64 (m=%d n=%d)", m_local,
+                n_global);
+  if (scale_dev == nullptr && (!(scale > 0.f) || scale > 40.f)) {
+    set_error("tic_itc_fwd_bwd_small: scale=%g outside the supported range (0 < scale <= 40)", scale);
+    return TIC_E_RANGE;
+  }
+  TIC_CHECK_ARG((!ss_t_part || n_ss_t > 0) && (!ss_v_part || n_ss_v > 0), "tic_itc_fwd_bwd_small: empty sum-of-squares partial list");
+  constexpr int BN = kItcBNSmall;
+  using Cfg = UmmaCfg<BN>;
+  const int m_tiles = ceil_div(m_local, kBM), n_tiles = ceil_div(n_global, BN);
+  ItcFwdEpi::Params fp{rinv_t, rinv_v, ss_t_part, ss_v_part, n_ss_t, n_ss_v, scale * kLog2e, scale * kLog2e, scale, scale,
+                       row_part, col_part, diag, logits_out, ld_logits, row_offset, scale_dev,
+                       static_cast<unsigned long long*>(qpart)};
+  // backward statistics straight from the forward partials of this launch (inline lse)
+  ItcBwdEpi::Params bp{rinv_t, rinv_v, nullptr, nullptr, scale * kLog2e, gscale, static_cast<__nv_bfloat16*>(GA), ld_ga,
+                       static_cast<__nv_bfloat16*>(GBT), ld_gbt, static_cast<__nv_bfloat16*>(GA_lo),
+                       static_cast<__nv_bfloat16*>(GBT_lo), row_part, col_part, n_tiles * (kItcEpiWarps / 4), m_tiles, scale,
+                       scale * kLog2e, ((scale_dev != nullptr || scale <= 20.f) && GBT == nullptr) ? 1 : 0, 0, scale_dev, {}};
+  CUtensorMap ta, tb, ta_lo, tb_lo;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&ta, T, (uint64_t)P, (uint64_t)m_local, (uint64_t)ldt, kBK, kBM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tb, V, (uint64_t)P, (uint64_t)n_global, (uint64_t)ldv, kBK, BN))) return rc;
+  if ((rc = make_tmap_bf16_2d(&ta_lo, T_lo ? T_lo : T, (uint64_t)P, (uint64_t)m_local, (uint64_t)ldt, kBK, kBM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tb_lo, V_lo ? V_lo : V, (uint64_t)P, (uint64_t)n_global, (uint64_t)ldv, kBK, BN))) return rc;
+  const int split = (T_lo ? 1 : 0) | (V_lo ? 2 : 0);
+  auto kern = itc_fused_small_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
+      set_error("tic_itc_fwd_bwd_small: cudaFuncSetAttribute failed");
+      return TIC_E_ATTR;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(m_tiles * n_tiles);
+  cfg.blockDim = dim3(64 + 32 * kItcEpiWarps);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = m_tiles * n_tiles;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta_lo, tb, tb_lo, split, m_local, n_global, P, fp, bp);
+  if (e != cudaSuccess) {
+    set_error("tic_itc_fwd_bwd_small: launch failed: %s", cudaGetErrorString(e));
+    return TIC_E_LAUNCH;
+  }
+  return TIC_OK;
 }
 
 int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const void* X_lo, int64_t ldx, const float* rinv,

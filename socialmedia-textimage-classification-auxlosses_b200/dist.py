@@ -139,8 +139,8 @@ def _make_dist_head_plan():
                 self.sharded.backward(Yt, Yv, self.scale, self.g_itc, dT_bf16=dYt, dV_bf16=dYv, r_sum=z["r_sum"], T_lo=Ytl,
                                       V_lo=Yvl, dT_lo=dYt_lo, dV_lo=dYv_lo)
                 tp_, vp_ = inp["t_pool"], inp["v_pool"]
-                P.gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo, accumulate=True)
-                P.gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=True)
+                P.gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo, accumulate=self._atomic["dW_t"])
+                P.gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=self._atomic["dW_v"])
                 P.gemm(dYt, self.P, 0, w["W_t"], E, 1, o["d_t_pool"], E, 0, B, E, self.P, A_lo=dYt_lo)
             else:
                 self.sharded.backward(Yt, Yv, self.scale, self.g_itc, dT_f32=o["d_t_emb"], dV_f32=o["d_v_emb"],

@@ -445,12 +445,12 @@ def _make_peer_head_plan():
 
                 def consume_t():
                     with br("w"):
-                        P.gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo, accumulate=True)
+                        P.gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo, accumulate=self._atomic["dW_t"])
                     P.gemm(dYt, self.P, 0, w["W_t"], E, 1, o["d_t_pool"], E, 0, B, E, self.P, A_lo=dYt_lo)
                     br.join("w")
 
                 def consume_v():
-                    P.gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=True)
+                    P.gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=self._atomic["dW_v"])
 
                 self.sym.backward(scale=self.scale, g=self.g_itc, dT_bf16=dYt, dV_bf16=dYv, r_sum=z["r_sum"], dT_lo=dYt_lo,
                                   dV_lo=dYv_lo, consume_t=consume_t, consume_v=consume_v, **self._ops())

@@ -161,6 +161,19 @@ class ItcPlan:
              ptr(self.logits), self.n if self.logits is not None else 0, ptr(ss_t), 0 if ss_t is None else ss_t.shape[0],
              ptr(ss_v), 0 if ss_v is None else ss_v.shape[0], sr, se, sc, ms, ptr(self.scale_dev), ptr(self.qpart), _stream())
 
+    @property
+    def can_fuse_small(self):
+        """forward + gradient-operand tiles in ONE cluster launch (at most 8 tiles of 128 x 64; csrc/itc.cu)"""
+        return (self.col_part is not None and self.m == self.n and self.row_offset == 0 and
+                bool(capi.load().tic_itc_fused_small_ok(self.m, self.n)))
+
+    def fwd_bwd_fused(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None, ss_t=None, ss_v=None):
+        call("tic_itc_fwd_bwd_small", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), self.m,
+             self.n, self.P, self.row_offset, float(scale), ptr(self.row_part), ptr(self.col_part), ptr(self.diag),
+             ptr(self.logits), self.n if self.logits is not None else 0, ptr(ss_t), 0 if ss_t is None else ss_t.shape[0],
+             ptr(ss_v), 0 if ss_v is None else ss_v.shape[0], ptr(self.scale_dev), ptr(self.qpart), float(gscale), ptr(self.GA),
+             self.ld_ga, ptr(self.GBT), self.ld_gbt, ptr(self.GA_lo), ptr(self.GBT_lo), _stream())
+
     def hard_locate(self, u_coin, u_pick, labels, src_idx):
         """labels / default sources for every row + (part, residual) of each mismatch row from the weight sums of fwd_tiles"""
         call("tic_itm_hard_locate", ptr(u_coin), ptr(u_pick), self.m, self.n, self.row_offset, ptr(self.qpart), self.nrp,
@@ -292,6 +305,8 @@ class HeadPlan:
         self.scale_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         if self.itc is not None:
             self.itc.scale_dev = self.scale_t
+        import os as _os2
+        self.fuse_itc_small = _os2.environ.get("TIC_ITC_FUSED_SMALL", "1") != "0"     # A/B switch (same kernels' epilogues)
         self.live_weights = False                # bind_params(live=True): the bf16 working copies are refreshed inside step()
         self._refresh_groups = {}
         self.generation = 0                      # autograd mode: bumped by forward(); backward() checks it (see mm_late._HeadFn)
@@ -321,26 +336,52 @@ class HeadPlan:
         # one contiguous block of accumulators that must be zero at the start of every step (one memset)
         sizes = {"losses": 2, "itc_sums": 2, "r_sum": 1, "_pad": 3, "dW_cls": C * E, "db_cls": C, "dW_tim": 2 * E,
                  "db_tim": 2, "db_f": E, "db_Q": E, "db_V": E, "db_gt": 2 * E, "db_gv": 2 * E, "dw_a": E, "db_a": 1}
-        # weight gradients are accumulated with fp32 atomics by split-K GEMMs: they start every step at zero too
+        n_small_keys = len(sizes)
+        # Weight gradients: a GEMM the library would split over K (long K, few output tiles: large batches) accumulates with
+        # fp32 atomics and must start at zero; one it runs un-split (the small-batch step: K = B is short) writes plain
+        # stores — no atomics, nothing to zero: at c2 the 8.5 MB memset of round 1 is gone.  (M, N, K, split operands):
+        import os as _os
+        sp = 1 if self.split else 0
+        self.pairwise = self.fusion == "concat" and _os.environ.get("TIC_CONCAT_PAIRWISE", "1") != "0"   # A/B switch
+        big = {}
         if self.P is not None:
-            sizes.update(dW_t=self.P * E, dW_v=self.P * E)
+            big.update(dW_t=(self.P * E, (self.P, E, B, sp)), dW_v=(self.P * E, (self.P, E, B, sp)))
         if self.fusion in ("concat", "attention", "gmu"):
-            sizes.update(dW_f=E * 2 * E, d_xt_cls=B * E)   # d_xt_cls: accumulated by tic_unpack_cls_grad (atomics)
+            if self.pairwise:   # two [E, E] halves, K = B; d_xt_cls is written by its GEMM directly
+                big.update(dW_f=(E * 2 * E, (E, E, B, sp)), d_xt_cls=(B * E, None))
+            else:               # d_xt_cls: accumulated by tic_unpack_cls_grad (atomics)
+                big.update(dW_f=(E * 2 * E, (E, 2 * E, R, sp + (0 if self.fusion == "concat" else sp))), d_xt_cls=(B * E, "atomic"))
         if self.fusion == "attention":
-            sizes.update(dW_Q=E * E, dW_V=E * E, dWK_aug=E * (E + 8))
+            big.update(dW_Q=(E * E, (E, E, R, sp)), dW_V=(E * E, (E, E, R, 2 * sp)), dWK_aug=(E * (E + 8), (E, E + 8, R, 2 * sp)))
         if self.fusion == "gmu":
-            sizes.update(dW_gt=2 * E * E, dW_gv=2 * E * E)
+            big.update(dW_gt=(2 * E * E, (2 * E, E, R, sp)), dW_gv=(2 * E * E, (2 * E, E, R, sp)))
+        self._atomic = {}
+        tn, ks, kc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        for k, (n, shape) in big.items():
+            if shape is None:
+                self._atomic[k] = False
+            elif shape == "atomic":
+                self._atomic[k] = True
+            else:
+                call("tic_gemm_plan", shape[0], shape[1], shape[2], shape[3], 1, ctypes.byref(tn), ctypes.byref(ks), ctypes.byref(kc))
+                self._atomic[k] = ks.value > 1
+        plain = {k: n for k, (n, _) in big.items() if not self._atomic[k]}
+        sizes.update({k: n for k, (n, _) in big.items() if self._atomic[k]})
         pad = (-sum(sizes.values())) % 4
         sizes["_pad2"] = pad
         self.zb = torch.zeros(sum(sizes.values()), dtype=F32, device=dev)
+        self.pb = torch.zeros(max(sum(plain.values()), 1), dtype=F32, device=dev)     # overwritten by plain stores every step
         self.z, off = {}, 0
         for k, n in sizes.items():
             self.z[k] = self.zb[off:off + n]
             off += n
+        off = 0
+        for k, n in plain.items():
+            self.z[k] = self.pb[off:off + n]
+            off += n
         # the first keys (loss sums, small-head gradients) are needed right away; the large weight-gradient accumulators only
         # by the parameter-gradient branches and the final unpack: their memset runs on a side branch (_zero_accumulators)
-        n_small = sum(n for k, n in sizes.items() if k in ("losses", "itc_sums", "r_sum", "_pad", "dW_cls", "db_cls", "dW_tim",
-                                                           "db_tim", "db_f", "db_Q", "db_V", "db_gt", "db_gv", "dw_a", "db_a"))
+        n_small = sum(n for k, n in list(sizes.items())[:n_small_keys])
         self.zb_small, self.zb_big = self.zb[:n_small], self.zb[n_small:]
         self.out: Dict[str, torch.Tensor] = {"loss": e(4)}
         o = self.out
@@ -375,8 +416,13 @@ class HeadPlan:
             o["d_t_pool_fusion"] = e(B, E)
             o["dw_a"], o["db_a"] = self.z["dw_a"], self.z["db_a"]
             return
-        self.Xcat = e(R, 2 * E, dt=BF16)
-        self.dXt = e(R, E)                            # gradient of the text half of Xcat (fp32)
+        if self.pairwise:
+            # concat in pairwise form (csrc/heads.cu): the two halves of linear_fusion projected once per sample
+            self.Pt, self.Pv = e(B, E), e(B, E)
+            self.dPt, self.dPt_lo, self.dPv, self.dPv_lo = (e(B, E, dt=BF16) for _ in range(4))
+        else:
+            self.Xcat = e(R, 2 * E, dt=BF16)
+            self.dXt = e(R, E)                            # gradient of the text half of Xcat (fp32)
         o["d_xt_cls"] = self.z["d_xt_cls"].view(B, E)
         o["dW_f"], o["db_f"] = self.z["dW_f"].view(E, 2 * E), self.z["db_f"]
         if self.fusion == "attention":
@@ -520,8 +566,14 @@ class HeadPlan:
         if not fused_norm:
             it.norm_t(Yt, ldt, T_lo=Ytl)
         br.join("v")
-        it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl, ss_t=self.ss_t if fused_norm else None,
-                     ss_v=self.ss_v if fused_norm else None)
+        # small batch, fused step: forward AND gradient-operand tiles in one cluster launch (S stays in TMEM in between)
+        self._itc_bwd_fused = bool(with_loss and getattr(self, "_in_step", False) and self.fuse_itc_small and it.can_fuse_small)
+        if self._itc_bwd_fused:
+            it.fwd_bwd_fused(Yt, ldt, Yv, ldv, self.scale, self.g_itc / (2.0 * B), T_lo=Ytl, V_lo=Yvl,
+                             ss_t=self.ss_t if fused_norm else None, ss_v=self.ss_v if fused_norm else None)
+        else:
+            it.fwd_tiles(Yt, ldt, Yv, ldv, self.scale, T_lo=Ytl, V_lo=Yvl, ss_t=self.ss_t if fused_norm else None,
+                         ss_v=self.ss_v if fused_norm else None)
         self._join_small_zero()        # itc_sums / r_sum live in the small zeroed block
         if with_loss:
             if it.can_inline_lse:      # small batch: the backward derives lse itself; the loss runs on a side branch
@@ -540,7 +592,8 @@ class HeadPlan:
         ldt, ldv = Yt.stride(0), Yv.stride(0)
         if dS is None:
             g = self.g_itc
-            it.bwd_operands(Yt, ldt, Yv, ldv, self.scale, g / (2.0 * B), T_lo=Ytl, V_lo=Yvl, inline_lse=it.can_inline_lse)
+            if not getattr(self, "_itc_bwd_fused", False):   # (else: emitted by the fused forward+backward launch already)
+                it.bwd_operands(Yt, ldt, Yv, ldv, self.scale, g / (2.0 * B), T_lo=Ytl, V_lo=Yvl, inline_lse=it.can_inline_lse)
             dcoef = g / B
         else:
             assert it.precise, "autograd mode (materialised dS) is meant for drop-in batch sizes (< 4096)"
@@ -558,12 +611,12 @@ class HeadPlan:
                 it.grad_gemm_v(Yt, ldt, T_lo=Ytl)
                 it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, dcoef, None, dYv,
                               dV_lo=dYv_lo, V_lo=Yvl, T_diag_lo=Ytl)
-                gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=True)
+                gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=self._atomic["dW_v"])
             it.grad_gemm_t(Yv, ldv, V_lo=Yvl)
             it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, dcoef, None, dYt, z["r_sum"], dT_lo=dYt_lo, T_lo=Ytl,
                           V_diag_lo=Yvl)
             with br("w"):   # dW_t = dYt^T t_pool (both operands read MN-major)  ||  d_t_pool = dYt W_t
-                gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo, accumulate=True)
+                gemm(dYt, self.P, 1, tp_, tp_.stride(0), 1, o["dW_t"], E, 0, self.P, E, B, A_lo=dYt_lo, accumulate=self._atomic["dW_t"])
             gemm(dYt, self.P, 0, w["W_t"], E, 1, o["d_t_pool"], E, 0, B, E, self.P, A_lo=dYt_lo)
             br.join("v")
             br.join("w")
@@ -605,6 +658,13 @@ class HeadPlan:
         return o
 
     def _step_body(self, inp):
+        self._in_step = True
+        try:
+            return self._step_body_inner(inp)
+        finally:
+            self._in_step = False
+
+    def _step_body_inner(self, inp):
         B, z, o = self.B, self.z, self.out
         s0 = torch.cuda.current_stream()
         self._zero_accumulators()
@@ -797,6 +857,7 @@ class HeadPlan:
         if y_soft is None:   # autograd mode: the classification loss is the caller's
             y_soft = self.y_dummy
         no = forward_only
+        pw = getattr(self, "_pairwise", None) or (None, None, 0, None)   # (Pt, Pv, ldp, src): pairwise concat fusion
         side = self.parallel_streams and not no      # dW/db of the two small heads run beside the input-gradient chain
         wg = no or side
         call("tic_heads_fwd_bwd", ptr(self.H), E, B, E, self.C, int(self.use_itm), ptr(w["W_cls"]), ptr(w["b_cls"]),
@@ -805,7 +866,7 @@ class HeadPlan:
              ptr(o["out_cls"]), ptr(o.get("out_tim")), ptr(z["losses"]), None if no else ptr(self.dHb),
              None if no else ptr(self._lo(self.dHb_lo)), E, None if no else ptr(dH_f32), E, None if wg else ptr(z["dW_cls"]),
              None if wg else ptr(z["db_cls"]), None if wg else ptr(z["dW_tim"]), None if wg else ptr(z["db_tim"]), 1,
-             ptr(self.heads_ws), ptr(dz_ext), _stream())
+             ptr(self.heads_ws), ptr(dz_ext), ptr(pw[0]), ptr(pw[1]), pw[2], ptr(pw[3]), _stream())
         if side:
             self.br.enabled = True
             with self.br("hw"):
@@ -824,6 +885,17 @@ class HeadPlan:
             return
         x_t, x_v = inp["x_t"], inp["x_v"]
         xt_stride, xv_stride = x_t.stride(0), x_v.stride(0)   # CLS rows: x[:,0,:]
+        if self.pairwise:
+            # linear_fusion([x_t | x_v]) = x_t W_f[:, :E]^T + (x_v W_f[:, E:]^T + b_f): both halves once per sample, on two
+            # branches; the heads kernel forms relu(Pt[src] + Pv) for the main and the ITM rows itself (mm_late.py:92-96,170-181)
+            self.br.enabled = self.parallel_streams
+            with self.br("pv"):
+                gemm(x_v, xv_stride, 0, w["W_f"].data_ptr() + 2 * E, E2, 0, self.Pv, E, 0, B, E, E, bias=w["b_f"])
+            gemm(x_t, xt_stride, 0, w["W_f"], E2, 0, self.Pt, E, 0, B, E, E)
+            self.br.join("pv")
+            self._pairwise = (self.Pt, self.Pv, E, src)
+            return
+        self._pairwise = None
         X = self.Xcat
         X_lo = None
         uc, up = (ptr(inp["u_coin"]), ptr(inp["u_pick"])) if self._inline_rule(inp) else (None, None)
@@ -859,15 +931,30 @@ class HeadPlan:
                  ptr(z["db_a"]), st)
             return
         x_v = inp["x_v"]
-        X, Hin, Hin_lo = self.Xcat, self.Hin, self.Hin_lo
-        # backward through linear_fusion (dH is a split bf16 pair: hi + lo)
         dH, dHl = self.dHb, self._lo(self.dHb_lo)
         lo = self._lo
         br = self.br
         br.enabled = self.parallel_streams
+        if self.pairwise:
+            x_t = inp["x_t"]
+            with br("f"):     # bias gradient: column sums of dH over all R rows
+                call("tic_colsum_bf16_pair", ptr(dH), ptr(dHl), E, R, E, ptr(z["db_f"]), _stream())
+            call("tic_fusion_pair_grad", ptr(dH), ptr(dHl), E, B, E, int(self.use_itm), ptr(src), ptr(self.dPt), ptr(lo(self.dPt_lo)),
+                 ptr(self.dPv), ptr(lo(self.dPv_lo)), E, st)
+            with br("fv"):    # dW_f[:, E:] = dPv^T x_v_cls
+                gemm(self.dPv, E, 1, x_v, x_v.stride(0), 1, o["dW_f"].data_ptr() + 4 * E, E2, 0, E, E, B, A_lo=lo(self.dPv_lo),
+                     accumulate=self._atomic["dW_f"])
+            with br("ft"):    # dW_f[:, :E] = dPt^T x_t_cls
+                gemm(self.dPt, E, 1, x_t, x_t.stride(0), 1, o["dW_f"], E2, 0, E, E, B, A_lo=lo(self.dPt_lo),
+                     accumulate=self._atomic["dW_f"])
+            gemm(self.dPt, E, 0, w["W_f"], E2, 1, o["d_xt_cls"], E, 0, B, E, E, A_lo=lo(self.dPt_lo))   # d x_t[:,0] = dPt W_f[:, :E]
+            br.join("f"); br.join("fv"); br.join("ft")
+            return
+        X, Hin, Hin_lo = self.Xcat, self.Hin, self.Hin_lo
+        # backward through linear_fusion (dH is a split bf16 pair: hi + lo)
         with br("f"):   # parameter gradients of linear_fusion run beside the input-gradient chain
             call("tic_colsum_bf16_pair", ptr(dH), ptr(dHl), E, R, E, ptr(z["db_f"]), _stream())     # hi + lo in one launch
-            gemm(dH, E, 1, Hin, E2, 1, o["dW_f"], E2, 0, E, E2, R, A_lo=dHl, B_lo=Hin_lo, accumulate=True)           # dW_f = dH^T Hin
+            gemm(dH, E, 1, Hin, E2, 1, o["dW_f"], E2, 0, E, E2, R, A_lo=dHl, B_lo=Hin_lo, accumulate=self._atomic["dW_f"])           # dW_f = dH^T Hin
         if self.fusion == "concat":
             gemm(dH, E, 0, w["W_f"], E2, 1, self.dXt, E, 0, R, E, E, A_lo=dHl)                      # dX_text = dH W_f[:, :E]
             call("tic_unpack_cls_grad", ptr(self.dXt), E, None, 0, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
@@ -876,15 +963,15 @@ class HeadPlan:
             gemm(dH, E, 0, w["W_f"], E2, 1, self.dXt, E, 0, R, E, E, A_lo=dHl)
             gemm(dH, E, 0, w["W_f"].data_ptr() + 2 * E, E2, 1, self.dctx, E, 1, R, E, E, A_lo=dHl, D_lo=lo(self.dctx_lo))
             call("tic_colsum_bf16_pair", ptr(self.dctx), ptr(lo(self.dctx_lo)), E, R, E, ptr(z["db_V"]), st)
-            gemm(self.dctx, E, 1, self.xbar_b, E, 1, o["dW_V"], E, 0, E, E, R, A_lo=lo(self.dctx_lo), B_lo=lo(self.xbar_lo), accumulate=True)
+            gemm(self.dctx, E, 1, self.xbar_b, E, 1, o["dW_V"], E, 0, E, E, R, A_lo=lo(self.dctx_lo), B_lo=lo(self.xbar_lo), accumulate=self._atomic["dW_V"])
             gemm(self.dctx, E, 0, w["W_V"], E, 1, self.dxbar, E, 0, R, E, E, A_lo=lo(self.dctx_lo))
             call("tic_attn_pool_bwd", ptr(x_v), x_v.stride(0), x_v.stride(1), ptr(self.attn), Lv, ptr(self.dxbar), E,
                  ptr(self.xbar_f), E, B, 2 if self.use_itm else 1, Lv, E, float(E) ** -0.5, ptr(self.dkq), ptr(lo(self.dkq_lo)),
                  Ea, st)
             gemm(self.dkq, Ea, 0, w["W_Kaug"], Ea, 0, self.dq0, E, 1, R, E, Ea, A_lo=lo(self.dkq_lo), D_lo=lo(self.dq0_lo))
-            gemm(self.q0, E, 1, self.dkq, Ea, 1, self.dWK_aug, Ea, 0, E, Ea, R, A_lo=lo(self.q0_lo), B_lo=lo(self.dkq_lo), accumulate=True)  # [dW_K|db_K]
+            gemm(self.q0, E, 1, self.dkq, Ea, 1, self.dWK_aug, Ea, 0, E, Ea, R, A_lo=lo(self.q0_lo), B_lo=lo(self.dkq_lo), accumulate=self._atomic["dWK_aug"])  # [dW_K|db_K]
             call("tic_colsum_bf16_pair", ptr(self.dq0), ptr(lo(self.dq0_lo)), E, R, E, ptr(z["db_Q"]), st)
-            gemm(self.dq0, E, 1, X, E2, 1, o["dW_Q"], E, 0, E, E, R, A_lo=lo(self.dq0_lo), accumulate=True)
+            gemm(self.dq0, E, 1, X, E2, 1, o["dW_Q"], E, 0, E, E, R, A_lo=lo(self.dq0_lo), accumulate=self._atomic["dW_Q"])
             gemm(self.dq0, E, 0, w["W_Q"], E, 1, self.dXt2, E, 0, R, E, E, A_lo=lo(self.dq0_lo))
             call("tic_unpack_cls_grad", ptr(self.dXt), E, ptr(self.dXt2), E, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
         elif self.fusion == "gmu":
@@ -893,8 +980,8 @@ class HeadPlan:
                  ptr(self.dvp), ptr(lo(self.dtp_lo)), ptr(lo(self.dvp_lo)), E2, ptr(self.dXg), E2, st)
             call("tic_colsum_bf16_pair", ptr(self.dtp), ptr(lo(self.dtp_lo)), E2, R, E2, ptr(z["db_gt"]), st)
             call("tic_colsum_bf16_pair", ptr(self.dvp), ptr(lo(self.dvp_lo)), E2, R, E2, ptr(z["db_gv"]), st)
-            gemm(self.dtp, E2, 1, X, E2, 1, o["dW_gt"], E, 0, E2, E, R, A_lo=lo(self.dtp_lo), accumulate=True)
-            gemm(self.dvp, E2, 1, X.data_ptr() + 2 * E, E2, 1, o["dW_gv"], E, 0, E2, E, R, A_lo=lo(self.dvp_lo), accumulate=True)
+            gemm(self.dtp, E2, 1, X, E2, 1, o["dW_gt"], E, 0, E2, E, R, A_lo=lo(self.dtp_lo), accumulate=self._atomic["dW_gt"])
+            gemm(self.dvp, E2, 1, X.data_ptr() + 2 * E, E2, 1, o["dW_gv"], E, 0, E2, E, R, A_lo=lo(self.dvp_lo), accumulate=self._atomic["dW_gv"])
             gemm(self.dtp, E2, 0, w["W_gt"], E, 1, self.dXt2, E, 0, R, E, E2, A_lo=lo(self.dtp_lo))
             call("tic_unpack_cls_grad", ptr(self.dXg), E2, ptr(self.dXt2), E, B, E, ptr(src), ptr(o["d_xt_cls"]), E, st)
         br.join("f")

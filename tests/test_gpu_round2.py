@@ -269,3 +269,35 @@ def test_attention_fusion_c4_size_default_mode():
     assert plan.split
     plan.set_weights(p32)
     _check_head(plan, dev_in, ora_in, p32, "attention", True, odev="cuda")
+
+
+# ---------------------------------------------------------------------------------------------------- c2 restructuring
+@pytest.mark.parametrize("B", [8, 200, 256])
+def test_c2_fused_forms_match_unfused(B, monkeypatch):
+    """The launch-count work on the small-batch step: (1) forward + gradient-operand ITC tiles in ONE cluster launch,
+    (2) concat fusion in pairwise form (Pt[src] + Pv, no packed operand), (3) weight gradients by plain stores.  Each
+    against the round-1 forms (switches TIC_ITC_FUSED_SMALL / TIC_CONCAT_PAIRWISE) on the same inputs, and the new default
+    against the fp64 oracle."""
+    P = _plan_mod()
+    C = 4
+    dev_in, ora_in = _make_head_case(B, C, 2, 2, seed=B + 77)
+    p32 = R.init_params(C, seed=13)
+    new = P.HeadPlan(B, C=C, fusion="concat", use_itc=True, use_itm=True, Lv=2)
+    assert new.pairwise and new.fuse_itc_small and new.itc.can_fuse_small
+    assert not any(new._atomic.values()), new._atomic          # K = B is short: no split-K, no atomics, no large memset
+    new.set_weights(p32)
+    _check_head(new, dev_in, ora_in, p32, "concat", True)
+    assert new._itc_bwd_fused
+    monkeypatch.setenv("TIC_CONCAT_PAIRWISE", "0")
+    monkeypatch.setenv("TIC_ITC_FUSED_SMALL", "0")
+    old = P.HeadPlan(B, C=C, fusion="concat", use_itc=True, use_itm=True, Lv=2)
+    assert not old.pairwise and not old.fuse_itc_small
+    old.set_weights(p32)
+    a, b = new.step(dev_in), old.step(dev_in)
+    torch.cuda.synchronize()
+    assert not old._itc_bwd_fused
+    for k in ("loss", "out_cls", "out_tim", "mm_features", "dW_f", "db_f", "dW_t", "dW_v", "d_t_pool", "d_xt_cls", "dW_cls", "dW_tim"):
+        assert _rel(a[k], b[k]) < 2e-4, k
+    assert torch.equal(a["src_idx"], b["src_idx"])
+    # the ITC half is the same arithmetic in both forms (same tiles, same epilogues): bit-identical statistics
+    assert torch.equal(new.itc.row_part, old.itc.row_part) and torch.equal(new.itc.GA, old.itc.GA)
