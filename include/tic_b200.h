@@ -109,18 +109,19 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
                 float* logits_out, int64_t ld_logits, const float* ss_t_part, int n_ss_t, const float* ss_v_part, int n_ss_v,
                 const uint32_t* seg_ready, const uint32_t* seg_epoch, int seg_cols, int my_seg,
                 const float* scale_dev /* optional DEVICE scalar exp(logit_scale): overrides scale and shift */,
-                void* qpart /* optional uint64 [tic_itc_row_parts(n_global)][m_local]: hard-negative weight sums, see below */,
+                void* qpart /* optional uint64 [tic_itc_q_parts(n_global)][m_local]: hard-negative weight sums, see below */,
                 void* stream);
 /* Trainable temperature: logit_scale is a parameter of the reference model (mm_late.py:59-69 keeps it trainable; HF :272
  * applies exp()).  Every ITC entry point takes `scale_dev`, a DEVICE pointer to exp(logit_scale) (written by
  * tic_refresh_weights at the head of the step); when it is non-NULL it replaces the host `scale` / `shift` arguments, so
  * a step captured into a CUDA graph follows the optimiser's updates of logit_scale without re-capture.
  * Hard-negative sampling without a materialised S (a-5', tile-stream form; spec oracle/restatement.py:itm_sample_hard with
- * ref = shift): with `qpart` the forward tiles also write, per row and per column part (part p = the columns the row
- * partial row_part[p] covers), the integer sum of q_ij = trunc(det_exp(min(S_ij - shift, 0)) * 2^40), j != positive.
+ * ref = shift): with `qpart` the forward tiles also write, per row and per column part (part p = columns [32p, 32p+32);
+ * tic_itc_q_parts(n_global) parts), the integer sum of q_ij = trunc(det_exp(min(S_ij - shift, 0)) * 2^40), j != positive.
  * tic_itm_hard_locate turns these sums and the row's uniform into (part, residual target); tic_itc_pick recomputes the
  * tiles (bit-identical accumulators: same operands, shapes and k order) and walks the located part:
- * src = first column whose running weight exceeds the residual.  Traffic: 8 bytes per (row, part) instead of 4*B bytes per row. */
+ * src = first column whose running weight exceeds the residual.  Traffic: 8 bytes per 32 logits instead of 128. */
+int tic_itc_q_parts(int n_global);
 int tic_itc_pick(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv, const float* rinv_t,
                  const float* rinv_v, int m_local, int n_global, int P, int row_offset, float scale, float shift,
                  const float* scale_dev, const int32_t* loc_part, const void* loc_res /* uint64 [m_local] */,
@@ -153,7 +154,8 @@ int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int 
 /* Recompute S tiles and emit the bf16 gradient operands (g = dLoss/d(clip_loss), B = n_global):
  *   Gp[i,j] = g/(2B) * (exp(S-lse_row[i]) + exp(S-lse_col[j]))      (the -I/B diagonal is applied in fp32 later)
  *   GA [m_local, ld_ga ] row-major:  Gp[i,j] * rinv_v[j]            (A operand of dT = GA * V)
- *   GBT[n_global, ld_gbt] row-major: Gp[i,j] * rinv_t[i] at [j,i]   (A operand of dV = GBT * T)
+ *   GB ("GBT" argument) [m_local, ld_ga] row-major: Gp[i,j] * rinv_t[i] at [i,j] — the SAME orientation and leading dimension
+ *       as GA; dV = GB^T * T reads it MN-major (a_mn_major = 1), so no transposed operand is ever written (ld_gbt is ignored)
  * GBT may be NULL ("GA-shared" mode, used from 4096 columns on): the image-side gradient is then computed as
  *   dV_acc'[j,:] = sum_i GA[i,j] * That[i,:]  (GA read MN-major, That = normalised bf16 text embeddings from
  *   tic_row_rnorm_bf16), which equals rinv_v[j] * dV_acc[j,:]; tic_itc_grad_finalize(acc_div_rinv=1) divides it out. */
@@ -178,7 +180,7 @@ int tic_itc_fwd_bwd_small(const void* T, const void* T_lo, int64_t ldt, const vo
  * derives lse_row / lse_col = shift + log(sum of partials) itself (same expression as tic_itc_lse_loss) and the matching
  * lse pointer may be NULL — tic_itc_lse_loss then only produces the loss and runs beside the backward, not before it. */
 /* Autograd path (materialised logits, drop-in batch sizes): the same operands from an upstream dL/dS [m_local, n_global]:
- *   GA[i,j] = dS[i,j]*rinv_v[j],  GBT[j,i] = dS[i,j]*rinv_t[i]  (+ optional bf16 residuals). Use diag_coef = 0 afterwards. */
+ *   GA[i,j] = dS[i,j]*rinv_v[j],  GB[i,j] = dS[i,j]*rinv_t[i]  (+ optional bf16 residuals), layouts as above. Use diag_coef = 0 afterwards. */
 int tic_itc_ds_operands(const float* dS, int64_t ldds, int m_local, int n_global, const float* rinv_t, const float* rinv_v,
                         void* GA, void* GA_lo, int64_t ld_ga, void* GBT, void* GBT_lo, int64_t ld_gbt, void* stream);
 /* Normalise-backward + diagonal term, one warp per row (HF :268-269 backward):
@@ -336,10 +338,12 @@ int tic_metrics_from_confusion(const void* state, int C, float* out6, void* stre
 /* Head of a captured TRAINING step: refresh the bf16 working copies of up to 8 fp32 master weight matrices (the optimiser
  * updates the masters in place between replays; models/utils.py:280-292 selects them) and scale_out[0] = exp(*logit_scale)
  * (HF :272; values outside (0, 40] are clamped to 40 and *status = 1, sticky) in ONE launch.  The *_host arrays are HOST
- * arrays of n entries; matrix i is [rows, cols] fp32 with leading dimension lds[i], written as bf16 with ldd[i]. */
+ * arrays of n entries; matrix i is [rows, cols] fp32 with leading dimension lds[i], written as bf16 with ldd[i].
+ * zero0 / zero1: up to two fp32 ranges the same launch sets to zero (the step's loss sums and small gradient accumulators),
+ * so that no memset node sits in front of the step's first kernel. */
 int tic_refresh_weights(int n, const float* const* src_host, void* const* dst_host, const int64_t* lds_host,
                         const int64_t* ldd_host, const int* rows_host, const int* cols_host, const float* logit_scale,
-                        float* scale_out, uint32_t* status, void* stream);
+                        float* scale_out, uint32_t* status, float* zero0, int nzero0, float* zero1, int nzero1, void* stream);
 int tic_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, void* stream);
 int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream);
 /* dst[r, c] (+)= column sums etc. are done by GEMMs; bias gradient: db[n] = sum_m dY[m,n] (bf16 in, fp32 out). */

@@ -36,7 +36,11 @@ def build_plan(spec, dev, variant):
         use_itc = False
     plan = P.HeadPlan(spec["B"], E=spec["E"], P=spec["P"], C=spec["C"], fusion=fusion, use_itc=use_itc, use_itm=use_itm,
                       Lv=max(spec["Lv"], 1), device=dev)
-    plan.set_weights(bench.synthetic_params(spec["C"], seed=40))
+    master = {k: v.to(dev) for k, v in bench.synthetic_params(spec["C"], seed=40).items()}
+    if os.environ.get("TIC_TIMELINE_SNAPSHOT", "0") == "1":
+        plan.set_weights(master)               # round-1 form: pre-cast weights, no refresh inside the step
+    else:
+        plan.bind_params(master, live=True)    # the step refreshes the bf16 working copies / exp(logit_scale) itself
     return plan
 
 

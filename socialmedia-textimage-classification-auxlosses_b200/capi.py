@@ -27,6 +27,7 @@ _SIGS = {
     "tic_gemm_bf16_simt": ("pliplipliiiifpip", ctypes.c_int),
     "tic_row_rnorm_bf16": ("ppliipplp", ctypes.c_int),
     "tic_itc_row_parts": ("i", ctypes.c_int),
+    "tic_itc_q_parts": ("i", ctypes.c_int),
     "tic_itc_col_parts": ("i", ctypes.c_int),
     "tic_itc_fwd": ("pplpplppiiiiffpppplpipippiippp", ctypes.c_int),
     "tic_itc_fused_small_ok": ("ii", ctypes.c_int),
@@ -65,7 +66,7 @@ _SIGS = {
     "tic_aspect_bwd": ("plpliippplpplplppp", ctypes.c_int),
     "tic_gmu_gate_fwd": ("plppliipplp", ctypes.c_int),
     "tic_gmu_gate_bwd": ("plpplpliipppplplp", ctypes.c_int),
-    "tic_refresh_weights": ("ipppppppppp", ctypes.c_int),
+    "tic_refresh_weights": ("ippppppppppipip", ctypes.c_int),
     "tic_cast_f32_to_bf16": ("plpliip", ctypes.c_int),
     "tic_cast_bf16_to_f32": ("plpliip", ctypes.c_int),
     "tic_colsum_bf16": ("pliipp", ctypes.c_int),

@@ -117,6 +117,7 @@ struct StoreEpi {
     int accumulate;   // D += result with fp32 atomics (D holds the initial value); required for split-K
     float* row_ss_part;   // optional [n_tiles][M]: per-tile sum of squares of each output row (fused L2-norm statistics)
   };
+  static constexpr int scratch_bytes(int bn) { return 2 * bn * 4 + 256; }   // double-buffered bias vector
   // bias of this tile's columns -> shared memory (double-buffered by tile parity), before the accumulator is waited for
   template <int BN>
   __device__ static void prefetch(const Params& p, EpiCtx& cx) {

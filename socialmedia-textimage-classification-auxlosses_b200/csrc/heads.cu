@@ -260,6 +260,157 @@ __global__ void heads_rows_kernel(float* __restrict__ H, int64_t ldh, int B, int
   }
 }
 
+// Latency-oriented form of heads_rows_kernel for 16-byte-aligned rows with E <= 4096: ONE BLOCK PER ROW, every thread owns
+// 4 consecutive features.  All global loads of a row (the two projected halves or H, the nc weight rows, the dropout mask)
+// are issued at once and everything — the weights too — stays in registers between the logits and the dH pass, so a row
+// costs one memory round trip + one block reduction instead of the warp-per-row kernel's chain of dependent passes
+// (CUPTI timeline of the c2 step: 20 us for 512 rows, the longest kernel of the fusion chain).
+__global__ void __launch_bounds__(1024)
+heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C, int has_tim, const float* __restrict__ W_cls,
+                        const float* __restrict__ b_cls, const float* __restrict__ W_tim, const float* __restrict__ b_tim,
+                        const float* __restrict__ y_soft, const float* __restrict__ class_w, const int64_t* __restrict__ lbl_tim,
+                        const uint8_t* __restrict__ keep, float keep_scale, float c_cls, float c_tim,
+                        float* __restrict__ logits_cls, float* __restrict__ logits_tim, float* __restrict__ losses,
+                        float* __restrict__ dlogits, const float* __restrict__ dz_ext, __nv_bfloat16* __restrict__ dHb,
+                        __nv_bfloat16* __restrict__ dHb_lo, int64_t ld_dhb, float* __restrict__ dHf, int64_t ld_dhf, int relu_mask,
+                        const float* __restrict__ Pt, const float* __restrict__ Pv, int64_t ldp, const int32_t* __restrict__ src) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, nw = blockDim.x >> 5;
+  const bool is_cls = r < B;
+  const int i = is_cls ? r : r - B;
+  const int nc = is_cls ? C : 2;
+  const float* W = is_cls ? W_cls : W_tim;
+  const float* bias = is_cls ? b_cls : b_tim;
+  const int k = tid * 4;
+  const bool act = k < E;
+  __shared__ float sz[32][kMaxClasses];
+  // ---- every load of this row, issued back to back
+  float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[kMaxClasses];
+  uchar4 m = make_uchar4(1, 1, 1, 1);
+  if (act) {
+    if (Pt != nullptr) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(Pt + static_cast<int64_t>(is_cls ? i : src[i]) * ldp + k));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(Pv + static_cast<int64_t>(i) * ldp + k));
+      hv = make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
+    } else {
+      hv = *reinterpret_cast<const float4*>(H + static_cast<int64_t>(r) * ldh + k);
+    }
+    if (is_cls && keep) m = *reinterpret_cast<const uchar4*>(keep + static_cast<int64_t>(i) * E + k);
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < nc) w[c] = __ldg(reinterpret_cast<const float4*>(W + c * E + k));
+  }
+  float yv[kMaxClasses], cw[kMaxClasses];
+  int ylab = 0;
+  if (is_cls) {
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < nc) { yv[c] = __ldg(y_soft + static_cast<int64_t>(i) * C + c); cw[c] = class_w ? __ldg(class_w + c) : 1.f; }
+  } else {
+    ylab = static_cast<int>(lbl_tim[i]);
+  }
+  if (act && Pt != nullptr) *reinterpret_cast<float4*>(H + static_cast<int64_t>(r) * ldh + k) = hv;   // mm_features / weight gradients
+  // ---- logits: per-thread partial dot products -> block reduction
+  const float4 hd = make_float4(m.x ? hv.x * keep_scale : 0.f, m.y ? hv.y * keep_scale : 0.f, m.z ? hv.z * keep_scale : 0.f,
+                                m.w ? hv.w * keep_scale : 0.f);
+  const float4 hx = (is_cls && keep) ? hd : hv;
+  float z[kMaxClasses];
+#pragma unroll
+  for (int c = 0; c < kMaxClasses; ++c) {
+    z[c] = 0.f;
+    if (c < nc && act) z[c] = fmaf(hx.x, w[c].x, fmaf(hx.y, w[c].y, fmaf(hx.z, w[c].z, hx.w * w[c].w)));
+    if (c < nc) z[c] = warp_sum(z[c]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) sz[wib][c] = c < nc ? z[c] : 0.f;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < kMaxClasses; ++c)
+    if (c < nc) {
+      float t = bias[c];
+      for (int q = 0; q < nw; ++q) t += sz[q][c];     // fixed order: every thread computes the same logits
+      z[c] = t;
+      mx = fmaxf(mx, t);
+    }
+  float se = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxClasses; ++c)
+    if (c < nc) se += expf(z[c] - mx);
+  const float lse = mx + logf(se);
+  float dz[kMaxClasses];
+  float loss_c = 0.f, loss_t = 0.f;
+  if (is_cls) {
+    float wy = 0.f, l = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < nc) { wy += cw[c] * yv[c]; l -= cw[c] * yv[c] * (z[c] - lse); }
+    loss_c = l / B;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < nc) {
+        dz[c] = c_cls / B * (expf(z[c] - lse) * wy - cw[c] * yv[c]);
+        if (tid == 0) logits_cls[static_cast<int64_t>(i) * C + c] = z[c];
+      }
+  } else {
+    loss_t = -((ylab == 0 ? z[0] : z[1]) - lse) / B;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      dz[c] = c_tim / B * (expf(z[c] - lse) - (c == ylab ? 1.f : 0.f));
+      if (tid == 0) logits_tim[static_cast<int64_t>(i) * 2 + c] = z[c];
+    }
+  }
+  if (dz_ext != nullptr) {  // autograd mode: the caller owns the loss; use its gradient w.r.t. the logits
+    loss_c = 0.f;
+    loss_t = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) dz[c] = c < nc ? __ldg(dz_ext + static_cast<int64_t>(r) * kMaxClasses + c) : 0.f;
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) dlogits[static_cast<int64_t>(r) * kMaxClasses + c] = c < nc ? dz[c] : 0.f;
+    if (loss_c != 0.f) atomicAdd(losses + 0, loss_c);
+    if (loss_t != 0.f) atomicAdd(losses + 1, loss_t);
+  }
+  // ---- dH for this thread's 4 features, from the weights still in registers
+  if (act && (dHb || dHf)) {
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+      if (c < nc) {
+        g[0] = fmaf(dz[c], w[c].x, g[0]); g[1] = fmaf(dz[c], w[c].y, g[1]);
+        g[2] = fmaf(dz[c], w[c].z, g[2]); g[3] = fmaf(dz[c], w[c].w, g[3]);
+      }
+    if (is_cls && keep) {
+      g[0] = m.x ? g[0] * keep_scale : 0.f; g[1] = m.y ? g[1] * keep_scale : 0.f;
+      g[2] = m.z ? g[2] * keep_scale : 0.f; g[3] = m.w ? g[3] * keep_scale : 0.f;
+    }
+    if (relu_mask) {
+      if (!(hv.x > 0.f)) g[0] = 0.f;
+      if (!(hv.y > 0.f)) g[1] = 0.f;
+      if (!(hv.z > 0.f)) g[2] = 0.f;
+      if (!(hv.w > 0.f)) g[3] = 0.f;
+    }
+    if (dHf) *reinterpret_cast<float4*>(dHf + static_cast<int64_t>(r) * ld_dhf + k) = make_float4(g[0], g[1], g[2], g[3]);
+    if (dHb) {
+      uint2 u;
+      u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]);
+      *reinterpret_cast<uint2*>(dHb + static_cast<int64_t>(r) * ld_dhb + k) = u;
+      if (dHb_lo) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] -= __bfloat162float(__float2bfloat16_rn(g[j]));
+        u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]);
+        *reinterpret_cast<uint2*>(dHb_lo + static_cast<int64_t>(r) * ld_dhb + k) = u;
+      }
+    }
+  }
+}
+
 // Backward of the pairwise form: gradients w.r.t. the two projected halves from dH [2B, E] (bf16 hi + lo):
 //   dPv[i] = dH[i] + dH[B+i]                                  (image half of sample i feeds its main row and its ITM row)
 //   dPt[k] = dH[k] + sum over {i : src[i] == k} of dH[B+i]    (text half of sample k feeds its main row and every ITM row that drew it)
@@ -273,18 +424,20 @@ __global__ void __launch_bounds__(256) fusion_pair_grad_kernel(const __nv_bfloat
   pdl_trigger();
   pdl_wait();
   constexpr int MAXC = 4;                         // E <= 1024: 8 consecutive features per lane per 256-wide chunk
+  constexpr int kSrcChunk = 2048;                 // src is staged through shared memory, shared by the block's 8 samples
+  __shared__ int32_t ssrc[kSrcChunk];
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (k >= B) return;
+  const bool live = k < B;
   auto ld8 = [&](const __nv_bfloat16* base, const __nv_bfloat16* base_lo, int row, int c, float (&f)[8]) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(row) * ld + c));
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (base_lo != nullptr) v = __ldg(reinterpret_cast<const uint4*>(base_lo + static_cast<int64_t>(row) * ld + c));
     const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(hh[q]); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
-    if (base_lo != nullptr) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base_lo + static_cast<int64_t>(row) * ld + c));
-      const __nv_bfloat162* hl = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(hl[q]); f[2 * q] += t.x; f[2 * q + 1] += t.y; }
+    for (int q = 0; q < 4; ++q) {
+      const float2 t = __bfloat1622float2(hh[q]), t2 = __bfloat1622float2(hl[q]);
+      f[2 * q] = t.x + t2.x; f[2 * q + 1] = t.y + t2.y;
     }
   };
   auto st8 = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, int row, int c, float (&g)[8]) {
@@ -298,42 +451,51 @@ __global__ void __launch_bounds__(256) fusion_pair_grad_kernel(const __nv_bfloat
       *reinterpret_cast<uint4*>(lo + static_cast<int64_t>(row) * ldo + c) = u;
     }
   };
+  // the first chunk of src and this sample's own two rows are requested together (one memory round trip)
+  if (has_tim)
+    for (int j = threadIdx.x; j < min(B, kSrcChunk); j += blockDim.x) ssrc[j] = __ldg(src + j);
   float at[MAXC][8], av[MAXC][8];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     const int col = c * 256 + lane * 8;
-    if (col < E) {
+    if (live && col < E) {
       ld8(dH, dH_lo, k, col, at[c]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) av[c][j] = at[c][j];
-      if (has_tim) {
-        float t[8];
-        ld8(dH, dH_lo, B + k, col, t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) av[c][j] += t[j];
-      }
+      if (has_tim) ld8(dH, dH_lo, B + k, col, av[c]);
     }
   }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) av[c][j] = has_tim ? av[c][j] + at[c][j] : at[c][j];
   if (has_tim) {
-    for (int j0 = 0; j0 < B; j0 += 32) {
-      const int j = j0 + lane;
-      unsigned hit = __ballot_sync(0xffffffffu, j < B && __ldg(src + j) == k);
-      while (hit != 0) {                       // ascending j: a fixed summation order
-        const int jj = j0 + __ffs(hit) - 1;
-        hit &= hit - 1;
+    for (int base = 0; base < B; base += kSrcChunk) {
+      if (base > 0) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < min(B - base, kSrcChunk); j += blockDim.x) ssrc[j] = __ldg(src + base + j);
+      }
+      __syncthreads();
+      const int n = min(B - base, kSrcChunk);
+      for (int j0 = 0; j0 < n && live; j0 += 32) {
+        const int j = j0 + lane;
+        unsigned hit = __ballot_sync(0xffffffffu, j < n && ssrc[j] == k);
+        while (hit != 0) {                       // ascending j: a fixed summation order
+          const int jj = base + j0 + __ffs(hit) - 1;
+          hit &= hit - 1;
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-          const int col = c * 256 + lane * 8;
-          if (col < E) {
-            float t[8];
-            ld8(dH, dH_lo, B + jj, col, t);
+          for (int c = 0; c < MAXC; ++c) {
+            const int col = c * 256 + lane * 8;
+            if (col < E) {
+              float t[8];
+              ld8(dH, dH_lo, B + jj, col, t);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) at[c][q] += t[q];
+              for (int q = 0; q < 8; ++q) at[c][q] += t[q];
+            }
           }
         }
       }
     }
   }
+  if (!live) return;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     const int col = c * 256 + lane * 8;
@@ -436,6 +598,8 @@ struct RefreshArgs {
   const float* logit_scale;   // optional device scalar (dual_encoder.logit_scale)
   float* scale_out;           // [1] exp(logit_scale), clamped to (0, 40]
   uint32_t* status;           // [1] sticky: 1 if logit_scale left the supported range (exp > 40 or not finite)
+  float* zero[2];             // optional: up to two fp32 ranges set to zero (the step's loss sums / small accumulators), so that
+  int nzero[2];               // the first node of a captured step is this kernel and not a memset in front of it
 };
 __global__ void __launch_bounds__(256) refresh_weights_kernel(RefreshArgs a) {
   pdl_trigger();
@@ -447,6 +611,12 @@ __global__ void __launch_bounds__(256) refresh_weights_kernel(RefreshArgs a) {
       sc = 40.f;
     }
     *a.scale_out = sc;
+  }
+  {
+    const int gtid = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x, gthreads = gridDim.x * gridDim.y * blockDim.x;
+#pragma unroll
+    for (int z = 0; z < 2; ++z)
+      for (int i = gtid; i < a.nzero[z]; i += gthreads) a.zero[z][i] = 0.f;
   }
   if (static_cast<int>(blockIdx.y) >= a.n) return;
   const RefreshDesc d = a.d[blockIdx.y];
@@ -557,6 +727,16 @@ int tic_heads_fwd_bwd(float* H, int64_t ldh, int B, int E, int C, int has_tim, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rows = has_tim ? 2 * B : B;
   float* dlogits = ws;
+  const bool blk = (E & 3) == 0 && E <= 4096 && (ldh & 3) == 0 && (ld_dhb & 3) == 0 && (ld_dhf & 3) == 0 && (ldp & 3) == 0 &&
+                   aligned16(H) && aligned16(W_cls) && aligned16(W_tim) && aligned16(dH_f32) && aligned16(keep) && aligned16(Pt) &&
+                   aligned16(Pv) && ((reinterpret_cast<uintptr_t>(dH_bf16) | reinterpret_cast<uintptr_t>(dH_bf16_lo)) & 7) == 0;
+  if (blk) {
+    const int threads = ceil_div(ceil_div(E, 4), 32) * 32;
+    launch_k(heads_rows_block_kernel, dim3(rows), dim3(threads), 0, st, H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft,
+             class_w, lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses, dlogits, dlogits_ext,
+             static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb, dH_f32, ld_dhf, relu_mask, Pt, Pv,
+             ldp, src_idx);
+  } else
   launch_k(heads_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft, class_w,
                                                         lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses,
                                                         dlogits, dlogits_ext, static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb,
@@ -617,15 +797,18 @@ int tic_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, 
 
 int tic_refresh_weights(int n, const float* const* src_host, void* const* dst_host, const int64_t* lds_host, const int64_t* ldd_host,
                         const int* rows_host, const int* cols_host, const float* logit_scale, float* scale_out, uint32_t* status,
-                        void* stream) {
+                        float* zero0, int nzero0, float* zero1, int nzero1, void* stream) {
   TIC_CHECK_ARG(n >= 0 && n <= kMaxRefresh, "tic_refresh_weights: at most %d matrices per call", kMaxRefresh);
-  TIC_CHECK_ARG(n > 0 || logit_scale, "tic_refresh_weights: nothing to do");
+  TIC_CHECK_ARG(n > 0 || logit_scale || nzero0 > 0 || nzero1 > 0, "tic_refresh_weights: nothing to do");
+  TIC_CHECK_ARG(nzero0 >= 0 && nzero1 >= 0 && (nzero0 == 0 || zero0) && (nzero1 == 0 || zero1), "tic_refresh_weights: bad zero ranges");
   TIC_CHECK_ARG(!logit_scale || scale_out, "tic_refresh_weights: scale_out is NULL");
   RefreshArgs a{};
   a.n = n;
   a.logit_scale = logit_scale;
   a.scale_out = scale_out;
   a.status = status;
+  a.zero[0] = zero0; a.nzero[0] = nzero0;
+  a.zero[1] = zero1; a.nzero[1] = nzero1;
   int64_t most = 1;
   for (int i = 0; i < n; ++i) {
     TIC_CHECK_ARG(src_host[i] && dst_host[i] && rows_host[i] > 0 && cols_host[i] > 0, "tic_refresh_weights: bad matrix %d", i);

@@ -109,8 +109,9 @@ struct ItcFwdEpi {
     int row_offset;
     const float* scale_dev;     // optional DEVICE scalar exp(logit_scale): overrides scale and shift (a trainable logit_scale
                                 // reaches a captured step by pointer, never as a launch-time constant)
-    unsigned long long* qpart;  // optional [n_tiles * nparts][M]: per-part integer sums of the hard-negative sampling weights
+    unsigned long long* qpart;  // optional [ceil(N/32)][M]: integer sums of the hard-negative sampling weights per 32-column chunk
   };
+  static constexpr int scratch_bytes(int bn) { return 6 * bn * 4 + 256; }   // 2 x rinv_v + 4 x partial column sums
   // column norms of this tile -> shared memory, this thread's row norm -> cx.pre[0]; runs while the MMAs of the tile are in flight
   template <int BN>
   __device__ static void prefetch(const Params& p, EpiCtx& cx) {
@@ -162,7 +163,6 @@ struct ItcFwdEpi {
     const float scale_log2e = sc * kLog2e, shift_log2e = sh * kLog2e;
     const float rt2 = rt * scale_log2e;
     const float negshift = valid_row ? -shift_log2e : -INFINITY;
-    unsigned long long qsum = 0;
     const int gcol = p.row_offset + row;  // column holding this row's positive
     const int cols_per_part = BN / cx.nparts;
     float rowsum = 0.f;
@@ -181,7 +181,34 @@ struct ItcFwdEpi {
       for (int j = 0; j < 32; ++j) v[j] = vn[j];
       if (c + 1 < nchunk && col0 + 32 < cx.N) tmem_ld_32x32(trow + cl + 32, vn);   // prefetch the next 32 columns
       float e[32];
-      if (col0 + 32 <= cx.N && p.logits == nullptr && p.qpart == nullptr) {
+      if (col0 + 32 <= cx.N && p.logits == nullptr && p.qpart != nullptr) {
+        // hard-negative fast path (interior tile, logits not materialised): the statistics as in the plain fast path plus the
+        // integer sampling weight of every logit, formed on the FMA / ALU pipes only (itm_rule.cuh) beside the one ex2 per
+        // element; the logit itself is itc_logit() — the expression the pick tiles repeat bit for bit.
+        unsigned long long qs = 0;
+        float dv = 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float cosv = __fmul_rn(__fmul_rn(__uint_as_float(v[j4 + q]), rt), bb[q]);
+            const float sij = __fmul_rn(cosv, sc);
+            e[j4 + q] = ex2_approx(fmaf(cosv, scale_log2e, negshift));
+            const unsigned long long qw = hard_qweight(sij, sh);
+            if (col0 + j4 + q == gcol) dv = sij; else qs += qw;
+          }
+        }
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) { r0 += e[j]; r1 += e[j + 1]; r2 += e[j + 2]; r3 += e[j + 3]; }
+        rowsum += (r0 + r1) + (r2 + r3);
+        if (valid_row) {
+          if (gcol >= col0 && gcol < col0 + 32) p.diag[row] = dv;
+          p.qpart[static_cast<int64_t>(col0 >> 5) * cx.M + row] = qs;
+        }
+      } else if (col0 + 32 <= cx.N && p.logits == nullptr) {
         // fast path (interior tile, logits not materialised): 1 FMUL + 1 FFMA + 1 MUFU + 1 FADD per element.
         // invalid rows carry negshift = -inf, so their exp is exactly 0 and they drop out of the column sums.
 #pragma unroll
@@ -207,6 +234,7 @@ struct ItcFwdEpi {
         // generic path: edge tiles (column tail), materialised logits (drop-in API) and the hard-negative weight sums.
         // The logit is formed by itc_logit() — the expression the pick tiles repeat bit for bit.
         float dsel = 0.f;
+        unsigned long long qsum = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float cosv = __fmul_rn(__fmul_rn(__uint_as_float(v[j]), rt), sb[cl + j]);   // cosine similarity
@@ -219,6 +247,7 @@ struct ItcFwdEpi {
           v[j] = __float_as_uint(sij);
         }
         if (valid_row && gcol >= col0 && gcol < col0 + 32) p.diag[row] = dsel;
+        if (p.qpart != nullptr && valid_row) p.qpart[static_cast<int64_t>(col0 >> 5) * cx.M + row] = qsum;
         if (p.logits != nullptr && valid_row) {
           float* d = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
           if (col0 + 32 <= cx.N && (p.ld_logits & 3) == 0) {
@@ -239,7 +268,6 @@ struct ItcFwdEpi {
       }
     }
     if (valid_row) p.row_part[static_cast<int64_t>(cx.n_blk * cx.nparts + cx.part) * cx.M + row] = rowsum;
-    if (p.qpart != nullptr && valid_row) p.qpart[static_cast<int64_t>(cx.n_blk * cx.nparts + cx.part) * cx.M + row] = qsum;
     if (p.col_part == nullptr) return;
     epi_bar_sync(cx.epi_threads);
     for (int j = cx.epi_tid; j < BN; j += cx.epi_threads)
@@ -263,10 +291,11 @@ struct ItcPickEpi {
     float scale, shift;
     const float* scale_dev;
     int row_offset;
-    const int32_t* loc_part;               // [M] part holding the row's target, -1 = nothing to pick
+    const int32_t* loc_part;               // [M] 32-column chunk holding the row's target, -1 = nothing to pick
     const unsigned long long* loc_res;     // [M] target minus the weight of the parts before it
     int32_t* src_idx;                      // [M] out (only located rows are written)
   };
+  static constexpr int scratch_bytes(int bn) { return 2 * bn * 4 + 256; }
   template <int BN>
   __device__ static void prefetch(const Params& p, EpiCtx& cx) {
     const int lane = threadIdx.x & 31;
@@ -291,34 +320,40 @@ struct ItcPickEpi {
     const int lane = threadIdx.x & 31;
     const int row = cx.m0 + cx.quad * 32 + lane;
     const int cols_per_part = BN / cx.nparts;
-    const bool mine = __float_as_int(cx.pre[3]) == cx.n_blk * cx.nparts + cx.part;
-    if (!__any_sync(0xffffffffu, mine)) return;          // warp-uniform: no row of this warp has its target in this part
+    const int lp = __float_as_int(cx.pre[3]);              // 32-column chunk holding this row's target (-1: none)
     const float* sb = reinterpret_cast<const float*>(cx.scratch) + (cx.iter & 1) * BN;
     const float rt = cx.pre[0], sc = cx.pre[1], sh = cx.pre[2];
     const unsigned long long res = static_cast<unsigned long long>(__float_as_uint(cx.pre[4])) |
                                    (static_cast<unsigned long long>(__float_as_uint(cx.pre[5])) << 32);
     const int gcol = p.row_offset + row;
     const uint32_t trow = cx.tmem_acc + (static_cast<uint32_t>(cx.quad * 32) << 16);
-    unsigned long long run = 0;
-    int found = -1;
 #pragma unroll 1
     for (int c = 0; c < cols_per_part / 32; ++c) {
       const int cl = cx.part * cols_per_part + c * 32;
       const int col0 = cx.n0 + cl;
       if (col0 >= cx.N) break;  // warp-uniform
+      const bool mine = lp == (col0 >> 5);
+      if (!__any_sync(0xffffffffu, mine)) continue;        // warp-uniform: no row of this warp has its target in this chunk
       uint32_t v[32];
       tmem_ld_32x32(trow + cl, v);
       tmem_ld_wait();
-      if (mine && found < 0) {
+      if (mine) {
+        unsigned long long q[32];                          // 32 independent weights first (ILP), then the short integer scan
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
-          if (col < cx.N && col != gcol) run += hard_qweight(itc_logit(__uint_as_float(v[j]), rt, sb[cl + j], sc), sh);
-          if (found < 0 && run > res) found = col;
+          q[j] = (col < cx.N && col != gcol) ? hard_qweight(itc_logit(__uint_as_float(v[j]), rt, sb[cl + j], sc), sh) : 0ull;
         }
+        unsigned long long run = 0;
+        int found = -1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          run += q[j];
+          if (found < 0 && run > res) found = col0 + j;
+        }
+        if (found >= 0) p.src_idx[row] = found;
       }
     }
-    if (mine && found >= 0) p.src_idx[row] = found;
   }
 };
 
@@ -333,7 +368,7 @@ struct ItcBwdEpi {
     float gscale;        // g / (2B)
     __nv_bfloat16* GA;   // [M, ld_ga]   Gp * rinv_v[j]
     int64_t ld_ga;
-    __nv_bfloat16* GBT;  // [N, ld_gbt]  Gp * rinv_t[i]  (transposed)
+    __nv_bfloat16* GBT;  // "GB" [M, ld_ga]  Gp * rinv_t[i], row-major like GA (read MN-major by the image-side GEMM); NULL = single-operand modes
     int64_t ld_gbt;
     __nv_bfloat16* GA_lo;   // optional bf16 residuals (split precision for small batches)
     __nv_bfloat16* GBT_lo;
@@ -348,6 +383,8 @@ struct ItcBwdEpi {
     const float* scale_dev;   // optional DEVICE scalar exp(logit_scale): overrides scale_log2e / shift / shift_log2e / factored
     alignas(64) CUtensorMap tmap_ga;
   };
+  // narrow tiles never use the TMA-store staging area (that path needs the single-operand large-batch mode)
+  static constexpr int scratch_bytes(int bn) { return bn == 64 ? 6 * bn * 4 + 256 : kEpiScratchBytes; }
   // per-column vectors of this tile -> shared memory, this thread's row norm / row lse -> cx.pre[0..1]; runs while the MMAs of
   // the tile are in flight (small batch: lse comes from up to 64 forward partials per row and column — a long load chain).
   // COH: the statistics were written by OTHER CTAs of this very kernel (fused forward+backward, below): they must not be
@@ -463,25 +500,65 @@ struct ItcBwdEpi {
           ga[j4 + 2] = (ex2_approx(s2_ - lr) + ex2_approx(s2_ - l4.z)) * g4.z;
           ga[j4 + 3] = (ex2_approx(s3 - lr) + ex2_approx(s3 - l4.w)) * g4.w;
         }
-      } else {
-      __nv_bfloat16* gbt = p.GBT ? p.GBT + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
-      __nv_bfloat16* gbt_lo = (p.GBT && p.GBT_lo) ? p.GBT_lo + static_cast<int64_t>(col0) * p.ld_gbt + row : nullptr;
+      } else if (p.GBT == nullptr) {
+        // edge tile of the single-operand modes
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float s2 = __uint_as_float(v[j]) * rt * sb[cl + j] * scale_log2e;  // S * log2e
-        if (factored) {   // (edge tile of the factored mode; GBT is NULL there) sl = Ec_j * g_j, sg = g_j
-          ga[j] = exp2f(s2 - lr) * fmaf(exp2f(lr - shift_log2e), sl[cl + j], sg[cl + j]);
-          continue;
+        for (int j = 0; j < 32; ++j) {
+          const float s2 = __uint_as_float(v[j]) * rt * sb[cl + j] * scale_log2e;  // S * log2e
+          if (factored) ga[j] = exp2f(s2 - lr) * fmaf(exp2f(lr - shift_log2e), sl[cl + j], sg[cl + j]);   // sl = Ec_j * g_j, sg = g_j
+          else ga[j] = p.gscale * (exp2f(s2 - lr) + exp2f(s2 - sl[cl + j])) * sb[cl + j];
         }
-        const float pr = p.gscale * (exp2f(s2 - lr) + exp2f(s2 - sl[cl + j]));
-        ga[j] = pr * sb[cl + j];
-        if (gbt != nullptr && valid_row && col0 + j < cx.N) {
-          const float gb = pr * rt;
-          const __nv_bfloat16 hi = __float2bfloat16_rn(gb);
-          gbt[static_cast<int64_t>(j) * p.ld_gbt] = hi;
-          if (gbt_lo) gbt_lo[static_cast<int64_t>(j) * p.ld_gbt] = __float2bfloat16_rn(gb - __bfloat162float(hi));
+      } else {
+        // Two-operand (small batch, split precision) mode: GA = Gp * rinv_v[j] and GB = Gp * rinv_t[i], BOTH row-major with the
+        // layout of S — the image-side GEMM reads GB MN-major, so no transposed operand is written (the transposed form cost
+        // 64 scattered 2-byte stores per thread and chunk, and was the longest part of this epilogue at B = 256).
+        // ga[] holds Gp here; the two scalings happen at the stores.
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j4);
+          const float4 l4 = *reinterpret_cast<const float4*>(sl + cl + j4);
+          const float s0 = __uint_as_float(v[j4 + 0]) * b4.x * rt2, s1 = __uint_as_float(v[j4 + 1]) * b4.y * rt2;
+          const float s2_ = __uint_as_float(v[j4 + 2]) * b4.z * rt2, s3 = __uint_as_float(v[j4 + 3]) * b4.w * rt2;
+          ga[j4 + 0] = p.gscale * (ex2_approx(s0 - lr) + ex2_approx(s0 - l4.x));
+          ga[j4 + 1] = p.gscale * (ex2_approx(s1 - lr) + ex2_approx(s1 - l4.y));
+          ga[j4 + 2] = p.gscale * (ex2_approx(s2_ - lr) + ex2_approx(s2_ - l4.z));
+          ga[j4 + 3] = p.gscale * (ex2_approx(s3 - lr) + ex2_approx(s3 - l4.w));
         }
-      }
+        if (valid_row) {
+          const bool full = col0 + 32 <= cx.N && vec_ok;
+          auto put = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, bool by_col) {
+            __nv_bfloat16* d = hi + static_cast<int64_t>(row) * p.ld_ga + col0;
+            __nv_bfloat16* dl = lo ? lo + static_cast<int64_t>(row) * p.ld_ga + col0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float x[8], r8[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                x[q] = ga[j + q] * (by_col ? sb[cl + j + q] : rt);
+                r8[q] = x[q] - __bfloat162float(__float2bfloat16_rn(x[q]));
+              }
+              if (full) {
+                uint4 u;
+                u.x = pack_bf16x2(x[0], x[1]); u.y = pack_bf16x2(x[2], x[3]); u.z = pack_bf16x2(x[4], x[5]); u.w = pack_bf16x2(x[6], x[7]);
+                *reinterpret_cast<uint4*>(d + j) = u;
+                if (dl) {
+                  u.x = pack_bf16x2(r8[0], r8[1]); u.y = pack_bf16x2(r8[2], r8[3]); u.z = pack_bf16x2(r8[4], r8[5]); u.w = pack_bf16x2(r8[6], r8[7]);
+                  *reinterpret_cast<uint4*>(dl + j) = u;
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (col0 + j + q < cx.N) {
+                    d[j + q] = __float2bfloat16_rn(x[q]);
+                    if (dl) dl[j + q] = __float2bfloat16_rn(r8[q]);
+                  }
+              }
+            }
+          };
+          put(p.GA, p.GA_lo, true);
+          put(p.GBT, p.GBT_lo, false);
+        }
+        continue;
       }
       if (p.tma_store && col0 + 32 <= cx.N) {
         // Each lane's 32 bf16 (64 B) go to its row of this warp's 32x32 staging tile (64-byte swizzle: 16-byte chunk q of row r
@@ -556,13 +633,15 @@ struct ItcBwdEpi {
 // cluster meets at ONE barrier (release/acquire at cluster scope: the partial sums every CTA wrote to global memory are
 // visible), and the backward epilogue derives lse_row / lse_col from those partials and emits the gradient operands from
 // the accumulator that is still in TMEM.  One launch and one k-loop less on the critical chain of the step.
+constexpr int kFusedSmallStages = 4;   // 4 x 24 KB ring + 3 KB scratch: the cluster's CTAs co-reside with other small launches
+constexpr int kFusedSmallSmem = kFusedSmallStages * UmmaCfg<kItcBNSmall>::kStageBytes + 1024 + 256 + 2 * (6 * kItcBNSmall * 4 + 256);
 template <int BN>
 __global__ void __launch_bounds__(64 + 32 * kItcEpiWarps, 1)
 itc_fused_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo,
                        const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_lo, int split, int M,
                        int N, int K, const __grid_constant__ ItcFwdEpi::Params fp, const __grid_constant__ ItcBwdEpi::Params bp) {
   using Cfg = UmmaCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
+  constexpr int STAGES = kFusedSmallStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -963,39 +1042,25 @@ itc_grad_finalize_vec_kernel(const float* __restrict__ acc, int64_t ld_acc, cons
 }
 
 // Gradient operands from a MATERIALISED dL/dS (autograd path at drop-in batch sizes):
-//   GA[i,j] = dS[i,j] * rinv_v[j],  GBT[j,i] = dS[i,j] * rinv_t[i]   (+ bf16 residuals).  32x32 smem-tile transpose.
+//   GA[i,j] = dS[i,j] * rinv_v[j],  GB[i,j] = dS[i,j] * rinv_t[i]   (+ bf16 residuals), both row-major like dS.
 __global__ void itc_ds_operands_kernel(const float* __restrict__ dS, int64_t ldds, int M, int N, const float* __restrict__ rinv_t,
                                        const float* __restrict__ rinv_v, __nv_bfloat16* __restrict__ GA,
-                                       __nv_bfloat16* __restrict__ GA_lo, int64_t ld_ga, __nv_bfloat16* __restrict__ GBT,
-                                       __nv_bfloat16* __restrict__ GBT_lo, int64_t ld_gbt) {
+                                       __nv_bfloat16* __restrict__ GA_lo, int64_t ld_ga, __nv_bfloat16* __restrict__ GB,
+                                       __nv_bfloat16* __restrict__ GB_lo) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
-  __shared__ float t[32][33];
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int i = i0 + r, j = j0 + threadIdx.x;
-    float v = 0.f;
-    if (i < M && j < N) {
-      v = dS[static_cast<int64_t>(i) * ldds + j];
-      const float ga = v * rinv_v[j];
-      const __nv_bfloat16 hi = __float2bfloat16_rn(ga);
-      GA[static_cast<int64_t>(i) * ld_ga + j] = hi;
-      if (GA_lo) GA_lo[static_cast<int64_t>(i) * ld_ga + j] = __float2bfloat16_rn(ga - __bfloat162float(hi));
-      v *= rinv_t[i];
-    }
-    t[r][threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (GBT == nullptr) return;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int j = j0 + r, i = i0 + threadIdx.x;
-    if (i < M && j < N) {
-      const float gb = t[threadIdx.x][r];
-      const __nv_bfloat16 hi = __float2bfloat16_rn(gb);
-      GBT[static_cast<int64_t>(j) * ld_gbt + i] = hi;
-      if (GBT_lo) GBT_lo[static_cast<int64_t>(j) * ld_gbt + i] = __float2bfloat16_rn(gb - __bfloat162float(hi));
-    }
-  }
+  const int i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M || j >= N) return;
+  const float v = dS[static_cast<int64_t>(i) * ldds + j];
+  const float ga = v * rinv_v[j];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(ga);
+  GA[static_cast<int64_t>(i) * ld_ga + j] = hi;
+  if (GA_lo) GA_lo[static_cast<int64_t>(i) * ld_ga + j] = __float2bfloat16_rn(ga - __bfloat162float(hi));
+  if (GB == nullptr) return;
+  const float gb = v * rinv_t[i];
+  const __nv_bfloat16 hb = __float2bfloat16_rn(gb);
+  GB[static_cast<int64_t>(i) * ld_ga + j] = hb;
+  if (GB_lo) GB_lo[static_cast<int64_t>(i) * ld_ga + j] = __float2bfloat16_rn(gb - __bfloat162float(hb));
 }
 
 }  // namespace tic
@@ -1004,6 +1069,7 @@ using namespace tic;
 
 extern "C" {
 
+int tic_itc_q_parts(int n_global) { return ceil_div(n_global, 32); }
 int tic_itc_row_parts(int n_global) { return ceil_div(n_global, itc_bn(n_global)) * (kItcEpiWarps / 4); }
 int tic_itc_col_parts(int m_local) { return ceil_div(m_local, kBM); }
 
@@ -1198,7 +1264,7 @@ int tic_itc_fwd_bwd_small(const void* T, const void* T_lo, int64_t ldt, const vo
   auto kern = itc_fused_small_kernel<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmallSmem) != cudaSuccess) {
       set_error("tic_itc_fwd_bwd_small: cudaFuncSetAttribute failed");
       return TIC_E_ATTR;
     }
@@ -1207,7 +1273,7 @@ int tic_itc_fwd_bwd_small(const void* T, const void* T_lo, int64_t ldt, const vo
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(m_tiles * n_tiles);
   cfg.blockDim = dim3(64 + 32 * kItcEpiWarps);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = kFusedSmallSmem;
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1249,10 +1315,11 @@ int tic_itc_grad_finalize(const float* acc, int64_t ld_acc, const void* X, const
 int tic_itc_ds_operands(const float* dS, int64_t ldds, int m_local, int n_global, const float* rinv_t, const float* rinv_v,
                         void* GA, void* GA_lo, int64_t ld_ga, void* GBT, void* GBT_lo, int64_t ld_gbt, void* stream) {
   TIC_CHECK_ARG(dS && rinv_t && rinv_v && GA && m_local > 0 && n_global > 0, "tic_itc_ds_operands: bad arguments");
-  dim3 grid(ceil_div(n_global, 32), ceil_div(m_local, 32)), block(32, 8);
-  launch_k(itc_ds_operands_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
+  dim3 grid(ceil_div(n_global, 32), ceil_div(m_local, 8)), block(32, 8);
+  (void)ld_gbt;   // GB shares GA's layout
+  launch_k(itc_ds_operands_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream),
       dS, ldds, m_local, n_global, rinv_t, rinv_v, static_cast<__nv_bfloat16*>(GA), static_cast<__nv_bfloat16*>(GA_lo), ld_ga,
-      static_cast<__nv_bfloat16*>(GBT), static_cast<__nv_bfloat16*>(GBT_lo), ld_gbt);
+      static_cast<__nv_bfloat16*>(GBT), static_cast<__nv_bfloat16*>(GBT_lo));
   TIC_CHECK_LAUNCH("tic_itc_ds_operands");
   return TIC_OK;
 }

@@ -18,9 +18,15 @@ __device__ __forceinline__ void uniform_rule(const float* u_coin, const float* u
 
 // Bit-reproducible fp32 exp for x <= 0, mirrored op-for-op by oracle/restatement.py:det_exp_f32 — every step is a single
 // IEEE-754 round-to-nearest operation (no FMA contraction, no library transcendental).
+//
+// Written for the FMA / ALU pipes only (this runs once per similarity element inside the tile epilogues, next to one
+// ex2.approx per element on the XU pipe): round-to-nearest-even by the 1.5 * 2^23 magic constant (two exact fp32 adds,
+// identical to rintf for |v| < 2^22), the integer n read off the magic sum's mantissa, the 2^n scaling by an exponent add.
 __device__ __forceinline__ float det_exp(float x) {
   x = fmaxf(x, -80.0f);
-  const float n = rintf(__fmul_rn(x, 1.44269504088896341f));
+  const float t = __fadd_rn(__fmul_rn(x, 1.44269504088896341f), 12582912.0f);
+  const float n = __fsub_rn(t, 12582912.0f);                 // == rintf(x * log2e)
+  const int ni = __float_as_int(t) - 0x4B400000;             // == (int)n
   float r = __fsub_rn(x, __fmul_rn(n, 0.693359375f));
   r = __fsub_rn(r, __fmul_rn(n, -2.12194440e-4f));
   float p = 1.9875691500e-4f;
@@ -30,14 +36,19 @@ __device__ __forceinline__ float det_exp(float x) {
   p = __fadd_rn(__fmul_rn(p, r), 1.6666665459e-1f);
   p = __fadd_rn(__fmul_rn(p, r), 5.0000001201e-1f);
   const float y = __fadd_rn(__fadd_rn(__fmul_rn(p, __fmul_rn(r, r)), r), 1.0f);
-  return __int_as_float(__float_as_int(y) + (static_cast<int>(n) << 23));  // exact scaling by 2^n (result stays normal)
+  return __int_as_float(__float_as_int(y) + (ni << 23));  // exact scaling by 2^n (result stays normal)
 }
 
 // Hard-negative sampling weight of one logit against the FIXED reference `ref` >= max S (oracle/restatement.py:
 // hard_qweights): q = trunc(det_exp(min(s - ref, 0)) * 2^40).  Integer weights make every prefix sum associative, the fixed
 // reference lets the similarity tiles sum them in any order without knowing the row maximum first.
 __device__ __forceinline__ unsigned long long hard_qweight(float s, float ref) {
-  return static_cast<unsigned long long>(__fmul_rn(det_exp(fminf(__fsub_rn(s, ref), 0.0f)), 1099511627776.0f));
+  // trunc(f * 2^40) for the normal fp32 f in (0, 1] by shifting its 24-bit significand: no float->int64 conversion
+  // instruction (those share the quarter-rate XU pipe with the exponentials of the softmax statistics)
+  const int b = __float_as_int(det_exp(fminf(__fsub_rn(s, ref), 0.0f)));
+  const int sh = (b >> 23) - 127 + 17;                                  // f = m * 2^(e-23), m in [2^23, 2^24)  ->  q = m * 2^(e+17)
+  const unsigned long long m = static_cast<unsigned long long>((b & 0x7FFFFF) | 0x800000);
+  return sh >= 0 ? (m << sh) : (sh > -24 ? (m >> (-sh)) : 0ull);
 }
 // target = floor(U * total / 2^24), U = trunc(u_pick * 2^24)  (no 128-bit product needed: total < 2^60)
 __device__ __forceinline__ unsigned long long hard_target(float u_pick, unsigned long long total) {

@@ -453,13 +453,20 @@ int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B
   if (ksplit < 1) ksplit = 1;
   if (ksplit > total_kb) ksplit = total_kb;
   int grid = m_tiles * n_tiles * ksplit;
+  // Small launches (the latency-bound small-batch step runs several of them side by side on parallel graph branches): a
+  // 4-deep ring (3 for 128-wide tiles) and only the scratch this epilogue needs, so that TWO CTAs fit on an SM.  With the
+  // full 200 KB ring every CTA owned an SM, and a 16-CTA kernel of the critical chain queued behind the 192 CTAs of two
+  // weight-gradient GEMMs of the other chain (CUPTI timeline, profiles/r02_timeline_c2_*.txt: a 6.6 us hole in the chain).
+  // The k-loop rate does not depend on the ring depth (4 vs 8: scripts/gemm_rate.py).
+  if (stages_rt == 0 && BN <= 128 && !(seg && seg->ready) && grid <= 2 * device_sm_count()) stages_rt = BN == 64 ? 4 : 3;
   int cap = max_ctas > 0 ? max_ctas : device_sm_count();
   if (seg && seg->ready && cap > device_sm_count() - kSegFreeSms) cap = device_sm_count() - kSegFreeSms;
   if (grid > cap) grid = cap;
   SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0};
   if (so.ready && (ksplit != 1 || so.tiles_per_seg <= 0 || so.tiles_per_seg * so.nseg != n_tiles)) so.tiles_per_seg = 0;
   size_t smem = Cfg::kSmemBytes;
-  if (stages_rt > 0 && stages_rt < Cfg::kStages) smem -= static_cast<size_t>(Cfg::kStages - stages_rt) * Cfg::kStageBytes;
+  if (stages_rt > 0 && stages_rt < Cfg::kStages)
+    smem = static_cast<size_t>(stages_rt) * Cfg::kStageBytes + 1024 + 256 + Epi::scratch_bytes(BN);
   launch_k(kern, dim3(grid), dim3(64 + 32 * EPI_WARPS), smem, stream, ta, ta_lo, tb, tb_lo, split, ksplit, M, N, K, ep, so, stages_rt);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }

@@ -41,7 +41,7 @@ def _device_scale(logit_scale, dev):
     ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
     sc = torch.empty(1, dtype=torch.float32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("tic_refresh_weights", 0, None, None, None, None, None, None, ptr(ls), ptr(sc), ptr(status), _stream())
+    call("tic_refresh_weights", 0, None, None, None, None, None, None, ptr(ls), ptr(sc), ptr(status), None, 0, None, 0, _stream())
     return sc
 
 

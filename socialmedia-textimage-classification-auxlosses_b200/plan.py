@@ -122,16 +122,18 @@ class ItcPlan:
         # precise (small batch): separate transposed operand GBT with residuals.  Otherwise "GA-shared": the image-side
         # gradient GEMM reads GA MN-major against a normalised bf16 copy of the text embeddings (no GBT at all).
         self.shared_ga = need_dv and not self.precise
-        self.GBT = torch.empty(n, self.ld_gbt, dtype=BF16, device=dev) if (need_dv and self.precise) else None
+        # "GB": Gp * rinv_t, row-major with GA's layout [m, ld_ga]; the image-side GEMM reads it MN-major (no transposed operand)
+        self.GBT = torch.empty(m, self.ld_ga, dtype=BF16, device=dev) if (need_dv and self.precise) else None
         self.GA_lo = torch.empty(m, self.ld_ga, dtype=BF16, device=dev) if self.precise else None
-        self.GBT_lo = torch.empty(n, self.ld_gbt, dtype=BF16, device=dev) if (need_dv and self.precise) else None
+        self.GBT_lo = torch.empty(m, self.ld_ga, dtype=BF16, device=dev) if (need_dv and self.precise) else None
         self.That = torch.empty(m, P, dtype=BF16, device=dev) if self.shared_ga else None
         self.acc_t = torch.empty(m, P, dtype=F32, device=dev)
         self.acc_v = torch.empty(n, P, dtype=F32, device=dev) if need_dv else None
         self.logits = torch.empty(m, n, dtype=F32, device=dev) if materialize_logits else None
         self.need_dv = need_dv
         # hard-negative sampling in tile-stream form (a-5'): per (row, column part) integer weight sums + the located part
-        self.qpart = torch.empty(self.nrp, m, dtype=torch.int64, device=dev) if hard else None
+        self.nqp = capi.load().tic_itc_q_parts(n)
+        self.qpart = torch.empty(self.nqp, m, dtype=torch.int64, device=dev) if hard else None
         self.loc_part = torch.empty(m, dtype=torch.int32, device=dev) if hard else None
         self.loc_res = torch.empty(m, dtype=torch.int64, device=dev) if hard else None
         # dT = GA[m,n] V[n,P] with m << n (multi-GPU row block at small per-rank batch): the un-split GEMM has m/128 * P/64
@@ -176,7 +178,7 @@ class ItcPlan:
 
     def hard_locate(self, u_coin, u_pick, labels, src_idx):
         """labels / default sources for every row + (part, residual) of each mismatch row from the weight sums of fwd_tiles"""
-        call("tic_itm_hard_locate", ptr(u_coin), ptr(u_pick), self.m, self.n, self.row_offset, ptr(self.qpart), self.nrp,
+        call("tic_itm_hard_locate", ptr(u_coin), ptr(u_pick), self.m, self.n, self.row_offset, ptr(self.qpart), self.nqp,
              ptr(labels), ptr(src_idx), ptr(self.loc_part), ptr(self.loc_res), _stream())
 
     def hard_pick(self, T, ldt, V, ldv, scale, src_idx, T_lo=None, V_lo=None):
@@ -219,8 +221,8 @@ class ItcPlan:
             # dV_acc'[n,P] = GA^T[n,m] * That[m,P]: GA is read MN-major (no transposed operand in HBM); rows carry rinv_v[j]
             gemm(self.GA, self.ld_ga, 1, self.That, self.P, 1, self.acc_v, self.P, 0, self.n, self.P, self.m)
         else:
-            # dV_acc[n,P] = GBT[n,m] * T[m,P]
-            gemm(self.GBT, self.ld_gbt, 0, T, ldt, 1, self.acc_v, self.P, 0, self.n, self.P, self.m, A_lo=self.GBT_lo,
+            # dV_acc[n,P] = GB^T[n,m] * T[m,P]   (GB row-major [m,n]: read MN-major)
+            gemm(self.GBT, self.ld_ga, 1, T, ldt, 1, self.acc_v, self.P, 0, self.n, self.P, self.m, A_lo=self.GBT_lo,
                  B_lo=T_lo)
 
     def grad_gemms(self, T, ldt, V, ldv, T_lo=None, V_lo=None):
@@ -518,8 +520,18 @@ class HeadPlan:
             return
         n, src, dst, lds, ldd, rows, cols = self._refresh_groups[group]
         with_scale = group == "itc"
+        # live mode inside a step: this launch also zeroes the chain's share of the small accumulator block, so no memset
+        # node sits in front of the first kernel of either chain (see _zero_accumulators)
+        z0 = z1 = None
+        if not force and self._refresh_zeroes:
+            zs, n_s = self.zb_small, self.zb_small.numel()
+            if group == "itc":       # itc_sums, r_sum (+ pad): floats [2, 8)
+                z0 = zs[2:8] if "fusion" in self._refresh_groups else zs
+            else:                    # losses [0, 2) and the small heads' gradient accumulators [8, n_small)
+                z0, z1 = (zs[0:2], zs[8:n_s]) if ("itc" in self._refresh_groups and self.use_itc) else (zs, None)
         call("tic_refresh_weights", n, src, dst, lds, ldd, rows, cols, ptr(self._logit_scale) if with_scale else None,
-             ptr(self.scale_t) if with_scale else None, ptr(self.scale_status) if with_scale else None, _stream())
+             ptr(self.scale_t) if with_scale else None, ptr(self.scale_status) if with_scale else None,
+             ptr(z0), 0 if z0 is None else z0.numel(), ptr(z1), 0 if z1 is None else z1.numel(), _stream())
 
     def set_weights(self, p: Dict[str, torch.Tensor]):
         """Snapshot form of bind_params: casts once, now; step() does not refresh.  Also reads exp(logit_scale) back into
@@ -718,18 +730,28 @@ class HeadPlan:
             self._loss_mix()
         return True
 
+    @property
+    def _refresh_zeroes(self):
+        """live weights on the base single-GPU plan: the refresh launches at the head of the two chains zero the small block"""
+        return (self.live_weights and getattr(self, "_in_step", False) and type(self)._itc_fwd is HeadPlan._itc_fwd and
+                (not self.use_itc or "itc" in self._refresh_groups) and (self.fusion is None or "fusion" in self._refresh_groups))
+
     def _zero_accumulators(self):
         # The small block (loss sums, small-head gradients) is first touched by lse_loss / heads, several kernels into the
         # step: its memset leaves the head of both chains too (base plan only: the multi-GPU plans touch it earlier).
         self._zs_pending = False
-        if self.parallel_streams and self._defer_small_zero and type(self)._itc_fwd is HeadPlan._itc_fwd:
+        if self._refresh_zeroes:
+            pass          # zeroed by tic_refresh_weights, the first kernel of each chain
+        elif self.parallel_streams and self._defer_small_zero and type(self)._itc_fwd is HeadPlan._itc_fwd:
             self.br.enabled = True
             with self.br("zs"):
                 self.zb_small.zero_()
             self._zs_pending = True
         else:
             self.zb_small.zero_()
-        if self.parallel_streams and self.zb_big.numel() > 0:
+        if not any(self._atomic.values()):
+            self._z_pending = False                    # every large gradient is written by plain stores: nothing to zero
+        elif self.parallel_streams and self.zb_big.numel() > 0:
             self.br.enabled = True
             with self.br("z"):
                 self.zb_big.zero_()

@@ -169,7 +169,7 @@ def test_captured_step_is_a_training_step():
     assert abs(float(dparams["dual_encoder.logit_scale"]) - float(oparams["dual_encoder.logit_scale"])) < 1e-3
     # the test is sensitive: the loss moved by far more than the tolerance, and logit_scale moved by ~3 * lr_s
     assert abs(losses_d[2] - losses_d[0]) > 20 * REL * abs(losses_d[0])
-    assert abs(scales_d[2] - scales_d[0]) > 0.05
+    assert abs(scales_d[2] - scales_d[0]) > 0.02          # ~2 Adam steps of lr_s = 0.05 (a stale graph would keep the scale)
     assert int(plan.scale_status.item()) == 0
 
 
