@@ -365,7 +365,7 @@ def main():
         plan.set_weights(master)
 
     # ---- count launches of one step (kernels per C-ABI call are fixed)
-    KPC = {"tic_itc_lse_loss": 2, "tic_heads_fwd_bwd": 1, "tic_ce_bidir_fwd": 2, "tic_gemm_rowss_parts": 0,
+    KPC = {"tic_itc_lse_loss": 2, "tic_heads_fwd_bwd": 1, "tic_ce_bidir_fwd": 3, "tic_gemm_rowss_parts": 0,
            "tic_itc_row_parts": 0, "tic_itc_col_parts": 0}
     KPC.update({"tic_peer_alloc": 0, "tic_peer_export": 0, "tic_peer_open": 0, "tic_peer_close": 0, "tic_gemm_plan": 0})
     counter = {"n": 0}

@@ -170,6 +170,9 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
  * barrier, by tic_itc_bwd_g with the inline statistics — the S tiles stay in TMEM in between, the second k-loop and one
  * launch leave the critical chain of the step (HF :268-273 + utils.py:225-231 forward, and the gradient operands). */
 int tic_itc_fused_small_ok(int m_local, int n_global);
+/* Measurement switch: register a device buffer (uint64[16 * CTAs], NULL = off) in which tic_itc_fwd_bwd_small stamps
+ * %globaltimer at its phase boundaries (scripts/kernel_times.py). */
+int tic_debug_set_trace(void* device_u64_buffer);
 int tic_itc_fwd_bwd_small(const void* T, const void* T_lo, int64_t ldt, const void* V, const void* V_lo, int64_t ldv,
                           float* rinv_t, float* rinv_v, int m_local, int n_global, int P, int row_offset, float scale,
                           float* row_part, float* col_part, float* diag, float* logits_out, int64_t ld_logits,

@@ -31,6 +31,7 @@ _SIGS = {
     "tic_itc_col_parts": ("i", ctypes.c_int),
     "tic_itc_fwd": ("pplpplppiiiiffpppplpipippiippp", ctypes.c_int),
     "tic_itc_fused_small_ok": ("ii", ctypes.c_int),
+    "tic_debug_set_trace": ("p", ctypes.c_int),
     "tic_itc_fwd_bwd_small": ("pplpplppiiiifpppplpipippfplplppp", ctypes.c_int),
     "tic_itc_pick": ("pplpplppiiiiffppppp", ctypes.c_int),
     "tic_reduce_parts": ("piipp", ctypes.c_int),

@@ -14,7 +14,7 @@ constexpr int kCeRows = 64;   // rows per smem tile
 __host__ __device__ inline int ce_nstrips(int B) { return (B + kCeCols - 1) / kCeCols; }
 __host__ __device__ inline int ce_nseg(int B) {
   const int tiles = (B + kCeRows - 1) / kCeRows;
-  int want = (2 * 148 + ce_nstrips(B) - 1) / ce_nstrips(B);
+  int want = (4 * 148 + ce_nstrips(B) - 1) / ce_nstrips(B);
   if (want < 1) want = 1;
   return want < tiles ? want : tiles;
 }
@@ -28,93 +28,121 @@ __device__ __forceinline__ void ms_combine(float& m, float& s, float m2, float s
 
 // grid (nstrips, nseg); block 256. Row partials: rp[strip][row] = (max, sumexp) over the strip's 128 columns.
 // Column partials: cp[seg][col] = (max, sumexp) over the segment's rows.
+// Bandwidth-oriented: every thread issues its 8 16-byte loads of a 64x128 tile back to back (32 KB in flight per block),
+// the tile is staged in shared memory with a 129-float row pitch (conflict-free for both walks), then 128 threads walk
+// COLUMNS (64 rows each) and 128 threads walk ROW halves (64 columns each) with a one-pass online softmax — each element of S
+// is read from HBM once and from shared memory twice.  (The round-1 form reduced every row with 10 warp shuffles per 512
+// bytes loaded and finished in a single 1024-thread block: 99 us at B = 4096 = 10 % of HBM.)
+__device__ __forceinline__ void ms_push(float& m, float& s, float x) {
+  if (x <= m) {
+    s += __expf(fmaxf(x - m, -INFINITY));   // (-inf) - (-inf) = NaN -> fmaxf picks -inf -> adds 0 (padding / masked logits)
+  } else {          // new maximum (rare after the first few elements): rescale the running sum
+    s = s * __expf(m - x) + 1.f;
+    m = x;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ce_bidir_fwd_kernel(const float* __restrict__ S, int64_t lds, int B, float2* __restrict__ rp, float2* __restrict__ cp,
                     float* __restrict__ diag) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
-  __shared__ float tile[kCeRows][kCeCols + 4];
-  __shared__ float2 ccomb[kCeCols];
+  constexpr int kPitch = kCeCols + 1;
+  __shared__ float tile[kCeRows * kPitch];
   const int strip = blockIdx.x, seg = blockIdx.y, nseg = gridDim.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = threadIdx.x;
   const int c0 = strip * kCeCols;
   const int tiles = (B + kCeRows - 1) / kCeRows;
   const int t_begin = static_cast<int>(static_cast<int64_t>(tiles) * seg / nseg);
   const int t_end = static_cast<int>(static_cast<int64_t>(tiles) * (seg + 1) / nseg);
-  const int ccol = threadIdx.x & (kCeCols - 1), chalf = threadIdx.x >> 7;  // 2 threads per column, 32 rows each
-  float cm = -INFINITY, cs = 0.f;
-  const bool vec = (lds & 3) == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
-  for (int t = t_begin; t < t_end; ++t) {
-    const int r0 = t * kCeRows;
-    for (int rr = warp; rr < kCeRows; rr += 8) {
+  const bool vec = (lds & 3) == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0 && c0 + kCeCols <= B;
+  float cm = -INFINITY, cs = 0.f;      // column walker state (threads 0..127: column c0 + t)
+  for (int tl = t_begin; tl < t_end; ++tl) {
+    const int r0 = tl * kCeRows;
+    // ---- global -> registers: 8 independent 16-byte loads per thread
+    float4 f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = t + 256 * i, rr = q >> 5, c4 = (q & 31) * 4;
       const int r = r0 + rr;
-      float x[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      const int c = c0 + lane * 4;
+      f[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       if (r < B) {
-        const float* p = S + static_cast<int64_t>(r) * lds + c;
-        if (vec && c + 3 < B) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(p));
-          x[0] = f.x; x[1] = f.y; x[2] = f.z; x[3] = f.w;
+        const float* p = S + static_cast<int64_t>(r) * lds + c0 + c4;
+        if (vec) {
+          f[i] = __ldg(reinterpret_cast<const float4*>(p));
         } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (c + k < B) x[k] = __ldg(p + k);
+          if (c0 + c4 + 0 < B) f[i].x = __ldg(p + 0);
+          if (c0 + c4 + 1 < B) f[i].y = __ldg(p + 1);
+          if (c0 + c4 + 2 < B) f[i].z = __ldg(p + 2);
+          if (c0 + c4 + 3 < B) f[i].w = __ldg(p + 3);
         }
-        if (r >= c && r < c + 4) diag[r] = x[r - c];
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) tile[rr][lane * 4 + k] = x[k];
-      float m = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
-      m = warp_max(m);
-      float s = 0.f;
-      if (m != -INFINITY) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s += __expf(x[k] - m);
-      }
-      s = warp_sum(s);
-      if (lane == 0 && r < B) rp[static_cast<int64_t>(strip) * B + r] = make_float2(m, s);
-    }
-    __syncthreads();
-    {
-      float m = -INFINITY;
-#pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) m = fmaxf(m, tile[chalf * 32 + rr][ccol]);
-      if (m != -INFINITY) {
-        float s = 0.f;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) s += __expf(tile[chalf * 32 + rr][ccol] - m);
-        ms_combine(cm, cs, m, s);
       }
     }
+    __syncthreads();          // the previous tile has been consumed
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = t + 256 * i, rr = q >> 5, c4 = (q & 31) * 4;
+      float* d = tile + rr * kPitch + c4;
+      d[0] = f[i].x; d[1] = f[i].y; d[2] = f[i].z; d[3] = f[i].w;
+      const int r = r0 + rr, dc = r - (c0 + c4);      // the diagonal element of this row, if it sits in this float4
+      if (r < B && dc >= 0 && dc < 4) diag[r] = dc == 0 ? f[i].x : (dc == 1 ? f[i].y : (dc == 2 ? f[i].z : f[i].w));
+    }
     __syncthreads();
+    if (t < kCeCols) {
+      // ---- column walk: 64 rows of column t
+#pragma unroll 8
+      for (int rr = 0; rr < kCeRows; ++rr) ms_push(cm, cs, tile[rr * kPitch + t]);
+    } else {
+      // ---- row walk: thread pair (2 x 64 columns) per row
+      const int rr = (t - kCeCols) >> 1, h = t & 1;
+      float m = -INFINITY, s = 0.f;
+      const float* row = tile + rr * kPitch + h * 64;
+#pragma unroll 8
+      for (int c = 0; c < 64; ++c) ms_push(m, s, row[c]);
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, 1), s2 = __shfl_xor_sync(0xffffffffu, s, 1);
+      ms_combine(m, s, m2, s2);
+      if (h == 0 && r0 + rr < B) rp[static_cast<int64_t>(strip) * B + r0 + rr] = make_float2(m, s);
+    }
   }
-  if (chalf == 1) ccomb[ccol] = make_float2(cm, cs);
+  if (t < kCeCols && c0 + t < B) cp[static_cast<int64_t>(seg) * B + c0 + t] = make_float2(cm, cs);
+}
+
+// Combine the partials into the lse vectors, many blocks; blockIdx.y = direction.  Block partials of the loss go to `bp`.
+__global__ void __launch_bounds__(256)
+ce_bidir_lse_kernel(const float2* __restrict__ rp, int nstrips, const float2* __restrict__ cp, int nseg, const float* __restrict__ diag,
+                    int B, float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ bp) {
+  pdl_trigger();
+  pdl_wait();
+  const int dir = blockIdx.y;
+  const float2* part = dir == 0 ? rp : cp;
+  const int np = dir == 0 ? nstrips : nseg;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (i < B) {
+    float m = -INFINITY, s = 0.f;
+    for (int k = 0; k < np; ++k) { const float2 p = part[static_cast<int64_t>(k) * B + i]; ms_combine(m, s, p.x, p.y); }
+    const float l = m + logf(s);
+    (dir == 0 ? lse_row : lse_col)[i] = l;
+    term = l - diag[i];
+  }
+  __shared__ float sw[8];
+  term = warp_sum(term);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = term;
   __syncthreads();
-  if (chalf == 0) {
-    ms_combine(cm, cs, ccomb[ccol].x, ccomb[ccol].y);
-    if (c0 + ccol < B) cp[static_cast<int64_t>(seg) * B + c0 + ccol] = make_float2(cm, cs);
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += sw[w];
+    bp[dir * gridDim.x + blockIdx.x] = a;
   }
 }
 
-// Single block: combine the partials into lse vectors and the loss.
-__global__ void ce_bidir_finalize_kernel(const float2* __restrict__ rp, int nstrips, const float2* __restrict__ cp, int nseg,
-                                         const float* __restrict__ diag, int B, float* __restrict__ lse_row,
-                                         float* __restrict__ lse_col, float* __restrict__ loss) {
-  pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
-  pdl_wait();      // ... while this one waits here for its own predecessors' writes
+// Single small block: fixed-order sum of the block partials -> loss (deterministic).
+__global__ void ce_bidir_loss_kernel(const float* __restrict__ bp, int n, int B, float* __restrict__ loss) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sred[32];
   float acc = 0.f;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    float m = -INFINITY, s = 0.f;
-    for (int k = 0; k < nstrips; ++k) { const float2 p = rp[static_cast<int64_t>(k) * B + i]; ms_combine(m, s, p.x, p.y); }
-    const float lr = m + logf(s);
-    m = -INFINITY; s = 0.f;
-    for (int k = 0; k < nseg; ++k) { const float2 p = cp[static_cast<int64_t>(k) * B + i]; ms_combine(m, s, p.x, p.y); }
-    const float lc = m + logf(s);
-    lse_row[i] = lr;
-    lse_col[i] = lc;
-    acc += (lr - diag[i]) + (lc - diag[i]);
-  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += bp[i];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -170,7 +198,8 @@ extern "C" {
 
 int64_t tic_ce_bidir_workspace_bytes(int B) {
   if (B <= 0) return 0;
-  return static_cast<int64_t>(sizeof(float2)) * B * (ce_nstrips(B) + ce_nseg(B)) + sizeof(float) * B + 64;
+  return static_cast<int64_t>(sizeof(float2)) * B * (ce_nstrips(B) + ce_nseg(B)) + sizeof(float) * B +
+         sizeof(float) * 2 * ((B + 255) / 256) + 64;
 }
 
 int tic_ce_bidir_fwd(const float* S, int64_t lds, int B, float* lse_row, float* lse_col, float* loss, void* workspace,
@@ -181,8 +210,11 @@ int tic_ce_bidir_fwd(const float* S, int64_t lds, int B, float* lse_row, float* 
   float2* rp = static_cast<float2*>(workspace);
   float2* cp = rp + static_cast<int64_t>(ns) * B;
   float* diag = reinterpret_cast<float*>(cp + static_cast<int64_t>(ng) * B);
+  float* bp = diag + B;
+  const int nb = ceil_div(B, 256);
   launch_k(ce_bidir_fwd_kernel, dim3(dim3(ns, ng)), dim3(256), 0, st, S, lds, B, rp, cp, diag);
-  launch_k(ce_bidir_finalize_kernel, dim3(1), dim3(1024), 0, st, rp, ns, cp, ng, diag, B, lse_row, lse_col, loss);
+  launch_k(ce_bidir_lse_kernel, dim3(nb, 2), dim3(256), 0, st, rp, ns, cp, ng, diag, B, lse_row, lse_col, bp);
+  launch_k(ce_bidir_loss_kernel, dim3(1), dim3(256), 0, st, bp, 2 * nb, B, loss);
   TIC_CHECK_LAUNCH("tic_ce_bidir_fwd");
   return TIC_OK;
 }

@@ -273,19 +273,26 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
                         float* __restrict__ logits_cls, float* __restrict__ logits_tim, float* __restrict__ losses,
                         float* __restrict__ dlogits, const float* __restrict__ dz_ext, __nv_bfloat16* __restrict__ dHb,
                         __nv_bfloat16* __restrict__ dHb_lo, int64_t ld_dhb, float* __restrict__ dHf, int64_t ld_dhf, int relu_mask,
-                        const float* __restrict__ Pt, const float* __restrict__ Pv, int64_t ldp, const int32_t* __restrict__ src) {
+                        const float* __restrict__ Pt, const float* __restrict__ Pv, int64_t ldp, const int32_t* __restrict__ src, int tpr) {
   pdl_trigger();
   pdl_wait();
-  const int r = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, nw = blockDim.x >> 5;
+  // tpr threads per row (a multiple of 32), rpb rows side by side in a block; the grid is capped (see the launch) so that the
+  // kernel occupies only part of the machine: its many small blocks otherwise land on EVERY SM and their registers keep the
+  // 8-CTA cluster of the ITC chain (51 K registers per CTA) from being scheduled until they retire (CUPTI timeline: 6 us).
+  const int rows = has_tim ? 2 * B : B;
+  const int rpb = blockDim.x / tpr, sub = threadIdx.x / tpr;
+  const int tid = threadIdx.x - sub * tpr, lane = tid & 31, wib = tid >> 5, nw = tpr >> 5;
+  __shared__ float sz[4][32][kMaxClasses];
+  for (int base = blockIdx.x * rpb; base < rows; base += gridDim.x * rpb) {
+  const int r = min(base + sub, rows - 1);
+  const bool rvalid = base + sub < rows;
   const bool is_cls = r < B;
   const int i = is_cls ? r : r - B;
   const int nc = is_cls ? C : 2;
   const float* W = is_cls ? W_cls : W_tim;
   const float* bias = is_cls ? b_cls : b_tim;
   const int k = tid * 4;
-  const bool act = k < E;
-  __shared__ float sz[32][kMaxClasses];
+  const bool act = k < E && rvalid;
   // ---- every load of this row, issued back to back
   float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 w[kMaxClasses];
@@ -324,9 +331,10 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
     if (c < nc && act) z[c] = fmaf(hx.x, w[c].x, fmaf(hx.y, w[c].y, fmaf(hx.z, w[c].z, hx.w * w[c].w)));
     if (c < nc) z[c] = warp_sum(z[c]);
   }
+  __syncthreads();      // (the previous row group has read its sums)
   if (lane == 0) {
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) sz[wib][c] = c < nc ? z[c] : 0.f;
+    for (int c = 0; c < kMaxClasses; ++c) sz[sub][wib][c] = c < nc ? z[c] : 0.f;
   }
   __syncthreads();
   float mx = -INFINITY;
@@ -334,7 +342,7 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
   for (int c = 0; c < kMaxClasses; ++c)
     if (c < nc) {
       float t = bias[c];
-      for (int q = 0; q < nw; ++q) t += sz[q][c];     // fixed order: every thread computes the same logits
+      for (int q = 0; q < nw; ++q) t += sz[sub][q][c];     // fixed order: every thread computes the same logits
       z[c] = t;
       mx = fmaxf(mx, t);
     }
@@ -355,14 +363,14 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
     for (int c = 0; c < kMaxClasses; ++c)
       if (c < nc) {
         dz[c] = c_cls / B * (expf(z[c] - lse) * wy - cw[c] * yv[c]);
-        if (tid == 0) logits_cls[static_cast<int64_t>(i) * C + c] = z[c];
+        if (tid == 0 && rvalid) logits_cls[static_cast<int64_t>(i) * C + c] = z[c];
       }
   } else {
     loss_t = -((ylab == 0 ? z[0] : z[1]) - lse) / B;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       dz[c] = c_tim / B * (expf(z[c] - lse) - (c == ylab ? 1.f : 0.f));
-      if (tid == 0) logits_tim[static_cast<int64_t>(i) * 2 + c] = z[c];
+      if (tid == 0 && rvalid) logits_tim[static_cast<int64_t>(i) * 2 + c] = z[c];
     }
   }
   if (dz_ext != nullptr) {  // autograd mode: the caller owns the loss; use its gradient w.r.t. the logits
@@ -371,7 +379,7 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c) dz[c] = c < nc ? __ldg(dz_ext + static_cast<int64_t>(r) * kMaxClasses + c) : 0.f;
   }
-  if (tid == 0) {
+  if (tid == 0 && rvalid) {
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c) dlogits[static_cast<int64_t>(r) * kMaxClasses + c] = c < nc ? dz[c] : 0.f;
     if (loss_c != 0.f) atomicAdd(losses + 0, loss_c);
@@ -409,6 +417,7 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
       }
     }
   }
+  }   // row groups
 }
 
 // Backward of the pairwise form: gradients w.r.t. the two projected halves from dH [2B, E] (bf16 hi + lo):
@@ -731,11 +740,16 @@ int tic_heads_fwd_bwd(float* H, int64_t ldh, int B, int E, int C, int has_tim, c
                    aligned16(H) && aligned16(W_cls) && aligned16(W_tim) && aligned16(dH_f32) && aligned16(keep) && aligned16(Pt) &&
                    aligned16(Pv) && ((reinterpret_cast<uintptr_t>(dH_bf16) | reinterpret_cast<uintptr_t>(dH_bf16_lo)) & 7) == 0;
   if (blk) {
-    const int threads = ceil_div(ceil_div(E, 4), 32) * 32;
-    launch_k(heads_rows_block_kernel, dim3(rows), dim3(threads), 0, st, H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft,
+    const int tpr = ceil_div(ceil_div(E, 4), 32) * 32;
+    int rpb = 1024 / tpr;
+    if (rpb > 4) rpb = 4;
+    if (rpb < 1) rpb = 1;
+    int grid = ceil_div(rows, rpb);
+    if (grid > 64) grid = 64;       // part of the machine only (see the kernel comment)
+    launch_k(heads_rows_block_kernel, dim3(grid), dim3(tpr * rpb), 0, st, H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft,
              class_w, lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses, dlogits, dlogits_ext,
              static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb, dH_f32, ld_dhf, relu_mask, Pt, Pv,
-             ldp, src_idx);
+             ldp, src_idx, tpr);
   } else
   launch_k(heads_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft, class_w,
                                                         lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses,

@@ -524,7 +524,42 @@ struct ItcBwdEpi {
           ga[j4 + 2] = p.gscale * (ex2_approx(s2_ - lr) + ex2_approx(s2_ - l4.z));
           ga[j4 + 3] = p.gscale * (ex2_approx(s3 - lr) + ex2_approx(s3 - l4.w));
         }
-        if (valid_row) {
+        if (cx.stage != nullptr && col0 + 32 <= cx.N && vec_ok) {
+          // Staged stores: a thread owns one ROW of the 32x32 chunk, so its direct 16-byte stores touch 32 different lines per
+          // instruction, each sector half-written — with a cold / dirty L2 these partial-sector writes took 11 of the kernel's
+          // 24 us (phase stamps, scripts/kernel_times.py).  Through a swizzled 2 KB staging tile per warp every store
+          // instruction writes 8 rows x 64 contiguous bytes (full sectors).  Swizzle as in the TMA-store path: 16-byte chunk q
+          // of row r sits at q ^ ((r >> 1) & 3): conflict-free on both sides.
+          const int wslot = (threadIdx.x >> 5) - 2;
+          uint8_t* stg = cx.stage + wslot * 2048;
+          const uint32_t rowb = smem_u32(stg) + lane * 64, sw = (lane >> 1) & 3;
+          auto put_staged = [&](__nv_bfloat16* dst, bool by_col, bool residual) {
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float x[8];
+#pragma unroll
+              for (int e8 = 0; e8 < 8; ++e8) {
+                x[e8] = ga[8 * q + e8] * (by_col ? sb[cl + 8 * q + e8] : rt);
+                if (residual) x[e8] -= __bfloat162float(__float2bfloat16_rn(x[e8]));
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((q ^ sw) << 4)), "r"(pack_bf16x2(x[0], x[1])),
+                           "r"(pack_bf16x2(x[2], x[3])), "r"(pack_bf16x2(x[4], x[5])), "r"(pack_bf16x2(x[6], x[7])) : "memory");
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2), c = lane & 3;
+              const uint4 u = *reinterpret_cast<const uint4*>(stg + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+              const int grow = cx.m0 + cx.quad * 32 + r;
+              if (grow < cx.M) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(grow) * p.ld_ga + col0 + c * 8) = u;
+            }
+          };
+          put_staged(p.GA, true, false);
+          if (p.GA_lo) put_staged(p.GA_lo, true, true);
+          put_staged(p.GBT, false, false);
+          if (p.GBT_lo) put_staged(p.GBT_lo, false, true);
+        } else if (valid_row) {
           const bool full = col0 + 32 <= cx.N && vec_ok;
           auto put = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, bool by_col) {
             __nv_bfloat16* d = hi + static_cast<int64_t>(row) * p.ld_ga + col0;
@@ -633,6 +668,17 @@ struct ItcBwdEpi {
 // cluster meets at ONE barrier (release/acquire at cluster scope: the partial sums every CTA wrote to global memory are
 // visible), and the backward epilogue derives lse_row / lse_col from those partials and emits the gradient operands from
 // the accumulator that is still in TMEM.  One launch and one k-loop less on the critical chain of the step.
+// Measurement switch (tic_debug_set_trace): when a device buffer is registered, the fused kernel stamps %globaltimer at its
+// phase boundaries into trace[blockIdx.x * 16 + i] — where the 27 us of this 8-CTA kernel go cannot be seen from outside.
+__device__ unsigned long long* g_tic_trace = nullptr;
+__device__ __forceinline__ void trace_stamp(int i) {
+  unsigned long long* t = g_tic_trace;
+  if (t != nullptr) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    t[blockIdx.x * 16 + i] = now;
+  }
+}
 constexpr int kFusedSmallStages = 4;   // 4 x 24 KB ring + 3 KB scratch: the cluster's CTAs co-reside with other small launches
 constexpr int kFusedSmallSmem = kFusedSmallStages * UmmaCfg<kItcBNSmall>::kStageBytes + 1024 + 256 + 2 * (6 * kItcBNSmall * 4 + 256);
 template <int BN>
@@ -657,6 +703,7 @@ itc_fused_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const int num_kb = (K + kBK - 1) / kBK;
   const int nseg = 1 + (split & 1) + ((split >> 1) & 1);
   const int total_kb = num_kb * nseg;
+  if (threadIdx.x == 64) trace_stamp(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -672,6 +719,7 @@ itc_fused_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   pdl_wait();
+  if (threadIdx.x == 64) trace_stamp(1);
   const int m0 = m_blk * kBM, n0 = n_blk * BN;
   EpiCtx cx;
   if (warp == 0) {
@@ -689,6 +737,7 @@ itc_fused_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         tma_load_2d(sa + kABytes, b_lo ? &tmap_b_lo : &tmap_b, full_bar(st), kb * kBK, n0);
         if (++st == STAGES) { st = 0; ph ^= 1u; }
       }
+      trace_stamp(2);
       pdl_trigger();
     }
   } else if (warp == 1) {
@@ -723,19 +772,26 @@ itc_fused_small_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     cx.m_blk = m_blk; cx.n_blk = n_blk; cx.m0 = m0; cx.n0 = n0;
     cx.tmem_acc = tmem_base;
     ItcFwdEpi::template prefetch<BN>(fp, cx);
+    if (threadIdx.x == 64) trace_stamp(8);
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) trace_stamp(3);
     ItcFwdEpi::template tile<BN>(fp, cx);
     tc_fence_before();
+    if (threadIdx.x == 64) trace_stamp(4);
   }
   __syncwarp();
   cluster_sync_all();    // every CTA's partial sums / inverse norms are in global memory and visible cluster-wide
   if (warp >= 2) {       // ---- epilogue, phase 2: gradient operands from the accumulator still in TMEM
     tc_fence_after();
+    if (threadIdx.x == 64) trace_stamp(5);
     cx.iter = 1;         // the other half of the double-buffered epilogue scratch
+    cx.stage = smem_gen; // the operand ring is idle (every MMA has completed): 2 KB of staging per epilogue warp
     ItcBwdEpi::template prefetch<BN, true>(bp, cx);
+    if (threadIdx.x == 64) trace_stamp(6);
     ItcBwdEpi::template tile<BN>(bp, cx);
     tma_store_wait<0>();
+    if (threadIdx.x == 64) trace_stamp(7);
   }
   tc_fence_before();
   __syncthreads();
@@ -1222,6 +1278,12 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
   if (rc == -3) { set_error("tic_itc_bwd_g: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_bwd_g: launch failed"); return TIC_E_LAUNCH; }
   return rc;
+}
+
+int tic_debug_set_trace(void* device_u64_buffer) {
+  unsigned long long* p = static_cast<unsigned long long*>(device_u64_buffer);
+  if (cudaMemcpyToSymbol(g_tic_trace, &p, sizeof(p)) != cudaSuccess) { set_error("tic_debug_set_trace: cudaMemcpyToSymbol failed"); return TIC_E_CUDA; }
+  return TIC_OK;
 }
 
 int tic_itc_fused_small_ok(int m_local, int n_global) {

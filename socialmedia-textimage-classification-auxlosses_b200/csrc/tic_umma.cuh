@@ -47,6 +47,7 @@ struct EpiCtx {
   int iter;             // tiles already processed by this CTA (for double-buffering the scratch)
   int ks, ksplit;       // split-K: this work item covers K-slice ks of ksplit (epilogue must accumulate atomically)
   uint8_t* scratch;    // kEpiScratchBytes of smem shared by the epilogue warps
+  uint8_t* stage = nullptr;   // optional 2 KB per epilogue warp of 1024-byte-aligned staging space (e.g. the idle operand ring)
   float pre[8];        // per-thread values loaded by Epi::prefetch for Epi::tile (row norms, row lse, logit scale)
 };
 

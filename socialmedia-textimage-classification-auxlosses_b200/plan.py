@@ -500,6 +500,8 @@ class HeadPlan:
                 cast("fusion", "W_gt", p["linear_gmu_t.weight"]); keep("b_gt", p["linear_gmu_t.bias"])
                 cast("fusion", "W_gv", p["linear_gmu_v.weight"]); keep("b_gv", p["linear_gmu_v.bias"])
         self._refresh_groups = {}
+        if len(groups["itc"]) + len(groups["fusion"]) <= 8:   # ONE launch for both chains (the root node of the captured step)
+            groups["all"] = groups["itc"] + groups["fusion"]
         for g, items in groups.items():
             n = len(items)
             if n == 0 and g != "itc":
@@ -518,14 +520,18 @@ class HeadPlan:
         """fp32 masters -> bf16 working copies of one chain's matrices (+ exp(logit_scale) with the ITC group): one launch"""
         if not (force or self.live_weights) or group not in self._refresh_groups:
             return
+        if not force and group != "all" and getattr(self, "_refreshed_all", False):
+            return                   # the step's root launch refreshed both chains' matrices already
         n, src, dst, lds, ldd, rows, cols = self._refresh_groups[group]
-        with_scale = group == "itc"
+        with_scale = group in ("itc", "all")
         # live mode inside a step: this launch also zeroes the chain's share of the small accumulator block, so no memset
         # node sits in front of the first kernel of either chain (see _zero_accumulators)
         z0 = z1 = None
         if not force and self._refresh_zeroes:
             zs, n_s = self.zb_small, self.zb_small.numel()
-            if group == "itc":       # itc_sums, r_sum (+ pad): floats [2, 8)
+            if group == "all":
+                z0 = zs
+            elif group == "itc":     # itc_sums, r_sum (+ pad): floats [2, 8)
                 z0 = zs[2:8] if "fusion" in self._refresh_groups else zs
             else:                    # losses [0, 2) and the small heads' gradient accumulators [8, n_small)
                 z0, z1 = (zs[0:2], zs[8:n_s]) if ("itc" in self._refresh_groups and self.use_itc) else (zs, None)
@@ -546,11 +552,16 @@ class HeadPlan:
         B, E, w = self.B, self.E, self.w
         if self.P is not None:
             tp_, vp_ = inp["t_pool"], inp["v_pool"]
-            Yt, Yv, Ytl, Yvl = self.Y[:B], self.Y[B:], self.Y_lo[:B], self.Y_lo[B:]
-            if not self.itc.precise:   # >= 4096 negatives: the residual K-segments are skipped (tensor time matters there)
-                Ytl = Yvl = None
-            return Yt, Yv, Ytl, Yvl
+            # Embeddings projected on the device are fp32 values: the similarity tiles always consume them as bf16 (hi, lo) pairs
+            # (a single-bf16 embedding moves every logit by ~1.5e-3 and the ITC gradients by 1.7e-3 at B = 4096 — over the 1e-3
+            # bar; measured).  Only the gradient GEMMs drop the residual K-segments at large batch (_itc_gemm_lo).
+            return self.Y[:B], self.Y[B:], self.Y_lo[:B], self.Y_lo[B:]
         return inp["t_pool"], inp["v_pool"], None, None
+
+    def _itc_gemm_lo(self, lo):
+        """residual of an embedding as a GEMM operand: kept while the step is latency-bound (< 4096 negatives), dropped where
+        tensor time matters (the rounding of a GEMM operand averages out over >= 4096 terms; measured < 1e-3)"""
+        return lo if self.itc.precise else None
 
     def _itc_fwd(self, inp, with_loss=True):
         B, E, w, it = self.B, self.E, self.w, self.itc
@@ -620,11 +631,11 @@ class HeadPlan:
                 dYt_lo = dYv_lo = None
             tp_, vp_ = inp["t_pool"], inp["v_pool"]
             with br("v"):   # image-side gradient branch
-                it.grad_gemm_v(Yt, ldt, T_lo=Ytl)
+                it.grad_gemm_v(Yt, ldt, T_lo=self._itc_gemm_lo(Ytl))
                 it.finalize_v(it.acc_v, Yv, ldv, it.rinv_v, Yt, ldt, it.rinv_t, B, self.scale, dcoef, None, dYv,
                               dV_lo=dYv_lo, V_lo=Yvl, T_diag_lo=Ytl)
                 gemm(dYv, self.P, 1, vp_, vp_.stride(0), 1, o["dW_v"], E, 0, self.P, E, B, A_lo=dYv_lo, accumulate=self._atomic["dW_v"])
-            it.grad_gemm_t(Yv, ldv, V_lo=Yvl)
+            it.grad_gemm_t(Yv, ldv, V_lo=self._itc_gemm_lo(Yvl))
             it.finalize_t(Yt, ldt, Yv, ldv, it.rinv_v, self.scale, dcoef, None, dYt, z["r_sum"], dT_lo=dYt_lo, T_lo=Ytl,
                           V_diag_lo=Yvl)
             with br("w"):   # dW_t = dYt^T t_pool (both operands read MN-major)  ||  d_t_pool = dYt W_t
@@ -675,10 +686,18 @@ class HeadPlan:
             return self._step_body_inner(inp)
         finally:
             self._in_step = False
+            self._refreshed_all = False
 
     def _step_body_inner(self, inp):
         B, z, o = self.B, self.z, self.out
         s0 = torch.cuda.current_stream()
+        # Live weights: ONE refresh launch is the root of the step (bf16 working copies of both chains' matrices,
+        # exp(logit_scale), the small accumulator block zeroed).  With one root per chain the graph launched the second
+        # chain's root ~14 us late (CUPTI timeline, profiles/r02_timeline_c2_*.txt).
+        self._refreshed_all = False
+        if self._refresh_zeroes and "all" in self._refresh_groups:
+            self._refresh("all")
+            self._refreshed_all = True
         self._zero_accumulators()
         two = self.use_itc and self.fusion is not None and self.parallel_streams
         if two:
