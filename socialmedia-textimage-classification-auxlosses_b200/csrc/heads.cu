@@ -8,6 +8,7 @@
 namespace tic {
 
 constexpr int kMaxClasses = 8;
+constexpr int kBlkC = 4;   // the block-per-row heads kernel keeps the class weights in registers: tasks have 2..4 classes (config.py:18-48)
 
 // ------------------------------------------------------------------ pack / unpack
 // One warp per output row; 16-byte copies. Row r < B: [xt[r] | xv[r]];  row B + i: [xt[src[i]] | xv[i]].
@@ -265,7 +266,7 @@ __global__ void heads_rows_kernel(float* __restrict__ H, int64_t ldh, int B, int
 // are issued at once and everything — the weights too — stays in registers between the logits and the dH pass, so a row
 // costs one memory round trip + one block reduction instead of the warp-per-row kernel's chain of dependent passes
 // (CUPTI timeline of the c2 step: 20 us for 512 rows, the longest kernel of the fusion chain).
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(768, 1)
 heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C, int has_tim, const float* __restrict__ W_cls,
                         const float* __restrict__ b_cls, const float* __restrict__ W_tim, const float* __restrict__ b_tim,
                         const float* __restrict__ y_soft, const float* __restrict__ class_w, const int64_t* __restrict__ lbl_tim,
@@ -282,7 +283,7 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
   const int rows = has_tim ? 2 * B : B;
   const int rpb = blockDim.x / tpr, sub = threadIdx.x / tpr;
   const int tid = threadIdx.x - sub * tpr, lane = tid & 31, wib = tid >> 5, nw = tpr >> 5;
-  __shared__ float sz[4][32][kMaxClasses];
+  __shared__ float sz[10][8][kBlkC];
   for (int base = blockIdx.x * rpb; base < rows; base += gridDim.x * rpb) {
   const int r = min(base + sub, rows - 1);
   const bool rvalid = base + sub < rows;
@@ -291,55 +292,65 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
   const int nc = is_cls ? C : 2;
   const float* W = is_cls ? W_cls : W_tim;
   const float* bias = is_cls ? b_cls : b_tim;
-  const int k = tid * 4;
-  const bool act = k < E && rvalid;
+  const int k = tid * 8;               // 8 consecutive features per thread (two 16-byte groups): E = 768 -> 96 threads per row
+  const bool act0 = k < E && rvalid, act1 = k + 4 < E && rvalid;
   // ---- every load of this row, issued back to back
-  float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 w[kMaxClasses];
-  uchar4 m = make_uchar4(1, 1, 1, 1);
-  if (act) {
-    if (Pt != nullptr) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(Pt + static_cast<int64_t>(is_cls ? i : src[i]) * ldp + k));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(Pv + static_cast<int64_t>(i) * ldp + k));
-      hv = make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
-    } else {
-      hv = *reinterpret_cast<const float4*>(H + static_cast<int64_t>(r) * ldh + k);
-    }
-    if (is_cls && keep) m = *reinterpret_cast<const uchar4*>(keep + static_cast<int64_t>(i) * E + k);
+  float4 hv[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  float4 w[2][kBlkC];
+  uchar4 m[2] = {make_uchar4(1, 1, 1, 1), make_uchar4(1, 1, 1, 1)};
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c)
-      if (c < nc) w[c] = __ldg(reinterpret_cast<const float4*>(W + c * E + k));
+  for (int v = 0; v < 2; ++v) {
+    const int kv = k + 4 * v;
+    if (v == 0 ? act0 : act1) {
+      if (Pt != nullptr) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(Pt + static_cast<int64_t>(is_cls ? i : src[i]) * ldp + kv));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(Pv + static_cast<int64_t>(i) * ldp + kv));
+        hv[v] = make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
+      } else {
+        hv[v] = *reinterpret_cast<const float4*>(H + static_cast<int64_t>(r) * ldh + kv);
+      }
+      if (is_cls && keep) m[v] = *reinterpret_cast<const uchar4*>(keep + static_cast<int64_t>(i) * E + kv);
+#pragma unroll
+      for (int c = 0; c < kBlkC; ++c)
+        if (c < nc) w[v][c] = __ldg(reinterpret_cast<const float4*>(W + c * E + kv));
+    }
   }
-  float yv[kMaxClasses], cw[kMaxClasses];
+  float yv[kBlkC], cw[kBlkC];
   int ylab = 0;
   if (is_cls) {
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c)
+    for (int c = 0; c < kBlkC; ++c)
       if (c < nc) { yv[c] = __ldg(y_soft + static_cast<int64_t>(i) * C + c); cw[c] = class_w ? __ldg(class_w + c) : 1.f; }
   } else {
     ylab = static_cast<int>(lbl_tim[i]);
   }
-  if (act && Pt != nullptr) *reinterpret_cast<float4*>(H + static_cast<int64_t>(r) * ldh + k) = hv;   // mm_features / weight gradients
-  // ---- logits: per-thread partial dot products -> block reduction
-  const float4 hd = make_float4(m.x ? hv.x * keep_scale : 0.f, m.y ? hv.y * keep_scale : 0.f, m.z ? hv.z * keep_scale : 0.f,
-                                m.w ? hv.w * keep_scale : 0.f);
-  const float4 hx = (is_cls && keep) ? hd : hv;
-  float z[kMaxClasses];
+  float z[kBlkC];
 #pragma unroll
-  for (int c = 0; c < kMaxClasses; ++c) {
-    z[c] = 0.f;
-    if (c < nc && act) z[c] = fmaf(hx.x, w[c].x, fmaf(hx.y, w[c].y, fmaf(hx.z, w[c].z, hx.w * w[c].w)));
-    if (c < nc) z[c] = warp_sum(z[c]);
+  for (int c = 0; c < kBlkC; ++c) z[c] = 0.f;
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const bool act = v == 0 ? act0 : act1;
+    if (act && Pt != nullptr) *reinterpret_cast<float4*>(H + static_cast<int64_t>(r) * ldh + k + 4 * v) = hv[v];   // mm_features / weight gradients
+    // ---- logits: per-thread partial dot products
+    const float4 hd = make_float4(m[v].x ? hv[v].x * keep_scale : 0.f, m[v].y ? hv[v].y * keep_scale : 0.f,
+                                  m[v].z ? hv[v].z * keep_scale : 0.f, m[v].w ? hv[v].w * keep_scale : 0.f);
+    const float4 hx = (is_cls && keep) ? hd : hv[v];
+#pragma unroll
+    for (int c = 0; c < kBlkC; ++c)
+      if (c < nc && act) z[c] = fmaf(hx.x, w[v][c].x, fmaf(hx.y, w[v][c].y, fmaf(hx.z, w[v][c].z, fmaf(hx.w, w[v][c].w, z[c]))));
   }
+#pragma unroll
+  for (int c = 0; c < kBlkC; ++c)
+    if (c < nc) z[c] = warp_sum(z[c]);
   __syncthreads();      // (the previous row group has read its sums)
   if (lane == 0) {
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) sz[sub][wib][c] = c < nc ? z[c] : 0.f;
+    for (int c = 0; c < kBlkC; ++c) sz[sub][wib][c] = c < nc ? z[c] : 0.f;
   }
   __syncthreads();
   float mx = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < kMaxClasses; ++c)
+  for (int c = 0; c < kBlkC; ++c)
     if (c < nc) {
       float t = bias[c];
       for (int q = 0; q < nw; ++q) t += sz[sub][q][c];     // fixed order: every thread computes the same logits
@@ -348,19 +359,19 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
     }
   float se = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxClasses; ++c)
+  for (int c = 0; c < kBlkC; ++c)
     if (c < nc) se += expf(z[c] - mx);
   const float lse = mx + logf(se);
-  float dz[kMaxClasses];
+  float dz[kBlkC];
   float loss_c = 0.f, loss_t = 0.f;
   if (is_cls) {
     float wy = 0.f, l = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c)
+    for (int c = 0; c < kBlkC; ++c)
       if (c < nc) { wy += cw[c] * yv[c]; l -= cw[c] * yv[c] * (z[c] - lse); }
     loss_c = l / B;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c)
+    for (int c = 0; c < kBlkC; ++c)
       if (c < nc) {
         dz[c] = c_cls / B * (expf(z[c] - lse) * wy - cw[c] * yv[c]);
         if (tid == 0 && rvalid) logits_cls[static_cast<int64_t>(i) * C + c] = z[c];
@@ -377,43 +388,47 @@ heads_rows_block_kernel(float* __restrict__ H, int64_t ldh, int B, int E, int C,
     loss_c = 0.f;
     loss_t = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) dz[c] = c < nc ? __ldg(dz_ext + static_cast<int64_t>(r) * kMaxClasses + c) : 0.f;
+    for (int c = 0; c < kBlkC; ++c) dz[c] = c < nc ? __ldg(dz_ext + static_cast<int64_t>(r) * kMaxClasses + c) : 0.f;
   }
   if (tid == 0 && rvalid) {
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) dlogits[static_cast<int64_t>(r) * kMaxClasses + c] = c < nc ? dz[c] : 0.f;
+    for (int c = 0; c < kMaxClasses; ++c) dlogits[static_cast<int64_t>(r) * kMaxClasses + c] = (c < kBlkC && c < nc) ? dz[c < kBlkC ? c : 0] : 0.f;
     if (loss_c != 0.f) atomicAdd(losses + 0, loss_c);
     if (loss_t != 0.f) atomicAdd(losses + 1, loss_t);
   }
-  // ---- dH for this thread's 4 features, from the weights still in registers
-  if (act && (dHb || dHf)) {
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
+  // ---- dH for this thread's 8 features, from the weights still in registers
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c)
-      if (c < nc) {
-        g[0] = fmaf(dz[c], w[c].x, g[0]); g[1] = fmaf(dz[c], w[c].y, g[1]);
-        g[2] = fmaf(dz[c], w[c].z, g[2]); g[3] = fmaf(dz[c], w[c].w, g[3]);
+  for (int v = 0; v < 2; ++v) {
+    const int kv = k + 4 * v;
+    if ((v == 0 ? act0 : act1) && (dHb || dHf)) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < kBlkC; ++c)
+        if (c < nc) {
+          g[0] = fmaf(dz[c], w[v][c].x, g[0]); g[1] = fmaf(dz[c], w[v][c].y, g[1]);
+          g[2] = fmaf(dz[c], w[v][c].z, g[2]); g[3] = fmaf(dz[c], w[v][c].w, g[3]);
+        }
+      if (is_cls && keep) {
+        g[0] = m[v].x ? g[0] * keep_scale : 0.f; g[1] = m[v].y ? g[1] * keep_scale : 0.f;
+        g[2] = m[v].z ? g[2] * keep_scale : 0.f; g[3] = m[v].w ? g[3] * keep_scale : 0.f;
       }
-    if (is_cls && keep) {
-      g[0] = m.x ? g[0] * keep_scale : 0.f; g[1] = m.y ? g[1] * keep_scale : 0.f;
-      g[2] = m.z ? g[2] * keep_scale : 0.f; g[3] = m.w ? g[3] * keep_scale : 0.f;
-    }
-    if (relu_mask) {
-      if (!(hv.x > 0.f)) g[0] = 0.f;
-      if (!(hv.y > 0.f)) g[1] = 0.f;
-      if (!(hv.z > 0.f)) g[2] = 0.f;
-      if (!(hv.w > 0.f)) g[3] = 0.f;
-    }
-    if (dHf) *reinterpret_cast<float4*>(dHf + static_cast<int64_t>(r) * ld_dhf + k) = make_float4(g[0], g[1], g[2], g[3]);
-    if (dHb) {
-      uint2 u;
-      u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]);
-      *reinterpret_cast<uint2*>(dHb + static_cast<int64_t>(r) * ld_dhb + k) = u;
-      if (dHb_lo) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) g[j] -= __bfloat162float(__float2bfloat16_rn(g[j]));
+      if (relu_mask) {
+        if (!(hv[v].x > 0.f)) g[0] = 0.f;
+        if (!(hv[v].y > 0.f)) g[1] = 0.f;
+        if (!(hv[v].z > 0.f)) g[2] = 0.f;
+        if (!(hv[v].w > 0.f)) g[3] = 0.f;
+      }
+      if (dHf) *reinterpret_cast<float4*>(dHf + static_cast<int64_t>(r) * ld_dhf + kv) = make_float4(g[0], g[1], g[2], g[3]);
+      if (dHb) {
+        uint2 u;
         u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]);
-        *reinterpret_cast<uint2*>(dHb_lo + static_cast<int64_t>(r) * ld_dhb + k) = u;
+        *reinterpret_cast<uint2*>(dHb + static_cast<int64_t>(r) * ld_dhb + kv) = u;
+        if (dHb_lo) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g[j] -= __bfloat162float(__float2bfloat16_rn(g[j]));
+          u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]);
+          *reinterpret_cast<uint2*>(dHb_lo + static_cast<int64_t>(r) * ld_dhb + kv) = u;
+        }
       }
     }
   }
@@ -736,16 +751,16 @@ int tic_heads_fwd_bwd(float* H, int64_t ldh, int B, int E, int C, int has_tim, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rows = has_tim ? 2 * B : B;
   float* dlogits = ws;
-  const bool blk = (E & 3) == 0 && E <= 4096 && (ldh & 3) == 0 && (ld_dhb & 3) == 0 && (ld_dhf & 3) == 0 && (ldp & 3) == 0 &&
+  const bool blk = C <= kBlkC && (E & 3) == 0 && E <= 2048 && (ldh & 3) == 0 && (ld_dhb & 3) == 0 && (ld_dhf & 3) == 0 && (ldp & 3) == 0 &&
                    aligned16(H) && aligned16(W_cls) && aligned16(W_tim) && aligned16(dH_f32) && aligned16(keep) && aligned16(Pt) &&
                    aligned16(Pv) && ((reinterpret_cast<uintptr_t>(dH_bf16) | reinterpret_cast<uintptr_t>(dH_bf16_lo)) & 7) == 0;
   if (blk) {
-    const int tpr = ceil_div(ceil_div(E, 4), 32) * 32;
-    int rpb = 1024 / tpr;
-    if (rpb > 4) rpb = 4;
+    const int tpr = ceil_div(ceil_div(E, 8), 32) * 32;    // 8 features per thread
+    int rpb = 768 / tpr;
+    if (rpb > 8) rpb = 8;
     if (rpb < 1) rpb = 1;
     int grid = ceil_div(rows, rpb);
-    if (grid > 64) grid = 64;       // part of the machine only (see the kernel comment)
+    if (grid > 64) grid = 64;       // part of the machine only (see the kernel comment); c2: 64 blocks of 8 rows, ONE round
     launch_k(heads_rows_block_kernel, dim3(grid), dim3(tpr * rpb), 0, st, H, ldh, B, E, C, has_tim, W_cls, b_cls, W_tim, b_tim, y_soft,
              class_w, lbl_tim, keep, keep_scale, c_cls, c_tim, logits_cls, logits_tim, losses, dlogits, dlogits_ext,
              static_cast<__nv_bfloat16*>(dH_bf16), static_cast<__nv_bfloat16*>(dH_bf16_lo), ld_dhb, dH_f32, ld_dhf, relu_mask, Pt, Pv,

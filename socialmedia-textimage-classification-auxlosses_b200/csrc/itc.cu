@@ -533,7 +533,13 @@ struct ItcBwdEpi {
           const int wslot = (threadIdx.x >> 5) - 2;
           uint8_t* stg = cx.stage + wslot * 2048;
           const uint32_t rowb = smem_u32(stg) + lane * 64, sw = (lane >> 1) & 3;
-          auto put_staged = [&](__nv_bfloat16* dst, bool by_col, bool residual) {
+          // ONE rolled loop over the four outputs (hi / residual x column- / row-scaled): the cold instruction fetch of this
+          // epilogue is on the step's critical chain (scripts/fused_in_step.py), so its code is kept small.
+#pragma unroll 1
+          for (int which = 0; which < 4; ++which) {
+            __nv_bfloat16* dst = which == 0 ? p.GA : (which == 1 ? p.GA_lo : (which == 2 ? p.GBT : p.GBT_lo));
+            if (dst == nullptr) continue;
+            const bool by_col = which < 2, residual = which & 1;
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -554,11 +560,7 @@ struct ItcBwdEpi {
               const int grow = cx.m0 + cx.quad * 32 + r;
               if (grow < cx.M) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(grow) * p.ld_ga + col0 + c * 8) = u;
             }
-          };
-          put_staged(p.GA, true, false);
-          if (p.GA_lo) put_staged(p.GA_lo, true, true);
-          put_staged(p.GBT, false, false);
-          if (p.GBT_lo) put_staged(p.GBT_lo, false, true);
+          }
         } else if (valid_row) {
           const bool full = col0 + 32 <= cx.N && vec_ok;
           auto put = [&](__nv_bfloat16* hi, __nv_bfloat16* lo, bool by_col) {

@@ -309,6 +309,15 @@ class HeadPlan:
             self.itc.scale_dev = self.scale_t
         import os as _os2
         self.fuse_itc_small = _os2.environ.get("TIC_ITC_FUSED_SMALL", "1") != "0"     # A/B switch (same kernels' epilogues)
+        # code warm-up launches at the head of the step (see _warm_calls): only where the step is latency-bound
+        self.code_warm = (_os2.environ.get("TIC_CODE_WARM", "1") != "0") and B <= 512 and type(self).__name__ == "HeadPlan"
+        self._warm = None
+        E_ = self.E
+        self._warm_H = torch.zeros(2, E_, dtype=F32, device=self.dev)
+        self._warm_P = torch.zeros(2, E_, dtype=F32, device=self.dev)
+        self._warm_dH = torch.zeros(2, E_, dtype=BF16, device=self.dev)
+        self._warm_dH_lo = torch.zeros(2, E_, dtype=BF16, device=self.dev)
+        self._warm_dP = [torch.zeros(2, E_, dtype=BF16, device=self.dev) for _ in range(4)]
         self.live_weights = False                # bind_params(live=True): the bf16 working copies are refreshed inside step()
         self._refresh_groups = {}
         self.generation = 0                      # autograd mode: bumped by forward(); backward() checks it (see mm_late._HeadFn)
@@ -688,6 +697,51 @@ class HeadPlan:
             self._in_step = False
             self._refreshed_all = False
 
+    # ------------------------------------------------------------------ code warm-up (small-batch step)
+    # Measured (scripts/fused_in_step.py, profiles/r02_fused_in_step.txt): inside the replayed step the fused ITC kernel takes
+    # 24 us, alone 14 us — and 14 us again inside the step if the SAME kernel (outputs to scratch) ran once after the L2 flush.
+    # What is cold is the kernel's CODE: ~1 us per KB of first-executed instructions when they come from HBM.  A latency-bound
+    # step cannot hide that behind data-parallel work, so the step issues, on a side branch at its head, ONE tiny instance of
+    # each kernel of the two critical chains (128-row problems on scratch buffers): by the time the real launches arrive, their
+    # code is L2-resident.  It is an instruction prefetch spelled as launches; TIC_CODE_WARM=0 turns it off (A/B switch).
+    def _build_warm(self):
+        dev = self.dev
+        e = lambda *sh, dt=F32: torch.zeros(*sh, dtype=dt, device=dev)  # noqa: E731
+        W = {"A": e(128, 128, dt=BF16), "B": e(128, 128, dt=BF16), "Al": e(128, 128, dt=BF16), "Bl": e(128, 128, dt=BF16),
+             "Df": e(128, 128), "Df2": e(128, 128), "Db": e(128, 128, dt=BF16), "Dl": e(128, 128, dt=BF16), "bias": e(128), "u": torch.full((128,), 0.75, device=dev),
+             "lbl": torch.zeros(128, dtype=torch.int64, device=dev), "src": torch.zeros(128, dtype=torch.int32, device=dev),
+             "ss": e(capi.load().tic_gemm_rowss_parts(64), 128), "y": e(8, self.C), "ws": e(16 * 8), "los": e(4), "lg": e(16, 8),
+             "r": e(4)}
+        W["A"].fill_(0.01); W["B"].fill_(0.02); W["ss"].fill_(1.0)
+        W["it"] = ItcPlan(128, 128, 64, dev, precise=True)
+        W["it"].scale_dev = self.scale_t
+        return W
+
+    def _warm_calls(self, grp):
+        """grp 0: the fused ITC tiles (the longest cold start, first needed);  1: the gradient-GEMM forms + normalise-backward;
+        2: the fusion chain's heads / pairwise-gradient kernels"""
+        if self._warm is None:
+            self._warm = self._build_warm()
+        W, E = self._warm, self.E
+        A, Bm, Al, Bl, it = W["A"], W["B"], W["Al"], W["Bl"], W["it"]
+        if grp == 0 and self.use_itc:
+            if it.can_fuse_small and self.fuse_itc_small:
+                it.fwd_bwd_fused(A, 128, Bm, 128, self.scale, 1e-3, T_lo=Al, V_lo=Bl, ss_t=W["ss"], ss_v=W["ss"])
+        if grp == 1 and self.use_itc:
+            gemm(A, 128, 0, Bm, 128, 1, W["Df"], 128, 0, 128, 64, 64, A_lo=Al, B_lo=Bl)          # dT / d_t_pool / dX form
+            gemm(A, 128, 1, Bm, 128, 1, W["Df2"], 128, 0, 128, 64, 64, A_lo=Al, B_lo=Bl)         # dV / weight-gradient form
+            call("tic_itc_grad_finalize", ptr(W["Df"]), 128, ptr(A), ptr(Al), 128, ptr(it.rinv_t), ptr(Bm), ptr(Bl), 128,
+                 ptr(it.rinv_v), 8, 64, float(self.scale), 0.0, None, 128, ptr(W["Db"]), ptr(W["Dl"]), 128, ptr(W["r"]), 0,
+                 ptr(self.scale_t), _stream())
+        if grp == 2 and self.fusion in ("concat", "attention", "gmu"):
+            if self.pairwise:
+                call("tic_heads_fwd_bwd", ptr(self._warm_H), E, 1, E, self.C, int(self.use_itm), ptr(self.w["W_cls"]),
+                     ptr(self.w["b_cls"]), ptr(self.w["W_tim"]), ptr(self.w["b_tim"]), ptr(W["y"]), None, ptr(W["lbl"]), None, 1.0,
+                     0.0, 0.0, ptr(W["lg"]), ptr(W["lg"]), ptr(W["los"]), ptr(self._warm_dH), ptr(self._warm_dH_lo), E, None, E,
+                     None, None, None, None, 1, ptr(W["ws"]), None, ptr(self._warm_P), ptr(self._warm_P), E, ptr(W["src"]), _stream())
+                call("tic_fusion_pair_grad", ptr(self._warm_dH), ptr(self._warm_dH_lo), E, 1, E, int(self.use_itm), ptr(W["src"]),
+                     ptr(self._warm_dP[0]), ptr(self._warm_dP[1]), ptr(self._warm_dP[2]), ptr(self._warm_dP[3]), E, _stream())
+
     def _step_body_inner(self, inp):
         B, z, o = self.B, self.z, self.out
         s0 = torch.cuda.current_stream()
@@ -698,6 +752,12 @@ class HeadPlan:
         if self._refresh_zeroes and "all" in self._refresh_groups:
             self._refresh("all")
             self._refreshed_all = True
+        if self.code_warm and self.w and self._refreshed_all:
+            # three short side branches BEHIND the root (a captured step with several roots starts its later roots ~14 us late)
+            self.br.enabled = True
+            for grp in (0, 1, 2):
+                with self.br("cw%d" % grp):
+                    self._warm_calls(grp)
         self._zero_accumulators()
         two = self.use_itc and self.fusion is not None and self.parallel_streams
         if two:
@@ -725,6 +785,8 @@ class HeadPlan:
             if self.use_itc:
                 self._itc_bwd(inp)
         self.br.join("l")      # ITC loss terms (+ the early loss mix) on their side branch
+        for grp in (0, 1, 2):
+            self.br.join("cw%d" % grp)
         if not mixed:
             self._loss_mix()
         return o
