@@ -332,7 +332,13 @@ class HeadPlan:
         self._ev_heads = None
         # programmatic dependent launch on the kernels of the latency-critical chains only (TIC_PDL_CHAINS=1; needs the
         # high-priority-chain mode): see _Branches and tic_set_pdl
-        self.pdl_chains = _os.environ.get("TIC_PDL_CHAINS", "0") == "1"
+        # Round 2: ON by default where the chains run on high-priority streams (B <= 1024).  With two CTAs per SM for the small
+        # tcgen05 launches and the heads kernel confined to part of the machine, the chains no longer starve each other and PDL
+        # pays on the full step too (c2: 73.2 -> 66.1 us; profiles/r02_c2_ab.txt).  TIC_PDL_CHAINS=0 turns it off.
+        _pc = _os.environ.get("TIC_PDL_CHAINS")
+        # (single-GPU plan only: the multi-GPU plans run spinning exchange kernels beside their tile kernels, where early-
+        # launched waiting CTAs are a liability)
+        self.pdl_chains = (self.hi_priority_chains and type(self).__name__ == "HeadPlan") if _pc is None else (_pc == "1")
         # TIC_STEP_TAIL bit 0: small memset on a side branch, bit 1: loss mix issued before the backward (A/B switch).
         # Measured on the c2 graph (scripts/timeline.py --plain-only, 400 replays): 0 -> 92.2 us, 1 -> 96.4 us (a memset node
         # joined into both chains costs more than the ~2 us it takes at the head), 2 -> 90.3 us, 3 -> 92.7 us.  Default 2.
