@@ -164,7 +164,11 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale,
                   float gscale, void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo /* optional residuals */,
                   void* GBT_lo, const float* row_part, int n_row_parts, const float* col_part, int n_col_parts, float shift,
-                  const float* scale_dev, void* stream);
+                  const float* scale_dev, const uint32_t* seg_ready, const uint32_t* seg_epoch, int seg_cols, int my_seg,
+                  void* stream);
+/* seg_ready (optional, as in tic_itc_fwd): the gathered lse_col / rinv_v vectors arrive segment by segment (tic_peer_push);
+ * the tiles of a column segment start once its flag has reached *seg_epoch.  In both kernels a NEGATIVE seg_cols marks flags
+ * that are written by the peers themselves (push form): the launch then keeps the whole machine (no pull kernel beside it). */
 /* Fused forward + backward tiles for the small-batch step (at most 8 tiles of 128 x 64: tic_itc_fused_small_ok): ONE launch
  * = tic_itc_fwd (same outputs: partials, diag, inverse norms, optional logits / qpart) followed, after a cluster-wide
  * barrier, by tic_itc_bwd_g with the inline statistics — the S tiles stay in TMEM in between, the second k-loop and one
@@ -386,6 +390,20 @@ int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag
  * that exchange) is published with release semantics — the consumer side of tic_itc_fwd(seg_ready = ready, seg_epoch = ctr)
  * may run concurrently on another stream.  ready / tickets: `world` zero-initialised uint32 each, local device memory.
  * max_blocks bounds the grid (0 = 148 blocks of 128 threads, 64 registers each) so the pull lives beside a persistent GEMM. */
+/* PUSH form (small global batches, where the exchange latency is on the critical chain): the producer stores nseg local
+ * ranges [src[s], +bytes[s]) into EVERY rank's block at dst_off[s] + rank * dst_stride[s] (its own included), then publishes
+ * flags[rank] = ++ctr[0] (uint32[world] at flag_off of every block) with release semantics at system scope.  No rank waits in
+ * this kernel; the consumer is tic_itc_fwd / tic_itc_bwd_g with seg_ready = the LOCAL flag words and seg_epoch = ctr: their
+ * TMA producer polls a column segment's flag right before its first load from it and visits the local segment first.
+ * wait_off >= 0: before storing into a peer, wait until that peer's word in the local uint32[world] at wait_off reaches
+ * ctr[0] (the previous step's epoch): the peer has finished reading the previous step's data (tic_peer_signal at the tail of
+ * its step).  ctr: 2 zero-initialised uint32 per phase in local device memory. */
+int tic_peer_push(void* const* bases_host, int world, int rank, int64_t flag_off, int64_t wait_off, uint32_t* ctr, int nseg,
+                  void* const* src_host, const int64_t* bytes_host, const int64_t* dst_off_host, const int64_t* dst_stride_host,
+                  void* stream);
+/* flags[rank] = ++ctr[0] in every rank's block (uint32[world] at flag_off), released at system scope: everything enqueued on
+ * `stream` before this call has completed. */
+int tic_peer_signal(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* ctr, void* stream);
 int tic_peer_pull(void* const* bases_host, int world, int rank, const uint32_t* ctr, uint32_t* ready, uint32_t* tickets, int nseg,
                   const int64_t* src_off_host, const int64_t* bytes_host, void* const* dst_host, const int64_t* dst_stride_host,
                   int max_blocks, void* stream);

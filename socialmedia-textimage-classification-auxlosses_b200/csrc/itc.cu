@@ -391,7 +391,8 @@ struct ItcBwdEpi {
   // read through the non-coherent path (ld.global.nc is only defined for data that is read-only during the kernel).
   template <int BN, bool COH = false>
   __device__ static void prefetch(const Params& p, EpiCtx& cx) {
-    auto ldf = [](const float* q) { return COH ? __ldcg(q) : __ldg(q); };
+    const bool coh = COH || cx.coherent;
+    auto ldf = [coh](const float* q) { return coh ? __ldcg(q) : __ldg(q); };
     const int lane = threadIdx.x & 31;
     const int row = cx.m0 + cx.quad * 32 + lane;
     const bool valid_row = row < cx.M;
@@ -1161,13 +1162,15 @@ int tic_itc_fwd(const void* T, const void* T_lo, int64_t ldt, const void* V, con
                        static_cast<unsigned long long*>(qpart)};
   const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
   // V arriving segment by segment (peer pull running beside this kernel): tiles go segment-major, local segment first
-  SegOrder so{nullptr, nullptr, 0, 0, 0};
+  SegOrder so{nullptr, nullptr, 0, 0, 0, 0};
   const SegOrder* sop = nullptr;
   if (seg_ready != nullptr) {
+    const int remote = seg_cols < 0 ? 1 : 0;        // negative seg_cols: the ready words are written by the peers (push form)
+    if (remote) seg_cols = -seg_cols;
     TIC_CHECK_ARG(seg_epoch && seg_cols > 0 && n_global % seg_cols == 0 && my_seg >= 0 && my_seg < n_global / seg_cols,
                   "tic_itc_fwd: bad segment description (seg_cols=%d my_seg=%d n_global=%d)", seg_cols, my_seg, n_global);
     const int bn = itc_bn(n_global);
-    so = SegOrder{seg_ready, seg_epoch, seg_cols % bn == 0 ? seg_cols / bn : 0, my_seg, n_global / seg_cols};
+    so = SegOrder{seg_ready, seg_epoch, seg_cols % bn == 0 ? seg_cols / bn : 0, my_seg, n_global / seg_cols, remote};
     sop = &so;
   }
   int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcFwdEpi>(T, ldt, V, ldv, m_local, n_global, P, ep,
@@ -1247,8 +1250,19 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
                   const float* rinv_t, const float* rinv_v,
                   const float* lse_row, const float* lse_col, int m_local, int n_global, int P, float scale, float gscale,
                   void* GA, int64_t ld_ga, void* GBT, int64_t ld_gbt, void* GA_lo, void* GBT_lo, const float* row_part,
-                  int n_row_parts, const float* col_part, int n_col_parts, float shift, const float* scale_dev, void* stream) {
+                  int n_row_parts, const float* col_part, int n_col_parts, float shift, const float* scale_dev,
+                  const uint32_t* seg_ready, const uint32_t* seg_epoch, int seg_cols, int my_seg, void* stream) {
   TIC_CHECK_ARG(T && V && rinv_t && rinv_v && GA, "tic_itc_bwd_g: null pointer");
+  SegOrder so{nullptr, nullptr, 0, 0, 0, 0};
+  const SegOrder* sop = nullptr;
+  if (seg_ready != nullptr) {       // gathered lse vectors landing segment by segment (push form: always remote)
+    const int cols = seg_cols < 0 ? -seg_cols : seg_cols;
+    TIC_CHECK_ARG(seg_epoch && cols > 0 && n_global % cols == 0 && my_seg >= 0 && my_seg < n_global / cols,
+                  "tic_itc_bwd_g: bad segment description (seg_cols=%d my_seg=%d n_global=%d)", seg_cols, my_seg, n_global);
+    const int bn = itc_bn(n_global);
+    so = SegOrder{seg_ready, seg_epoch, cols % bn == 0 ? cols / bn : 0, my_seg, n_global / cols, 1};
+    sop = &so;
+  }
   TIC_CHECK_ARG((lse_row || (row_part && n_row_parts > 0)) && (lse_col || (col_part && n_col_parts > 0)),
                 "tic_itc_bwd_g: need lse_row/lse_col or the forward partials");
   TIC_CHECK_ARG(m_local > 0 && n_global > 0 && P > 0, "tic_itc_bwd_g: empty problem");
@@ -1264,19 +1278,19 @@ int tic_itc_bwd_g(const void* T, const void* T_lo, int64_t ldt, const void* V, c
   }
   const bool mc = itc_multicast() && itc_bn(n_global) == kItcBN && !T_lo && !V_lo && m_local >= 2 * kBM;
   int rc = mc ? launch_umma_gemm_cluster2<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, ldt, V, ldv, m_local, n_global, P, ep,
-                                                                                        static_cast<cudaStream_t>(stream))
+                                                                                        static_cast<cudaStream_t>(stream), sop)
            : itc_bn(n_global) == kItcBN
                ? launch_umma_gemm<kItcBN, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local, n_global,
-                                                                                P, ep, static_cast<cudaStream_t>(stream), 1)
-               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, nullptr) == 4
+                                                                                P, ep, static_cast<cudaStream_t>(stream), 1, 0, sop)
+               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, sop) == 4
                    ? launch_umma_gemm_kc<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi, 4>(
                          T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, static_cast<cudaStream_t>(stream))
-               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, nullptr) == 2
+               : itc_small_kc(m_local, n_global, P, T_lo, V_lo, sop) == 2
                    ? launch_umma_gemm_kc<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi, 2>(
                          T, T_lo, ldt, V, V_lo, ldv, m_local, n_global, P, ep, static_cast<cudaStream_t>(stream))
                    : launch_umma_gemm<kItcBNSmall, false, false, kItcEpiWarps, ItcBwdEpi>(T, T_lo, ldt, V, V_lo, ldv, m_local,
                                                                                          n_global, P, ep,
-                                                                                         static_cast<cudaStream_t>(stream), 1);
+                                                                                         static_cast<cudaStream_t>(stream), 1, 0, sop);
   if (rc == -3) { set_error("tic_itc_bwd_g: cudaFuncSetAttribute failed"); return TIC_E_ATTR; }
   if (rc == -4) { set_error("tic_itc_bwd_g: launch failed"); return TIC_E_LAUNCH; }
   return rc;

@@ -160,6 +160,87 @@ peer_pull_kernel(PeerPtrs sym, int world, int rank, const uint32_t* __restrict__
   }
 }
 
+// ------------------------------------------------------------------ push form (small global batches)
+// The pull form above costs a rank two NVLink round trips per exchange (flag out -> flags in, then loads from the peers) inside
+// a kernel of its own that the next kernel has to wait for: 11-16 us at 2 GPUs for 1 MB (CUPTI timeline,
+// profiles/r02_timeline_c2_g2_before.txt), two of them on the critical chain of the small-batch step.  The push form turns the
+// exchange around: the PRODUCER writes its ranges straight into every peer's gathered buffers (posted stores over NVLink: no
+// round trip), then releases one flag word per peer; nobody waits in this kernel.  The CONSUMER is the tile kernel itself:
+// its TMA producer thread polls the (local) flag of a column segment right before its first load from it (SegOrder,
+// tic_umma.cuh) and visits the local segment first, so the remote data has most of the kernel to arrive.
+//   ctr[0] = epoch of this phase (incremented here once per step; the consumers compare the flags against it), ctr[1] = ticket.
+//   flags of this phase: uint32[world] at flag_off of EVERY block; slot r is written by rank r only.
+//   wait_off >= 0: before touching a peer's buffers, wait until that peer's slot in MY uint32[world] at wait_off reaches
+//   epoch - 1: the peer has finished reading what the previous step pushed (tic_peer_signal at the tail of its step).
+struct PushSeg {
+  const uint8_t* src;     // local source
+  int64_t bytes;          // multiple of 16
+  int64_t dst_off;        // byte offset of rank 0's slot inside every rank's block
+  int64_t dst_stride;     // this rank's slot: dst_off + rank * dst_stride
+};
+struct PushArgs {
+  PushSeg seg[kMaxSeg];
+  int nseg;
+};
+__global__ void __launch_bounds__(256)
+peer_push_kernel(PeerPtrs sym, int world, int rank, PushArgs xa, int64_t flag_off, int64_t wait_off, uint32_t* __restrict__ ctr,
+                 unsigned long long timeout_ns) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
+  if (wait_off >= 0) {
+    if (threadIdx.x < world && threadIdx.x != rank) {
+      const uint32_t* f = reinterpret_cast<const uint32_t*>(sym.base[rank] + wait_off) + threadIdx.x;
+      const uint64_t t0 = globaltimer_ns();
+      while (static_cast<int32_t>(ld_acquire_sys(f) - (epoch - 1u)) < 0) {
+        if (globaltimer_ns() - t0 > timeout_ns) {
+          printf("tic: peer push timeout (rank %d waiting for rank %d to release its buffers, epoch %u)\n", rank, threadIdx.x, epoch);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int s = 0; s < xa.nseg; ++s) {
+    const PushSeg sg = xa.seg[s];
+    const int64_t words = sg.bytes >> 4;
+    const uint4* src = reinterpret_cast<const uint4*>(sg.src);
+    for (int64_t i = tid; i < words; i += nthr) {
+      const uint4 v = src[i];
+      for (int k = 1; k <= world; ++k) {          // remote peers first, the local copy last
+        int q = rank + k;
+        if (q >= world) q -= world;
+        reinterpret_cast<uint4*>(sym.base[q] + sg.dst_off + rank * sg.dst_stride)[i] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+      ctr[1] = 0u;
+      ctr[0] = epoch;
+      __threadfence_system();
+      for (int q = 0; q < world; ++q) st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
+    }
+  }
+}
+
+// One thread: flags[rank] = ++ctr[0] in every peer's block (release at system scope): "everything this stream did before this
+// point is done" — the tail-of-step signal the next step's push waits for.
+__global__ void peer_signal_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32_t* __restrict__ ctr) {
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
+    ctr[0] = epoch;
+    __threadfence_system();
+    for (int q = 0; q < world; ++q) st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
+  }
+}
+
 }  // namespace tic
 
 using namespace tic;
@@ -243,6 +324,49 @@ int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag
   launch_k(peer_exchange_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), sym, world, rank, flag_off, ctr, xa,
                                                                            20ull * 1000ull * 1000ull * 1000ull);
   TIC_CHECK_LAUNCH("tic_peer_exchange");
+  return TIC_OK;
+}
+
+int tic_peer_push(void* const* bases_host, int world, int rank, int64_t flag_off, int64_t wait_off, uint32_t* ctr, int nseg,
+                  void* const* src_host, const int64_t* bytes_host, const int64_t* dst_off_host, const int64_t* dst_stride_host,
+                  void* stream) {
+  TIC_CHECK_ARG(bases_host && ctr && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+                "tic_peer_push: bad group (world=%d rank=%d, at most %d peers)", world, rank, kMaxPeers);
+  TIC_CHECK_ARG(nseg >= 1 && nseg <= kMaxSeg && (flag_off & 3) == 0 && (wait_off < 0 || (wait_off & 3) == 0), "tic_peer_push: bad arguments");
+  PeerPtrs sym{};
+  for (int p = 0; p < world; ++p) {
+    TIC_CHECK_ARG(bases_host[p] != nullptr, "tic_peer_push: rank %d has no mapped block", p);
+    sym.base[p] = static_cast<uint8_t*>(bases_host[p]);
+  }
+  PushArgs xa{};
+  xa.nseg = nseg;
+  int64_t total = 0;
+  for (int s = 0; s < nseg; ++s) {
+    TIC_CHECK_ARG(aligned16(src_host[s]) && (bytes_host[s] & 15) == 0 && (dst_off_host[s] & 15) == 0 && (dst_stride_host[s] & 15) == 0 &&
+                      bytes_host[s] >= 0,
+                  "tic_peer_push: segment %d is not 16-byte aligned", s);
+    xa.seg[s] = PushSeg{static_cast<const uint8_t*>(src_host[s]), bytes_host[s], dst_off_host[s], dst_stride_host[s]};
+    total += bytes_host[s];
+  }
+  int grid = static_cast<int>((total / 16 + 256 * 2 - 1) / (256 * 2));
+  if (grid < 1) grid = 1;
+  if (grid > 2 * 148) grid = 2 * 148;
+  launch_k(peer_push_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), sym, world, rank, xa, flag_off, wait_off, ctr,
+           20ull * 1000ull * 1000ull * 1000ull);
+  TIC_CHECK_LAUNCH("tic_peer_push");
+  return TIC_OK;
+}
+
+int tic_peer_signal(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* ctr, void* stream) {
+  TIC_CHECK_ARG(bases_host && ctr && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && (flag_off & 3) == 0,
+                "tic_peer_signal: bad arguments");
+  PeerPtrs sym{};
+  for (int p = 0; p < world; ++p) {
+    TIC_CHECK_ARG(bases_host[p] != nullptr, "tic_peer_signal: rank %d has no mapped block", p);
+    sym.base[p] = static_cast<uint8_t*>(bases_host[p]);
+  }
+  launch_k(peer_signal_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), sym, world, rank, flag_off, ctr);
+  TIC_CHECK_LAUNCH("tic_peer_signal");
   return TIC_OK;
 }
 

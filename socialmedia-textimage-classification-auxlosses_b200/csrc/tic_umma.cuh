@@ -47,6 +47,7 @@ struct EpiCtx {
   int iter;             // tiles already processed by this CTA (for double-buffering the scratch)
   int ks, ksplit;       // split-K: this work item covers K-slice ks of ksplit (epilogue must accumulate atomically)
   uint8_t* scratch;    // kEpiScratchBytes of smem shared by the epilogue warps
+  bool coherent = false;      // the epilogue's inputs may be written (by peers) while this kernel runs: no ld.global.nc on them
   uint8_t* stage = nullptr;   // optional 2 KB per epilogue warp of 1024-byte-aligned staging space (e.g. the idle operand ring)
   float pre[8];        // per-thread values loaded by Epi::prefetch for Epi::tile (row norms, row lse, logit scale)
 };
@@ -61,15 +62,18 @@ struct SegOrder {
   int tiles_per_seg;       // N tiles per segment; 0 = layout not tile-aligned: wait for every segment up front
   int my_seg;              // visited first (the pull copies it first: a local copy, no NVLink hop)
   int nseg;
+  int remote;              // 1: the ready words are written by the PEERS themselves (push form, tic_peer_push): no pull kernel runs
+                           // beside this one (the launch keeps the whole machine) and the data may land while this kernel runs
 };
-__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+// system scope: in the push form the flag is released by another GPU
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void seg_wait(const SegOrder& so, int seg, uint32_t epoch) {
   uint32_t spins = 0;
-  while (static_cast<int32_t>(ld_acquire_gpu_u32(so.ready + seg) - epoch) < 0) {
+  while (static_cast<int32_t>(ld_acquire_sys_u32(so.ready + seg) - epoch) < 0) {
     if (++spins > (1u << 28)) { printf("tic: segment %d never became ready\n", seg); __trap(); }
   }
   asm volatile("fence.proxy.async.global;" ::: "memory");   // the pulled data is read by the TMA (async proxy) next
@@ -306,6 +310,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     cx.epi_tid = threadIdx.x - 64;
     cx.epi_threads = 32 * EPI_WARPS;
     cx.scratch = scratch;
+    cx.coherent = so.ready != nullptr;
     int as = 0;
     uint32_t aph = 0;
     cx.iter = 0;
@@ -323,7 +328,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // the later tiles of a persistent CTA the epilogue is the busy side (the MMAs run a tile ahead) and the early placement
       // measured slower (ITC forward at 16384x768: 0.306 -> 0.391 ms), so those keep the loads after the wait.
       const bool have_rows = cx.m0 < M && (KC == 1 || krank == 0);
-      const bool early = cx.iter == 0;
+      // (not in segment-consuming mode: what the prefetch reads — gathered norms / lse — belongs to the segment the producer
+      // waits for, and only the accumulator barrier orders the epilogue behind that wait)
+      const bool early = cx.iter == 0 && so.ready == nullptr;
       if (have_rows && early) Epi::template prefetch<BN>(ep, cx);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
@@ -459,11 +466,11 @@ int launch_umma_gemm(const void* A, const void* A_lo, int64_t lda, const void* B
   // full 200 KB ring every CTA owned an SM, and a 16-CTA kernel of the critical chain queued behind the 192 CTAs of two
   // weight-gradient GEMMs of the other chain (CUPTI timeline, profiles/r02_timeline_c2_*.txt: a 6.6 us hole in the chain).
   // The k-loop rate does not depend on the ring depth (4 vs 8: scripts/gemm_rate.py).
-  if (stages_rt == 0 && BN <= 128 && !(seg && seg->ready) && grid <= 2 * device_sm_count()) stages_rt = BN == 64 ? 4 : 3;
+  if (stages_rt == 0 && BN <= 128 && !(seg && seg->ready && !seg->remote) && grid <= 2 * device_sm_count()) stages_rt = BN == 64 ? 4 : 3;
   int cap = max_ctas > 0 ? max_ctas : device_sm_count();
-  if (seg && seg->ready && cap > device_sm_count() - kSegFreeSms) cap = device_sm_count() - kSegFreeSms;
+  if (seg && seg->ready && !seg->remote && cap > device_sm_count() - kSegFreeSms) cap = device_sm_count() - kSegFreeSms;
   if (grid > cap) grid = cap;
-  SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0};
+  SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0, 0};
   if (so.ready && (ksplit != 1 || so.tiles_per_seg <= 0 || so.tiles_per_seg * so.nseg != n_tiles)) so.tiles_per_seg = 0;
   size_t smem = Cfg::kSmemBytes;
   if (stages_rt > 0 && stages_rt < Cfg::kStages)
@@ -517,7 +524,7 @@ int launch_umma_gemm_kc(const void* A, const void* A_lo, int64_t lda, const void
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  SegOrder so{nullptr, nullptr, 0, 0, 0};
+  SegOrder so{nullptr, nullptr, 0, 0, 0, 0};
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta_lo, tb, tb_lo, split, 1, M, N, K, ep, so, 0);
   return e == cudaSuccess ? 0 : -4;
 }
@@ -564,7 +571,7 @@ int launch_umma_gemm_cluster2(const void* A, int64_t lda, const void* B, int64_t
   // Segment-consuming mode: leave kSegFreeSms SMs to the concurrent pull kernel.  Co-residency of its blocks with this
   // kernel's CTAs (one per SM, ~all shared memory) is not something the hardware scheduler promises, and a pull that cannot
   // be scheduled while the producers wait for its segments is a deadlock.
-  int clusters = (device_sm_count() - (seg && seg->ready ? kSegFreeSms : 0)) / 2;
+  int clusters = (device_sm_count() - (seg && seg->ready && !seg->remote ? kSegFreeSms : 0)) / 2;
   if (clusters > items) clusters = items;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
@@ -579,7 +586,7 @@ int launch_umma_gemm_cluster2(const void* A, int64_t lda, const void* B, int64_t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int split = 0, ksplit = 1;
-  SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0};
+  SegOrder so = seg ? *seg : SegOrder{nullptr, nullptr, 0, 0, 0, 0};
   if (so.ready && (so.tiles_per_seg <= 0 || so.tiles_per_seg * so.nseg != n_tiles)) so.tiles_per_seg = 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, ta, tb, tb_half, split, ksplit, M, N, K, ep, so, 0);
   return e == cudaSuccess ? 0 : -4;

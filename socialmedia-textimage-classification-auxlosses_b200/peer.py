@@ -41,7 +41,12 @@ class SymmetricItc:
     lse_rows(rb, cb, scale, loss_sums): row partials of both blocks -> rb.lse_row, cb.lse_row (published), loss terms.
     """
 
-    def __init__(self, rb, cb, exchange, lse_rows, b_local: int, world: int, rank: int, branches=None):
+    def __init__(self, rb, cb, exchange, lse_rows, b_local: int, world: int, rank: int, branches=None, push=None):
+        """push (optional): {"emb": callable, "seg_emb": seg tuple, "lse": callable, "seg_lse": seg tuple, "done": callable} — the
+        PUSH form of the two exchanges (tic_peer_push): the producer stores into every peer's gathered buffers and releases a
+        flag, the tile kernels wait per column segment themselves (seg tuples as in ItcPlan.fwd_tiles); "done" signals the
+        peers, after the last read of the gathered embeddings, that the next step may overwrite them."""
+        self.push = push
         self.rb, self.cb, self.exchange, self.lse_rows = rb, cb, exchange, lse_rows
         self.b, self.world, self.rank, self.N = b_local, world, rank, b_local * world
         # the row block and the swapped block are independent between the exchanges: issue them on parallel branches
@@ -61,13 +66,21 @@ class SymmetricItc:
             produce_t()
         rb.norm_t(T, ldt, T_lo=T_lo)                      # -> ... of my text rows
         br.join("cb")
-        self.exchange("emb")
+        pu = self.push
+        seg = pu["seg_emb"] if pu else None
+        if pu:
+            pu["emb"]()               # my rows -> every rank's gathered buffers + flag; nobody waits here
+        else:
+            self.exchange("emb")
         with br("cb"):
-            cb.fwd_tiles(V, ldv, T_all, T_all.stride(0), scale, T_lo=V_lo, V_lo=T_all_lo)
-        rb.fwd_tiles(T, ldt, V_all, V_all.stride(0), scale, T_lo=T_lo, V_lo=V_all_lo)
+            cb.fwd_tiles(V, ldv, T_all, T_all.stride(0), scale, T_lo=V_lo, V_lo=T_all_lo, seg=seg)
+        rb.fwd_tiles(T, ldt, V_all, V_all.stride(0), scale, T_lo=T_lo, V_lo=V_all_lo, seg=seg)
         br.join("cb")
         self.lse_rows(rb, cb, scale, loss_sums)
-        self.exchange("lse")
+        if pu:
+            pu["lse"]()
+        else:
+            self.exchange("lse")
 
     def backward(self, T, V, T_all, V_all, scale, g, dT_f32=None, dT_bf16=None, dV_f32=None, dV_bf16=None, r_sum=None,
                  T_lo=None, V_lo=None, T_all_lo=None, V_all_lo=None, dT_lo=None, dV_lo=None, consume_t=None, consume_v=None):
@@ -75,18 +88,30 @@ class SymmetricItc:
         consume_t / consume_v: optional callables issued right after dT / dV exist (projection weight gradients)."""
         rb, cb, N, br = self.rb, self.cb, self.N, self.br
         ldt, ldv = T.stride(0), V.stride(0)
+        pu = self.push
+        seg = pu["seg_lse"] if pu else None
+        ev_cb = None
         with br("cb"):
-            cb.bwd_operands(V, ldv, T_all, T_all.stride(0), scale, g / (2.0 * N), T_lo=V_lo, V_lo=T_all_lo)
+            cb.bwd_operands(V, ldv, T_all, T_all.stride(0), scale, g / (2.0 * N), T_lo=V_lo, V_lo=T_all_lo, seg=seg)
             cb.grad_gemm_t(T_all, T_all.stride(0), V_lo=T_all_lo)
+            if pu:
+                ev_cb = torch.cuda.Event()
+                ev_cb.record(torch.cuda.current_stream())
             cb.finalize_t(V, ldv, T, ldt, rb.rinv_t, scale, g / N, dV_f32, dV_bf16, None, dT_lo=dV_lo, T_lo=V_lo, V_diag_lo=T_lo)
             if consume_v is not None:
                 consume_v()
-        rb.bwd_operands(T, ldt, V_all, V_all.stride(0), scale, g / (2.0 * N), T_lo=T_lo, V_lo=V_all_lo)
+        rb.bwd_operands(T, ldt, V_all, V_all.stride(0), scale, g / (2.0 * N), T_lo=T_lo, V_lo=V_all_lo, seg=seg)
         rb.grad_gemm_t(V_all, V_all.stride(0), V_lo=V_all_lo)
+        if pu:      # both gradient GEMMs were the last readers of the gathered embeddings: tell the peers (side branch)
+            with br("dn"):
+                torch.cuda.current_stream().wait_event(ev_cb)
+                pu["done"]()
         rb.finalize_t(T, ldt, V, ldv, cb.rinv_t, scale, g / N, dT_f32, dT_bf16, r_sum, dT_lo=dT_lo, T_lo=T_lo, V_diag_lo=V_lo)
         if consume_t is not None:
             consume_t()
         br.join("cb")
+        if pu:
+            br.join("dn")
 
 
 class RowBlockItc:
@@ -249,6 +274,39 @@ class PeerGroup:
         self.capi.call("tic_peer_exchange", self._bases_c, self.world, self.rank, self.flag_off, self.ctr.data_ptr(), n, so, nb,
                        dst, ds, torch.cuda.current_stream().cuda_stream)
 
+    # flag words of the push form: uint32[8] slots inside the 256-byte flag area of every block (slot 0 = the pull barrier)
+    FLAG_SLOT_BYTES = 32
+
+    def flags_view(self, slot: int) -> torch.Tensor:
+        """the LOCAL uint32[world] flag words of a slot (written by the peers), as an int32 tensor"""
+        off = self.flag_off + slot * self.FLAG_SLOT_BYTES
+        return self.block[off:off + 4 * self.world].view(torch.int32)
+
+    def define_push(self, name: str, segs, slot: int, wait_slot: int = -1):
+        """segs: [(src_tensor (local, contiguous), nbytes, dst_off_bytes of rank 0's slot in every block, dst_stride_bytes)]"""
+        n = len(segs)
+        ctr = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self._pushes = getattr(self, "_pushes", {})
+        self._pushes[name] = (n, (ctypes.c_void_p * n)(*[s[0].data_ptr() for s in segs]), (ctypes.c_int64 * n)(*[s[1] for s in segs]),
+                              (ctypes.c_int64 * n)(*[s[2] for s in segs]), (ctypes.c_int64 * n)(*[s[3] for s in segs]),
+                              self.flag_off + slot * self.FLAG_SLOT_BYTES,
+                              (self.flag_off + wait_slot * self.FLAG_SLOT_BYTES) if wait_slot >= 0 else -1, ctr, [s[0] for s in segs])
+        return ctr
+
+    def push(self, name: str):
+        n, src, nb, doff, dstr, foff, woff, ctr, _keep = self._pushes[name]
+        self.capi.call("tic_peer_push", self._bases_c, self.world, self.rank, foff, woff, ctr.data_ptr(), n, src, nb, doff, dstr,
+                       torch.cuda.current_stream().cuda_stream)
+
+    def define_signal(self, name: str, slot: int):
+        self._signals = getattr(self, "_signals", {})
+        self._signals[name] = (self.flag_off + slot * self.FLAG_SLOT_BYTES, torch.zeros(2, dtype=torch.int32, device=self.dev))
+
+    def signal(self, name: str):
+        foff, ctr = self._signals[name]
+        self.capi.call("tic_peer_signal", self._bases_c, self.world, self.rank, foff, ctr.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+
     def define_pull(self, name: str, segs, max_blocks: int = 148):
         n = len(segs)
         ready = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
@@ -323,7 +381,18 @@ def _make_peer_head_plan():
             off_hi, off_lo = 0, _up(ybytes)
             off_rinv = off_lo + (_up(ybytes) if self.has_lo else 0)
             off_lse = off_rinv + _up(2 * b * 4)
-            self.pg = PeerGroup(off_lse + _up(2 * b * 4), world, rank, dev, group)
+            end_pub = off_lse + _up(2 * b * 4)
+            import os as _os
+            # PUSH form of the two exchanges (default): the gathered copies live INSIDE the peer-mapped block so that the
+            # producers can store into them; TIC_PEER_PUSH=0 keeps the round-1 pull form (A/B switch)
+            self.push_mode = _os.environ.get("TIC_PEER_PUSH", "1") != "0"
+            g_emb = _up(N * Pe * 2)
+            off_Tall, off_Vall = end_pub, end_pub + g_emb
+            off_Tall_lo, off_Vall_lo = off_Vall + g_emb, off_Vall + 2 * g_emb
+            off_rt_all = off_Vall + (3 * g_emb if self.has_lo else g_emb)
+            off_rv_all, off_lr_all, off_lc_all = off_rt_all + _up(N * 4), off_rt_all + 2 * _up(N * 4), off_rt_all + 3 * _up(N * 4)
+            total = (off_rt_all + 4 * _up(N * 4)) if self.push_mode else end_pub
+            self.pg = PeerGroup(total, world, rank, dev, group)
             pg = self.pg
             e = lambda *s, dt=F32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
             # published (symmetric) views: [text rows ; image rows]
@@ -331,11 +400,17 @@ def _make_peer_head_plan():
             self.Y_lo = pg.view(off_lo, (2 * b, Pe), BF16) if self.has_lo else (e(2 * b, Pe, dt=BF16) if self.P is not None else None)
             self.rinv_mine = pg.view(off_rinv, (2 * b,), F32)
             self.lse_mine = pg.view(off_lse, (2 * b,), F32)
-            # gathered copies in local HBM
-            self.T_all, self.V_all = e(N, Pe, dt=BF16), e(N, Pe, dt=BF16)
-            self.T_all_lo = e(N, Pe, dt=BF16) if self.has_lo else None
-            self.V_all_lo = e(N, Pe, dt=BF16) if self.has_lo else None
-            self.rinv_t_all, self.rinv_v_all, self.lse_row_all, self.lse_col_all = e(N), e(N), e(N), e(N)
+            if self.push_mode:   # gathered copies inside the peer-mapped block (the peers write them)
+                self.T_all, self.V_all = pg.view(off_Tall, (N, Pe), BF16), pg.view(off_Vall, (N, Pe), BF16)
+                self.T_all_lo = pg.view(off_Tall_lo, (N, Pe), BF16) if self.has_lo else None
+                self.V_all_lo = pg.view(off_Vall_lo, (N, Pe), BF16) if self.has_lo else None
+                self.rinv_t_all, self.rinv_v_all = pg.view(off_rt_all, (N,), F32), pg.view(off_rv_all, (N,), F32)
+                self.lse_row_all, self.lse_col_all = pg.view(off_lr_all, (N,), F32), pg.view(off_lc_all, (N,), F32)
+            else:                # gathered copies in local HBM (pulled)
+                self.T_all, self.V_all = e(N, Pe, dt=BF16), e(N, Pe, dt=BF16)
+                self.T_all_lo = e(N, Pe, dt=BF16) if self.has_lo else None
+                self.V_all_lo = e(N, Pe, dt=BF16) if self.has_lo else None
+                self.rinv_t_all, self.rinv_v_all, self.lse_row_all, self.lse_col_all = e(N), e(N), e(N), e(N)
             half = b * Pe * 2
             segs = [(off_hi, half, self.T_all, half), (off_hi + half, half, self.V_all, half)]
             if self.has_lo:
@@ -351,7 +426,20 @@ def _make_peer_head_plan():
             self.cb.lse_row, self.cb.lse_col = self.lse_mine[b:], self.lse_row_all
             self.itc = self.rb
             self.lse_ws = torch.zeros(int(capi_load().tic_itc_lse_rows_workspace_bytes(b)) // 4, dtype=F32, device=dev)
-            self.sym = SymmetricItc(self.rb, self.cb, pg.exchange, self._lse_rows, b, world, rank, branches=self.br)
+            push = None
+            if self.push_mode:
+                psegs = [(self.Y[:b], half, off_Tall, half), (self.Y[b:], half, off_Vall, half)]
+                if self.has_lo:
+                    psegs += [(self.Y_lo[:b], half, off_Tall_lo, half), (self.Y_lo[b:], half, off_Vall_lo, half)]
+                psegs += [(self.rinv_mine[:b], b * 4, off_rt_all, b * 4), (self.rinv_mine[b:], b * 4, off_rv_all, b * 4)]
+                ctr_emb = pg.define_push("emb", psegs, slot=1, wait_slot=3)
+                ctr_lse = pg.define_push("lse", [(self.lse_mine[:b], b * 4, off_lr_all, b * 4),
+                                                 (self.lse_mine[b:], b * 4, off_lc_all, b * 4)], slot=2)
+                pg.define_signal("done", slot=3)
+                # seg tuples: (ready words, epoch counter, -columns per segment [negative: flags written by the peers], my segment)
+                push = {"emb": lambda: pg.push("emb"), "lse": lambda: pg.push("lse"), "done": lambda: pg.signal("done"),
+                        "seg_emb": (pg.flags_view(1), ctr_emb, -b, rank), "seg_lse": (pg.flags_view(2), ctr_lse, -b, rank)}
+            self.sym = SymmetricItc(self.rb, self.cb, pg.exchange, self._lse_rows, b, world, rank, branches=self.br, push=push)
 
         def _init_rowblock(self, b, N, group):
             world, rank, dev, Pe = self.world, self.rank, self.dev, self.Pe

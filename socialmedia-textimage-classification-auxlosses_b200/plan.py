@@ -193,15 +193,16 @@ class ItcPlan:
         call("tic_itc_lse_loss", ptr(self.row_part), self.nrp, ptr(cp), ncp, ptr(self.diag), self.m, self.n,
              self.row_offset, float(scale), ptr(self.lse_row), ptr(self.lse_col), ptr(loss_sums), ptr(self.scale_dev), _stream())
 
-    def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None, inline_lse=False):
+    def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None, inline_lse=False, seg=None):
         """inline_lse: derive lse_row/lse_col inside the kernel from the forward partials (few partials = small batch), so
         that lse_loss() is only needed for the loss value and can run beside the backward instead of before it."""
         rp = (ptr(self.row_part), self.nrp) if inline_lse else (None, 0)
         cp = (ptr(self.col_part), self.ncp) if inline_lse else (None, 0)
+        sr, se, sc, ms = (ptr(seg[0]), ptr(seg[1]), int(seg[2]), int(seg[3])) if seg is not None else (None, None, 0, 0)
         call("tic_itc_bwd_g", ptr(T), ptr(T_lo), ldt, ptr(V), ptr(V_lo), ldv, ptr(self.rinv_t), ptr(self.rinv_v), ptr(self.lse_row),
              ptr(self.lse_col), self.m, self.n, self.P, float(scale), float(gscale), ptr(self.GA), self.ld_ga,
              ptr(self.GBT), self.ld_gbt, ptr(self.GA_lo), ptr(self.GBT_lo), rp[0], rp[1], cp[0], cp[1], float(scale),
-             ptr(self.scale_dev), _stream())
+             ptr(self.scale_dev), sr, se, sc, ms, _stream())
 
     @property
     def can_inline_lse(self):
@@ -310,7 +311,7 @@ class HeadPlan:
         import os as _os2
         self.fuse_itc_small = _os2.environ.get("TIC_ITC_FUSED_SMALL", "1") != "0"     # A/B switch (same kernels' epilogues)
         # code warm-up launches at the head of the step (see _warm_calls): only where the step is latency-bound
-        self.code_warm = (_os2.environ.get("TIC_CODE_WARM", "1") != "0") and B <= 512 and type(self).__name__ == "HeadPlan"
+        self.code_warm = (_os2.environ.get("TIC_CODE_WARM", "1") != "0") and B <= 512
         self._warm = None
         E_ = self.E
         self._warm_H = torch.zeros(2, E_, dtype=F32, device=self.dev)
@@ -721,6 +722,10 @@ class HeadPlan:
         W["A"].fill_(0.01); W["B"].fill_(0.02); W["ss"].fill_(1.0)
         W["it"] = ItcPlan(128, 128, 64, dev, precise=True)
         W["it"].scale_dev = self.scale_t
+        # multi-GPU symmetric form: separate forward / gradient-operand launches on a row block without column statistics
+        W["it_rb"] = ItcPlan(128, 128, 64, dev, precise=True, need_dv=False, col_sums=False)
+        W["it_rb"].lse_row.fill_(3.0); W["it_rb"].lse_col.fill_(3.0)
+        W["it_rb"].rinv_t.fill_(1.0); W["it_rb"].rinv_v.fill_(1.0)
         return W
 
     def _warm_calls(self, grp):
@@ -731,7 +736,11 @@ class HeadPlan:
         W, E = self._warm, self.E
         A, Bm, Al, Bl, it = W["A"], W["B"], W["Al"], W["Bl"], W["it"]
         if grp == 0 and self.use_itc:
-            if it.can_fuse_small and self.fuse_itc_small:
+            if type(self).__name__ != "HeadPlan":      # multi-GPU plans: the un-fused tile kernels of the row / swapped blocks
+                rb = W["it_rb"]
+                rb.fwd_tiles(A, 128, Bm, 128, self.scale, T_lo=Al, V_lo=Bl)
+                rb.bwd_operands(A, 128, Bm, 128, self.scale, 1e-3, T_lo=Al, V_lo=Bl)
+            elif it.can_fuse_small and self.fuse_itc_small:
                 it.fwd_bwd_fused(A, 128, Bm, 128, self.scale, 1e-3, T_lo=Al, V_lo=Bl, ss_t=W["ss"], ss_v=W["ss"])
         if grp == 1 and self.use_itc:
             gemm(A, 128, 0, Bm, 128, 1, W["Df"], 128, 0, 128, 64, 64, A_lo=Al, B_lo=Bl)          # dT / d_t_pool / dX form
@@ -758,13 +767,14 @@ class HeadPlan:
         if self._refresh_zeroes and "all" in self._refresh_groups:
             self._refresh("all")
             self._refreshed_all = True
-        if self.code_warm and self.w and self._refreshed_all:
-            # three short side branches BEHIND the root (a captured step with several roots starts its later roots ~14 us late)
+        self._zero_accumulators()
+        if self.code_warm and self.w and (self._refreshed_all or not self.live_weights):
+            # three short side branches BEHIND the root — the refresh launch, or the accumulator memset of the snapshot /
+            # multi-GPU plans (a captured step with several roots starts its later roots ~14 us late)
             self.br.enabled = True
             for grp in (0, 1, 2):
                 with self.br("cw%d" % grp):
                     self._warm_calls(grp)
-        self._zero_accumulators()
         two = self.use_itc and self.fusion is not None and self.parallel_streams
         if two:
             if self._side is None:
@@ -807,8 +817,10 @@ class HeadPlan:
         """The mixed loss depends on the forward halves only (heads' loss sums, ITC lse sums): issue it on the `l` side branch
         as soon as both are there instead of after the backward of both chains, where it was one more serialised ~3 us
         launch at the tail of the step.  Base single-GPU plan only (the multi-GPU plans finish their lse sums elsewhere)."""
-        if not (self._early_mix and self.parallel_streams and self.use_itc and self.itc.can_inline_lse
-                and type(self)._itc_fwd is HeadPlan._itc_fwd):
+        base = self.itc.can_inline_lse and type(self)._itc_fwd is HeadPlan._itc_fwd
+        # multi-GPU symmetric form: the rank's lse sums are complete when its forward returns (tic_itc_lse_rows)
+        sym = getattr(self, "itc_mode", None) == "symmetric"
+        if not (self._early_mix and self.parallel_streams and self.use_itc and (base or sym)):
             return False
         self.br.enabled = True
         with self.br("l"):          # same side stream as lse_loss: ordered after it
