@@ -780,8 +780,14 @@ def global_loss_check(plan, dist, dev, n_global):
     """SCALE correctness: the ITC loss of the multi-GPU step (own peer-memory kernels) against NCCL all_gather of the ranks'
     projected embeddings + a plain torch fp32 (TF32 off) clip_loss on the global matrix, row-chunked.  Raises on > 1e-3."""
     b = plan.B
-    Yt = plan.Y[:b].float() + (plan.Y_lo[:b].float() if getattr(plan, "has_lo", False) else 0)
-    Yv = plan.Y[b:].float() + (plan.Y_lo[b:].float() if getattr(plan, "has_lo", False) else 0)
+    if hasattr(plan, "_rows") and getattr(plan, "itc_mode", None) == "symmetric":
+        yt, yv, ytl, yvl = plan._rows()
+    else:
+        yt, yv = plan.Y[:b], plan.Y[b:]
+        ytl, yvl = (plan.Y_lo[:b], plan.Y_lo[b:]) if getattr(plan, "Y_lo", None) is not None else (None, None)
+    lo = getattr(plan, "has_lo", False)
+    Yt = yt.float() + (ytl.float() if (lo and ytl is not None) else 0)
+    Yv = yv.float() + (yvl.float() if (lo and yvl is not None) else 0)
     world = dist.get_world_size()
     Ta = [torch.empty_like(Yt) for _ in range(world)]
     Va = [torch.empty_like(Yv) for _ in range(world)]

@@ -390,20 +390,22 @@ int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag
  * that exchange) is published with release semantics — the consumer side of tic_itc_fwd(seg_ready = ready, seg_epoch = ctr)
  * may run concurrently on another stream.  ready / tickets: `world` zero-initialised uint32 each, local device memory.
  * max_blocks bounds the grid (0 = 148 blocks of 128 threads, 64 registers each) so the pull lives beside a persistent GEMM. */
-/* PUSH form (small global batches, where the exchange latency is on the critical chain): the producer stores nseg local
- * ranges [src[s], +bytes[s]) into EVERY rank's block at dst_off[s] + rank * dst_stride[s] (its own included), then publishes
- * flags[rank] = ++ctr[0] (uint32[world] at flag_off of every block) with release semantics at system scope.  No rank waits in
- * this kernel; the consumer is tic_itc_fwd / tic_itc_bwd_g with seg_ready = the LOCAL flag words and seg_epoch = ctr: their
- * TMA producer polls a column segment's flag right before its first load from it and visits the local segment first.
- * wait_off >= 0: before storing into a peer, wait until that peer's word in the local uint32[world] at wait_off reaches
- * ctr[0] (the previous step's epoch): the peer has finished reading the previous step's data (tic_peer_signal at the tail of
- * its step).  ctr: 2 zero-initialised uint32 per phase in local device memory. */
-int tic_peer_push(void* const* bases_host, int world, int rank, int64_t flag_off, int64_t wait_off, uint32_t* ctr, int nseg,
-                  void* const* src_host, const int64_t* bytes_host, const int64_t* dst_off_host, const int64_t* dst_stride_host,
-                  void* stream);
-/* flags[rank] = ++ctr[0] in every rank's block (uint32[world] at flag_off), released at system scope: everything enqueued on
- * `stream` before this call has completed. */
-int tic_peer_signal(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* ctr, void* stream);
+/* PUSH form (small global batches, where the exchange latency is on the critical chain).  Every rank keeps its share of a
+ * gathered buffer IN PLACE (the producing kernel writes this rank's slot of the rank's own gathered buffer); tic_peer_push
+ * stores the nseg local ranges [src[s], +bytes[s]) into every REMOTE rank's block at dst_off[s] + rank * dst_stride[s] and
+ * then publishes flags[rank] = step[1] (uint32[world] at flag_off of every remote block) with release semantics at system
+ * scope.  No rank waits in this kernel.  The consumer is tic_itc_fwd / tic_itc_bwd_g with seg_ready = the LOCAL flag words,
+ * seg_epoch = step + 1 and a negative seg_cols: the TMA producer polls a column segment's flag right before its first load
+ * from it, visits the local segment first and never waits for it — so the consumers need no stream dependency on the push
+ * and run beside it.
+ *   step (2 x uint32, local, initialised {0, 1}): step[0] = completed steps, step[1] = epoch of the step in flight; advanced
+ *   by tic_peer_signal at the tail of a step, which also publishes flags[rank] = step[0] at its own flag_off.
+ *   wait_off >= 0: before storing into the peers, wait until every peer's word in the local uint32[world] at wait_off has
+ *   reached step[1] - 1: it has finished reading what the previous step delivered.   ticket: 1 zeroed uint32 per push. */
+int tic_peer_push(void* const* bases_host, int world, int rank, int64_t flag_off, int64_t wait_off, const uint32_t* step,
+                  uint32_t* ticket, int nseg, void* const* src_host, const int64_t* bytes_host, const int64_t* dst_off_host,
+                  const int64_t* dst_stride_host, void* stream);
+int tic_peer_signal(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* step, void* stream);
 int tic_peer_pull(void* const* bases_host, int world, int rank, const uint32_t* ctr, uint32_t* ready, uint32_t* tickets, int nseg,
                   const int64_t* src_off_host, const int64_t* bytes_host, void* const* dst_host, const int64_t* dst_stride_host,
                   int max_blocks, void* stream);

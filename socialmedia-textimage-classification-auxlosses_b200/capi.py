@@ -46,7 +46,7 @@ _SIGS = {
     "tic_peer_close": ("p", ctypes.c_int),
     "tic_peer_exchange": ("piilpippppp", ctypes.c_int),
     "tic_peer_pull": ("piipppippppip", ctypes.c_int),
-    "tic_peer_push": ("piillpippppp", ctypes.c_int),
+    "tic_peer_push": ("piillppippppp", ctypes.c_int),
     "tic_peer_signal": ("piilpp", ctypes.c_int),
     "tic_itc_bwd_g": ("pplpplppppiiiffplplpppipifpppiip", ctypes.c_int),
     "tic_itc_ds_operands": ("pliipppplpplp", ctypes.c_int),

@@ -6,6 +6,7 @@
 //   tic_peer_alloc / export / open / close / free : plumbing (host)
 //   tic_peer_exchange                             : ONE kernel = cross-rank barrier (release/acquire flags at system scope)
 //                                                   + pull of up to kMaxSeg byte ranges from every peer into local buffers
+#include <cstdlib>
 #include "common.cuh"
 
 namespace tic {
@@ -160,6 +161,13 @@ peer_pull_kernel(PeerPtrs sym, int world, int rank, const uint32_t* __restrict__
   }
 }
 
+// TIC_PEER_SYSFENCE=1: explicit system-scope fences in the push / signal kernels (A/B measurement switch)
+inline int peer_sys_fence() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIC_PEER_SYSFENCE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+
 // ------------------------------------------------------------------ push form (small global batches)
 // The pull form above costs a rank two NVLink round trips per exchange (flag out -> flags in, then loads from the peers) inside
 // a kernel of its own that the next kernel has to wait for: 11-16 us at 2 GPUs for 1 MB (CUPTI timeline,
@@ -173,7 +181,7 @@ peer_pull_kernel(PeerPtrs sym, int world, int rank, const uint32_t* __restrict__
 //   wait_off >= 0: before touching a peer's buffers, wait until that peer's slot in MY uint32[world] at wait_off reaches
 //   epoch - 1: the peer has finished reading what the previous step pushed (tic_peer_signal at the tail of its step).
 struct PushSeg {
-  const uint8_t* src;     // local source
+  const uint8_t* src;     // local source = this rank's slot of its own gathered buffer
   int64_t bytes;          // multiple of 16
   int64_t dst_off;        // byte offset of rank 0's slot inside every rank's block
   int64_t dst_stride;     // this rank's slot: dst_off + rank * dst_stride
@@ -182,12 +190,16 @@ struct PushArgs {
   PushSeg seg[kMaxSeg];
   int nseg;
 };
+// step[0] = number of completed steps (written by tic_peer_signal at the tail of a step), step[1] = step[0] + 1 = the epoch
+// of the step in flight: every push of a step publishes flags = step[1], every consumer of that step waits for flags >=
+// step[1] (SegOrder.epoch = step + 1) — the expected value does not depend on when the push kernel runs, so the consumers
+// need NO stream dependency on it: they are launched beside it and start on their local segment at once.
 __global__ void __launch_bounds__(256)
-peer_push_kernel(PeerPtrs sym, int world, int rank, PushArgs xa, int64_t flag_off, int64_t wait_off, uint32_t* __restrict__ ctr,
-                 unsigned long long timeout_ns) {
+peer_push_kernel(PeerPtrs sym, int world, int rank, PushArgs xa, int64_t flag_off, int64_t wait_off, const uint32_t* __restrict__ step,
+                 uint32_t* __restrict__ ticket, unsigned long long timeout_ns, int sys_fence) {
   pdl_trigger();
   pdl_wait();
-  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(step + 1);
   if (wait_off >= 0) {
     if (threadIdx.x < world && threadIdx.x != rank) {
       const uint32_t* f = reinterpret_cast<const uint32_t*>(sym.base[rank] + wait_off) + threadIdx.x;
@@ -209,7 +221,7 @@ peer_push_kernel(PeerPtrs sym, int world, int rank, PushArgs xa, int64_t flag_of
     const uint4* src = reinterpret_cast<const uint4*>(sg.src);
     for (int64_t i = tid; i < words; i += nthr) {
       const uint4 v = src[i];
-      for (int k = 1; k <= world; ++k) {          // remote peers first, the local copy last
+      for (int k = 1; k < world; ++k) {          // the REMOTE peers only: the local slot is where the data was produced
         int q = rank + k;
         if (q >= world) q -= world;
         reinterpret_cast<uint4*>(sym.base[q] + sg.dst_off + rank * sg.dst_stride)[i] = v;
@@ -218,26 +230,38 @@ peer_push_kernel(PeerPtrs sym, int world, int rank, PushArgs xa, int64_t flag_of
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
-    if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
-      ctr[1] = 0u;
-      ctr[0] = epoch;
-      __threadfence_system();
-      for (int q = 0; q < world; ++q) st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
+    // Block-local stores -> (bar.sync) -> gpu-scope fence + ticket -> the LAST block's release stores at system scope: the
+    // release is cumulative over everything that happens-before it, including the other blocks' stores it observed through
+    // the ticket.  No fence.sc.sys: explicit system-scope fences cost this kernel ~8 us (19.2 -> 10.4 us at 2 GPUs,
+    // profiles/r02_timeline_c2_g2_push_v1.txt vs _v2); sys_fence != 0 restores them (A/B switch).
+    if (sys_fence) __threadfence_system(); else __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0u;
+      if (sys_fence) __threadfence_system(); else __threadfence();
+      for (int k = 1; k < world; ++k) {
+        int q = rank + k;
+        if (q >= world) q -= world;
+        st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
+      }
     }
   }
 }
 
-// One thread: flags[rank] = ++ctr[0] in every peer's block (release at system scope): "everything this stream did before this
-// point is done" — the tail-of-step signal the next step's push waits for.
-__global__ void peer_signal_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32_t* __restrict__ ctr) {
+// One thread, tail of a step: step[0] = the finished step, step[1] = the next epoch, and flags[rank] = step[0] in every peer's
+// block (release at system scope): "this rank has finished reading what step[0]'s pushes delivered".
+__global__ void peer_signal_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32_t* __restrict__ step, int sys_fence) {
   pdl_trigger();
   pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
-    ctr[0] = epoch;
-    __threadfence_system();
-    for (int q = 0; q < world; ++q) st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(step + 1);
+    step[0] = epoch;
+    step[1] = epoch + 1u;
+    if (sys_fence) __threadfence_system();
+    for (int k = 1; k < world; ++k) {
+      int q = rank + k;
+      if (q >= world) q -= world;
+      st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
+    }
   }
 }
 
@@ -327,10 +351,10 @@ int tic_peer_exchange(void* const* bases_host, int world, int rank, int64_t flag
   return TIC_OK;
 }
 
-int tic_peer_push(void* const* bases_host, int world, int rank, int64_t flag_off, int64_t wait_off, uint32_t* ctr, int nseg,
-                  void* const* src_host, const int64_t* bytes_host, const int64_t* dst_off_host, const int64_t* dst_stride_host,
-                  void* stream) {
-  TIC_CHECK_ARG(bases_host && ctr && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+int tic_peer_push(void* const* bases_host, int world, int rank, int64_t flag_off, int64_t wait_off, const uint32_t* step,
+                  uint32_t* ticket, int nseg, void* const* src_host, const int64_t* bytes_host, const int64_t* dst_off_host,
+                  const int64_t* dst_stride_host, void* stream) {
+  TIC_CHECK_ARG(bases_host && step && ticket && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
                 "tic_peer_push: bad group (world=%d rank=%d, at most %d peers)", world, rank, kMaxPeers);
   TIC_CHECK_ARG(nseg >= 1 && nseg <= kMaxSeg && (flag_off & 3) == 0 && (wait_off < 0 || (wait_off & 3) == 0), "tic_peer_push: bad arguments");
   PeerPtrs sym{};
@@ -351,21 +375,21 @@ int tic_peer_push(void* const* bases_host, int world, int rank, int64_t flag_off
   int grid = static_cast<int>((total / 16 + 256 * 2 - 1) / (256 * 2));
   if (grid < 1) grid = 1;
   if (grid > 2 * 148) grid = 2 * 148;
-  launch_k(peer_push_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), sym, world, rank, xa, flag_off, wait_off, ctr,
-           20ull * 1000ull * 1000ull * 1000ull);
+  launch_k(peer_push_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), sym, world, rank, xa, flag_off, wait_off, step,
+           ticket, 20ull * 1000ull * 1000ull * 1000ull, peer_sys_fence());
   TIC_CHECK_LAUNCH("tic_peer_push");
   return TIC_OK;
 }
 
-int tic_peer_signal(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* ctr, void* stream) {
-  TIC_CHECK_ARG(bases_host && ctr && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && (flag_off & 3) == 0,
+int tic_peer_signal(void* const* bases_host, int world, int rank, int64_t flag_off, uint32_t* step, void* stream) {
+  TIC_CHECK_ARG(bases_host && step && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && (flag_off & 3) == 0,
                 "tic_peer_signal: bad arguments");
   PeerPtrs sym{};
   for (int p = 0; p < world; ++p) {
     TIC_CHECK_ARG(bases_host[p] != nullptr, "tic_peer_signal: rank %d has no mapped block", p);
     sym.base[p] = static_cast<uint8_t*>(bases_host[p]);
   }
-  launch_k(peer_signal_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), sym, world, rank, flag_off, ctr);
+  launch_k(peer_signal_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), sym, world, rank, flag_off, step, peer_sys_fence());
   TIC_CHECK_LAUNCH("tic_peer_signal");
   return TIC_OK;
 }

@@ -239,7 +239,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (so.ready != nullptr) {
         seg_epoch = *reinterpret_cast<const volatile uint32_t*>(so.epoch);
         if (!seg_major)   // segments are not tile-aligned: the whole operand has to be there before the first load
-          for (int g = 0; g < so.nseg; ++g) seg_wait(so, g, seg_epoch);
+          for (int g = 0; g < so.nseg; ++g)
+            if (!(so.remote && g == so.my_seg)) seg_wait(so, g, seg_epoch);
       }
       for (int w = worker; w < num_items; w += nworkers) {
         int t, ks;
@@ -249,7 +250,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int m0 = m_blk * kBM, n0 = n_blk * BN;
         if (seg_major) {
           const int seg = n_blk / so.tiles_per_seg;
-          if (seg != seg_ok) { seg_wait(so, seg, seg_epoch); seg_ok = seg; }   // the local segment is copied first, but copied too
+          // pull form: the local segment is copied first, but copied too; push form: it was produced in place (stream order)
+          if (seg != seg_ok) { if (!(so.remote && seg == so.my_seg)) seg_wait(so, seg, seg_epoch); seg_ok = seg; }
         }
         const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kb) * ks / kslices);
         const int kt_end = static_cast<int>(static_cast<int64_t>(total_kb) * (ks + 1) / kslices);

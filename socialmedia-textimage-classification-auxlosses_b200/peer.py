@@ -69,7 +69,8 @@ class SymmetricItc:
         pu = self.push
         seg = pu["seg_emb"] if pu else None
         if pu:
-            pu["emb"]()               # my rows -> every rank's gathered buffers + flag; nobody waits here
+            with br("px"):            # my rows -> every REMOTE rank's gathered buffers + flag, on a side branch: the tile kernels
+                pu["emb"]()           # below do not wait for this kernel, they poll the peers' flags segment by segment
         else:
             self.exchange("emb")
         with br("cb"):
@@ -78,7 +79,8 @@ class SymmetricItc:
         br.join("cb")
         self.lse_rows(rb, cb, scale, loss_sums)
         if pu:
-            pu["lse"]()
+            with br("pl"):
+                pu["lse"]()
         else:
             self.exchange("lse")
 
@@ -112,6 +114,8 @@ class SymmetricItc:
         br.join("cb")
         if pu:
             br.join("dn")
+            br.join("px")
+            br.join("pl")
 
 
 class RowBlockItc:
@@ -282,29 +286,34 @@ class PeerGroup:
         off = self.flag_off + slot * self.FLAG_SLOT_BYTES
         return self.block[off:off + 4 * self.world].view(torch.int32)
 
+    def step_counter(self) -> torch.Tensor:
+        """{completed steps, epoch of the step in flight} (tic_peer_signal advances it at the tail of a step)"""
+        if getattr(self, "_step", None) is None:
+            self._step = torch.tensor([0, 1], dtype=torch.int32, device=self.dev)
+        return self._step
+
     def define_push(self, name: str, segs, slot: int, wait_slot: int = -1):
-        """segs: [(src_tensor (local, contiguous), nbytes, dst_off_bytes of rank 0's slot in every block, dst_stride_bytes)]"""
+        """segs: [(src_tensor = this rank's slot of its own gathered buffer, nbytes, dst_off_bytes of rank 0's slot in every
+        block, dst_stride_bytes)]"""
         n = len(segs)
-        ctr = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._pushes = getattr(self, "_pushes", {})
         self._pushes[name] = (n, (ctypes.c_void_p * n)(*[s[0].data_ptr() for s in segs]), (ctypes.c_int64 * n)(*[s[1] for s in segs]),
                               (ctypes.c_int64 * n)(*[s[2] for s in segs]), (ctypes.c_int64 * n)(*[s[3] for s in segs]),
                               self.flag_off + slot * self.FLAG_SLOT_BYTES,
-                              (self.flag_off + wait_slot * self.FLAG_SLOT_BYTES) if wait_slot >= 0 else -1, ctr, [s[0] for s in segs])
-        return ctr
+                              (self.flag_off + wait_slot * self.FLAG_SLOT_BYTES) if wait_slot >= 0 else -1, ticket, [s[0] for s in segs])
 
     def push(self, name: str):
-        n, src, nb, doff, dstr, foff, woff, ctr, _keep = self._pushes[name]
-        self.capi.call("tic_peer_push", self._bases_c, self.world, self.rank, foff, woff, ctr.data_ptr(), n, src, nb, doff, dstr,
-                       torch.cuda.current_stream().cuda_stream)
+        n, src, nb, doff, dstr, foff, woff, ticket, _keep = self._pushes[name]
+        self.capi.call("tic_peer_push", self._bases_c, self.world, self.rank, foff, woff, self.step_counter().data_ptr(),
+                       ticket.data_ptr(), n, src, nb, doff, dstr, torch.cuda.current_stream().cuda_stream)
 
     def define_signal(self, name: str, slot: int):
         self._signals = getattr(self, "_signals", {})
-        self._signals[name] = (self.flag_off + slot * self.FLAG_SLOT_BYTES, torch.zeros(2, dtype=torch.int32, device=self.dev))
+        self._signals[name] = self.flag_off + slot * self.FLAG_SLOT_BYTES
 
     def signal(self, name: str):
-        foff, ctr = self._signals[name]
-        self.capi.call("tic_peer_signal", self._bases_c, self.world, self.rank, foff, ctr.data_ptr(),
+        self.capi.call("tic_peer_signal", self._bases_c, self.world, self.rank, self._signals[name], self.step_counter().data_ptr(),
                        torch.cuda.current_stream().cuda_stream)
 
     def define_pull(self, name: str, segs, max_blocks: int = 148):
@@ -400,12 +409,19 @@ def _make_peer_head_plan():
             self.Y_lo = pg.view(off_lo, (2 * b, Pe), BF16) if self.has_lo else (e(2 * b, Pe, dt=BF16) if self.P is not None else None)
             self.rinv_mine = pg.view(off_rinv, (2 * b,), F32)
             self.lse_mine = pg.view(off_lse, (2 * b,), F32)
+            self._Yt = self._Yv = self._Yt_lo = self._Yv_lo = None
             if self.push_mode:   # gathered copies inside the peer-mapped block (the peers write them)
                 self.T_all, self.V_all = pg.view(off_Tall, (N, Pe), BF16), pg.view(off_Vall, (N, Pe), BF16)
                 self.T_all_lo = pg.view(off_Tall_lo, (N, Pe), BF16) if self.has_lo else None
                 self.V_all_lo = pg.view(off_Vall_lo, (N, Pe), BF16) if self.has_lo else None
                 self.rinv_t_all, self.rinv_v_all = pg.view(off_rt_all, (N,), F32), pg.view(off_rv_all, (N,), F32)
                 self.lse_row_all, self.lse_col_all = pg.view(off_lr_all, (N,), F32), pg.view(off_lc_all, (N,), F32)
+                # this rank's rows are produced IN PLACE in its slot of its own gathered buffers (no local copy, and the local
+                # column segment of the tile kernels is ready by stream order)
+                sl = slice(rank * b, (rank + 1) * b)
+                self._Yt, self._Yv = self.T_all[sl], self.V_all[sl]
+                if self.has_lo:
+                    self._Yt_lo, self._Yv_lo = self.T_all_lo[sl], self.V_all_lo[sl]
             else:                # gathered copies in local HBM (pulled)
                 self.T_all, self.V_all = e(N, Pe, dt=BF16), e(N, Pe, dt=BF16)
                 self.T_all_lo = e(N, Pe, dt=BF16) if self.has_lo else None
@@ -420,25 +436,34 @@ def _make_peer_head_plan():
             pg.define_phase("lse", [(off_lse, b * 4, self.lse_row_all, b * 4), (off_lse + b * 4, b * 4, self.lse_col_all, b * 4)])
             mk = lambda: P.ItcPlan(b, N, Pe, dev, row_offset=rank * b, need_dv=False, precise=precise, col_sums=False)  # noqa: E731
             self.rb, self.cb = mk(), mk()
-            self.rb.rinv_t, self.rb.rinv_v = self.rinv_mine[:b], self.rinv_v_all
-            self.cb.rinv_t, self.cb.rinv_v = self.rinv_mine[b:], self.rinv_t_all
-            self.rb.lse_row, self.rb.lse_col = self.lse_mine[:b], self.lse_col_all
-            self.cb.lse_row, self.cb.lse_col = self.lse_mine[b:], self.lse_row_all
+            if self.push_mode:
+                sl = slice(rank * b, (rank + 1) * b)
+                self.rb.rinv_t, self.rb.rinv_v = self.rinv_t_all[sl], self.rinv_v_all
+                self.cb.rinv_t, self.cb.rinv_v = self.rinv_v_all[sl], self.rinv_t_all
+                self.rb.lse_row, self.rb.lse_col = self.lse_row_all[sl], self.lse_col_all
+                self.cb.lse_row, self.cb.lse_col = self.lse_col_all[sl], self.lse_row_all
+            else:
+                self.rb.rinv_t, self.rb.rinv_v = self.rinv_mine[:b], self.rinv_v_all
+                self.cb.rinv_t, self.cb.rinv_v = self.rinv_mine[b:], self.rinv_t_all
+                self.rb.lse_row, self.rb.lse_col = self.lse_mine[:b], self.lse_col_all
+                self.cb.lse_row, self.cb.lse_col = self.lse_mine[b:], self.lse_row_all
             self.itc = self.rb
             self.lse_ws = torch.zeros(int(capi_load().tic_itc_lse_rows_workspace_bytes(b)) // 4, dtype=F32, device=dev)
             push = None
             if self.push_mode:
-                psegs = [(self.Y[:b], half, off_Tall, half), (self.Y[b:], half, off_Vall, half)]
+                sl = slice(rank * b, (rank + 1) * b)
+                psegs = [(self._Yt, half, off_Tall, half), (self._Yv, half, off_Vall, half)]
                 if self.has_lo:
-                    psegs += [(self.Y_lo[:b], half, off_Tall_lo, half), (self.Y_lo[b:], half, off_Vall_lo, half)]
-                psegs += [(self.rinv_mine[:b], b * 4, off_rt_all, b * 4), (self.rinv_mine[b:], b * 4, off_rv_all, b * 4)]
-                ctr_emb = pg.define_push("emb", psegs, slot=1, wait_slot=3)
-                ctr_lse = pg.define_push("lse", [(self.lse_mine[:b], b * 4, off_lr_all, b * 4),
-                                                 (self.lse_mine[b:], b * 4, off_lc_all, b * 4)], slot=2)
+                    psegs += [(self._Yt_lo, half, off_Tall_lo, half), (self._Yv_lo, half, off_Vall_lo, half)]
+                psegs += [(self.rinv_t_all[sl], b * 4, off_rt_all, b * 4), (self.rinv_v_all[sl], b * 4, off_rv_all, b * 4)]
+                pg.define_push("emb", psegs, slot=1, wait_slot=3)
+                pg.define_push("lse", [(self.lse_row_all[sl], b * 4, off_lr_all, b * 4), (self.lse_col_all[sl], b * 4, off_lc_all, b * 4)],
+                               slot=2)
                 pg.define_signal("done", slot=3)
-                # seg tuples: (ready words, epoch counter, -columns per segment [negative: flags written by the peers], my segment)
+                step = pg.step_counter()
+                # seg tuples: (ready words, epoch word = step[1], -columns per segment [negative: flags written by the peers], my segment)
                 push = {"emb": lambda: pg.push("emb"), "lse": lambda: pg.push("lse"), "done": lambda: pg.signal("done"),
-                        "seg_emb": (pg.flags_view(1), ctr_emb, -b, rank), "seg_lse": (pg.flags_view(2), ctr_lse, -b, rank)}
+                        "seg_emb": (pg.flags_view(1), step[1:2], -b, rank), "seg_lse": (pg.flags_view(2), step[1:2], -b, rank)}
             self.sym = SymmetricItc(self.rb, self.cb, pg.exchange, self._lse_rows, b, world, rank, branches=self.br, push=push)
 
         def _init_rowblock(self, b, N, group):
@@ -500,23 +525,36 @@ def _make_peer_head_plan():
             finally:
                 self.beta_itm = saved
 
+        def _rows(self):
+            """(Yt, Yv, Yt_lo, Yv_lo): where this rank's projected / handed-in embeddings live"""
+            b = self.B
+            if getattr(self, "_Yt", None) is not None:      # push form: in place in the gathered buffers
+                lo_t = self._Yt_lo if self._Yt_lo is not None else (self.Y_lo[:b] if self.Y_lo is not None else None)
+                lo_v = self._Yv_lo if self._Yv_lo is not None else (self.Y_lo[b:] if self.Y_lo is not None else None)
+                return self._Yt, self._Yv, lo_t, lo_v
+            return self.Y[:b], self.Y[b:], (self.Y_lo[:b] if self.Y_lo is not None else None), (self.Y_lo[b:] if self.Y_lo is not None else None)
+
         def _ops(self):
             b = self.B
             lo = self.has_lo
             if self.itc_mode == "rowblock":
                 return dict(T=self.Y[:b], V=self.Y[b:], V_all=self.V_all)
-            return dict(T=self.Y[:b], V=self.Y[b:], T_all=self.T_all, V_all=self.V_all,
-                        T_lo=self.Y_lo[:b] if lo else None, V_lo=self.Y_lo[b:] if lo else None,
+            Yt, Yv, Ytl, Yvl = self._rows()
+            return dict(T=Yt, V=Yv, T_all=self.T_all, V_all=self.V_all, T_lo=Ytl if lo else None, V_lo=Yvl if lo else None,
                         T_all_lo=self.T_all_lo, V_all_lo=self.V_all_lo)
 
         def _itc_fwd(self, inp, with_loss=True):
             B, E, w = self.B, self.E, self.w
-            Yt, Yv = self.Y[:B], self.Y[B:]
+            if self.itc_mode == "rowblock":
+                Yt, Yv, Ytl, Yvl = self.Y[:B], self.Y[B:], (self.Y_lo[:B] if self.Y_lo is not None else None), \
+                    (self.Y_lo[B:] if self.Y_lo is not None else None)
+            else:
+                Yt, Yv, Ytl, Yvl = self._rows()
             self.br.enabled = self.parallel_streams
             if self.P is not None:
                 tp_, vp_ = inp["t_pool"], inp["v_pool"]
-                pt = lambda: P.gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=self.Y_lo[:B])  # noqa: E731  HF :265
-                pv = lambda: P.gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=self.Y_lo[B:])  # noqa: E731  HF :262
+                pt = lambda: P.gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)  # noqa: E731  HF :265
+                pv = lambda: P.gemm(vp_, vp_.stride(0), 0, w["W_v"], E, 0, Yv, self.P, 1, B, self.P, E, D_lo=Yvl)  # noqa: E731  HF :262
             else:   # embeddings handed in by the caller: publish them
                 pt = lambda: Yt.copy_(inp["t_pool"])  # noqa: E731
                 pv = lambda: Yv.copy_(inp["v_pool"])  # noqa: E731
