@@ -151,6 +151,13 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
 int64_t tic_itc_lse_rows_workspace_bytes(int m);
 int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift, float* lse_a,
                      float* lse_b, float* loss_sums, void* workspace, const float* scale_dev, void* stream);
+/* Same, and the PUSH of the two vectors rides on the launch (see tic_peer_push): lse_a / lse_b are this rank's slots of its
+ * own gathered vectors; every value is also stored into the remote ranks' blocks at off_a / off_b + (rank * m + i) * 4, and
+ * the last block releases flags[rank] = step[1] at flag_off of every remote block.  bases_host: HOST array of world pointers. */
+int tic_itc_lse_rows_push(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift,
+                          float* lse_a, float* lse_b, float* loss_sums, void* workspace, const float* scale_dev,
+                          void* const* bases_host, int world, int rank, int64_t off_a, int64_t off_b, int64_t flag_off,
+                          const uint32_t* step, void* stream);
 /* Recompute S tiles and emit the bf16 gradient operands (g = dLoss/d(clip_loss), B = n_global):
  *   Gp[i,j] = g/(2B) * (exp(S-lse_row[i]) + exp(S-lse_col[j]))      (the -I/B diagonal is applied in fp32 later)
  *   GA [m_local, ld_ga ] row-major:  Gp[i,j] * rinv_v[j]            (A operand of dT = GA * V)

@@ -38,6 +38,7 @@ _SIGS = {
     "tic_itc_lse_loss": ("pipipiiifppppp", ctypes.c_int),
     "tic_itc_lse_rows_workspace_bytes": ("i", ctypes.c_int64),
     "tic_itc_lse_rows": ("ppiipfpppppp", ctypes.c_int),
+    "tic_itc_lse_rows_push": ("ppiipfppppppiilllpp", ctypes.c_int),
     "tic_peer_handle_bytes": ("", ctypes.c_int),
     "tic_peer_alloc": ("lp", ctypes.c_int),
     "tic_peer_free": ("p", ctypes.c_int),

@@ -904,10 +904,20 @@ __global__ void itc_loss_kernel(const float* __restrict__ lse_row, const float* 
 // Symmetric (peer-memory) mode: both softmax directions are ROW statistics — of the row block S[rows_r, :] and of the
 // swapped block S^T[cols_r, :].  blockIdx.y selects the direction; lse = shift + log(sum of the per-tile partials);
 // the loss terms sum_i (lse_i - diag_i) are reduced in a fixed order (block partials, last block adds them up).
+// Optional PUSH of the two lse vectors (multi-GPU symmetric form): every value is also stored into the remote peers' gathered
+// vectors (slot of this rank), and the last block of the launch releases the peers' flags = step[1] — the exchange costs no
+// kernel of its own (it was a 6-8 us launch between the forward and the gradient-operand tiles).
+struct LsePush {
+  uint8_t* base[8];       // every rank's peer-mapped block (world == 0: no push)
+  int world, rank;
+  int64_t off_a, off_b;   // byte offsets of the gathered vectors (element 0 of rank 0's slot) inside every block
+  int64_t flag_off;       // uint32[world] flag words inside every block
+  const uint32_t* step;   // {completed steps, epoch in flight} (tic_peer_signal)
+};
 __global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int nparts, int m,
                                     const float* __restrict__ diag, float shift, const float* __restrict__ scale_dev,
                                     float* __restrict__ lse_a, float* __restrict__ lse_b, float* __restrict__ loss_sums,
-                                    float* __restrict__ ws) {
+                                    float* __restrict__ ws, LsePush px) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
   if (scale_dev != nullptr) shift = __ldg(scale_dev);
@@ -924,6 +934,11 @@ __global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const floa
     const float l = shift + logf(s);
     lse[i] = l;
     term = l - diag[i];
+    for (int k = 1; k < px.world; ++k) {     // remote peers' copies of this rank's slot
+      int q = px.rank + k;
+      if (q >= px.world) q -= px.world;
+      reinterpret_cast<float*>(px.base[q] + (dir == 0 ? px.off_a : px.off_b))[static_cast<int64_t>(px.rank) * m + i] = l;
+    }
   }
   __shared__ float sw[32];
   __shared__ bool last;
@@ -942,6 +957,20 @@ __global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const floa
       for (int b = 0; b < static_cast<int>(gridDim.x); ++b) tot += reinterpret_cast<volatile float*>(blk_part)[b];
       loss_sums[dir] += tot;
       *ticket = 0u;
+    }
+    if (px.world > 1) {      // the last block of BOTH directions publishes the flags (release at system scope, cumulative)
+      unsigned int* all = reinterpret_cast<unsigned int*>(ws) + 2 + 2 * gridDim.x;
+      __threadfence();
+      if (atomicAdd(all, 1u) == 2 * gridDim.x - 1) {
+        *all = 0u;
+        __threadfence();
+        const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(px.step + 1);
+        for (int k = 1; k < px.world; ++k) {
+          int q = px.rank + k;
+          if (q >= px.world) q -= px.world;
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(px.base[q] + px.flag_off) + px.rank), "r"(epoch) : "memory");
+        }
+      }
     }
   }
 }
@@ -1233,7 +1262,7 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
   return TIC_OK;
 }
 
-int64_t tic_itc_lse_rows_workspace_bytes(int m) { return static_cast<int64_t>(2 + 2 * ceil_div(m, 256)) * 4; }
+int64_t tic_itc_lse_rows_workspace_bytes(int m) { return static_cast<int64_t>(3 + 2 * ceil_div(m, 256)) * 4; }
 
 int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift, float* lse_a,
                      float* lse_b, float* loss_sums, void* workspace, const float* scale_dev, void* stream) {
@@ -1241,8 +1270,29 @@ int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int 
                 "tic_itc_lse_rows: bad arguments");
   dim3 grid(ceil_div(m, 256), 2);
   launch_k(itc_lse_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), part_a, part_b, n_parts, m, diag, shift,
-           scale_dev, lse_a, lse_b, loss_sums, static_cast<float*>(workspace));
+           scale_dev, lse_a, lse_b, loss_sums, static_cast<float*>(workspace), LsePush{});
   TIC_CHECK_LAUNCH("tic_itc_lse_rows");
+  return TIC_OK;
+}
+
+int tic_itc_lse_rows_push(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift, float* lse_a,
+                          float* lse_b, float* loss_sums, void* workspace, const float* scale_dev, void* const* bases_host, int world,
+                          int rank, int64_t off_a, int64_t off_b, int64_t flag_off, const uint32_t* step, void* stream) {
+  TIC_CHECK_ARG(part_a && part_b && diag && lse_a && lse_b && loss_sums && workspace && n_parts > 0 && m > 0,
+                "tic_itc_lse_rows_push: bad arguments");
+  TIC_CHECK_ARG(bases_host && step && world >= 1 && world <= 8 && rank >= 0 && rank < world && (off_a & 3) == 0 && (off_b & 3) == 0 &&
+                    (flag_off & 3) == 0,
+                "tic_itc_lse_rows_push: bad peer description");
+  LsePush px{};
+  for (int p = 0; p < world; ++p) {
+    TIC_CHECK_ARG(bases_host[p] != nullptr, "tic_itc_lse_rows_push: rank %d has no mapped block", p);
+    px.base[p] = static_cast<uint8_t*>(bases_host[p]);
+  }
+  px.world = world; px.rank = rank; px.off_a = off_a; px.off_b = off_b; px.flag_off = flag_off; px.step = step;
+  dim3 grid(ceil_div(m, 256), 2);
+  launch_k(itc_lse_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), part_a, part_b, n_parts, m, diag, shift,
+           scale_dev, lse_a, lse_b, loss_sums, static_cast<float*>(workspace), px);
+  TIC_CHECK_LAUNCH("tic_itc_lse_rows_push");
   return TIC_OK;
 }
 

@@ -48,6 +48,9 @@ class SymmetricItc:
         peers, after the last read of the gathered embeddings, that the next step may overwrite them."""
         self.push = push
         self.rb, self.cb, self.exchange, self.lse_rows = rb, cb, exchange, lse_rows
+        # residual (lo) K-segment of the GATHERED embeddings in the two gradient GEMMs: kept while the sum is short; from 1024
+        # gathered rows on its rounding averages out (K = N terms) and the segment is a third of a long k-loop (N = 2048: 23 us)
+        self.gemm_lo = b_local * world < 1024
         self.b, self.world, self.rank, self.N = b_local, world, rank, b_local * world
         # the row block and the swapped block are independent between the exchanges: issue them on parallel branches
         self.br = branches if branches is not None else _NoBranches()
@@ -95,7 +98,7 @@ class SymmetricItc:
         ev_cb = None
         with br("cb"):
             cb.bwd_operands(V, ldv, T_all, T_all.stride(0), scale, g / (2.0 * N), T_lo=V_lo, V_lo=T_all_lo, seg=seg)
-            cb.grad_gemm_t(T_all, T_all.stride(0), V_lo=T_all_lo)
+            cb.grad_gemm_t(T_all, T_all.stride(0), V_lo=T_all_lo if self.gemm_lo else None)
             if pu:
                 ev_cb = torch.cuda.Event()
                 ev_cb.record(torch.cuda.current_stream())
@@ -103,7 +106,7 @@ class SymmetricItc:
             if consume_v is not None:
                 consume_v()
         rb.bwd_operands(T, ldt, V_all, V_all.stride(0), scale, g / (2.0 * N), T_lo=T_lo, V_lo=V_all_lo, seg=seg)
-        rb.grad_gemm_t(V_all, V_all.stride(0), V_lo=V_all_lo)
+        rb.grad_gemm_t(V_all, V_all.stride(0), V_lo=V_all_lo if self.gemm_lo else None)
         if pu:      # both gradient GEMMs were the last readers of the gathered embeddings: tell the peers (side branch)
             with br("dn"):
                 torch.cuda.current_stream().wait_event(ev_cb)
@@ -395,6 +398,7 @@ def _make_peer_head_plan():
             # PUSH form of the two exchanges (default): the gathered copies live INSIDE the peer-mapped block so that the
             # producers can store into them; TIC_PEER_PUSH=0 keeps the round-1 pull form (A/B switch)
             self.push_mode = _os.environ.get("TIC_PEER_PUSH", "1") != "0"
+            self._lse_push = None
             g_emb = _up(N * Pe * 2)
             off_Tall, off_Vall = end_pub, end_pub + g_emb
             off_Tall_lo, off_Vall_lo = off_Vall + g_emb, off_Vall + 2 * g_emb
@@ -462,7 +466,9 @@ def _make_peer_head_plan():
                 pg.define_signal("done", slot=3)
                 step = pg.step_counter()
                 # seg tuples: (ready words, epoch word = step[1], -columns per segment [negative: flags written by the peers], my segment)
-                push = {"emb": lambda: pg.push("emb"), "lse": lambda: pg.push("lse"), "done": lambda: pg.signal("done"),
+                # the lse exchange rides on tic_itc_lse_rows (no kernel of its own): "lse" below is a no-op
+                self._lse_push = (off_lr_all, off_lc_all, pg.flag_off + 2 * pg.FLAG_SLOT_BYTES)
+                push = {"emb": lambda: pg.push("emb"), "lse": lambda: None, "done": lambda: pg.signal("done"),
                         "seg_emb": (pg.flags_view(1), step[1:2], -b, rank), "seg_lse": (pg.flags_view(2), step[1:2], -b, rank)}
             self.sym = SymmetricItc(self.rb, self.cb, pg.exchange, self._lse_rows, b, world, rank, branches=self.br, push=push)
 
@@ -514,6 +520,13 @@ def _make_peer_head_plan():
                                    seg=(v_ready, pg.ctr, b, rank))
 
         def _lse_rows(self, rb, cb, scale, loss_sums):
+            if getattr(self, "_lse_push", None) is not None:     # push form: the lse exchange rides on this launch
+                off_a, off_b, flag_off = self._lse_push
+                pg = self.pg
+                call("tic_itc_lse_rows_push", ptr(rb.row_part), ptr(cb.row_part), rb.nrp, self.B, ptr(rb.diag), float(scale),
+                     ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), None, pg._bases_c, pg.world, pg.rank,
+                     off_a, off_b, flag_off, pg.step_counter().data_ptr(), P._stream())
+                return
             call("tic_itc_lse_rows", ptr(rb.row_part), ptr(cb.row_part), rb.nrp, self.B, ptr(rb.diag), float(scale),
                  ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), None, P._stream())
 

@@ -43,7 +43,9 @@ def main():
     from oracle import restatement as R   # weight init + sampling rule only
 
     ok = True
-    for fusion, b, use_itm in (("concat", 96, True), (None, 2048, False)):
+    # concat head at a small batch (symmetric form, push exchange), the c2 shape (256 per rank), a long gathered dimension in the
+    # symmetric form (1024 per rank: 2048 global, the 8-GPU c2 width), the row-block form (2048 per rank)
+    for fusion, b, use_itm in (("concat", 96, True), ("concat", 256, True), ("concat", 1024, False), (None, 2048, False)):
         C, E = 4, 768
         N = b * world
         g = torch.Generator().manual_seed(11)
