@@ -357,15 +357,15 @@ def main():
             plan.out["d_v_emb"] = torch.empty(B, spec["d"], device=dev)
     # fp32 MASTER weights resident on the device; the step itself (first node of the captured graph) refreshes the bf16
     # working copies and exp(logit_scale) from them, so the timed step is a training step's forward+backward, not a step on
-    # pre-cast constants.  (Multi-GPU plans take a snapshot: set_weights.)
+    # pre-cast constants.  (The NCCL comparison plan takes a snapshot: set_weights; TIC_BENCH_SNAPSHOT=1 forces it: A/B.)
     master = {k: v.to(dev) for k, v in synthetic_params(spec["C"], seed=40).items()}
-    if world == 1:
+    if (world == 1 or args.dist == "peer") and os.environ.get("TIC_BENCH_SNAPSHOT", "0") != "1":
         plan.bind_params(master, live=True)
     else:
         plan.set_weights(master)
 
     # ---- count launches of one step (kernels per C-ABI call are fixed)
-    KPC = {"tic_itc_lse_loss": 2, "tic_heads_fwd_bwd": 1, "tic_ce_bidir_fwd": 3, "tic_gemm_rowss_parts": 0,
+    KPC = {"tic_itc_lse_loss": 2, "tic_heads_fwd_bwd": 1, "tic_ce_bidir_fwd": 2, "tic_gemm_rowss_parts": 0,
            "tic_itc_row_parts": 0, "tic_itc_col_parts": 0}
     KPC.update({"tic_peer_alloc": 0, "tic_peer_export": 0, "tic_peer_open": 0, "tic_peer_close": 0, "tic_gemm_plan": 0})
     counter = {"n": 0}

@@ -43,6 +43,12 @@ def main():
         use_itc = False
     plan = P.HeadPlan(spec["B"], E=spec["E"], P=spec["P"], C=spec["C"], fusion=fusion, use_itc=use_itc, use_itm=use_itm,
                       Lv=max(spec["Lv"], 1), device=dev, itm_mode=spec.get("itm_mode", "uniform") if use_itc else "uniform")
+    if spec["P"] is None:      # ITC-only sweep point ("itc:<B>x<d>"): the embeddings are the inputs
+        B = spec["B"]
+        plan.itc = P.ItcPlan(B, B, spec["d"], dev)
+        plan.itc.scale_dev = plan.scale_t
+        plan.Pe = spec["d"]
+        plan.out["d_t_emb"], plan.out["d_v_emb"] = torch.empty(B, spec["d"], device=dev), torch.empty(B, spec["d"], device=dev)
     master = {k: v.to(dev) for k, v in bench.synthetic_params(spec["C"], seed=40).items()}
     if args.snapshot:
         plan.set_weights(master)

@@ -36,7 +36,11 @@ def main():
     B = spec["B"]
     plan = PeerHeadPlan(B, world=world, rank=rank, E=spec["E"], P=spec["P"] if spec["P"] is not None else None, d=spec.get("d"),
                         C=spec["C"], fusion=spec["fusion"], use_itc=spec["use_itc"], use_itm=spec["use_itm"], Lv=spec["Lv"], device=dev)
-    plan.set_weights({k: v.to(dev) for k, v in bench.synthetic_params(spec["C"], seed=40).items()})
+    master = {k: v.to(dev) for k, v in bench.synthetic_params(spec["C"], seed=40).items()}
+    if os.environ.get("TIC_BENCH_SNAPSHOT", "0") == "1":
+        plan.set_weights(master)
+    else:
+        plan.bind_params(master, live=True)      # as bench.py: fp32 masters refreshed by the root launch of the step
     for _ in range(3):
         plan.step(dev_in)
     torch.cuda.synchronize()

@@ -1,8 +1,8 @@
 // clip_loss on a MATERIALISED similarity matrix (models/utils.py:225-231):  (CE(S, I) + CE(S^T, I)) / 2.
 // This is the drop-in for `utils.clip_loss(similarity)` when the caller hands over an arbitrary [B,B] fp32 matrix
 // (the fused ITC path in itc.cu never materialises S).  HBM-bound: the forward reads every element of S exactly
-// once — each 64x128 tile is staged in shared memory and feeds both the row and the column online-softmax — and the
-// backward is one read of S plus one write of dS.
+// once — each 64x128 tile lives in the registers of 8 warps and feeds both the row and the column softmax statistics with
+// one exponential per element — and the backward is one read of S plus one write of dS.
 #include "common.cuh"
 #include "tic_ptx.cuh"
 
@@ -14,7 +14,7 @@ constexpr int kCeRows = 64;   // rows per smem tile
 __host__ __device__ inline int ce_nstrips(int B) { return (B + kCeCols - 1) / kCeCols; }
 __host__ __device__ inline int ce_nseg(int B) {
   const int tiles = (B + kCeRows - 1) / kCeRows;
-  int want = (4 * 148 + ce_nstrips(B) - 1) / ce_nstrips(B);
+  int want = (4 * 148) / ce_nstrips(B);      // 4 resident blocks per SM: one full wave, no tail
   if (want < 1) want = 1;
   return want < tiles ? want : tiles;
 }
@@ -26,45 +26,55 @@ __device__ __forceinline__ void ms_combine(float& m, float& s, float m2, float s
   m = mn;
 }
 
-// grid (nstrips, nseg); block 256. Row partials: rp[strip][row] = (max, sumexp) over the strip's 128 columns.
-// Column partials: cp[seg][col] = (max, sumexp) over the segment's rows.
-// Bandwidth-oriented: every thread issues its 8 16-byte loads of a 64x128 tile back to back (32 KB in flight per block),
-// the tile is staged in shared memory with a 129-float row pitch (conflict-free for both walks), then 128 threads walk
-// COLUMNS (64 rows each) and 128 threads walk ROW halves (64 columns each) with a one-pass online softmax — each element of S
-// is read from HBM once and from shared memory twice.  (The round-1 form reduced every row with 10 warp shuffles per 512
-// bytes loaded and finished in a single 1024-thread block: 99 us at B = 4096 = 10 % of HBM.)
-__device__ __forceinline__ void ms_push(float& m, float& s, float x) {
-  if (x <= m) {
-    s += __expf(fmaxf(x - m, -INFINITY));   // (-inf) - (-inf) = NaN -> fmaxf picks -inf -> adds 0 (padding / masked logits)
-  } else {          // new maximum (rare after the first few elements): rescale the running sum
-    s = s * __expf(m - x) + 1.f;
-    m = x;
-  }
+// grid (nstrips, nseg); block 256 = 8 warps.  Row partials: rp[strip][row] = (reference, sum of exp(x - reference)) over the
+// strip's 128 columns.  Column partials: cp[seg][col] = the same over the segment's rows.
+//
+// Instruction-bound, not latency-bound: 16.7 M elements at B = 4096 leave ~20 issue slots per element at HBM speed.  The
+// round-1 form (10 shuffles per 512 bytes) and the first round-2 form (shared-memory tile + two branchy online-softmax walks,
+// 2 exponentials and ~22 instructions per element: 70 us = 15 % of HBM) were both issue-bound.  This form spends ~8:
+//   * warp w owns rows w, w+8, .., w+56 of each 64 x 128 tile; a lane owns 4 consecutive columns (one 16-byte load per row);
+//   * ONE exponential per element against a warp-wide running reference (the maximum the warp has seen so far in its
+//     columns): row sums and column sums are plain additions of the same e = 2^((x - ref) log2 e);
+//   * column sums accumulate in registers across all tiles of the block (rescaled when the reference grows);
+//   * the 8 row sums of a tile are reduced across the 32 lanes with a transposing butterfly (9 shuffles for 8 rows).
+// Exactness on arbitrary input: a row (or column) whose own maximum lies more than ~69 below the shared reference would
+// underflow; such sums (< 1e-30) are recomputed exactly against their own maximum (warp-cooperative for rows, a serial
+// re-read of the column segment for columns) — never taken for logits of bounded spread, but the kernel is a drop-in for
+// utils.clip_loss on ANY matrix (-inf padding included).
+constexpr float kCeTiny = 1e-30f;
+constexpr float kCeLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ce_ex2(float x) {     // ex2.approx.ftz: 2^(-inf) = +0, relative error ~2^-22
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 ce_bidir_fwd_kernel(const float* __restrict__ S, int64_t lds, int B, float2* __restrict__ rp, float2* __restrict__ cp,
-                    float* __restrict__ diag) {
+                    float* __restrict__ diag, unsigned int* __restrict__ ticket) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
   pdl_wait();      // ... while this one waits here for its own predecessors' writes
-  constexpr int kPitch = kCeCols + 1;
-  __shared__ float tile[kCeRows * kPitch];
+  __shared__ float sm_s[8][kCeCols];
+  __shared__ float sm_m[8];
   const int strip = blockIdx.x, seg = blockIdx.y, nseg = gridDim.y;
-  const int t = threadIdx.x;
-  const int c0 = strip * kCeCols;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (strip == 0 && seg == 0 && t == 0) *ticket = 0u;      // the lse kernel behind this one counts its blocks on it
+  const int c0 = strip * kCeCols, c4 = lane * 4;
   const int tiles = (B + kCeRows - 1) / kCeRows;
-  const int t_begin = static_cast<int>(static_cast<int64_t>(tiles) * seg / nseg);
-  const int t_end = static_cast<int>(static_cast<int64_t>(tiles) * (seg + 1) / nseg);
+  // half tiles of 32 rows: warp w owns rows w, w+8, w+16, w+24 of each
+  const int h_begin = 2 * static_cast<int>(static_cast<int64_t>(tiles) * seg / nseg);
+  const int h_end = 2 * static_cast<int>(static_cast<int64_t>(tiles) * (seg + 1) / nseg);
   const bool vec = (lds & 3) == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0 && c0 + kCeCols <= B;
-  float cm = -INFINITY, cs = 0.f;      // column walker state (threads 0..127: column c0 + t)
-  for (int tl = t_begin; tl < t_end; ++tl) {
-    const int r0 = tl * kCeRows;
-    // ---- global -> registers: 8 independent 16-byte loads per thread
-    float4 f[8];
+  float mref = -INFINITY;                      // warp-uniform running reference
+  float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;   // column sums of exp(x - mref), columns c0 + c4 .. + 3, this warp's rows
+  const bool b4 = lane & 16, b3 = lane & 8;
+  const int my_i = (b4 ? 2 : 0) + (b3 ? 1 : 0);       // the row (of the 4 in a half tile) whose sum the butterfly leaves here
+
+  auto load4 = [&](float4 (&f)[4], int h) {
+    const int r0 = h * 32;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int q = t + 256 * i, rr = q >> 5, c4 = (q & 31) * 4;
-      const int r = r0 + rr;
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + w + 8 * i;
       f[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       if (r < B) {
         const float* p = S + static_cast<int64_t>(r) * lds + c0 + c4;
@@ -78,39 +88,103 @@ ce_bidir_fwd_kernel(const float* __restrict__ S, int64_t lds, int B, float2* __r
         }
       }
     }
-    __syncthreads();          // the previous tile has been consumed
+  };
+  auto consume = [&](const float4 (&f)[4], int h) {
+    const int r0 = h * 32;
+    float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int q = t + 256 * i, rr = q >> 5, c4 = (q & 31) * 4;
-      float* d = tile + rr * kPitch + c4;
-      d[0] = f[i].x; d[1] = f[i].y; d[2] = f[i].z; d[3] = f[i].w;
-      const int r = r0 + rr, dc = r - (c0 + c4);      // the diagonal element of this row, if it sits in this float4
+    for (int i = 0; i < 4; ++i) {
+      mx = fmaxf(fmaxf(mx, fmaxf(f[i].x, f[i].y)), fmaxf(f[i].z, f[i].w));
+      const int r = r0 + w + 8 * i, dc = r - (c0 + c4);      // the diagonal element of this row, if it sits in this float4
       if (r < B && dc >= 0 && dc < 4) diag[r] = dc == 0 ? f[i].x : (dc == 1 ? f[i].y : (dc == 2 ? f[i].z : f[i].w));
     }
-    __syncthreads();
-    if (t < kCeCols) {
-      // ---- column walk: 64 rows of column t
-#pragma unroll 8
-      for (int rr = 0; rr < kCeRows; ++rr) ms_push(cm, cs, tile[rr * kPitch + t]);
-    } else {
-      // ---- row walk: thread pair (2 x 64 columns) per row
-      const int rr = (t - kCeCols) >> 1, h = t & 1;
-      float m = -INFINITY, s = 0.f;
-      const float* row = tile + rr * kPitch + h * 64;
-#pragma unroll 8
-      for (int c = 0; c < 64; ++c) ms_push(m, s, row[c]);
-      const float m2 = __shfl_xor_sync(0xffffffffu, m, 1), s2 = __shfl_xor_sync(0xffffffffu, s, 1);
-      ms_combine(m, s, m2, s2);
-      if (h == 0 && r0 + rr < B) rp[static_cast<int64_t>(strip) * B + r0 + rr] = make_float2(m, s);
+    // The reference only has to keep exp(x - ref) inside the fp32 range, not to BE the maximum: it is raised when some
+    // element exceeds it by more than 40 (one vote per half tile; the 5-shuffle warp maximum runs a few times per block).
+    if (__any_sync(0xffffffffu, mx > mref + 40.f)) {
+      mx = warp_max(mx);
+      if (mref != -INFINITY) {
+        const float sc = __expf(mref - mx);
+        cs0 *= sc; cs1 *= sc; cs2 *= sc; cs3 *= sc;
+      }
+      mref = mx;
     }
+    const float mm = mref == -INFINITY ? 0.f : mref;
+    float rs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float e0 = ce_ex2((f[i].x - mm) * kCeLog2e), e1 = ce_ex2((f[i].y - mm) * kCeLog2e);
+      const float e2 = ce_ex2((f[i].z - mm) * kCeLog2e), e3 = ce_ex2((f[i].w - mm) * kCeLog2e);
+      cs0 += e0; cs1 += e1; cs2 += e2; cs3 += e3;
+      rs[i] = (e0 + e1) + (e2 + e3);
+    }
+    // transposing butterfly: 4 row sums x 32 lanes -> lane holds the full sum of row my_i (2 + 1 + 3 shuffles)
+    const float a0 = (b4 ? rs[2] : rs[0]) + __shfl_xor_sync(0xffffffffu, b4 ? rs[0] : rs[2], 16);
+    const float a1 = (b4 ? rs[3] : rs[1]) + __shfl_xor_sync(0xffffffffu, b4 ? rs[1] : rs[3], 16);
+    float d = (b3 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, b3 ? a0 : a1, 8);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    const int r = r0 + w + 8 * my_i;
+    const bool writer = (lane & 7) == 0 && r < B;
+    const bool tiny = !(d >= kCeTiny);         // underflow against the shared reference (or an all -inf row)
+    if (writer && !tiny) rp[static_cast<int64_t>(strip) * B + r] = make_float2(mref, d);
+    const unsigned fl = __ballot_sync(0xffffffffu, tiny && writer);
+    if (fl != 0u) {                            // rare: exact partial of the flagged rows against their own maximum
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int holder = ((i >> 1) & 1) * 16 + (i & 1) * 8;
+        if ((fl >> holder) & 1u) {             // warp-uniform
+          const float m = warp_max(fmaxf(fmaxf(f[i].x, f[i].y), fmaxf(f[i].z, f[i].w)));
+          float sx = 0.f;
+          if (m != -INFINITY) sx = (__expf(f[i].x - m) + __expf(f[i].y - m)) + (__expf(f[i].z - m) + __expf(f[i].w - m));
+          sx = warp_sum(sx);
+          if (lane == 0) rp[static_cast<int64_t>(strip) * B + r0 + w + 8 * i] = make_float2(m, sx);
+        }
+      }
+    }
+  };
+
+  // software pipeline over half tiles: the loads of the next half tile are in flight while this one is consumed
+  float4 fa[4], fb[4];
+  if (h_begin < h_end) load4(fa, h_begin);
+  for (int h = h_begin; h < h_end; h += 2) {
+    if (h + 1 < h_end) load4(fb, h + 1);
+    consume(fa, h);
+    if (h + 2 < h_end) load4(fa, h + 2);
+    if (h + 1 < h_end) consume(fb, h + 1);
   }
-  if (t < kCeCols && c0 + t < B) cp[static_cast<int64_t>(seg) * B + c0 + t] = make_float2(cm, cs);
+  // ---- column partials of the block: combine the 8 warps' (reference, sums)
+  sm_s[w][c4 + 0] = cs0; sm_s[w][c4 + 1] = cs1; sm_s[w][c4 + 2] = cs2; sm_s[w][c4 + 3] = cs3;
+  if (lane == 0) sm_m[w] = mref;
+  __syncthreads();
+  if (t < kCeCols && c0 + t < B) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, sm_m[k]);
+    float sum = 0.f;
+    if (m != -INFINITY) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (sm_m[k] != -INFINITY) sum += sm_s[k][t] * __expf(sm_m[k] - m);
+    }
+    if (!(sum >= kCeTiny)) {                   // rare: exact online softmax over the segment's rows of this column
+      const int r_begin = h_begin * 32, r_end = min(h_end * 32, B);
+      m = -INFINITY;
+      for (int r = r_begin; r < r_end; ++r) m = fmaxf(m, __ldg(S + static_cast<int64_t>(r) * lds + c0 + t));
+      sum = 0.f;
+      if (m != -INFINITY)
+        for (int r = r_begin; r < r_end; ++r) sum += __expf(__ldg(S + static_cast<int64_t>(r) * lds + c0 + t) - m);
+    }
+    cp[static_cast<int64_t>(seg) * B + c0 + t] = make_float2(m, sum);
+  }
 }
 
-// Combine the partials into the lse vectors, many blocks; blockIdx.y = direction.  Block partials of the loss go to `bp`.
+// Combine the partials into the lse vectors, many blocks; blockIdx.y = direction.  Block partials of the loss go to `bp`; the
+// LAST block to finish (ticket, zeroed by the forward kernel) adds them in index order -> loss (deterministic, no third launch).
 __global__ void __launch_bounds__(256)
 ce_bidir_lse_kernel(const float2* __restrict__ rp, int nstrips, const float2* __restrict__ cp, int nseg, const float* __restrict__ diag,
-                    int B, float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ bp) {
+                    int B, float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ bp,
+                    unsigned int* __restrict__ ticket, float* __restrict__ loss) {
   pdl_trigger();
   pdl_wait();
   const int dir = blockIdx.y;
@@ -126,6 +200,7 @@ ce_bidir_lse_kernel(const float2* __restrict__ rp, int nstrips, const float2* __
     term = l - diag[i];
   }
   __shared__ float sw[8];
+  __shared__ bool last;
   term = warp_sum(term);
   if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = term;
   __syncthreads();
@@ -133,21 +208,15 @@ ce_bidir_lse_kernel(const float2* __restrict__ rp, int nstrips, const float2* __
     float a = 0.f;
     for (int w = 0; w < 8; ++w) a += sw[w];
     bp[dir * gridDim.x + blockIdx.x] = a;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
   }
-}
-
-// Single small block: fixed-order sum of the block partials -> loss (deterministic).
-__global__ void ce_bidir_loss_kernel(const float* __restrict__ bp, int n, int B, float* __restrict__ loss) {
-  pdl_trigger();
-  pdl_wait();
-  __shared__ float sred[32];
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += bp[i];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    acc = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    const int n = gridDim.x * gridDim.y;
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < n; k += 32) acc += reinterpret_cast<const volatile float*>(bp)[k];
     acc = warp_sum(acc);
     if (threadIdx.x == 0) loss[0] = acc / (2.0f * B);
   }
@@ -212,9 +281,9 @@ int tic_ce_bidir_fwd(const float* S, int64_t lds, int B, float* lse_row, float* 
   float* diag = reinterpret_cast<float*>(cp + static_cast<int64_t>(ng) * B);
   float* bp = diag + B;
   const int nb = ceil_div(B, 256);
-  launch_k(ce_bidir_fwd_kernel, dim3(dim3(ns, ng)), dim3(256), 0, st, S, lds, B, rp, cp, diag);
-  launch_k(ce_bidir_lse_kernel, dim3(nb, 2), dim3(256), 0, st, rp, ns, cp, ng, diag, B, lse_row, lse_col, bp);
-  launch_k(ce_bidir_loss_kernel, dim3(1), dim3(256), 0, st, bp, 2 * nb, B, loss);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(bp + 2 * nb);      // inside the 64-byte tail of the workspace
+  launch_k(ce_bidir_fwd_kernel, dim3(dim3(ns, ng)), dim3(256), 0, st, S, lds, B, rp, cp, diag, ticket);
+  launch_k(ce_bidir_lse_kernel, dim3(nb, 2), dim3(256), 0, st, rp, ns, cp, ng, diag, B, lse_row, lse_col, bp, ticket, loss);
   TIC_CHECK_LAUNCH("tic_ce_bidir_fwd");
   return TIC_OK;
 }

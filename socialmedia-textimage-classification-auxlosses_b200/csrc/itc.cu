@@ -941,7 +941,8 @@ __global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const floa
     }
   }
   __shared__ float sw[32];
-  __shared__ bool last;
+  __shared__ bool last, pub;
+  if (threadIdx.x == 0) pub = false;
   term = warp_sum(term);
   if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = term;
   __syncthreads();
@@ -961,16 +962,20 @@ __global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const floa
     if (px.world > 1) {      // the last block of BOTH directions publishes the flags (release at system scope, cumulative)
       unsigned int* all = reinterpret_cast<unsigned int*>(ws) + 2 + 2 * gridDim.x;
       __threadfence();
-      if (atomicAdd(all, 1u) == 2 * gridDim.x - 1) {
+      pub = atomicAdd(all, 1u) == 2 * gridDim.x - 1;
+      if (pub) {
         *all = 0u;
         __threadfence();
-        const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(px.step + 1);
-        for (int k = 1; k < px.world; ++k) {
-          int q = px.rank + k;
-          if (q >= px.world) q -= px.world;
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(px.base[q] + px.flag_off) + px.rank), "r"(epoch) : "memory");
-        }
       }
+    }
+  }
+  if (px.world > 1) {
+    __syncthreads();
+    if (pub && threadIdx.x >= 1 && static_cast<int>(threadIdx.x) < px.world) {   // one releasing thread per peer (csrc/peer.cu)
+      const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(px.step + 1);
+      int q = px.rank + threadIdx.x;
+      if (q >= px.world) q -= px.world;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(px.base[q] + px.flag_off) + px.rank), "r"(epoch) : "memory");
     }
   }
 }

@@ -85,20 +85,21 @@ peer_exchange_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32
     const int64_t words = sg.bytes >> 4;
     const int64_t total = words * world;
     int64_t i = tid;
-    for (; i + 3 * nthr < total; i += 4 * nthr) {   // 4 independent loads in flight per thread
-      uint4 v[4];
-      int64_t pw[4];
+    // 8 independent 16-byte loads in flight per thread: a load over NVLink / NVSwitch takes ~3 us under load, so the link's
+    // 900 GB/s need ~3 MB outstanding on the GPU (4 per thread measured 270 GB/s on the 59 MB "dv" reduction at 8 GPUs)
+    for (; i + 7 * nthr < total; i += 8 * nthr) {
+      uint4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int64_t j = i + u * nthr;
         const int p = static_cast<int>(j / words);
-        pw[u] = j;
         v[u] = ld_nc_na(reinterpret_cast<const uint4*>(sym.base[p] + sg.src_off) + (j - p * words));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int p = static_cast<int>(pw[u] / words);
-        reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride)[pw[u] - p * words] = v[u];
+      for (int u = 0; u < 8; ++u) {
+        const int64_t j = i + u * nthr;
+        const int p = static_cast<int>(j / words);
+        reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride)[j - p * words] = v[u];
       }
     }
     for (; i < total; i += nthr) {
@@ -141,12 +142,12 @@ peer_pull_kernel(PeerPtrs sym, int world, int rank, const uint32_t* __restrict__
       const uint4* src = reinterpret_cast<const uint4*>(sym.base[p] + sg.src_off);
       uint4* dst = reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride);
       int64_t i = tid;
-      for (; i + 3 * nthr < words; i += 4 * nthr) {
-        uint4 v[4];
+      for (; i + 7 * nthr < words; i += 8 * nthr) {     // 8 loads in flight per thread (see tic_peer_exchange)
+        uint4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_nc_na(src + i + u * nthr);
+        for (int u = 0; u < 8; ++u) v[u] = ld_nc_na(src + i + u * nthr);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) dst[i + u * nthr] = v[u];
+        for (int u = 0; u < 8; ++u) dst[i + u * nthr] = v[u];
       }
       for (; i < words; i += nthr) dst[i] = ld_nc_na(src + i);
     }
@@ -228,6 +229,7 @@ peer_push_kernel(PeerPtrs sym, int world, int rank, PushArgs xa, int64_t flag_of
       }
     }
   }
+  __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     // Block-local stores -> (bar.sync) -> gpu-scope fence + ticket -> the LAST block's release stores at system scope: the
@@ -235,33 +237,40 @@ peer_push_kernel(PeerPtrs sym, int world, int rank, PushArgs xa, int64_t flag_of
     // the ticket.  No fence.sc.sys: explicit system-scope fences cost this kernel ~8 us (19.2 -> 10.4 us at 2 GPUs,
     // profiles/r02_timeline_c2_g2_push_v1.txt vs _v2); sys_fence != 0 restores them (A/B switch).
     if (sys_fence) __threadfence_system(); else __threadfence();
-    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (s_last) {
       *ticket = 0u;
       if (sys_fence) __threadfence_system(); else __threadfence();
-      for (int k = 1; k < world; ++k) {
-        int q = rank + k;
-        if (q >= world) q -= world;
-        st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
-      }
     }
+  }
+  __syncthreads();
+  // one releasing THREAD per peer (ordered behind thread 0's fence by the bar.sync): each release store waits a fabric round
+  // trip, and a single thread looping over 7 peers made that 7 round trips (push 38 us, signal 17 us at 8 GPUs;
+  // profiles/r02_timeline_c2_g8_push_serial_flags.txt)
+  if (s_last && threadIdx.x >= 1 && threadIdx.x < world) {
+    int q = rank + threadIdx.x;
+    if (q >= world) q -= world;
+    st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
   }
 }
 
-// One thread, tail of a step: step[0] = the finished step, step[1] = the next epoch, and flags[rank] = step[0] in every peer's
+// One small block, tail of a step: step[0] = the finished step, step[1] = the next epoch, and flags[rank] = step[0] in every peer's
 // block (release at system scope): "this rank has finished reading what step[0]'s pushes delivered".
 __global__ void peer_signal_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32_t* __restrict__ step, int sys_fence) {
   pdl_trigger();
   pdl_wait();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(step + 1);
+  if (blockIdx.x != 0) return;
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(step + 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
     step[0] = epoch;
     step[1] = epoch + 1u;
+  }
+  if (threadIdx.x >= 1 && threadIdx.x < world) {      // one releasing thread per peer (see peer_push_kernel)
     if (sys_fence) __threadfence_system();
-    for (int k = 1; k < world; ++k) {
-      int q = rank + k;
-      if (q >= world) q -= world;
-      st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
-    }
+    int q = rank + threadIdx.x;
+    if (q >= world) q -= world;
+    st_release_sys(reinterpret_cast<uint32_t*>(sym.base[q] + flag_off) + rank, epoch);
   }
 }
 

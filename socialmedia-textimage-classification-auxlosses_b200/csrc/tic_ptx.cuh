@@ -41,13 +41,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Blocking wait with a watchdog: a broken pipeline traps instead of hanging the GPU box.
+// Blocking wait with a watchdog: a broken pipeline traps instead of hanging the GPU box.  The limit is WALL time (30 s on
+// %globaltimer, sampled every 64 Ki polls), not a poll count: in the multi-GPU step the producer warp of a tile kernel may
+// legitimately wait on a peer rank's flags for as long as that rank's host is late (graph instantiation, module loading),
+// and the warps behind it wait here meanwhile — a 2^26-poll limit (a few seconds) fired intermittently in the 2-GPU tests.
+__device__ __forceinline__ uint64_t watchdog_now_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr uint64_t kWatchdogNs = 30ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("tic: mbarrier watchdog (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
+    if ((++spins & 0xFFFFu) == 0u) {
+      const uint64_t t = watchdog_now_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kWatchdogNs) {
+        printf("tic: mbarrier watchdog (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }
@@ -98,6 +112,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
 // wait on a local mbarrier whose arrivals come from other CTAs (acquire at cluster scope); same watchdog as mbar_wait
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   for (;;) {
     uint32_t ok;
     asm volatile(
@@ -108,9 +123,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) break;
-    if (++spins > (1u << 26)) {
-      printf("tic: cluster mbarrier watchdog (block %d thread %d bar 0x%x)\n", blockIdx.x, threadIdx.x, bar);
-      __trap();
+    if ((++spins & 0xFFFFu) == 0u) {
+      const uint64_t t = watchdog_now_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kWatchdogNs) {
+        printf("tic: cluster mbarrier watchdog (block %d thread %d bar 0x%x)\n", blockIdx.x, threadIdx.x, bar);
+        __trap();
+      }
     }
   }
 }

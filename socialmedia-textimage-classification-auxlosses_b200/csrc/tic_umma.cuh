@@ -73,8 +73,13 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void seg_wait(const SegOrder& so, int seg, uint32_t epoch) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (static_cast<int32_t>(ld_acquire_sys_u32(so.ready + seg) - epoch) < 0) {
-    if (++spins > (1u << 28)) { printf("tic: segment %d never became ready\n", seg); __trap(); }
+    if ((++spins & 0xFFFu) == 0u) {        // wall-time limit, as mbar_wait (tic_ptx.cuh)
+      const uint64_t t = watchdog_now_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kWatchdogNs) { printf("tic: segment %d never became ready\n", seg); __trap(); }
+    }
   }
   asm volatile("fence.proxy.async.global;" ::: "memory");   // the pulled data is read by the TMA (async proxy) next
 }

@@ -52,6 +52,12 @@ class SymmetricItc:
         # gathered rows on its rounding averages out (K = N terms) and the segment is a third of a long k-loop (N = 2048: 23 us)
         self.gemm_lo = b_local * world < 1024
         self.b, self.world, self.rank, self.N = b_local, world, rank, b_local * world
+        # The push kernel may run BESIDE the tile kernels that poll the peers' flags only while those kernels cannot occupy
+        # every SM: a polling CTA holds its SM (whole register file) until the peers' pushes land, and the peers' pushes need
+        # their own SMs the same way — with both ranks' machines full of polling CTAs nobody pushes (seen as an intermittent
+        # hang at b = 1024 on 2 GPUs).  Bound: CTAs of the two forward tile kernels (128 x 64 tiles) <= 132 of the 148 SMs;
+        # above it the push is stream-ordered in front of them (its ~10 us are small against a step of that size).
+        self.push_beside = 2 * (-(-b_local // 128)) * (-(-(b_local * world) // 64)) <= 132
         # the row block and the swapped block are independent between the exchanges: issue them on parallel branches
         self.br = branches if branches is not None else _NoBranches()
 
@@ -71,9 +77,11 @@ class SymmetricItc:
         br.join("cb")
         pu = self.push
         seg = pu["seg_emb"] if pu else None
-        if pu:
+        if pu and self.push_beside:
             with br("px"):            # my rows -> every REMOTE rank's gathered buffers + flag, on a side branch: the tile kernels
                 pu["emb"]()           # below do not wait for this kernel, they poll the peers' flags segment by segment
+        elif pu:
+            pu["emb"]()               # large tile grids: the push is a predecessor of the polling kernels (see push_beside)
         else:
             self.exchange("emb")
         with br("cb"):
@@ -99,7 +107,7 @@ class SymmetricItc:
         with br("cb"):
             cb.bwd_operands(V, ldv, T_all, T_all.stride(0), scale, g / (2.0 * N), T_lo=V_lo, V_lo=T_all_lo, seg=seg)
             cb.grad_gemm_t(T_all, T_all.stride(0), V_lo=T_all_lo if self.gemm_lo else None)
-            if pu:
+            if pu and T.is_cuda:
                 ev_cb = torch.cuda.Event()
                 ev_cb.record(torch.cuda.current_stream())
             cb.finalize_t(V, ldv, T, ldt, rb.rinv_t, scale, g / N, dV_f32, dV_bf16, None, dT_lo=dV_lo, T_lo=V_lo, V_diag_lo=T_lo)
@@ -109,7 +117,8 @@ class SymmetricItc:
         rb.grad_gemm_t(V_all, V_all.stride(0), V_lo=V_all_lo if self.gemm_lo else None)
         if pu:      # both gradient GEMMs were the last readers of the gathered embeddings: tell the peers (side branch)
             with br("dn"):
-                torch.cuda.current_stream().wait_event(ev_cb)
+                if ev_cb is not None:
+                    torch.cuda.current_stream().wait_event(ev_cb)
                 pu["done"]()
         rb.finalize_t(T, ldt, V, ldv, cb.rinv_t, scale, g / N, dT_f32, dT_bf16, r_sum, dT_lo=dT_lo, T_lo=T_lo, V_diag_lo=V_lo)
         if consume_t is not None:
@@ -452,6 +461,7 @@ def _make_peer_head_plan():
                 self.rb.lse_row, self.rb.lse_col = self.lse_mine[:b], self.lse_col_all
                 self.cb.lse_row, self.cb.lse_col = self.lse_mine[b:], self.lse_row_all
             self.itc = self.rb
+            self.rb.scale_dev = self.cb.scale_dev = self.scale_t      # exp(logit_scale) by device pointer (live weights)
             self.lse_ws = torch.zeros(int(capi_load().tic_itc_lse_rows_workspace_bytes(b)) // 4, dtype=F32, device=dev)
             push = None
             if self.push_mode:
@@ -515,6 +525,7 @@ def _make_peer_head_plan():
                 publish_v_norm, publish_col_sums, lse_loss_gathered, reduce_dv
             blk.rinv_v_mine = lambda: rinv_pub
             self.itc = self.rb = blk
+            blk.scale_dev = self.scale_t
             self._keep = (col_all, dv_parts, acc_v_mine, rinv_pub, plan)
             self.sym = RowBlockItc(blk, pg.exchange, b, world, rank, branches=self.br, pull=pg.pull,
                                    seg=(v_ready, pg.ctr, b, rank))
@@ -524,11 +535,11 @@ def _make_peer_head_plan():
                 off_a, off_b, flag_off = self._lse_push
                 pg = self.pg
                 call("tic_itc_lse_rows_push", ptr(rb.row_part), ptr(cb.row_part), rb.nrp, self.B, ptr(rb.diag), float(scale),
-                     ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), None, pg._bases_c, pg.world, pg.rank,
+                     ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), ptr(self.scale_t), pg._bases_c, pg.world, pg.rank,
                      off_a, off_b, flag_off, pg.step_counter().data_ptr(), P._stream())
                 return
             call("tic_itc_lse_rows", ptr(rb.row_part), ptr(cb.row_part), rb.nrp, self.B, ptr(rb.diag), float(scale),
-                 ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), None, P._stream())
+                 ptr(rb.lse_row), ptr(cb.lse_row), ptr(loss_sums), ptr(self.lse_ws), ptr(self.scale_t), P._stream())
 
         def _heads(self, inp, dH_f32=None, forward_only=False, dz_ext=None):
             saved = self.beta_itm
@@ -564,6 +575,7 @@ def _make_peer_head_plan():
             else:
                 Yt, Yv, Ytl, Yvl = self._rows()
             self.br.enabled = self.parallel_streams
+            self._refresh("itc")       # live weights without a root refresh launch (more than 8 matrices): W_t / W_v + exp(logit_scale)
             if self.P is not None:
                 tp_, vp_ = inp["t_pool"], inp["v_pool"]
                 pt = lambda: P.gemm(tp_, tp_.stride(0), 0, w["W_t"], E, 0, Yt, self.P, 1, B, self.P, E, D_lo=Ytl)  # noqa: E731  HF :265

@@ -12,6 +12,7 @@ for device memory and streams.
 """
 import ctypes
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -206,7 +207,11 @@ class ItcPlan:
 
     @property
     def can_inline_lse(self):
-        return self.col_part is not None and self.nrp <= 64 and self.ncp <= 64
+        # every tile re-reads its nrp + ncp partials: free while the step is latency-bound, but from ~32 partials on the load
+        # chain outlasts the tile's MMAs (c5 point 8192 x 256: tic_itc_bwd_g 220 us inline vs ~75 us after the 7 us lse kernel;
+        # profiles/r02_c5_timelines.txt).  TIC_INLINE_LSE_MAX: A/B switch.
+        cap = int(os.environ.get("TIC_INLINE_LSE_MAX", "16"))      # column partials (= row tiles of 128): B <= 2048
+        return self.col_part is not None and self.nrp <= 2 * cap and self.ncp <= cap
 
     def grad_gemm_t(self, V, ldv, V_lo=None):
         # dT_acc[m,P] = GA[m,n] * V[n,P]   (A K-major, B = V read MN-major: no transposed copy of V)
@@ -831,8 +836,11 @@ class HeadPlan:
 
     @property
     def _refresh_zeroes(self):
-        """live weights on the base single-GPU plan: the refresh launches at the head of the two chains zero the small block"""
-        return (self.live_weights and getattr(self, "_in_step", False) and type(self)._itc_fwd is HeadPlan._itc_fwd and
+        """live weights: the refresh launches at the head of the two chains zero the small block (base single-GPU plan), or
+        the ONE root launch zeroes all of it (any plan whose matrices fit one launch — the multi-GPU plans touch the block
+        earlier in their chains, which only a root can precede)"""
+        base = type(self)._itc_fwd is HeadPlan._itc_fwd
+        return (self.live_weights and getattr(self, "_in_step", False) and (base or "all" in self._refresh_groups) and
                 (not self.use_itc or "itc" in self._refresh_groups) and (self.fusion is None or "fusion" in self._refresh_groups))
 
     def _zero_accumulators(self):

@@ -2,7 +2,7 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py
 
-    ... tests/dist_gpu_check.py [--mode peer|nccl] [--graph]
+    ... tests/dist_gpu_check.py [--mode peer|nccl] [--graph] [--live]
 
 --mode peer (default): tic_b200.peer.PeerHeadPlan — symmetric row/column blocks over CUDA-IPC peer memory, no collective on
 the data path; --mode nccl: tic_b200.dist.DistHeadPlan — all_gather / all_reduce / reduce_scatter.  --graph replays the step
@@ -36,6 +36,7 @@ def main():
     if "--mode" in sys.argv:
         mode = sys.argv[sys.argv.index("--mode") + 1]
     use_graph = "--graph" in sys.argv
+    live = "--live" in sys.argv       # peer mode: fp32 master weights refreshed by the root launch of every step (as bench.py)
     if mode == "peer":
         from tic_b200.peer import PeerHeadPlan as DistHeadPlan
     else:
@@ -70,7 +71,10 @@ def main():
         w32 = R.init_params(C, seed=5)
         kw = dict(E=E, P=(512 if fusion is not None else None), C=C, fusion=fusion, use_itc=True, use_itm=use_itm, Lv=1)
         dplan = DistHeadPlan(b, world=world, rank=rank, d=(E if fusion is None else None), device=dev, **kw)
-        dplan.set_weights(w32)
+        if live and mode == "peer":
+            dplan.bind_params({k: torch.as_tensor(v).to(dev) for k, v in w32.items()}, live=True)
+        else:
+            dplan.set_weights(w32)
         out = dplan.step(shard)
         torch.cuda.synchronize()
         if use_graph:      # the whole multi-GPU step (exchanges included) as one CUDA graph, replayed twice

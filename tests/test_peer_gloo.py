@@ -29,12 +29,14 @@ class CpuBlock:
     def norm_t(self, T, ldt, T_lo=None):
         self.rinv_t.copy_(1.0 / T.norm(dim=1))
 
-    def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None):
+    def fwd_tiles(self, T, ldt, V, ldv, scale, T_lo=None, V_lo=None, seg=None):
+        self.seen_seg_fwd = seg
         self.S = scale * (T * self.rinv_t[:, None]) @ (V * self.rinv_v[:, None]).t()
         self.row_sum = torch.exp(self.S - scale).sum(1)
         self.diag = self.S[torch.arange(self.m), self.row_offset + torch.arange(self.m)]
 
-    def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None):
+    def bwd_operands(self, T, ldt, V, ldv, scale, gscale, T_lo=None, V_lo=None, seg=None):
+        self.seen_seg_bwd = seg
         Gp = gscale * (torch.exp(self.S - self.lse_row[:, None]) + torch.exp(self.S - self.lse_col[None, :]))
         self.GA = Gp * self.rinv_v[None, :]
 
@@ -50,7 +52,10 @@ class CpuBlock:
             r_sum += r.sum()
 
 
-def _worker(rank, world, port, b, P, out_q):
+def _worker(rank, world, port, b, P, out_q, push=None):
+    """push: None = the pull form (exchange phases); "beside" / "before" = the PUSH form's sequencing (tic_peer_push): the
+    embeddings are delivered by the "emb" callable (on a side branch / stream-ordered before the polling tile kernels), the
+    lse vectors by the lse_rows launch itself, the tile kernels receive the flag tuples, and "done" is signalled once."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -78,7 +83,23 @@ def _worker(rank, world, port, b, P, out_q):
             loss_sums[0] += (rb_.lse_row - rb_.diag).sum()
             loss_sums[1] += (cb_.lse_row - rb_.diag).sum()
 
-        sym = SymmetricItc(rb, cb, exchange, lse_rows, b, world, rank)
+        calls = []
+        pu = None
+        if push is not None:
+            def lse_rows_push(rb_, cb_, s, loss_sums):      # the lse exchange rides on this launch in the push form
+                lse_rows(rb_, cb_, s, loss_sums)
+                exchange("lse")
+                calls.append("lse_rows+push")
+            pu = {"emb": lambda: (exchange("emb"), calls.append("emb")), "lse": lambda: calls.append("lse(no-op)"),
+                  "done": lambda: calls.append("done"), "seg_emb": ("flags-emb", rank), "seg_lse": ("flags-lse", rank)}
+
+            def no_pull(phase):
+                raise AssertionError("the push form must not run the pull-form exchange %r" % phase)
+            sym = SymmetricItc(rb, cb, no_pull, lse_rows_push, b, world, rank, push=pu)
+            assert sym.push_beside            # tiny grids: the push runs beside the polling kernels
+            sym.push_beside = push == "beside"
+        else:
+            sym = SymmetricItc(rb, cb, exchange, lse_rows, b, world, rank)
         sums = torch.zeros(2, dtype=torch.float64)
         sym.forward(T, V, T_all, V_all, scale, sums)
         dT, dV = torch.empty(b, P, dtype=torch.float64), torch.empty(b, P, dtype=torch.float64)
@@ -96,6 +117,10 @@ def _worker(rank, world, port, b, P, out_q):
               and torch.allclose(dV, Vq.grad[rank * b:(rank + 1) * b], rtol=1e-8, atol=1e-12)
               and abs(float(rsum) - float(ls.grad)) < 1e-9
               and torch.allclose(rb.diag, cb.diag, rtol=1e-12))
+        if push is not None:     # sequencing of the push form
+            ok = (ok and calls == ["emb", "lse_rows+push", "lse(no-op)", "done"]
+                  and rb.seen_seg_fwd == pu["seg_emb"] and cb.seen_seg_fwd == pu["seg_emb"]
+                  and rb.seen_seg_bwd == pu["seg_lse"] and cb.seen_seg_bwd == pu["seg_lse"])
         out_q.put((rank, bool(ok), float(loss), float(ref)))
     finally:
         dist.destroy_process_group()
@@ -241,6 +266,24 @@ def test_peer_itc_matches_oracle_world2(worker, b, P):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=worker, args=(r, 2, port, b, P, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    assert all(ok for _, ok, _, _ in res), res
+
+
+@pytest.mark.parametrize("push", ["beside", "before"])
+def test_peer_itc_push_form_sequencing_world2(push):
+    """The PUSH form of the symmetric exchange (SymmetricItc(push=...)): same losses and gradients as the oracle, the
+    pull-form exchange is never called, the embeddings are pushed once, the lse vectors ride on lse_rows, every tile call
+    receives the flag tuple of its phase, and `done` is signalled exactly once after the last reader."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 8, 16, q, push)) for r in range(2)]
     for p_ in procs:
         p_.start()
     res = [q.get(timeout=120) for _ in procs]
