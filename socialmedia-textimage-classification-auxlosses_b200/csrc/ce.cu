@@ -9,7 +9,8 @@
 namespace tic {
 
 constexpr int kCeCols = 128;  // columns per strip
-constexpr int kCeRows = 64;   // rows per smem tile
+constexpr int kCeRows = 64;   // rows per tile (two half tiles of 32)
+constexpr int kCeLseThreads = 64;   // combine kernel: small blocks, so that 2 x B outputs spread over the SMs
 
 __host__ __device__ inline int ce_nstrips(int B) { return (B + kCeCols - 1) / kCeCols; }
 __host__ __device__ inline int ce_nseg(int B) {
@@ -181,7 +182,7 @@ ce_bidir_fwd_kernel(const float* __restrict__ S, int64_t lds, int B, float2* __r
 
 // Combine the partials into the lse vectors, many blocks; blockIdx.y = direction.  Block partials of the loss go to `bp`; the
 // LAST block to finish (ticket, zeroed by the forward kernel) adds them in index order -> loss (deterministic, no third launch).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCeLseThreads)
 ce_bidir_lse_kernel(const float2* __restrict__ rp, int nstrips, const float2* __restrict__ cp, int nseg, const float* __restrict__ diag,
                     int B, float* __restrict__ lse_row, float* __restrict__ lse_col, float* __restrict__ bp,
                     unsigned int* __restrict__ ticket, float* __restrict__ loss) {
@@ -193,20 +194,31 @@ ce_bidir_lse_kernel(const float2* __restrict__ rp, int nstrips, const float2* __
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float term = 0.f;
   if (i < B) {
-    float m = -INFINITY, s = 0.f;
-    for (int k = 0; k < np; ++k) { const float2 p = part[static_cast<int64_t>(k) * B + i]; ms_combine(m, s, p.x, p.y); }
+    // two passes over the (few, L2-resident) partials instead of a serial chain of combines: all loads of a pass are
+    // independent, and the second pass costs one exponential per partial
+    float m = -INFINITY;
+#pragma unroll 8
+    for (int k = 0; k < np; ++k) m = fmaxf(m, part[static_cast<int64_t>(k) * B + i].x);
+    float s = 0.f;
+    if (m != -INFINITY) {
+#pragma unroll 8
+      for (int k = 0; k < np; ++k) {
+        const float2 p = part[static_cast<int64_t>(k) * B + i];
+        s += p.y * __expf(fmaxf(p.x - m, -INFINITY));      // (-inf) - m = -inf -> 0; never NaN (m is finite here)
+      }
+    }
     const float l = m + logf(s);
     (dir == 0 ? lse_row : lse_col)[i] = l;
     term = l - diag[i];
   }
-  __shared__ float sw[8];
+  __shared__ float sw[kCeLseThreads / 32];
   __shared__ bool last;
   term = warp_sum(term);
   if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = term;
   __syncthreads();
   if (threadIdx.x == 0) {
     float a = 0.f;
-    for (int w = 0; w < 8; ++w) a += sw[w];
+    for (int w = 0; w < kCeLseThreads / 32; ++w) a += sw[w];
     bp[dir * gridDim.x + blockIdx.x] = a;
     __threadfence();
     last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
@@ -268,7 +280,7 @@ extern "C" {
 int64_t tic_ce_bidir_workspace_bytes(int B) {
   if (B <= 0) return 0;
   return static_cast<int64_t>(sizeof(float2)) * B * (ce_nstrips(B) + ce_nseg(B)) + sizeof(float) * B +
-         sizeof(float) * 2 * ((B + 255) / 256) + 64;
+         sizeof(float) * 2 * ((B + kCeLseThreads - 1) / kCeLseThreads) + 64;
 }
 
 int tic_ce_bidir_fwd(const float* S, int64_t lds, int B, float* lse_row, float* lse_col, float* loss, void* workspace,
@@ -280,10 +292,10 @@ int tic_ce_bidir_fwd(const float* S, int64_t lds, int B, float* lse_row, float* 
   float2* cp = rp + static_cast<int64_t>(ns) * B;
   float* diag = reinterpret_cast<float*>(cp + static_cast<int64_t>(ng) * B);
   float* bp = diag + B;
-  const int nb = ceil_div(B, 256);
+  const int nb = ceil_div(B, kCeLseThreads);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(bp + 2 * nb);      // inside the 64-byte tail of the workspace
   launch_k(ce_bidir_fwd_kernel, dim3(dim3(ns, ng)), dim3(256), 0, st, S, lds, B, rp, cp, diag, ticket);
-  launch_k(ce_bidir_lse_kernel, dim3(nb, 2), dim3(256), 0, st, rp, ns, cp, ng, diag, B, lse_row, lse_col, bp, ticket, loss);
+  launch_k(ce_bidir_lse_kernel, dim3(nb, 2), dim3(kCeLseThreads), 0, st, rp, ns, cp, ng, diag, B, lse_row, lse_col, bp, ticket, loss);
   TIC_CHECK_LAUNCH("tic_ce_bidir_fwd");
   return TIC_OK;
 }

@@ -907,6 +907,7 @@ __global__ void itc_loss_kernel(const float* __restrict__ lse_row, const float* 
 // Optional PUSH of the two lse vectors (multi-GPU symmetric form): every value is also stored into the remote peers' gathered
 // vectors (slot of this rank), and the last block of the launch releases the peers' flags = step[1] — the exchange costs no
 // kernel of its own (it was a 6-8 us launch between the forward and the gradient-operand tiles).
+constexpr int kLseRowsPerBlock = 32;   // itc_lse_rows_kernel: 256 threads = 32 rows x 8 lanes
 struct LsePush {
   uint8_t* base[8];       // every rank's peer-mapped block (world == 0: no push)
   int world, rank;
@@ -926,18 +927,29 @@ __global__ void itc_lse_rows_kernel(const float* __restrict__ part_a, const floa
   float* lse = dir == 0 ? lse_a : lse_b;
   float* blk_part = ws + 2 + dir * gridDim.x;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(ws) + dir;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // 8 lanes per row (32 rows per block): the partials of a row are loaded by 8 threads at once — one thread per row walked
+  // up to 64 partials through a serial add chain, ~12 us at 4 GPUs for 2 x 256 rows on the step's critical chain
+  // (profiles/r02_timeline_c2_g4.txt)
+  const int sub = threadIdx.x & 7;
+  const int i = blockIdx.x * kLseRowsPerBlock + (threadIdx.x >> 3);
   float term = 0.f;
-  if (i < m) {
+  {
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[static_cast<int64_t>(p) * m + i];
-    const float l = shift + logf(s);
-    lse[i] = l;
-    term = l - diag[i];
-    for (int k = 1; k < px.world; ++k) {     // remote peers' copies of this rank's slot
-      int q = px.rank + k;
-      if (q >= px.world) q -= px.world;
-      reinterpret_cast<float*>(px.base[q] + (dir == 0 ? px.off_a : px.off_b))[static_cast<int64_t>(px.rank) * m + i] = l;
+    if (i < m)
+      for (int p = sub; p < nparts; p += 8) s += part[static_cast<int64_t>(p) * m + i];
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (i < m) {
+      const float l = shift + logf(s);
+      if (sub == 0) {
+        lse[i] = l;
+        term = l - diag[i];
+      } else if (sub < px.world) {          // lane k of the row's group: the remote copy in peer rank + k
+        int q = px.rank + sub;
+        if (q >= px.world) q -= px.world;
+        reinterpret_cast<float*>(px.base[q] + (dir == 0 ? px.off_a : px.off_b))[static_cast<int64_t>(px.rank) * m + i] = l;
+      }
     }
   }
   __shared__ float sw[32];
@@ -1267,13 +1279,13 @@ int tic_itc_lse_loss(const float* row_part, int n_row_parts, const float* col_pa
   return TIC_OK;
 }
 
-int64_t tic_itc_lse_rows_workspace_bytes(int m) { return static_cast<int64_t>(3 + 2 * ceil_div(m, 256)) * 4; }
+int64_t tic_itc_lse_rows_workspace_bytes(int m) { return static_cast<int64_t>(3 + 2 * ceil_div(m, kLseRowsPerBlock)) * 4; }
 
 int tic_itc_lse_rows(const float* part_a, const float* part_b, int n_parts, int m, const float* diag, float shift, float* lse_a,
                      float* lse_b, float* loss_sums, void* workspace, const float* scale_dev, void* stream) {
   TIC_CHECK_ARG(part_a && part_b && diag && lse_a && lse_b && loss_sums && workspace && n_parts > 0 && m > 0,
                 "tic_itc_lse_rows: bad arguments");
-  dim3 grid(ceil_div(m, 256), 2);
+  dim3 grid(ceil_div(m, kLseRowsPerBlock), 2);
   launch_k(itc_lse_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), part_a, part_b, n_parts, m, diag, shift,
            scale_dev, lse_a, lse_b, loss_sums, static_cast<float*>(workspace), LsePush{});
   TIC_CHECK_LAUNCH("tic_itc_lse_rows");
@@ -1294,7 +1306,7 @@ int tic_itc_lse_rows_push(const float* part_a, const float* part_b, int n_parts,
     px.base[p] = static_cast<uint8_t*>(bases_host[p]);
   }
   px.world = world; px.rank = rank; px.off_a = off_a; px.off_b = off_b; px.flag_off = flag_off; px.step = step;
-  dim3 grid(ceil_div(m, 256), 2);
+  dim3 grid(ceil_div(m, kLseRowsPerBlock), 2);
   launch_k(itc_lse_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), part_a, part_b, n_parts, m, diag, shift,
            scale_dev, lse_a, lse_b, loss_sums, static_cast<float*>(workspace), px);
   TIC_CHECK_LAUNCH("tic_itc_lse_rows_push");

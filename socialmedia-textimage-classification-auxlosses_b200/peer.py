@@ -104,9 +104,23 @@ class SymmetricItc:
         pu = self.push
         seg = pu["seg_lse"] if pu else None
         ev_cb = None
+        # split-K gradient GEMMs accumulate with atomics: their accumulators are zeroed on side branches beside the tile kernels
+        # (in stream order the two ~2 us memsets sat between the tiles and the GEMMs of the step's critical chain)
+        zc = getattr(cb, "splitk_grad", False) and getattr(br, "enabled", False)
+        zr = getattr(rb, "splitk_grad", False) and getattr(br, "enabled", False)
+        if zc:
+            with br("zc"):
+                cb.acc_t.zero_()
+        if zr:
+            with br("zr"):
+                rb.acc_t.zero_()
         with br("cb"):
             cb.bwd_operands(V, ldv, T_all, T_all.stride(0), scale, g / (2.0 * N), T_lo=V_lo, V_lo=T_all_lo, seg=seg)
-            cb.grad_gemm_t(T_all, T_all.stride(0), V_lo=T_all_lo if self.gemm_lo else None)
+            if zc:
+                br.join("zc")
+                cb.grad_gemm_t(T_all, T_all.stride(0), V_lo=T_all_lo if self.gemm_lo else None, prezeroed=True)
+            else:
+                cb.grad_gemm_t(T_all, T_all.stride(0), V_lo=T_all_lo if self.gemm_lo else None)
             if pu and T.is_cuda:
                 ev_cb = torch.cuda.Event()
                 ev_cb.record(torch.cuda.current_stream())
@@ -114,7 +128,11 @@ class SymmetricItc:
             if consume_v is not None:
                 consume_v()
         rb.bwd_operands(T, ldt, V_all, V_all.stride(0), scale, g / (2.0 * N), T_lo=T_lo, V_lo=V_all_lo, seg=seg)
-        rb.grad_gemm_t(V_all, V_all.stride(0), V_lo=V_all_lo if self.gemm_lo else None)
+        if zr:
+            br.join("zr")
+            rb.grad_gemm_t(V_all, V_all.stride(0), V_lo=V_all_lo if self.gemm_lo else None, prezeroed=True)
+        else:
+            rb.grad_gemm_t(V_all, V_all.stride(0), V_lo=V_all_lo if self.gemm_lo else None)
         if pu:      # both gradient GEMMs were the last readers of the gathered embeddings: tell the peers (side branch)
             with br("dn"):
                 if ev_cb is not None:

@@ -213,10 +213,11 @@ class ItcPlan:
         cap = int(os.environ.get("TIC_INLINE_LSE_MAX", "16"))      # column partials (= row tiles of 128): B <= 2048
         return self.col_part is not None and self.nrp <= 2 * cap and self.ncp <= cap
 
-    def grad_gemm_t(self, V, ldv, V_lo=None):
+    def grad_gemm_t(self, V, ldv, V_lo=None, prezeroed=False):
         # dT_acc[m,P] = GA[m,n] * V[n,P]   (A K-major, B = V read MN-major: no transposed copy of V)
         if self.splitk_grad:   # few output tiles, long K (a small row block against many gathered columns): split K over CTAs
-            self.acc_t.zero_()
+            if not prezeroed:  # (the multi-GPU sequencing zeroes acc_t on a side branch beside the gradient-operand tiles)
+                self.acc_t.zero_()
             gemm(self.GA, self.ld_ga, 0, V, ldv, 1, self.acc_t, self.P, 0, self.m, self.P, self.n, A_lo=self.GA_lo, B_lo=V_lo,
                  accumulate=True)
             return
