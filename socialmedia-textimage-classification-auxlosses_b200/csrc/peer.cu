@@ -85,21 +85,22 @@ peer_exchange_kernel(PeerPtrs sym, int world, int rank, int64_t flag_off, uint32
     const int64_t words = sg.bytes >> 4;
     const int64_t total = words * world;
     int64_t i = tid;
-    // 8 independent 16-byte loads in flight per thread: a load over NVLink / NVSwitch takes ~3 us under load, so the link's
-    // 900 GB/s need ~3 MB outstanding on the GPU (4 per thread measured 270 GB/s on the 59 MB "dv" reduction at 8 GPUs)
-    for (; i + 7 * nthr < total; i += 8 * nthr) {
-      uint4 v[8];
+    // 4 independent loads in flight per thread.  (8 were tried for the 59 MB "dv" reduction at 8 GPUs, which runs at 270 GB/s:
+    // no gain there — the transfer is not bound by the loads in flight — and the short exchanges fell into the scalar tail loop.)
+    for (; i + 3 * nthr < total; i += 4 * nthr) {
+      uint4 v[4];
+      int64_t pw[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const int64_t j = i + u * nthr;
         const int p = static_cast<int>(j / words);
+        pw[u] = j;
         v[u] = ld_nc_na(reinterpret_cast<const uint4*>(sym.base[p] + sg.src_off) + (j - p * words));
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int64_t j = i + u * nthr;
-        const int p = static_cast<int>(j / words);
-        reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride)[j - p * words] = v[u];
+      for (int u = 0; u < 4; ++u) {
+        const int p = static_cast<int>(pw[u] / words);
+        reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride)[pw[u] - p * words] = v[u];
       }
     }
     for (; i < total; i += nthr) {
@@ -142,12 +143,12 @@ peer_pull_kernel(PeerPtrs sym, int world, int rank, const uint32_t* __restrict__
       const uint4* src = reinterpret_cast<const uint4*>(sym.base[p] + sg.src_off);
       uint4* dst = reinterpret_cast<uint4*>(sg.dst + p * sg.dst_stride);
       int64_t i = tid;
-      for (; i + 7 * nthr < words; i += 8 * nthr) {     // 8 loads in flight per thread (see tic_peer_exchange)
-        uint4 v[8];
+      for (; i + 3 * nthr < words; i += 4 * nthr) {
+        uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ld_nc_na(src + i + u * nthr);
+        for (int u = 0; u < 4; ++u) v[u] = ld_nc_na(src + i + u * nthr);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) dst[i + u * nthr] = v[u];
+        for (int u = 0; u < 4; ++u) dst[i + u * nthr] = v[u];
       }
       for (; i < words; i += nthr) dst[i] = ld_nc_na(src + i);
     }

@@ -251,6 +251,11 @@ class MMLate_Model(object):
                   eval_txt_test=False, compute_class_weights=True, random_labels=False):
         """mm_late.py:346-387.  Dataset construction is outside this path: it is delegated to
         the reference's own `utils.prepare_data` and `datasets.MM_Dataset`, which must be importable."""
+        if eval_txt_test:
+            # reference mm_late.py:372-387 builds a text-only test loader from a second CSV; dataset plumbing is outside this
+            # path, and returning None here would make --eval_txt_test silently skip the preds_txt / metrics_txt files
+            raise NotImplementedError("eval_txt_test: the text-only test loader (reference mm_late.py:372-387) is not built by "
+                                      "this package — construct it with the reference's datasets.MM_Dataset and call eval() on it")
         try:
             from datasets import MM_Dataset          # reference models/datasets.py
             from utils import prepare_data           # reference models/utils.py
