@@ -647,14 +647,30 @@ __global__ void __launch_bounds__(256) refresh_weights_kernel(RefreshArgs a) {
   const bool vec = (d.cols & 3) == 0 && (d.lds & 3) == 0 && (d.ldd & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(d.dst) & 7) == 0);
   if (vec) {
-    const int64_t n4 = static_cast<int64_t>(d.rows) * (d.cols >> 2);
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-      const int64_t r = i / (d.cols >> 2), c = (i - r * (d.cols >> 2)) << 2;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(d.src + r * d.lds + c));
-      uint2 u;
-      u.x = pack_bf16x2(v.x, v.y);
-      u.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(d.dst + r * d.ldd + c) = u;
+    // this kernel is the root of the captured step and reads cold HBM: 4 independent 16-byte loads per thread and round
+    const int64_t n4 = static_cast<int64_t>(d.rows) * (d.cols >> 2), c4 = d.cols >> 2;
+    const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * nthr) {
+      float4 v[4];
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const int64_t i = i0 + u4 * nthr;
+        if (i < n4) {
+          const int64_t r = i / c4, c = (i - r * c4) << 2;
+          v[u4] = __ldg(reinterpret_cast<const float4*>(d.src + r * d.lds + c));
+        }
+      }
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const int64_t i = i0 + u4 * nthr;
+        if (i < n4) {
+          const int64_t r = i / c4, c = (i - r * c4) << 2;
+          uint2 u;
+          u.x = pack_bf16x2(v[u4].x, v[u4].y);
+          u.y = pack_bf16x2(v[u4].z, v[u4].w);
+          *reinterpret_cast<uint2*>(d.dst + r * d.ldd + c) = u;
+        }
+      }
     }
   } else {
     const int64_t n = static_cast<int64_t>(d.rows) * d.cols;
@@ -845,8 +861,9 @@ int tic_refresh_weights(int n, const float* const* src_host, void* const* dst_ho
     const int64_t e = static_cast<int64_t>(rows_host[i]) * cols_host[i];
     if (e > most) most = e;
   }
-  // ~2 vectors per thread for the largest matrix; smaller matrices leave their surplus blocks idle (they exit at once)
-  int gx = static_cast<int>((most / 4 + 511) / 512);
+  // 4 vectors per thread (one round of 4 independent loads) for the largest matrix: ~1150 blocks for the c2 weights = one
+  // resident wave; smaller matrices leave their surplus blocks idle (they exit at once)
+  int gx = static_cast<int>((most / 4 + 1023) / 1024);
   if (gx < 1) gx = 1;
   if (gx > 592) gx = 592;
   launch_k(refresh_weights_kernel, dim3(gx, n > 0 ? n : 1), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
