@@ -663,6 +663,16 @@ def kernel_rooflines(P, plan, spec, dev_in, n_global, flush):
         ks.append(dict(kernel="tic_gemm_bf16 x2 (dT = GA*V, dV = GBT*T)", bound="tensor", ms=ms,
                        achieved=4.0 * B * B * d / ms * 1e-9, unit="TFLOP/s", algorithmic="4*B^2*d FLOP",
                        traffic_key="gemm_dtdv_" + shp))
+        if getattr(plan, "fuse_itc_small", False) and it.can_fuse_small and spec["P"] is not None:
+            # what the step itself launches at this size instead of the forward / gradient-operand pair above (timed with the
+            # step's own operands: split-precision embeddings)
+            Ft, Fv, Ftl, Fvl = plan._itc_operands(dev_in)
+            ms = time_kernel_graph(lambda: it.fwd_bwd_fused(Ft, Ft.stride(0), Fv, Fv.stride(0), plan.scale, 1.0 / (2 * B), T_lo=Ftl,
+                                                            V_lo=Fvl), flush)
+            ks.append(dict(kernel="tic_itc_fwd_bwd_small (ONE cluster launch: similarity tiles, softmax statistics, gradient operands; "
+                                  "the form the step uses at this size)", bound="tensor", ms=ms,
+                           achieved=2.0 * B * B * d / ms * 1e-9, unit="TFLOP/s",
+                           algorithmic="2*B^2*d FLOP (the k-loop runs once; split-precision operands execute 3x that)"))
     if spec["use_itc"] and getattr(plan, "itc_mode", None) == "rowblock":
         # multi-GPU row block (this rank's m = B rows against the n_global gathered columns): the rank-local tensor kernels
         blk, T, V_all = plan.rb, plan.Y[:B], plan.V_all
