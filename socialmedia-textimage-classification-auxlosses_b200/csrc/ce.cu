@@ -15,7 +15,7 @@ constexpr int kCeLseThreads = 64;   // combine kernel: small blocks, so that 2 x
 __host__ __device__ inline int ce_nstrips(int B) { return (B + kCeCols - 1) / kCeCols; }
 __host__ __device__ inline int ce_nseg(int B) {
   const int tiles = (B + kCeRows - 1) / kCeRows;
-  int want = (4 * 148) / ce_nstrips(B);      // 4 resident blocks per SM: one full wave, no tail
+  int want = (3 * 148) / ce_nstrips(B);      // 3 resident blocks per SM: one full wave, no tail
   if (want < 1) want = 1;
   return want < tiles ? want : tiles;
 }
@@ -50,7 +50,7 @@ __device__ __forceinline__ float ce_ex2(float x) {     // ex2.approx.ftz: 2^(-in
   return y;
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 ce_bidir_fwd_kernel(const float* __restrict__ S, int64_t lds, int B, float2* __restrict__ rp, float2* __restrict__ cp,
                     float* __restrict__ diag, unsigned int* __restrict__ ticket) {
   pdl_trigger();   // let the next kernel of the chain start its prologue (programmatic dependent launch)
@@ -145,14 +145,20 @@ ce_bidir_fwd_kernel(const float* __restrict__ S, int64_t lds, int B, float2* __r
     }
   };
 
-  // software pipeline over half tiles: the loads of the next half tile are in flight while this one is consumed
-  float4 fa[4], fb[4];
-  if (h_begin < h_end) load4(fa, h_begin);
-  for (int h = h_begin; h < h_end; h += 2) {
-    if (h + 1 < h_end) load4(fb, h + 1);
-    consume(fa, h);
-    if (h + 2 < h_end) load4(fa, h + 2);
-    if (h + 1 < h_end) consume(fb, h + 1);
+  // software pipeline over half tiles, depth 2: the loads of the next TWO half tiles (8 x 16 bytes per thread) are in flight
+  // while this one is consumed — 96 KB outstanding per SM with 3 resident blocks.  Measured equal to depth 1 x 4 blocks (64 KB
+  // outstanding): 24.3 vs 24.1 us for the call at B = 4096, so bytes in flight are not what holds the statistics kernel at
+  // 3.5 TB/s; the 512-byte row pieces per warp (16 KB apart) are the remaining suspect.
+  float4 f0[4], f1[4], f2[4];
+  if (h_begin < h_end) load4(f0, h_begin);
+  if (h_begin + 1 < h_end) load4(f1, h_begin + 1);
+  for (int h = h_begin; h < h_end; h += 3) {
+    if (h + 2 < h_end) load4(f2, h + 2);
+    consume(f0, h);
+    if (h + 3 < h_end) load4(f0, h + 3);
+    if (h + 1 < h_end) consume(f1, h + 1);
+    if (h + 4 < h_end) load4(f1, h + 4);
+    if (h + 2 < h_end) consume(f2, h + 2);
   }
   // ---- column partials of the block: combine the 8 warps' (reference, sums)
   sm_s[w][c4 + 0] = cs0; sm_s[w][c4 + 1] = cs1; sm_s[w][c4 + 2] = cs2; sm_s[w][c4 + 3] = cs3;
