@@ -267,6 +267,13 @@ static bool gemm_multicast() {
   return v == 1;
 }
 
+// Smallest tile count for which the 2-CTA multicast form is used (TIC_GEMM_MULTICAST_MIN_TILES: measurement switch).
+static int gemm_multicast_min_tiles(int sms) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TIC_GEMM_MULTICAST_MIN_TILES"); v = e ? atoi(e) : 0; }
+  return v > 0 ? v : 2 * sms;
+}
+
 // ------------------------------------------------------------------ SIMT reference GEMM (self-test only)
 __global__ void simt_gemm_kernel(const __nv_bfloat16* A, int64_t lda, int a_mn, const __nv_bfloat16* B, int64_t ldb,
                                  int b_mn, void* D, int64_t ldd, int d_bf16, int M, int N, int K, float alpha,
@@ -352,7 +359,7 @@ static int gemm_impl(const void* A, const void* A_lo, int64_t lda, int a_mn, con
   gemm_config(M, N, K, (A_lo ? 1 : 0) + (B_lo ? 1 : 0), accumulate, row_ss_part != nullptr, best_bn, best_ks, kc);
   int rc;
   const bool cluster = gemm_multicast() && !A_lo && !B_lo && best_ks == 1 && best_bn == 256 && m_tiles >= 16 &&
-                       static_cast<int64_t>(m_tiles) * ceil_div(N, best_bn) >= 2 * sms;
+                       static_cast<int64_t>(m_tiles) * ceil_div(N, best_bn) >= gemm_multicast_min_tiles(sms);
   if (cluster) rc = dispatch_major_cluster<256>(A, lda, a_mn, B, ldb, b_mn, M, N, K, ep, st);
   else if (best_bn == 256) rc = dispatch_major<256>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks);
   else if (best_bn == 128) rc = dispatch_major<128>(A, A_lo, lda, a_mn, B, B_lo, ldb, b_mn, M, N, K, ep, st, best_ks, kc);
